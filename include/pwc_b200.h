@@ -1,0 +1,91 @@
+/* pwc_b200.h -- C ABI of libpwc_b200.so: the sm_100a compute path behind the Python call
+ * surface of daigo0927/pwcnet (PWCDCNet.__call__, modules.py callables, losses.py).
+ *
+ * The reference has no FFI layer of its own (it is pure TensorFlow-1.8 Python); every entry
+ * point below replaces the TF graph ops that one reference function builds, and cites that
+ * function.  Conventions for every call:
+ *   - all pointers are DEVICE pointers to float32 unless said otherwise; tensors are NHWC;
+ *   - a "*_cs" argument is the channel stride (floats between consecutive pixels) of that
+ *     tensor, so an op can read from / write into a channel slot of a wider concat buffer
+ *     (this is how tf.concat, modules.py:262-264,305, is eliminated); pass C for a dense tensor;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work: no allocation, no
+ *     synchronisation, no hidden state; entry points are re-entrant;
+ *   - return value 0 = success; >0 = cudaError_t; <0 = PWC_E_* argument error.  Nothing throws
+ *     or aborts.  pwc_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef PWC_B200_H_
+#define PWC_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PWC_ABI_VERSION 1
+
+#define PWC_E_BADARG   (-1)  /* null pointer, non-positive dim, unsupported combination      */
+#define PWC_E_ALIGN    (-2)  /* pointer / stride alignment required by the kernel not met    */
+#define PWC_E_NOTBUILT (-3)  /* entry point compiled out                                     */
+
+int pwc_version(void);
+const char* pwc_last_error(void);
+
+/* CostVolumeLayer.__call__ -> get_cost x (2r+1)^2  (modules.py:164-204).
+ * out[b,y,x,(v+r)*(2r+1)+(h+r)] = leaky_alpha( (1/C) sum_c f0[b,y,x,c] * f1[b,y+v,x+h,c] ),
+ * zero outside the image.  If f0_copy != NULL the f0 tile staged on chip is also written to
+ * f0_copy (channel stride f0_copy_cs) -- the estimator's concat slot (modules.py:262).
+ * Requires C % 4 == 0, 16-byte aligned f0/f1 and f0_cs % 4 == 0, f1_cs % 4 == 0. */
+int pwc_cost_volume_fwd(const float* f0, int f0_cs, const float* f1, int f1_cs,
+                        float* out, int out_cs, float* f0_copy, int f0_copy_cs,
+                        int B, int H, int W, int C, int search_range, float alpha, void* stream);
+
+/* Fused WarpingLayer + CostVolumeLayer (model.py:109-112 -> modules.py:99-137,189-204):
+ * f1 is warped by flow*flow_scale on chip while the halo tile is staged; the warped features
+ * never reach HBM.  warp_type 0 = bilinear (modules.py:99-137), 1 = nearest (modules.py:83-97). */
+int pwc_warp_cost_volume_fwd(const float* f0, int f0_cs, const float* f1, int f1_cs,
+                             const float* flow, int flow_cs, float flow_scale, int warp_type,
+                             float* out, int out_cs, float* f0_copy, int f0_copy_cs,
+                             int B, int H, int W, int C, int search_range, float alpha, void* stream);
+
+/* WarpingLayer.__call__ (modules.py:139-154): bilinear_warp (99-137) / nearest_warp (83-97).
+ * flow channel 0 = x, channel 1 = y, in pixels, multiplied by flow_scale first (model.py:109). */
+int pwc_warp_fwd(const float* x, int x_cs, const float* flow, int flow_cs, float flow_scale,
+                 int warp_type, float* out, int out_cs, int B, int H, int W, int C, void* stream);
+
+/* tf.layers.Conv2D(filters,(3,3),strides,'same',dilation_rate) + bias [+ residual] [+ leaky]
+ * (modules.py:62-67, 266-277, 306-326).  w is HWIO (3,3,Cin,Cout) exactly as in the reference
+ * checkpoint; TF asymmetric SAME padding.  alpha = leaky slope (1.0f = no activation).
+ * residual (may be NULL, channel stride res_cs) is added AFTER the activation-free head
+ * (modules.py:275-277, 326).  CUDA-core fp32 path: any Cin/Cout/stride/dilation. */
+int pwc_conv3x3_fwd(const float* x, int x_cs, const float* w_hwio, const float* bias,
+                    const float* residual, int res_cs, float* y, int y_cs,
+                    int B, int H, int W, int Cin, int Cout, int stride, int dilation,
+                    float alpha, void* stream);
+
+/* Same function on the tcgen05 tensor cores (implicit GEMM, TMA-staged taps, TMEM accumulators).
+ * w_packed: [9][Cout_pad][Cin_pad] fp32 (tap-major, K contiguous) produced by
+ * pwc_conv3x3_pack_weights; n_split = 1 (TF32) or 3 (3xTF32 error-compensated, fp32-class).
+ * Requires stride 1, x 16-byte aligned, x_cs % 4 == 0, Cout % 16 == 0, Cout <= 256. */
+int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packed, const float* bias,
+                       float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int dilation,
+                       float alpha, int n_split, void* stream);
+/* bytes needed for w_packed (hi and lo planes) */
+long long pwc_conv3x3_packed_bytes(int Cin, int Cout);
+int pwc_conv3x3_pack_weights(const float* w_hwio, float* w_packed, int Cin, int Cout, void* stream);
+
+/* tf.image.resize_bilinear(x,(OH,OW)) with align_corners=False as in TF 1.8 (no half-pixel
+ * offset; modules.py:283-284, model.py:127), result multiplied by `mul` (model.py:127 "*20."). */
+int pwc_resize_bilinear_fwd(const float* x, int x_cs, float* y, int y_cs, int B, int H, int W, int C,
+                            int OH, int OW, float mul, void* stream);
+
+/* losses.py:4-8,15-31: one pyramid level of multiscale_loss (ord 2 = L2loss, ord 1 = L1loss).
+ * acc[0] += weight * (1/B) * sum_{b,y,x} || gt[b, y*H/h, x*W/w, :]/gt_div - fs[b,y,x,:] ||_ord
+ * (resize_nearest_neighbor of the scaled ground truth, losses.py:20,27).  acc is a device float. */
+int pwc_lploss_level_fwd(const float* gt, int H, int W, const float* fs, int fs_cs, int h, int w,
+                         int B, float gt_div, float weight, int ord, float* acc, void* stream);
+/* losses.py:11-13 EPE: acc[0] += (1/(B*H*W)) * sum || gt - flows ||_2 */
+int pwc_epe_fwd(const float* gt, const float* flows, int B, int H, int W, float* acc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PWC_B200_H_ */

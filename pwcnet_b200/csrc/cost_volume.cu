@@ -1,0 +1,290 @@
+// Cost volume (+ optional fused feature warp) for PWC-Net, sm_100a.
+//
+// Replaces CostVolumeLayer.__call__ / get_cost (reference modules.py:164-204) -- 81 x
+// (pad, pad, mul, crop, mean) graph nodes per level -- and, in the fused entry point, also
+// WarpingLayer / bilinear_warp / nearest_warp (modules.py:83-154) by ONE kernel per level:
+//
+//   out[b,y,x,(v+4)*9+(h+4)] = leaky( (1/C) * sum_c f0[b,y,x,c] * f1w[b,y+v,x+h,c] )
+//
+// HBM-bound by design: f0 and f1 are read once (the f1 halo re-reads hit L2), the 81-channel
+// result is written once, straight into the estimator's concat buffer.
+//
+// Tiling (R = 4): a CTA owns a TY x TX = 7 x 32 output tile.  Per 32-channel chunk it stages the
+// f0 tile and the (TY+8) x (TX+8) f1 halo tile in shared memory (the halo pixels are bilinearly
+// gathered from f1 on the fly in the fused variant, zero outside the image = the reference's
+// zero padding).  Each thread owns one (row y, vertical shift v, 8-pixel x strip) item and keeps
+// an 8 x 9 accumulator tile in registers: per 4 channels it issues 8 + 16 LDS.128 for 288 FMAs.
+// Lanes of a warp enumerate (y, v) for the same strip, so the f0 loads hit <= 4 and the f1 loads
+// <= 12 distinct 16-byte rows per instruction (shared-memory broadcast), which keeps the kernel
+// FMA-issue bound rather than LDS bound.  Results are transposed through shared memory so the
+// 81 channels of a pixel leave as one contiguous 324-byte run.
+#include "common.cuh"
+
+namespace pwc {
+
+constexpr int CV_R = 4;
+constexpr int CV_D = 2 * CV_R + 1;     // 9
+constexpr int CV_ND = CV_D * CV_D;     // 81
+static_assert(CV_ND == 81, "r=4 kernel");
+constexpr int CV_TY = 7;
+constexpr int CV_TX = 32;
+constexpr int CV_SX = 8;               // strip width (pixels per thread)
+constexpr int CV_CH = 32;              // channels per chunk
+constexpr int CV_HY = CV_TY + 2 * CV_R;   // 15
+constexpr int CV_HX = CV_TX + 2 * CV_R;   // 40
+constexpr int CV_F0_ROW = CV_TX * CV_CH + 4;   // floats; +4 -> rows land in distinct 16B bank groups
+constexpr int CV_F1_ROW = CV_HX * CV_CH + 4;
+constexpr int CV_F0_FLOATS = CV_TY * CV_F0_ROW;
+constexpr int CV_F1_FLOATS = CV_HY * CV_F1_ROW;
+constexpr int CV_OPIX = 84;                    // smem floats per output pixel (81 padded to 16B multiple)
+constexpr int CV_OROW = CV_TX * CV_OPIX + 8;   // + 8 floats: de-phase rows across banks
+constexpr int CV_THREADS = 256;
+constexpr int CV_SMEM_BYTES = (CV_F0_FLOATS + CV_F1_FLOATS) * 4;
+static_assert(CV_TY * CV_OROW <= CV_F1_FLOATS, "output staging must fit in the f1 halo buffer");
+
+struct CvParams {
+    const float* f0; const float* f1; const float* flow;
+    float* out; float* f0_copy;
+    int f0_cs, f1_cs, flow_cs, out_cs, f0_copy_cs;
+    int B, H, W, C;
+    float flow_scale, alpha, inv_c;
+    int warp_type;   // 0 bilinear, 1 nearest
+};
+
+// Bilinear / nearest sample of 4 channels of f1 at pixel (y,x) displaced by the flow there.
+// Index clamping and weights follow modules.py:107-137 (clamped taps, un-clamped weights).
+template <int WARP>
+__device__ __forceinline__ float4 sample_f1(const CvParams& p, const float* f1b, const float* flowb,
+                                            int y, int x, int c) {
+    if (WARP == 0) return ldg4(f1b + ((size_t)y * p.W + x) * p.f1_cs + c);
+    const float* fl = flowb + ((size_t)y * p.W + x) * p.flow_cs;
+    const float fx = __ldg(fl) * p.flow_scale, fy = __ldg(fl + 1) * p.flow_scale;
+    if (WARP == 2) {  // nearest: tf.cast(flow, int32) truncates toward zero (modules.py:85)
+        int ix = min(max(x + (int)fx, 0), p.W - 1);
+        int iy = min(max(y + (int)fy, 0), p.H - 1);
+        return ldg4(f1b + ((size_t)iy * p.W + ix) * p.f1_cs + c);
+    }
+    const float fx0 = floorf(fx), fy0 = floorf(fy);
+    const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+    const float wl = (float)(p.W - 1), hl = (float)(p.H - 1);
+    const int gy0 = (int)fminf(fmaxf((float)y + fy0, 0.f), hl);
+    const int gy1 = (int)fminf(fmaxf((float)y + fy1, 0.f), hl);
+    const int gx0 = (int)fminf(fmaxf((float)x + fx0, 0.f), wl);
+    const int gx1 = (int)fminf(fmaxf((float)x + fx1, 0.f), wl);
+    const float c00 = (fy1 - fy) * (fx1 - fx), c01 = (fy1 - fy) * (fx - fx0);
+    const float c10 = (fy - fy0) * (fx1 - fx), c11 = (fy - fy0) * (fx - fx0);
+    const float4 a = ldg4(f1b + ((size_t)gy0 * p.W + gx0) * p.f1_cs + c);
+    const float4 b = ldg4(f1b + ((size_t)gy0 * p.W + gx1) * p.f1_cs + c);
+    const float4 d = ldg4(f1b + ((size_t)gy1 * p.W + gx0) * p.f1_cs + c);
+    const float4 e = ldg4(f1b + ((size_t)gy1 * p.W + gx1) * p.f1_cs + c);
+    float4 r;
+    r.x = c00 * a.x + c01 * b.x + c10 * d.x + c11 * e.x;
+    r.y = c00 * a.y + c01 * b.y + c10 * d.y + c11 * e.y;
+    r.z = c00 * a.z + c01 * b.z + c10 * d.z + c11 * e.z;
+    r.w = c00 * a.w + c01 * b.w + c10 * d.w + c11 * e.w;
+    return r;
+}
+
+// WARP: 0 = f1 used as is, 1 = bilinear, 2 = nearest
+template <int WARP>
+__global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* f0s = smem;
+    float* f1s = smem + CV_F0_FLOATS;
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * CV_TX, y0 = blockIdx.y * CV_TY, b = blockIdx.z;
+    const float* f0b = p.f0 + (size_t)b * p.H * p.W * p.f0_cs;
+    const float* f1b = p.f1 + (size_t)b * p.H * p.W * p.f1_cs;
+    const float* flowb = WARP ? p.flow + (size_t)b * p.H * p.W * p.flow_cs : nullptr;
+
+    // work item of this thread
+    const int warp = tid >> 5, lane = tid & 31;
+    const int xs = warp >> 1;                       // strip 0..3
+    const int item = (warp & 1) * 32 + lane;        // 0..63, 63 idle
+    const bool active = item < CV_TY * CV_D;
+    const int iy = active ? item / CV_D : 0;        // output row in tile
+    const int iv = active ? item % CV_D : 0;        // vertical shift index 0..8 (v = iv - 4)
+
+    float acc[CV_SX][CV_D];
+#pragma unroll
+    for (int i = 0; i < CV_SX; ++i)
+#pragma unroll
+        for (int j = 0; j < CV_D; ++j) acc[i][j] = 0.f;
+
+    for (int c0 = 0; c0 < p.C; c0 += CV_CH) {
+        const int nch4 = min(CV_CH, p.C - c0) >> 2;   // float4 groups valid in this chunk
+        if (c0) __syncthreads();
+        // ---- stage f0 tile (and optionally copy it out to the concat slot)
+        for (int e = tid; e < CV_TY * CV_TX * (CV_CH / 4); e += CV_THREADS) {
+            const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e >> 8;
+            const int gy = y0 + py, gx = x0 + px;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy < p.H && gx < p.W && k < nch4) {
+                v = ldg4(f0b + ((size_t)gy * p.W + gx) * p.f0_cs + c0 + 4 * k);
+                if (p.f0_copy)
+                    *reinterpret_cast<float4*>(p.f0_copy + (((size_t)b * p.H + gy) * p.W + gx) * p.f0_copy_cs + c0 + 4 * k) = v;
+            }
+            *reinterpret_cast<float4*>(f0s + py * CV_F0_ROW + px * CV_CH + 4 * k) = v;
+        }
+        // ---- stage f1 halo tile (warped on the fly), zeros outside the image
+        for (int e = tid; e < CV_HY * CV_HX * (CV_CH / 4); e += CV_THREADS) {
+            const int k = e & 7, pix = e >> 3;
+            const int py = pix / CV_HX, px = pix - py * CV_HX;
+            const int gy = y0 + py - CV_R, gx = x0 + px - CV_R;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && k < nch4)
+                v = sample_f1<WARP>(p, f1b, flowb, gy, gx, c0 + 4 * k);
+            *reinterpret_cast<float4*>(f1s + py * CV_F1_ROW + px * CV_CH + 4 * k) = v;
+        }
+        __syncthreads();
+        // ---- correlate
+        const float* a_base = f0s + iy * CV_F0_ROW + xs * CV_SX * CV_CH;
+        const float* b_base = f1s + (iy + iv) * CV_F1_ROW + xs * CV_SX * CV_CH;
+#pragma unroll 1
+        for (int k = 0; k < CV_CH / 4; ++k) {
+            float4 a[CV_SX];
+#pragma unroll
+            for (int i = 0; i < CV_SX; ++i) a[i] = *reinterpret_cast<const float4*>(a_base + i * CV_CH + 4 * k);
+#pragma unroll
+            for (int q = 0; q < CV_SX + 2 * CV_R; ++q) {
+                const float4 f = *reinterpret_cast<const float4*>(b_base + q * CV_CH + 4 * k);
+#pragma unroll
+                for (int i = 0; i < CV_SX; ++i) {
+                    const int j = q - i;   // horizontal shift index: f1 column (x + i) + (j - 4) + 4 = q
+                    if (j >= 0 && j < CV_D) {
+                        acc[i][j] = fmaf(a[i].x, f.x, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].y, f.y, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].z, f.z, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].w, f.w, acc[i][j]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();   // everyone is done reading f1s -> reuse it as the output staging tile
+    float* outs = f1s;
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < CV_SX; ++i)
+#pragma unroll
+            for (int j = 0; j < CV_D; ++j)
+                outs[iy * CV_OROW + (xs * CV_SX + i) * CV_OPIX + iv * CV_D + j] = leaky(acc[i][j] * p.inv_c, p.alpha);
+    }
+    __syncthreads();
+    // ---- contiguous 324-byte runs per pixel
+    const bool vec = ((p.out_cs & 3) == 0) && aligned16(p.out);
+    constexpr int UNITS = 21;   // 20 float4 + 1 scalar
+    for (int e = tid; e < CV_TY * CV_TX * UNITS; e += CV_THREADS) {
+        const int pix = e / UNITS, u = e - pix * UNITS;
+        const int py = pix >> 5, px = pix & 31;
+        const int gy = y0 + py, gx = x0 + px;
+        if (gy >= p.H || gx >= p.W) continue;
+        const float* s = outs + py * CV_OROW + px * CV_OPIX + 4 * u;
+        float* g = p.out + (((size_t)b * p.H + gy) * p.W + gx) * p.out_cs + 4 * u;
+        if (u < 20) {
+            const float4 v = *reinterpret_cast<const float4*>(s);
+            if (vec) *reinterpret_cast<float4*>(g) = v;
+            else { g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w; }
+        } else {
+            g[0] = s[0];
+        }
+    }
+}
+
+// Generic search range (reference ctor arg search_range, model.py:88): one thread per output
+// value.  Only used when search_range != 4; not tuned.
+__global__ void cost_volume_generic_kernel(const CvParams p, int r) {
+    const int d = 2 * r + 1, nd = d * d;
+    const size_t total = (size_t)p.B * p.H * p.W * nd;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int dd = idx % nd;
+        size_t pix = idx / nd;
+        const int x = pix % p.W; pix /= p.W;
+        const int y = pix % p.H; const int b = pix / p.H;
+        const int v = dd / d - r, h = dd % d - r;
+        const int yy = y + v, xx = x + h;
+        float s = 0.f;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+            const float* a = p.f0 + (((size_t)b * p.H + y) * p.W + x) * p.f0_cs;
+            const float* f1b = p.f1 + (size_t)b * p.H * p.W * p.f1_cs;
+            const float* flowb = p.flow ? p.flow + (size_t)b * p.H * p.W * p.flow_cs : nullptr;
+            for (int c = 0; c < p.C; c += 4) {
+                const float4 av = ldg4(a + c);
+                float4 bv;
+                if (!p.flow) bv = sample_f1<0>(p, f1b, flowb, yy, xx, c);
+                else if (p.warp_type == 0) bv = sample_f1<1>(p, f1b, flowb, yy, xx, c);
+                else bv = sample_f1<2>(p, f1b, flowb, yy, xx, c);
+                s = fmaf(av.x, bv.x, s); s = fmaf(av.y, bv.y, s); s = fmaf(av.z, bv.z, s); s = fmaf(av.w, bv.w, s);
+            }
+        }
+        p.out[(((size_t)b * p.H + y) * p.W + x) * p.out_cs + dd] = leaky(s * p.inv_c, p.alpha);
+    }
+}
+
+__global__ void copy_channels_kernel(const float* src, int src_cs, float* dst, int dst_cs, size_t npix, int C4) {
+    const size_t total = npix * C4;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = idx / C4; const int k = idx % C4;
+        *reinterpret_cast<float4*>(dst + pix * dst_cs + 4 * k) = ldg4(src + pix * src_cs + 4 * k);
+    }
+}
+
+static int launch_cv(CvParams p, int search_range, cudaStream_t st) {
+    PWC_REQUIRE(p.f0 && p.f1 && p.out, PWC_E_BADARG, "cost_volume: null pointer");
+    PWC_REQUIRE(p.B > 0 && p.H > 0 && p.W > 0 && p.C > 0 && search_range >= 0, PWC_E_BADARG, "cost_volume: bad dims");
+    PWC_REQUIRE(p.B <= 65535, PWC_E_BADARG, "cost_volume: batch > 65535");
+    PWC_REQUIRE((p.C & 3) == 0 && (p.f0_cs & 3) == 0 && (p.f1_cs & 3) == 0 && aligned16(p.f0) && aligned16(p.f1),
+                PWC_E_ALIGN, "cost_volume: C, f0_cs, f1_cs must be multiples of 4 and f0/f1 16-byte aligned");
+    PWC_REQUIRE(p.f0_cs >= p.C && p.f1_cs >= p.C, PWC_E_BADARG, "cost_volume: channel stride < C");
+    if (p.f0_copy)
+        PWC_REQUIRE((p.f0_copy_cs & 3) == 0 && aligned16(p.f0_copy), PWC_E_ALIGN, "cost_volume: f0_copy alignment");
+    p.inv_c = 1.0f / (float)p.C;
+    const int nd = (2 * search_range + 1) * (2 * search_range + 1);
+    PWC_REQUIRE(p.out_cs >= nd, PWC_E_BADARG, "cost_volume: out_cs < (2r+1)^2");
+    if (search_range == CV_R) {
+        dim3 grid((p.W + CV_TX - 1) / CV_TX, (p.H + CV_TY - 1) / CV_TY, p.B);
+        auto kern = !p.flow ? cost_volume_r4_kernel<0> : (p.warp_type == 0 ? cost_volume_r4_kernel<1> : cost_volume_r4_kernel<2>);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("cost_volume: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        kern<<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(p);
+        PWC_CHECK_LAUNCH("cost_volume_r4_kernel");
+    } else {
+        const size_t total = (size_t)p.B * p.H * p.W * nd;
+        int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        cost_volume_generic_kernel<<<blocks, 256, 0, st>>>(p, search_range);
+        PWC_CHECK_LAUNCH("cost_volume_generic_kernel");
+        if (p.f0_copy) {
+            const size_t npix = (size_t)p.B * p.H * p.W;
+            copy_channels_kernel<<<148 * 8, 256, 0, st>>>(p.f0, p.f0_cs, p.f0_copy, p.f0_copy_cs, npix, p.C / 4);
+            PWC_CHECK_LAUNCH("copy_channels_kernel");
+        }
+    }
+    return 0;
+}
+
+}  // namespace pwc
+
+extern "C" int pwc_cost_volume_fwd(const float* f0, int f0_cs, const float* f1, int f1_cs,
+                                   float* out, int out_cs, float* f0_copy, int f0_copy_cs,
+                                   int B, int H, int W, int C, int search_range, float alpha, void* stream) {
+    pwc::CvParams p{};
+    p.f0 = f0; p.f1 = f1; p.flow = nullptr; p.out = out; p.f0_copy = f0_copy;
+    p.f0_cs = f0_cs; p.f1_cs = f1_cs; p.flow_cs = 0; p.out_cs = out_cs; p.f0_copy_cs = f0_copy_cs;
+    p.B = B; p.H = H; p.W = W; p.C = C; p.flow_scale = 1.f; p.alpha = alpha; p.warp_type = 0;
+    return pwc::launch_cv(p, search_range, (cudaStream_t)stream);
+}
+
+extern "C" int pwc_warp_cost_volume_fwd(const float* f0, int f0_cs, const float* f1, int f1_cs,
+                                        const float* flow, int flow_cs, float flow_scale, int warp_type,
+                                        float* out, int out_cs, float* f0_copy, int f0_copy_cs,
+                                        int B, int H, int W, int C, int search_range, float alpha, void* stream) {
+    PWC_REQUIRE(flow != nullptr, PWC_E_BADARG, "warp_cost_volume: null flow");
+    PWC_REQUIRE(warp_type == 0 || warp_type == 1, PWC_E_BADARG, "warp_cost_volume: warp_type must be 0 (bilinear) or 1 (nearest)");
+    PWC_REQUIRE(flow_cs >= 2, PWC_E_BADARG, "warp_cost_volume: flow_cs < 2");
+    pwc::CvParams p{};
+    p.f0 = f0; p.f1 = f1; p.flow = flow; p.out = out; p.f0_copy = f0_copy;
+    p.f0_cs = f0_cs; p.f1_cs = f1_cs; p.flow_cs = flow_cs; p.out_cs = out_cs; p.f0_copy_cs = f0_copy_cs;
+    p.B = B; p.H = H; p.W = W; p.C = C; p.flow_scale = flow_scale; p.alpha = alpha; p.warp_type = warp_type;
+    return pwc::launch_cv(p, search_range, (cudaStream_t)stream);
+}

@@ -1,0 +1,166 @@
+// Stand-alone feature warp, legacy bilinear resize and loss reductions (all HBM-bound), sm_100a.
+//
+//  pwc_warp_fwd            <- WarpingLayer / bilinear_warp / nearest_warp   (modules.py:83-154)
+//  pwc_resize_bilinear_fwd <- tf.image.resize_bilinear, align_corners=False (modules.py:283-284, model.py:127)
+//  pwc_lploss_level_fwd    <- L1loss/L2loss + resize_nearest_neighbor + /20 (losses.py:4-8,20,27-29)
+//  pwc_epe_fwd             <- EPE                                           (losses.py:11-13)
+#include "common.cuh"
+
+namespace pwc {
+
+// One thread per (pixel, 4-channel group): 4 x 16-byte gathers, 16-byte store.
+template <bool NEAREST>
+__global__ void warp_kernel(const float* __restrict__ x, int x_cs, const float* __restrict__ flow, int flow_cs,
+                            float flow_scale, float* __restrict__ out, int out_cs, int B, int H, int W, int C4) {
+    const size_t total = (size_t)B * H * W * C4;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int k = idx % C4;
+        size_t pix = idx / C4;
+        const int px = pix % W; const size_t row = pix / W;
+        const int py = row % H; const int b = row / H;
+        const float* fl = flow + pix * flow_cs;
+        const float fx = __ldg(fl) * flow_scale, fy = __ldg(fl + 1) * flow_scale;
+        const float* xb = x + (size_t)b * H * W * x_cs + 4 * k;
+        float4 r;
+        if (NEAREST) {
+            const int ix = min(max(px + (int)fx, 0), W - 1);
+            const int iy = min(max(py + (int)fy, 0), H - 1);
+            r = ldg4(xb + ((size_t)iy * W + ix) * x_cs);
+        } else {
+            const float fx0 = floorf(fx), fy0 = floorf(fy);
+            const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+            const float wl = (float)(W - 1), hl = (float)(H - 1);
+            const int gy0 = (int)fminf(fmaxf((float)py + fy0, 0.f), hl);
+            const int gy1 = (int)fminf(fmaxf((float)py + fy1, 0.f), hl);
+            const int gx0 = (int)fminf(fmaxf((float)px + fx0, 0.f), wl);
+            const int gx1 = (int)fminf(fmaxf((float)px + fx1, 0.f), wl);
+            const float c00 = (fy1 - fy) * (fx1 - fx), c01 = (fy1 - fy) * (fx - fx0);
+            const float c10 = (fy - fy0) * (fx1 - fx), c11 = (fy - fy0) * (fx - fx0);
+            const float4 a = ldg4(xb + ((size_t)gy0 * W + gx0) * x_cs);
+            const float4 bq = ldg4(xb + ((size_t)gy0 * W + gx1) * x_cs);
+            const float4 d = ldg4(xb + ((size_t)gy1 * W + gx0) * x_cs);
+            const float4 e = ldg4(xb + ((size_t)gy1 * W + gx1) * x_cs);
+            r.x = c00 * a.x + c01 * bq.x + c10 * d.x + c11 * e.x;
+            r.y = c00 * a.y + c01 * bq.y + c10 * d.y + c11 * e.y;
+            r.z = c00 * a.z + c01 * bq.z + c10 * d.z + c11 * e.z;
+            r.w = c00 * a.w + c01 * bq.w + c10 * d.w + c11 * e.w;
+        }
+        *reinterpret_cast<float4*>(out + pix * out_cs + 4 * k) = r;
+    }
+}
+
+// Legacy TF-1.8 bilinear resize: src = dst * in/out (no half-pixel offset), hi = min(lo+1, in-1).
+// One thread per output scalar (C is 2 or 32 here; channel-fastest so accesses coalesce).
+__global__ void resize_bilinear_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int y_cs,
+                                       int B, int H, int W, int C, int OH, int OW, float sy, float sx, float mul) {
+    const size_t total = (size_t)B * OH * OW * C;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = idx % C;
+        size_t pix = idx / C;
+        const int ox = pix % OW; const size_t row = pix / OW;
+        const int oy = row % OH; const int b = row / OH;
+        const float fy = (float)oy * sy, fx = (float)ox * sx;
+        const int ylo = (int)floorf(fy), xlo = (int)floorf(fx);
+        const int yhi = min(ylo + 1, H - 1), xhi = min(xlo + 1, W - 1);
+        const float yl = fy - (float)ylo, xl = fx - (float)xlo;
+        const float* xb = x + (size_t)b * H * W * x_cs + c;
+        const float tl = __ldg(xb + ((size_t)ylo * W + xlo) * x_cs), tr = __ldg(xb + ((size_t)ylo * W + xhi) * x_cs);
+        const float bl = __ldg(xb + ((size_t)yhi * W + xlo) * x_cs), br = __ldg(xb + ((size_t)yhi * W + xhi) * x_cs);
+        const float top = tl + (tr - tl) * xl;
+        const float bot = bl + (br - bl) * xl;
+        y[pix * y_cs + c] = (top + (bot - top) * yl) * mul;
+    }
+}
+
+__device__ __forceinline__ float block_sum(float v) {
+    __shared__ float red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;
+}
+
+// sum over (b,y,x) of || gt[b, iy(y), ix(x), :] / gt_div - fs[b,y,x,:] ||_2, scaled, atomically added.
+__global__ void l2loss_level_kernel(const float* __restrict__ gt, int H, int W, const float* __restrict__ fs, int fs_cs,
+                                    int h, int w, int B, float sy, float sx, float gt_div, float scale, int ord, float* acc) {
+    const size_t total = (size_t)B * h * w;
+    float s = 0.f;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = idx % w; const size_t row = idx / w;
+        const int y = row % h; const int b = row / h;
+        const int iy = min((int)floorf((float)y * sy), H - 1), ix = min((int)floorf((float)x * sx), W - 1);
+        const float2 g = __ldg(reinterpret_cast<const float2*>(gt + (((size_t)b * H + iy) * W + ix) * 2));
+        const float* f = fs + idx * fs_cs;
+        const float dx = g.x / gt_div - f[0], dy = g.y / gt_div - f[1];
+        s += ord == 1 ? fabsf(dx) + fabsf(dy) : sqrtf(dx * dx + dy * dy);
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0) atomicAdd(acc, s * scale);
+}
+
+}  // namespace pwc
+
+extern "C" int pwc_warp_fwd(const float* x, int x_cs, const float* flow, int flow_cs, float flow_scale,
+                            int warp_type, float* out, int out_cs, int B, int H, int W, int C, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(x && flow && out, PWC_E_BADARG, "warp: null pointer");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, PWC_E_BADARG, "warp: bad dims");
+    PWC_REQUIRE(warp_type == 0 || warp_type == 1, PWC_E_BADARG, "warp: warp_type must be 0 (bilinear) or 1 (nearest)");
+    PWC_REQUIRE((C & 3) == 0 && (x_cs & 3) == 0 && (out_cs & 3) == 0 && aligned16(x) && aligned16(out), PWC_E_ALIGN,
+                "warp: C, x_cs, out_cs must be multiples of 4 and x/out 16-byte aligned");
+    const size_t total = (size_t)B * H * W * (C / 4);
+    const int blocks = (int)((total + 255) / 256 < (size_t)148 * 16 ? (total + 255) / 256 : (size_t)148 * 16);
+    if (warp_type == 1)
+        warp_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, flow, flow_cs, flow_scale, out, out_cs, B, H, W, C / 4);
+    else
+        warp_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, flow, flow_cs, flow_scale, out, out_cs, B, H, W, C / 4);
+    PWC_CHECK_LAUNCH("warp_kernel");
+    return 0;
+}
+
+extern "C" int pwc_resize_bilinear_fwd(const float* x, int x_cs, float* y, int y_cs, int B, int H, int W, int C,
+                                       int OH, int OW, float mul, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(x && y, PWC_E_BADARG, "resize: null pointer");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, PWC_E_BADARG, "resize: bad dims");
+    const size_t total = (size_t)B * OH * OW * C;
+    const int blocks = (int)((total + 255) / 256 < (size_t)148 * 16 ? (total + 255) / 256 : (size_t)148 * 16);
+    // TF computes the scale in float32: in / out
+    const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+    resize_bilinear_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
+    PWC_CHECK_LAUNCH("resize_bilinear_kernel");
+    return 0;
+}
+
+extern "C" int pwc_lploss_level_fwd(const float* gt, int H, int W, const float* fs, int fs_cs, int h, int w,
+                                    int B, float gt_div, float weight, int ord, float* acc, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(gt && fs && acc, PWC_E_BADARG, "lploss: null pointer");
+    PWC_REQUIRE(ord == 1 || ord == 2, PWC_E_BADARG, "lploss: ord must be 1 or 2");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0 && h > 0 && w > 0 && fs_cs >= 2, PWC_E_BADARG, "l2loss: bad dims");
+    const size_t total = (size_t)B * h * w;
+    const int blocks = (int)((total + 255) / 256 < (size_t)148 * 4 ? (total + 255) / 256 : (size_t)148 * 4);
+    l2loss_level_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gt, H, W, fs, fs_cs, h, w, B, (float)H / (float)h,
+                                                                 (float)W / (float)w, gt_div, weight / (float)B, ord, acc);
+    PWC_CHECK_LAUNCH("l2loss_level_kernel");
+    return 0;
+}
+
+extern "C" int pwc_epe_fwd(const float* gt, const float* flows, int B, int H, int W, float* acc, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(gt && flows && acc, PWC_E_BADARG, "epe: null pointer");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0, PWC_E_BADARG, "epe: bad dims");
+    const size_t total = (size_t)B * H * W;
+    const int blocks = (int)((total + 255) / 256 < (size_t)148 * 4 ? (total + 255) / 256 : (size_t)148 * 4);
+    l2loss_level_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gt, H, W, flows, 2, H, W, B, 1.f, 1.f, 1.f,
+                                                                 1.f / (float)total, 2, acc);
+    PWC_CHECK_LAUNCH("epe_kernel");
+    return 0;
+}

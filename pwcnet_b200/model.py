@@ -1,0 +1,417 @@
+"""PWCDCNet / PWCNet with the reference's Python call surface (daigo0927/pwcnet model.py) on the
+B200-native compute path.
+
+    model = PWCDCNet(num_levels=6, search_range=4, warp_type='bilinear', use_dc=False,
+                     output_level=4, name='pwcdcnet')                      # model.py:75-77
+    flows_final, flows_pyramid = model(images_0, images_1)                  # model.py:95,129-132
+    flows_final, flows_pyramid, pyramid_0 = model(images_0, images_1, with_features=True)
+
+images: (B,H,W,3) float32 RGB in [0,1], H and W multiples of 2**num_levels (the reference crops to
+/64, test.py:13-17).  torch CUDA tensors are used in place; numpy arrays / CPU tensors are copied
+host->device first (that is the end-to-end path bench.py times).  Outputs are torch CUDA tensors that
+stay valid until the next call with the same input shape (the workspace is reused).
+
+What is different from the reference by design: there is no graph of 37k TF nodes.  A forward pass
+is ~75 launches of hand-written sm_100a kernels over a pre-planned workspace, captured in a CUDA
+graph: both images run through the pyramid as one batch of 2B; warp + cost volume are one kernel that
+writes straight into the estimator's concat buffer; tf.concat / residual adds / leaky-relu / the
+legacy x2 up-sampling are epilogues or slot writes.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from ._abi import PwcError
+from .modules import (CONTEXT_DILATIONS, CONTEXT_FILTERS, ESTIMATOR_FILTERS, PYRAMID_FILTERS)
+
+PRECISIONS = ("fp32", "3xtf32", "tf32", "cudnn")
+DEFAULT_PRECISION = "fp32"
+
+
+def _round_up(a: int, m: int) -> int:
+    return (a + m - 1) // m * m
+
+
+def layer_table(num_levels=6, use_dc=False, search_range=4, output_level=4, name="pwcdcnet"):
+    """[(variable scope, Cin, Cout)] in the reference's variable-creation order."""
+    rows = []
+    cin = 3
+    for l in range(num_levels):
+        for j in range(3):
+            idx = 3 * l + j
+            rows.append((f"{name}/fp_extractor/conv2d" + (f"_{idx}" if idx else ""), cin, PYRAMID_FILTERS[l]))
+            cin = PYRAMID_FILTERS[l]
+    nd = (2 * search_range + 1) ** 2
+    deep_first = PYRAMID_FILTERS[:num_levels][::-1]
+    up_ch = 0
+    for l in range(output_level + 1):
+        c = nd + deep_first[l] + (0 if l == 0 else 2 + up_ch)
+        for i, f in enumerate(ESTIMATOR_FILTERS):
+            rows.append((f"{name}/optflow_{l}/conv2d" + (f"_{i}" if i else ""), c, f))
+            c = f + c if use_dc else f
+        rows.append((f"{name}/optflow_{l}/conv2d_{len(ESTIMATOR_FILTERS)}", c, 2))
+        up_ch = c
+    cin = 2 + up_ch
+    for i, f in enumerate(CONTEXT_FILTERS):
+        rows.append((f"{name}/context/conv2d" + (f"_{i}" if i else ""), cin, f))
+        cin = f
+    return rows
+
+
+def glorot_init(seed=0, **kw) -> Dict[str, np.ndarray]:
+    """Glorot-uniform kernels / zero biases: the initialisers tf.layers.Conv2D records in the
+    reference GraphDef (limit sqrt(6/(9 Cin + 9 Cout)))."""
+    rng = np.random.default_rng(seed)
+    W = {}
+    for scope, cin, cout in layer_table(**kw):
+        lim = math.sqrt(6.0 / (9 * cin + 9 * cout))
+        W[scope + "/kernel"] = rng.uniform(-lim, lim, size=(3, 3, cin, cout)).astype(np.float32)
+        W[scope + "/bias"] = np.zeros((cout,), np.float32)
+    return W
+
+
+class _Plan:
+    """Workspace for one input shape."""
+    pass
+
+
+class PWCDCNet(object):
+    def __init__(self, num_levels=6, search_range=4, warp_type='bilinear', use_dc=False,
+                 output_level=4, name='pwcdcnet', *, device=None, weights=None, seed=0,
+                 precision=None, use_cuda_graph=True):
+        self.num_levels = num_levels
+        self.s_range = search_range
+        self.warp_type = warp_type
+        self.use_dc = use_dc
+        assert output_level < num_levels, 'Should set output_level < num_levels'
+        assert warp_type in ['nearest', 'bilinear']
+        assert num_levels <= len(PYRAMID_FILTERS)
+        self.output_level = output_level
+        self.name = name
+        # Upscale factors from deep -> shallow level (model.py:93)
+        self.scales = [None, 0.625, 1.25, 2.5, 5.0, 10., 20.]
+        precision = DEFAULT_PRECISION if precision is None else precision
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        self.precision = precision
+        self.use_cuda_graph = use_cuda_graph
+        if not torch.cuda.is_available():
+            raise PwcError("PWCDCNet needs a CUDA device: the compute path is sm_100a CUDA only (no CPU fallback)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        ops.lib()   # fail now if the extension is not built
+        self._table = layer_table(num_levels, use_dc, search_range, output_level, name)
+        self.params: Dict[str, torch.Tensor] = {}
+        self._plans: Dict[tuple, _Plan] = {}
+        self._layout()
+        self.load_weights(weights if weights is not None else
+                          glorot_init(seed, num_levels=num_levels, use_dc=use_dc, search_range=search_range,
+                                      output_level=output_level, name=name))
+
+    # ------------------------------------------------------------------ variables
+    @property
+    def vars(self) -> List[torch.Tensor]:
+        """model.py:136-138: all variables of the model, creation order (kernel, bias, kernel, ...)."""
+        out = []
+        for scope, _, _ in self._table:
+            out += [self.params[scope + "/kernel"], self.params[scope + "/bias"]]
+        return out
+
+    @property
+    def var_names(self) -> List[str]:
+        return [scope + sfx for scope, _, _ in self._table for sfx in ("/kernel", "/bias")]
+
+    def load_weights(self, weights) -> None:
+        """weights: dict name -> array in the reference's checkpoint naming, or the prefix of a TF
+        checkpoint written by the reference (e.g. '.../model_250.ckpt')."""
+        if isinstance(weights, str):
+            from .checkpoint import load_checkpoint
+            weights = load_checkpoint(weights, self.name)
+        for scope, cin, cout in self._table:
+            for sfx, shape in (("/kernel", (3, 3, cin, cout)), ("/bias", (cout,))):
+                if scope + sfx not in weights:
+                    raise KeyError(f"weights lack variable {scope + sfx}")
+                a = weights[scope + sfx]
+                t = a.detach().to(torch.float32) if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a, np.float32))
+                if tuple(t.shape) != shape:
+                    raise ValueError(f"{scope + sfx}: shape {tuple(t.shape)} != expected {shape}")
+                self.params[scope + sfx] = t.to(self.device).contiguous()
+        self._prepare()
+
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        return {k: v.detach().cpu().numpy() for k, v in self.params.items()}
+
+    # ------------------------------------------------------------------ layouts
+    def _layout(self) -> None:
+        """Internal channel layouts of the concat buffers and the permutations that map them to the
+        reference's concat order [cv, f0, flows_up, features_up] (modules.py:262-264)."""
+        nd = (2 * self.s_range + 1) ** 2
+        deep_first = PYRAMID_FILTERS[:self.num_levels][::-1]
+        pre_total = sum(ESTIMATOR_FILTERS) if self.use_dc else 0
+        self._nd = nd
+        self._lv = []
+        prev_stack_perm: Optional[List[int]] = None
+        for l in range(self.output_level + 1):
+            C = deep_first[l]
+            up = 0 if l == 0 else len(prev_stack_perm)
+            off_flow = nd
+            off_f0 = _round_up(nd + (2 if l else 0), 4)
+            off_feat = off_f0 + C
+            cin_int = _round_up(off_feat + up, 4)
+            perm = [-1] * cin_int
+            for i in range(nd):
+                perm[i] = i
+            for i in range(C):
+                perm[off_f0 + i] = nd + i
+            if l:
+                perm[off_flow], perm[off_flow + 1] = nd + C, nd + C + 1
+                for i, r in enumerate(prev_stack_perm):
+                    perm[off_feat + i] = -1 if r < 0 else nd + C + 2 + r
+            if self.use_dc:
+                stack_perm = list(range(pre_total)) + [(-1 if r < 0 else pre_total + r) for r in perm]
+            else:
+                stack_perm = list(range(ESTIMATOR_FILTERS[-1]))
+            self._lv.append(dict(C=C, up=up, off_flow=off_flow, off_f0=off_f0, off_feat=off_feat, cin_int=cin_int,
+                                 perm=perm, stack_ch=len(stack_perm)))
+            prev_stack_perm = stack_perm
+        # context input, internal order [features stack | flows(2) | pad(2)], reference [flows, features]
+        self._ctx_perm = [(-1 if r < 0 else 2 + r) for r in prev_stack_perm] + [0, 1, -1, -1]
+
+    @staticmethod
+    def _permute_kernel(k: torch.Tensor, perm: Sequence[int]) -> torch.Tensor:
+        perm_t = torch.tensor(perm, device=k.device, dtype=torch.long)
+        valid = perm_t >= 0
+        out = torch.zeros((3, 3, len(perm), k.shape[3]), dtype=k.dtype, device=k.device)
+        out[:, :, valid, :] = k[:, :, perm_t[valid], :]
+        return out.contiguous()
+
+    def _prepare(self) -> None:
+        """Derive the kernels the launches use (internal channel order; packed tensor-core form)."""
+        self._k: Dict[str, torch.Tensor] = {}
+        n = self.name
+        for scope, cin, cout in self._table:
+            self._k[scope] = self.params[scope + "/kernel"]
+        for l, lv in enumerate(self._lv):
+            pre = 0
+            for i in range(len(ESTIMATOR_FILTERS) + 1):
+                scope = f"{n}/optflow_{l}/conv2d" + (f"_{i}" if i else "")
+                if i == 0 or self.use_dc:
+                    perm = list(range(pre)) + [(-1 if r < 0 else pre + r) for r in lv["perm"]]
+                    self._k[scope] = self._permute_kernel(self.params[scope + "/kernel"], perm)
+                if self.use_dc and i < len(ESTIMATOR_FILTERS):
+                    pre += ESTIMATOR_FILTERS[i]
+        self._k[f"{n}/context/conv2d"] = self._permute_kernel(self.params[f"{n}/context/conv2d/kernel"], self._ctx_perm)
+        self._packed: Dict[str, torch.Tensor] = {}
+        for plan in self._plans.values():
+            plan.graph = None   # weights changed -> re-capture
+
+    # ------------------------------------------------------------------ conv dispatch
+    def _conv(self, x, scope, out, stride=1, dilation=1, alpha=0.1, residual=None):
+        k = self._k[scope]
+        b = self.params[scope + "/bias"]
+        cin, cout = k.shape[2], k.shape[3]
+        if self.precision == "cudnn":
+            return self._conv_cudnn(x, k, b, out, stride, dilation, alpha, residual)
+        if self.precision in ("3xtf32", "tf32") and stride == 1 and residual is None and cout % 16 == 0 \
+                and cin >= 16 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
+            return self._conv_tc(x, scope, k, b, out, dilation, alpha)
+        return ops.conv3x3(x, k, b, stride=stride, dilation=dilation, alpha=alpha, residual=residual, out=out)
+
+    def _conv_tc(self, x, scope, k, b, out, dilation, alpha):
+        from . import ops_tc
+        if scope not in self._packed:
+            self._packed[scope] = ops_tc.pack_weights(k)
+        return ops_tc.conv3x3_tc(x, self._packed[scope], b, k.shape[2], k.shape[3], dilation=dilation, alpha=alpha,
+                                 n_split=3 if self.precision == "3xtf32" else 1, out=out)
+
+    @staticmethod
+    def _conv_cudnn(x, k, b, out, stride, dilation, alpha, residual):
+        """Library baseline arm only (BASELINE config 2 'convs via cuDNN'); never chosen implicitly."""
+        import torch.nn.functional as F
+        H, W = x.shape[1], x.shape[2]
+
+        def pad(n):
+            o = -(-n // stride)
+            t = max((o - 1) * stride + 2 * dilation + 1 - n, 0)
+            return t // 2, t - t // 2
+        (pt, pb), (pl, pr) = pad(H), pad(W)
+        xn = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+        y = F.conv2d(xn, k.permute(3, 2, 0, 1), b, stride=stride, dilation=dilation)
+        if alpha != 1.0:
+            y = torch.maximum(alpha * y, y)
+        y = y.permute(0, 2, 3, 1)
+        if residual is not None:
+            y = y + residual
+        out.copy_(y)
+        return out
+
+    # ------------------------------------------------------------------ workspace
+    def _make_plan(self, B, H, W) -> _Plan:
+        dev = self.device
+        p = _Plan()
+        p.B, p.H, p.W = B, H, W
+        p.graph = None
+        p.im = torch.zeros((2 * B, H, W, 3), dtype=torch.float32, device=dev)
+        p.pyr = []
+        h, w = H, W
+        for l in range(self.num_levels):
+            h, w = h // 2, w // 2
+            C = PYRAMID_FILTERS[l]
+            p.pyr.append([torch.empty((2 * B, h, w, C), dtype=torch.float32, device=dev) for _ in range(3)])
+        pre_total = sum(ESTIMATOR_FILTERS) if self.use_dc else 0
+        p.S, p.tmp, p.flows = [], [], []
+        for l, lv in enumerate(self._lv):
+            ph, pw = p.pyr[self.num_levels - 1 - l][2].shape[1:3]
+            is_out = l == self.output_level
+            if self.use_dc:
+                tot = pre_total + lv["cin_int"] + (4 if is_out else 0)
+                S = torch.zeros((B, ph, pw, tot), dtype=torch.float32, device=dev)
+                p.S.append(S)
+                p.tmp.append(None)
+            else:
+                p.S.append(torch.zeros((B, ph, pw, lv["cin_int"]), dtype=torch.float32, device=dev))
+                tmps = [torch.empty((B, ph, pw, f), dtype=torch.float32, device=dev) for f in ESTIMATOR_FILTERS[:-1]]
+                last = torch.zeros((B, ph, pw, ESTIMATOR_FILTERS[-1] + (4 if is_out else 0)), dtype=torch.float32, device=dev)
+                p.tmp.append(tmps + [last])
+            p.flows.append(torch.empty((B, ph, pw, 2), dtype=torch.float32, device=dev))
+        ph, pw = p.flows[-1].shape[1:3]
+        p.ctx = [torch.empty((B, ph, pw, f), dtype=torch.float32, device=dev) for f in CONTEXT_FILTERS[:-1]]
+        up = 2 ** (self.num_levels - self.output_level)
+        p.flows_final = torch.empty((B, ph * up, pw * up, 2), dtype=torch.float32, device=dev)
+        return p
+
+    # ------------------------------------------------------------------ forward
+    def _forward(self, p: _Plan) -> None:
+        n, B = self.name, p.B
+        nd = self._nd
+        x = p.im
+        for l in range(self.num_levels):
+            for j, stride in enumerate((2, 1, 1)):
+                idx = 3 * l + j
+                scope = f"{n}/fp_extractor/conv2d" + (f"_{idx}" if idx else "")
+                x = self._conv(x, scope, p.pyr[l][j], stride=stride, alpha=0.1)
+        pre_total = sum(ESTIMATOR_FILTERS) if self.use_dc else 0
+        nest = len(ESTIMATOR_FILTERS)
+        for l, lv in enumerate(self._lv):
+            F = p.pyr[self.num_levels - 1 - l][2]
+            f0, f1 = F[:B], F[B:]
+            S = p.S[l]
+            X = S[..., pre_total:pre_total + lv["cin_int"]]
+            cv = X[..., 0:nd]
+            f0slot = X[..., lv["off_f0"]:lv["off_f0"] + lv["C"]]
+            flow_up = X[..., lv["off_flow"]:lv["off_flow"] + 2] if l else None
+            if l == 0:
+                ops.cost_volume(f0, f1, self.s_range, 0.1, out=cv, f0_copy=f0slot)
+            else:
+                ops.warp_cost_volume(f0, f1, flow_up, self.scales[l], self.warp_type, self.s_range, 0.1,
+                                     out=cv, f0_copy=f0slot)
+            is_out = l == self.output_level
+            # ---- estimator convs (modules.py:266-274)
+            if self.use_dc:
+                start = pre_total
+                end = pre_total + lv["cin_int"]
+                for i, f in enumerate(ESTIMATOR_FILTERS):
+                    scope = f"{n}/optflow_{l}/conv2d" + (f"_{i}" if i else "")
+                    self._conv(S[..., start:end], scope, S[..., start - f:start], alpha=0.1)
+                    start -= f
+                feats = S[..., 0:end]
+            else:
+                feats = X
+                for i, f in enumerate(ESTIMATOR_FILTERS):
+                    scope = f"{n}/optflow_{l}/conv2d" + (f"_{i}" if i else "")
+                    feats = self._conv(feats, scope, p.tmp[l][i][..., 0:f], alpha=0.1)
+            head = f"{n}/optflow_{l}/conv2d_{nest}"
+            if not is_out:
+                flows = self._conv(feats, head, p.flows[l], alpha=1.0, residual=flow_up)
+                nxt = self._lv[l + 1]
+                Sn = p.S[l + 1]
+                Xn = Sn[..., pre_total:pre_total + nxt["cin_int"]]
+                h2, w2 = Sn.shape[1], Sn.shape[2]
+                ops.resize_bilinear(flows, h2, w2, out=Xn[..., nxt["off_flow"]:nxt["off_flow"] + 2])
+                ops.resize_bilinear(feats, h2, w2, out=Xn[..., nxt["off_feat"]:nxt["off_feat"] + feats.shape[3]])
+            else:
+                # context input buffer = [features | flows(2) | pad(2)]
+                Cbuf = S if self.use_dc else p.tmp[l][-1]
+                nf = feats.shape[3]
+                flow_slot = Cbuf[..., nf:nf + 2]
+                self._conv(feats, head, flow_slot, alpha=1.0, residual=flow_up)
+                x = Cbuf[..., 0:nf + 4]
+                nctx = len(CONTEXT_FILTERS)
+                for i, d in enumerate(CONTEXT_DILATIONS):
+                    scope = f"{n}/context/conv2d" + (f"_{i}" if i else "")
+                    if i < nctx - 1:
+                        x = self._conv(x, scope, p.ctx[i], dilation=d, alpha=0.1)
+                    else:
+                        self._conv(x, scope, p.flows[l], dilation=d, alpha=1.0, residual=flow_slot)
+                ops.resize_bilinear(p.flows[l], p.flows_final.shape[1], p.flows_final.shape[2], mul=20.0,
+                                    out=p.flows_final)
+
+    def __call__(self, images_0, images_1, with_features=False, reuse=False):
+        i0 = self._as_input(images_0, "images_0")
+        i1 = self._as_input(images_1, "images_1")
+        if i0.shape != i1.shape:
+            raise ValueError(f"images_0 {tuple(i0.shape)} and images_1 {tuple(i1.shape)} differ in shape")
+        B, H, W, C = i0.shape
+        m = 2 ** self.num_levels
+        if C != 3 or H % m or W % m or min(B, H, W) <= 0:
+            raise ValueError(f"images must be (B,H,W,3) with H, W multiples of {m} (test.py:13-17 crops to /64); "
+                             f"got {tuple(i0.shape)}")
+        key = (B, H, W)
+        p = self._plans.get(key)
+        if p is None:
+            p = self._plans[key] = self._make_plan(B, H, W)
+        p.im[:B].copy_(i0, non_blocking=True)
+        p.im[B:].copy_(i1, non_blocking=True)
+        if self.use_cuda_graph and self.precision != "cudnn":
+            if p.graph is None:
+                self._forward(p)                      # warm-up (also sets kernel attributes)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._forward(p)
+                p.graph = g
+            p.graph.replay()
+        else:
+            self._forward(p)
+        flows_pyramid = list(p.flows)
+        if with_features:
+            pyramid_0 = [p.pyr[self.num_levels - 1 - l][2][:B] for l in range(self.num_levels)]
+            return p.flows_final, flows_pyramid, pyramid_0
+        return p.flows_final, flows_pyramid
+
+    def _as_input(self, a, name):
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        if not isinstance(a, torch.Tensor):
+            raise TypeError(f"{name}: expected torch.Tensor or numpy.ndarray, got {type(a)}")
+        if a.dtype != torch.float32:
+            raise TypeError(f"{name}: dtype must be float32, got {a.dtype}")
+        if a.dim() != 4:
+            raise ValueError(f"{name}: expected (B,H,W,3), got {tuple(a.shape)}")
+        return a
+
+    def launches_per_forward(self) -> int:
+        """Number of kernel launches of ours in one forward (for bench.py's gpu_launches)."""
+        n = 3 * self.num_levels                      # pyramid (both images batched)
+        n += (self.output_level + 1) * (1 + len(ESTIMATOR_FILTERS) + 1)   # cv + estimator convs + head
+        n += self.output_level * 2                    # up-sampling of flows and features
+        n += len(CONTEXT_FILTERS) + 1                 # context + final x4 resize
+        return n
+
+
+class PWCNet(PWCDCNet):
+    """The reference's `PWCNet` class (model.py:6-71) cannot be instantiated (it reads
+    attributes that are never set), has no checkpoint and no caller; BASELINE configs that say
+    "PWCNet" mean the runnable network, `PWCDCNet(use_dc=False)`.  This shim keeps the name and
+    constructor signature and runs that network; it returns the reference PWCNet's 3-tuple
+    (finalflow, flows, pyramid_0) (model.py:67).  Parity unpinned (nothing executable to compare to)."""
+
+    def __init__(self, num_levels=6, search_range=4, warp_type='bilinear', output_level=4, name='pwcnet', **kw):
+        super().__init__(num_levels, search_range, warp_type, False, output_level, name, **kw)
+
+    def __call__(self, images_0, images_1):
+        return super().__call__(images_0, images_1, with_features=True)

@@ -1,0 +1,209 @@
+"""GPU parity of every C-ABI operator against the CPU oracle on the same seeded inputs.
+Tolerances: these are float32 kernels whose only difference from the oracle is summation order
+(and FMA contraction), so max-abs 1e-5 on O(1) data; stated per test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pwc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pwcnet_b200 as P
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    P.ops.lib()
+    return P
+
+
+def _rand(shape, seed, scale=1.0):
+    return (np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32)
+
+
+def _cuda(a):
+    return torch.from_numpy(a).cuda()
+
+
+# the five pyramid levels of a 448x1024 pair scaled down, plus ragged / tiny / odd shapes
+CV_SHAPES = [(2, 7, 16, 192), (1, 14, 32, 128), (1, 28, 64, 96), (1, 56, 128, 64), (1, 112, 256, 32),
+             (2, 5, 9, 16), (1, 1, 2, 32), (3, 13, 45, 36), (1, 9, 40, 4)]
+
+
+@pytest.mark.parametrize("shape", CV_SHAPES)
+def test_cost_volume_matches_oracle(P, shape):
+    f0, f1 = _rand(shape, 1), _rand(shape, 2)
+    ref = O.cost_volume(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy()
+    out = P.ops.cost_volume(_cuda(f0), _cuda(f1), 4).cpu().numpy()
+    assert out.shape == ref.shape
+    np.testing.assert_allclose(out, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_cost_volume_all_81_displacements_at_corners(P):
+    """Adversarial: impulses in the four corners; every displacement channel must pick exactly the
+    reference's (v outer, h inner) neighbour and zero-pad outside the image."""
+    C, H, W = 4, 9, 35
+    f0 = np.zeros((1, H, W, C), np.float32); f1 = _rand((1, H, W, C), 5)
+    for (y, x) in [(0, 0), (0, W - 1), (H - 1, 0), (H - 1, W - 1)]:
+        f0[0, y, x, :] = [1.0, -2.0, 0.5, 3.0]
+    ref = O.cost_volume(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy()
+    out = P.ops.cost_volume(_cuda(f0), _cuda(f1), 4).cpu().numpy()
+    np.testing.assert_allclose(out, ref, atol=1e-6)
+    assert (out[0, 0, 0, :4 * 9] == 0).all()          # v < 0 rows are outside the image at y = 0
+
+
+@pytest.mark.parametrize("r", [1, 2, 3])
+def test_cost_volume_other_search_ranges(P, r):
+    f0, f1 = _rand((2, 10, 12, 8), 1), _rand((2, 10, 12, 8), 2)
+    ref = O.cost_volume(torch.from_numpy(f0), torch.from_numpy(f1), r).numpy()
+    out = P.ops.cost_volume(_cuda(f0), _cuda(f1), r).cpu().numpy()
+    np.testing.assert_allclose(out, ref, atol=1e-5)
+
+
+def test_cost_volume_into_concat_slot_with_f0_copy(P):
+    B, H, W, C = 2, 14, 40, 32
+    f0, f1 = _rand((B, H, W, C), 1), _rand((B, H, W, C), 2)
+    buf = torch.full((B, H, W, 148), -7.0, device="cuda")
+    P.ops.cost_volume(_cuda(f0), _cuda(f1), 4, out=buf[..., 0:81], f0_copy=buf[..., 84:116])
+    ref = O.cost_volume(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy()
+    got = buf.cpu().numpy()
+    np.testing.assert_allclose(got[..., 0:81], ref, atol=1e-5)
+    np.testing.assert_array_equal(got[..., 84:116], f0)
+    assert (got[..., 81:84] == -7.0).all() and (got[..., 116:] == -7.0).all()     # nothing else touched
+
+
+@pytest.mark.parametrize("warp_type", ["bilinear", "nearest"])
+@pytest.mark.parametrize("shape", [(2, 14, 32, 128), (1, 28, 64, 96), (2, 9, 21, 16)])
+def test_warp_matches_oracle(P, shape, warp_type):
+    B, H, W, C = shape
+    x = _rand(shape, 3)
+    flow = _rand((B, H, W, 2), 4, scale=6.0)      # many samples beyond the borders
+    flow[0, 0, 0] = [0.0, 0.0]; flow[0, 1, 1] = [2.0, -1.0]; flow[0, 2, 2] = [-100.0, 100.0]   # integer / far flows
+    ref = O.warping_layer(torch.from_numpy(x), torch.from_numpy(flow), warp_type).numpy()
+    out = P.ops.warp(_cuda(x), _cuda(flow), 1.0, warp_type).cpu().numpy()
+    np.testing.assert_allclose(out, ref, atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("warp_type", ["bilinear", "nearest"])
+def test_fused_warp_cost_volume_equals_warp_then_cost_volume(P, warp_type):
+    B, H, W, C = 2, 28, 64, 96
+    f0, f1 = _rand((B, H, W, C), 1), _rand((B, H, W, C), 2)
+    flow = _rand((B, H, W, 2), 4, scale=3.0)
+    scale = 2.5
+    fl = torch.from_numpy(flow) * scale
+    ref = O.cost_volume(torch.from_numpy(f0), O.warping_layer(torch.from_numpy(f1), fl, warp_type), 4).numpy()
+    out = P.ops.warp_cost_volume(_cuda(f0), _cuda(f1), _cuda(flow), scale, warp_type).cpu().numpy()
+    np.testing.assert_allclose(out, ref, atol=2e-5, rtol=1e-5)
+
+
+CONV_CASES = [
+    # (B, H, W, Cin, Cout, stride, dilation, alpha)
+    (2, 16, 24, 3, 16, 2, 1, 0.1),      # first pyramid conv: Cin=3, stride 2 (asymmetric SAME)
+    (1, 15, 17, 3, 16, 2, 1, 0.1),      # odd sizes
+    (2, 16, 24, 16, 16, 1, 1, 0.1),
+    (1, 14, 32, 16, 32, 2, 1, 0.1),     # stride-2 with Cin >= 16
+    (1, 7, 16, 273, 128, 1, 1, 0.1),    # estimator conv 0 at the coarsest level
+    (1, 12, 20, 147, 128, 1, 1, 0.1),
+    (1, 12, 20, 128, 96, 1, 1, 0.1),
+    (2, 12, 20, 32, 2, 1, 1, 1.0),      # flow head
+    (1, 24, 40, 34, 128, 1, 1, 0.1),    # context conv 0
+    (1, 24, 40, 128, 128, 1, 2, 0.1),
+    (1, 24, 40, 128, 128, 1, 4, 0.1),
+    (1, 24, 40, 128, 96, 1, 8, 0.1),
+    (1, 24, 40, 96, 64, 1, 16, 0.1),    # dilation 16 on a small map: mostly padding
+    (1, 9, 11, 5, 7, 1, 1, 0.1),        # nothing aligned
+    (1, 8, 8, 64, 2, 1, 1, 1.0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3x3_matches_oracle(P, case):
+    B, H, W, Cin, Cout, stride, dil, alpha = case
+    x = _rand((B, H, W, Cin), 1)
+    k = _rand((3, 3, Cin, Cout), 2, scale=1.0 / np.sqrt(9 * Cin))
+    b = _rand((Cout,), 3, scale=0.1)
+    y = O.conv2d_same(torch.from_numpy(x), torch.from_numpy(k), torch.from_numpy(b), stride, dil)
+    ref = (O.leaky_relu(y, alpha) if alpha != 1.0 else y).numpy()
+    out = P.ops.conv3x3(_cuda(x), _cuda(k), _cuda(b), stride=stride, dilation=dil, alpha=alpha).cpu().numpy()
+    assert out.shape == ref.shape
+    np.testing.assert_allclose(out, ref, atol=2e-5, rtol=1e-5)
+
+
+def test_conv3x3_strided_views_and_residual(P):
+    B, H, W, Cin, Cout = 2, 10, 12, 32, 2
+    x = _rand((B, H, W, Cin), 1); k = _rand((3, 3, Cin, Cout), 2, 0.1); b = _rand((Cout,), 3, 0.1)
+    res = _rand((B, H, W, 2), 4)
+    xin = torch.zeros((B, H, W, 40), device="cuda"); xin[..., 4:36] = _cuda(x)
+    buf = torch.zeros((B, H, W, 148), device="cuda"); buf[..., 81:83] = _cuda(res)
+    out = torch.zeros((B, H, W, 36), device="cuda")
+    P.ops.conv3x3(xin[..., 4:36], _cuda(k), _cuda(b), alpha=1.0, residual=buf[..., 81:83], out=out[..., 32:34])
+    ref = O.conv2d_same(torch.from_numpy(x), torch.from_numpy(k), torch.from_numpy(b)).numpy() + res
+    np.testing.assert_allclose(out[..., 32:34].cpu().numpy(), ref, atol=2e-5)
+    assert (out[..., :32] == 0).all() and (out[..., 34:] == 0).all()
+
+
+@pytest.mark.parametrize("shape,oh,ow,mul", [((2, 7, 16, 2), 14, 32, 1.0), ((1, 14, 32, 32), 28, 64, 1.0),
+                                            ((1, 16, 32, 2), 64, 128, 20.0), ((1, 5, 7, 3), 9, 20, 1.0)])
+def test_resize_bilinear_legacy_matches_oracle(P, shape, oh, ow, mul):
+    x = _rand(shape, 1)
+    ref = (O.resize_bilinear_legacy(torch.from_numpy(x), oh, ow) * mul).numpy()
+    out = P.ops.resize_bilinear(_cuda(x), oh, ow, mul).cpu().numpy()
+    np.testing.assert_allclose(out, ref, atol=1e-6 * max(1.0, mul), rtol=1e-6)
+
+
+def test_losses_match_oracle(P):
+    B, H, W = 2, 64, 128
+    gt = _rand((B, H, W, 2), 1, 5.0)
+    pyr = [_rand((B, H >> (6 - l), W >> (6 - l), 2), 10 + l, 0.3) for l in range(5)]
+    ff = _rand((B, H, W, 2), 3, 5.0)
+    w = O.DEFAULT_LOSS_WEIGHTS
+    ref_loss = O.multiscale_loss(torch.from_numpy(gt), [torch.from_numpy(p) for p in pyr], w).item()
+    ref_epe = O.EPE(torch.from_numpy(gt), torch.from_numpy(ff)).item()
+    loss = P.multiscale_loss(_cuda(gt), [_cuda(p) for p in pyr], w).item()
+    epe = P.EPE(_cuda(gt), _cuda(ff)).item()
+    assert loss == pytest.approx(ref_loss, rel=1e-5)
+    assert epe == pytest.approx(ref_epe, rel=1e-5)
+    a, b = _rand((B, 8, 16, 2), 7), _rand((B, 8, 16, 2), 8)
+    assert P.L2loss(_cuda(a), _cuda(b)).item() == pytest.approx(O.L2loss(torch.from_numpy(a), torch.from_numpy(b)).item(), rel=1e-5)
+    assert P.L1loss(_cuda(a), _cuda(b)).item() == pytest.approx(O.L1loss(torch.from_numpy(a), torch.from_numpy(b)).item(), rel=1e-5)
+
+
+def test_modules_read_like_the_reference(P):
+    """The stand-alone module classes keep the reference's names / signatures (modules.py)."""
+    W = O.glorot_weights(2)
+    params = {k: _cuda(v) for k, v in W.items()}
+    im = _rand((1, 64, 128, 3), 0, 0.3) + 0.5
+    pyr = P.modules.FeaturePyramidExtractor_custom(6, params=params)(_cuda(im))
+    ref = O.pyramid_extractor(torch.from_numpy(im), W)
+    assert [tuple(p.shape) for p in pyr] == [tuple(p.shape) for p in ref]
+    for a, b in zip(pyr, ref):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), atol=1e-5)
+    f0, f1 = pyr[2], pyr[2].flip(2).contiguous()
+    cv = P.modules.CostVolumeLayer(4)(f0, f1)
+    flows_up = _cuda(_rand((1,) + tuple(f0.shape[1:3]) + (2,), 5, 0.5))
+    feats_up = _cuda(_rand((1,) + tuple(f0.shape[1:3]) + (32,), 6, 0.5))
+    est = P.modules.OpticalFlowEstimator_custom(name="optflow_2", params=params)
+    flows, fu, featu = est(cv, f0, flows_up, feats_up)
+    r_flows, r_fu, r_featu = O.flow_estimator(W, "pwcdcnet/optflow_2", cv.cpu(), f0.cpu(), flows_up.cpu(), feats_up.cpu())
+    np.testing.assert_allclose(flows.cpu().numpy(), r_flows.numpy(), atol=1e-5)
+    np.testing.assert_allclose(fu.cpu().numpy(), r_fu.numpy(), atol=1e-5)
+    np.testing.assert_allclose(featu.cpu().numpy(), r_featu.numpy(), atol=1e-5)
+    feats = _cuda(_rand((1, 16, 32, 32), 8, 0.5)); fl = _cuda(_rand((1, 16, 32, 2), 9, 0.5))
+    out = P.modules.ContextNetwork(params=params)(fl, feats)
+    np.testing.assert_allclose(out.cpu().numpy(), O.context_network(W, fl.cpu(), feats.cpu()).numpy(), atol=1e-5)
+    with pytest.raises(AssertionError):
+        P.modules.WarpingLayer("cubic")(f0, flows_up)
+
+
+def test_host_layer_rejects_bad_inputs(P):
+    with pytest.raises(TypeError):
+        P.ops.cost_volume(torch.zeros(1, 8, 8, 32, device="cuda", dtype=torch.float16), torch.zeros(1, 8, 8, 32, device="cuda"))
+    with pytest.raises(ValueError):
+        P.ops.cost_volume(torch.zeros(1, 8, 8, 32, device="cuda"), torch.zeros(1, 8, 9, 32, device="cuda"))
+    with pytest.raises(ValueError):   # NCHW-permuted view is not pixel-strided NHWC
+        P.ops.cost_volume(torch.zeros(1, 32, 8, 8, device="cuda").permute(0, 2, 3, 1), torch.zeros(1, 8, 8, 32, device="cuda"))
+    with pytest.raises(P.ops.PwcError):
+        P.ops.cost_volume(torch.zeros(1, 8, 8, 32), torch.zeros(1, 8, 8, 32))
+    with pytest.raises(P.ops.PwcError):   # C not a multiple of 4 -> PWC_E_ALIGN from the C entry point
+        P.ops.cost_volume(torch.zeros(1, 8, 8, 30, device="cuda"), torch.zeros(1, 8, 8, 30, device="cuda"))
