@@ -385,7 +385,9 @@ class PWCDCNet(object):
 
     def _as_input(self, a, name):
         if isinstance(a, np.ndarray):
-            a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+            if a.dtype != np.float32:
+                raise TypeError(f"{name}: dtype must be float32, got {a.dtype}")
+            a = torch.from_numpy(np.ascontiguousarray(a))
         if not isinstance(a, torch.Tensor):
             raise TypeError(f"{name}: expected torch.Tensor or numpy.ndarray, got {type(a)}")
         if a.dtype != torch.float32:

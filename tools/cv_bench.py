@@ -1,0 +1,35 @@
+"""Launches the level-2 cost-volume kernel (B x 112 x 256 x 32) a few times: target for ncu captures
+and quick timing.  usage: python tools/cv_bench.py [B] [iters] [fused]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import pwcnet_b200 as P
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+fused = len(sys.argv) > 3 and sys.argv[3] == "fused"
+h, w, C = 112, 256, 32
+g = torch.Generator(device="cuda").manual_seed(0)
+f0 = torch.randn((B, h, w, C), device="cuda", generator=g)
+f1 = torch.randn((B, h, w, C), device="cuda", generator=g)
+flow = torch.randn((B, h, w, 2), device="cuda", generator=g) * 3
+cv = torch.empty((B, h, w, 81), device="cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+def run():
+    if fused:
+        P.ops.warp_cost_volume(f0, f1, flow, 5.0, out=cv)
+    else:
+        P.ops.cost_volume(f0, f1, out=cv)
+for _ in range(3):
+    run()
+ts = []
+for _ in range(iters):
+    flush.fill_(1)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); run(); e.record()
+    torch.cuda.synchronize()
+    ts.append(s.elapsed_time(e) * 1e3)
+alg = 4 * h * w * (2 * C + 81 + (2 if fused else 0)) * B
+import statistics
+us = statistics.mean(ts)
+print(f"cost_volume level-2 B={B} fused={fused}: {us:.1f} us/launch (min {min(ts):.1f}), {alg/us/1e3:.0f} GB/s algorithmic, frac of 6550 = {alg/us/1e3/6550:.3f}")
