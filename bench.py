@@ -192,17 +192,24 @@ def main():
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
 
     # ---------------------------------------------------------------- e2e: host buffers through the public API
-    out_host = None
+    ff, pyr = model(host0, host1)
+    outs_dev = [ff] + list(pyr)
+    out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs_dev]   # pinned result buffers
+
+    def e2e_step():
+        ff, pyr = model(host0, host1)                        # H2D of both images from pinned memory inside
+        for h, d in zip(out_host, [ff] + list(pyr)):         # D2H of the final flow + the 5 pyramid flows
+            h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()            # results are on the host when the step ends
+
     for _ in range(2):
-        ff, pyr = model(host0, host1)
-        out_host = [ff.cpu()] + [p.cpu() for p in pyr]
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        ff, pyr = model(host0, host1)                        # H2D of both images inside
-        out_host = [ff.cpu()] + [p.cpu() for p in pyr]      # D2H of the final flow + the 5 pyramid flows
+        e2e_step()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)

@@ -1,12 +1,419 @@
-// placeholder: tcgen05 implicit-GEMM conv (filled in next)
+// 3x3 convolution (stride 1, any dilation, TF 'SAME' padding) + bias + leaky on the 5th-generation
+// tensor cores: implicit GEMM with tcgen05.mma.kind::tf32, TMA-staged operands, TMEM accumulators.
+//
+// Replaces the Conv2D + BiasAdd + Mul + Maximum node groups of the reference's estimator / context /
+// pyramid stacks (modules.py:62-67, 266-274, 306-323) for the layers that are genuine dense
+// contractions (Cin >= 32, Cout % 16 == 0).
+//
+// GEMM view per CTA: D[128 pixels x Cout] = sum over (tap, 32-channel slice) A_tap[128 x 32] * W_tap[32 x Cout]
+//   * A_tap tile = one 4-D TMA box {32 ch, 16 px, 8 rows, 1 image} of the NHWC input at the tap's
+//     (dy,dx)*dilation offset; out-of-image coordinates are zero-filled by TMA = SAME padding; channels
+//     beyond Cin are zero-filled too, so concat buffers of any width work.  128B-swizzled, K-major.
+//   * W_tap tile = TMA box {32, Cout} of the packed weights [tap][Cout][Cin_pad] (K-major, 128B swizzle).
+//   * one elected thread issues tcgen05.mma (M=128, N=Cout, K=8 per instruction), fp32 accumulators live
+//     in TMEM; 4 epilogue warps read them back with tcgen05.ld, add bias, apply leaky-relu and store NHWC
+//     with an arbitrary channel stride (concat slots).
+//
+// Precision: kind::tf32 reads fp32 bit patterns and uses the top 19 bits.  n_split = 1 is plain TF32.
+// n_split = 3 is the error-compensated "3xTF32" scheme: x = hi + lo with hi = x & 0xffffe000 and
+// lo = rn_tf32(x - hi); D += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo.  W_hi/W_lo are precomputed by
+// pwc_conv3x3_pack_weights; A_lo is produced on chip by the 4 epilogue warps between TMA arrival and
+// MMA issue (generic-proxy writes + fence.proxy.async), A_hi is the raw tile (hardware truncation).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = A_lo converter during the main loop, then epilogue (TMEM lane quadrant = warp % 4).
 #include "common.cuh"
-extern "C" int pwc_conv3x3_tc_fwd(const float*, int, const float*, const float*, float*, int, int, int, int, int, int, int,
-                                  float, int, void*) {
-    pwc::set_error("conv3x3_tc: not built");
-    return PWC_E_NOTBUILT;
+#include <cuda.h>
+
+namespace pwc {
+
+constexpr int TC_BM = 128;        // pixels per CTA
+constexpr int TC_TW = 16, TC_TH = 8;
+constexpr int TC_BK = 32;         // channels per stage (128 bytes = swizzle span)
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+
+struct TcParams {
+    const float* bias; float* y;
+    int y_cs, B, H, W, Cin, Cout, dil;
+    int tiles_x, tiles_y, kchunks;
+    float alpha;
+    int b_bytes;      // Cout * 128
+    int stage_bytes;  // per-stage smem
+    int stages;
+    int tmem_cols;
+    int n_main;       // number of main accumulators the K loop rotates over
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-extern "C" long long pwc_conv3x3_packed_bytes(int, int) { return 0; }
-extern "C" int pwc_conv3x3_pack_weights(const float*, float*, int, int, void*) {
-    pwc::set_error("conv3x3_pack_weights: not built");
-    return PWC_E_NOTBUILT;
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: next 8-row atom
+    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// lo part of the 3xTF32 split: x - trunc_tf32(x) (exact, 13 significant bits), then rounded to
+// nearest tf32 so that the hardware's operand truncation is a no-op and the rounding error has a
+// random sign (truncating lo instead leaves a coherent -2^-21 bias per product).
+__device__ __forceinline__ float tf32_residual(float x) {
+    const float lo = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int NSPLIT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte aligned operand area (dynamic smem base alignment is not guaranteed beyond 16)
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+
+    __shared__ __align__(8) uint64_t bars[3 * 8 + 1];   // full[8], conv[8], empty[8], acc_full
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[8]), bar_empty = smem_u32(&bars[16]);
+    const uint32_t bar_acc = smem_u32(&bars[24]);
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
+    const int x0 = tx * TC_TW, y0 = ty * TC_TH;
+    const int KT = 9 * p.kchunks;
+
+    // per-stage layout: [A raw 16K][A lo 16K (NSPLIT==3)][B hi][B lo (NSPLIT==3)]
+    const uint32_t off_alo = TC_A_BYTES;
+    const uint32_t off_b = (NSPLIT == 3 ? 2 : 1) * TC_A_BYTES;
+    const uint32_t off_blo = off_b + p.b_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 128);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+            const uint32_t tx_bytes = TC_A_BYTES + (NSPLIT == 3 ? 2 : 1) * p.b_bytes;
+            for (int it = 0; it < KT; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const uint32_t st = base + s * p.stage_bytes;
+                mbar_expect_tx(bar_full + 8 * s, tx_bytes);
+                tma_load_4d(st, &tmX, bar_full + 8 * s, kc * TC_BK, x0 + (kx - 1) * p.dil, y0 + (ky - 1) * p.dil, b);
+                tma_load_3d(st + off_b, &tmW, bar_full + 8 * s, kc * TC_BK, 0, tap);
+                if (NSPLIT == 3) tma_load_3d(st + off_blo, &tmW, bar_full + 8 * s, kc * TC_BK, 0, 9 + tap);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int it = 0; it < KT; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                mbar_wait((NSPLIT == 3 ? bar_conv : bar_full) + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t st = base + s * p.stage_bytes;
+                // The tensor core truncates (round-toward-zero) when it adds into the fp32 accumulator, so
+                // the error grows with the length of the accumulation chain.  Main products rotate over
+                // n_main TMEM accumulators, the two small correction products go to their own accumulator
+                // (|corr| ~ 2^-11 |D|, its truncation error is negligible); the epilogue sums them in fp32.
+                const int am = it % p.n_main;
+                const uint32_t d_main = tmem_acc + am * p.Cout;
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k)
+                    tc_mma_tf32(d_main, make_desc_sw128(st + k * 32), make_desc_sw128(st + off_b + k * 32), idesc,
+                                (it >= p.n_main || k > 0) ? 1u : 0u);
+                if (NSPLIT == 3) {
+                    const uint32_t d_corr = tmem_acc + p.n_main * p.Cout;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        tc_mma_tf32(d_corr, make_desc_sw128(st + off_alo + k * 32), make_desc_sw128(st + off_b + k * 32), idesc,
+                                    (it | k) != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        tc_mma_tf32(d_corr, make_desc_sw128(st + k * 32), make_desc_sw128(st + off_blo + k * 32), idesc, 1u);
+                }
+                tc_commit(bar_empty + 8 * s);     // frees the stage when these MMAs have read it
+            }
+            tc_commit(bar_acc);                   // accumulator complete
+        }
+    } else {
+        // ===================== converter (3xTF32) then epilogue =====================
+        const int ct = threadIdx.x - 64;          // 0..127
+        if (NSPLIT == 3) {
+            for (int it = 0; it < KT; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                mbar_wait(bar_full + 8 * s, ph);
+                const float4* a = reinterpret_cast<const float4*>(base_ptr + (size_t)s * p.stage_bytes);
+                float4* alo = reinterpret_cast<float4*>(base_ptr + (size_t)s * p.stage_bytes + off_alo);
+#pragma unroll
+                for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+                    const float4 v = a[ct + 128 * i];
+                    float4 l;
+                    l.x = tf32_residual(v.x); l.y = tf32_residual(v.y);
+                    l.z = tf32_residual(v.z); l.w = tf32_residual(v.w);
+                    alo[ct + 128 * i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // make generic writes visible to the MMA (async proxy)
+                mbar_arrive(bar_conv + 8 * s);
+            }
+        }
+        // ---- epilogue: TMEM -> registers -> bias + leaky -> global (NHWC, channel stride y_cs)
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int m = q * 32 + lane;               // accumulator row = pixel within the tile
+        const int oy = y0 + m / TC_TW, ox = x0 + (m % TC_TW);
+        const bool valid = oy < p.H && ox < p.W;
+        float* yrow = p.y + (((size_t)b * p.H + oy) * p.W + ox) * p.y_cs;
+        const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y);
+        const int n_acc = p.n_main + (NSPLIT == 3 ? 1 : 0);
+        for (int n0 = 0; n0 < p.Cout; n0 += 16) {
+            uint32_t r[16];
+            float acc[16];
+            // smallest-magnitude accumulator (the correction) first
+            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (n_acc - 1) * p.Cout + n0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
+            for (int a = n_acc - 2; a >= 0; --a) {
+                tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + a * p.Cout + n0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+            }
+            if (valid) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = leaky(acc[j] + __ldg(p.bias + n0 + j), p.alpha);
+                if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) yrow[n0 + j] = v[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(p.tmem_cols));
+    }
+}
+
+// Packs HWIO (3,3,Cin,Cout) weights into [2][9][Cout][Cin_pad]: plane 0 = w & 0xffffe000 (tf32-exact),
+// plane 1 = rn_tf32(w - plane0), zero for channels >= Cin.
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout, int Cin_pad) {
+    const size_t total = (size_t)9 * Cout * Cin_pad;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = idx % Cin_pad; size_t r = idx / Cin_pad;
+        const int n = r % Cout; const int tap = r / Cout;
+        float hi = 0.f, lo = 0.f;
+        if (c < Cin) {
+            const float v = w[((size_t)tap * Cin + c) * Cout + n];
+            hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            lo = tf32_residual(v);
+        }
+        out[idx] = hi;
+        out[total + idx] = lo;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+static inline int cin_pad(int Cin) { return (Cin + TC_BK - 1) / TC_BK * TC_BK; }
+
+}  // namespace pwc
+
+extern "C" long long pwc_conv3x3_packed_bytes(int Cin, int Cout) {
+    if (Cin <= 0 || Cout <= 0) return 0;
+    return 2LL * 9 * Cout * pwc::cin_pad(Cin) * 4;
+}
+
+extern "C" int pwc_conv3x3_pack_weights(const float* w_hwio, float* w_packed, int Cin, int Cout, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(w_hwio && w_packed, PWC_E_BADARG, "pack_weights: null pointer");
+    PWC_REQUIRE(Cin > 0 && Cout > 0, PWC_E_BADARG, "pack_weights: bad dims");
+    pack_weights_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(w_hwio, w_packed, Cin, Cout, cin_pad(Cin));
+    PWC_CHECK_LAUNCH("pack_weights_kernel");
+    return 0;
+}
+
+extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packed, const float* bias,
+                                  float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int dilation,
+                                  float alpha, int n_split, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(x && w_packed && bias && y, PWC_E_BADARG, "conv3x3_tc: null pointer");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && dilation >= 1, PWC_E_BADARG, "conv3x3_tc: bad dims");
+    PWC_REQUIRE(n_split == 1 || n_split == 3, PWC_E_BADARG, "conv3x3_tc: n_split must be 1 or 3");
+    PWC_REQUIRE(Cout % 16 == 0 && Cout <= 256, PWC_E_BADARG, "conv3x3_tc: Cout must be a multiple of 16, <= 256");
+    PWC_REQUIRE(Cin >= TC_BK, PWC_E_BADARG, "conv3x3_tc: Cin must be >= 32");
+    PWC_REQUIRE(x_cs >= Cin && y_cs >= Cout, PWC_E_BADARG, "conv3x3_tc: channel stride smaller than channel count");
+    PWC_REQUIRE(aligned16(x) && (x_cs % 4 == 0) && aligned16(w_packed), PWC_E_ALIGN,
+                "conv3x3_tc: x / w_packed must be 16-byte aligned and x_cs a multiple of 4");
+    EncodeTiledFn enc = get_encode();
+    PWC_REQUIRE(enc != nullptr, PWC_E_NOTBUILT, "conv3x3_tc: cuTensorMapEncodeTiled not available from the driver");
+
+    const int cpad = cin_pad(Cin);
+    CUtensorMap tmX, tmW;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)x_cs * 4, (cuuint64_t)W * x_cs * 4, (cuuint64_t)H * W * x_cs * 4};
+        cuuint32_t box[4] = {TC_BK, TC_TW, TC_TH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PWC_REQUIRE(r == CUDA_SUCCESS, PWC_E_BADARG, "conv3x3_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)cpad, (cuuint64_t)Cout, 18};
+        cuuint64_t strides[2] = {(cuuint64_t)cpad * 4, (cuuint64_t)Cout * cpad * 4};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)Cout, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)w_packed, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PWC_REQUIRE(r == CUDA_SUCCESS, PWC_E_BADARG, "conv3x3_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
+    }
+    TcParams p{};
+    p.bias = bias; p.y = y; p.y_cs = y_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dil = dilation;
+    p.tiles_x = (W + TC_TW - 1) / TC_TW; p.tiles_y = (H + TC_TH - 1) / TC_TH;
+    p.kchunks = cpad / TC_BK;
+    p.alpha = alpha;
+    p.b_bytes = Cout * 128;
+    p.stage_bytes = (n_split == 3 ? 2 : 1) * (TC_A_BYTES + p.b_bytes);
+    p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
+    const int budget = 220 * 1024;
+    p.stages = budget / p.stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    PWC_REQUIRE(p.stages >= 2, PWC_E_BADARG, "conv3x3_tc: tile does not fit in shared memory");
+    // TMEM columns: n_main main accumulators (+1 correction accumulator for 3xTF32), N columns each
+    p.n_main = 1;
+    if (n_split == 3) {
+        p.n_main = 512 / Cout - 1;
+        if (p.n_main > 3) p.n_main = 3;
+        PWC_REQUIRE(p.n_main >= 1, PWC_E_BADARG, "conv3x3_tc: Cout too large for the 3xTF32 accumulator layout");
+    }
+    int cols = 32;
+    while (cols < (p.n_main + (n_split == 3 ? 1 : 0)) * Cout) cols *= 2;
+    p.tmem_cols = cols;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * B;
+    PWC_REQUIRE(tiles < (1LL << 31), PWC_E_BADARG, "conv3x3_tc: too many tiles");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (n_split == 3) {
+        e = cudaFuncSetAttribute(conv3x3_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        conv3x3_tc_kernel<3><<<(unsigned)tiles, TC_THREADS, smem, st>>>(tmX, tmW, p);
+    } else {
+        e = cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        conv3x3_tc_kernel<1><<<(unsigned)tiles, TC_THREADS, smem, st>>>(tmX, tmW, p);
+    }
+    PWC_CHECK_LAUNCH("conv3x3_tc_kernel");
+    return 0;
 }

@@ -30,7 +30,7 @@ from ._abi import PwcError
 from .modules import (CONTEXT_DILATIONS, CONTEXT_FILTERS, ESTIMATOR_FILTERS, PYRAMID_FILTERS)
 
 PRECISIONS = ("fp32", "3xtf32", "tf32", "cudnn")
-DEFAULT_PRECISION = "fp32"
+DEFAULT_PRECISION = "3xtf32"
 
 
 def _round_up(a: int, m: int) -> int:
@@ -217,7 +217,7 @@ class PWCDCNet(object):
         if self.precision == "cudnn":
             return self._conv_cudnn(x, k, b, out, stride, dilation, alpha, residual)
         if self.precision in ("3xtf32", "tf32") and stride == 1 and residual is None and cout % 16 == 0 \
-                and cin >= 16 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
+                and cin >= 32 and cout <= 256 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
             return self._conv_tc(x, scope, k, b, out, dilation, alpha)
         return ops.conv3x3(x, k, b, stride=stride, dilation=dilation, alpha=alpha, residual=residual, out=out)
 

@@ -1,0 +1,40 @@
+"""tcgen05 tensor-core convolution operators (see csrc/conv_tc.cu)."""
+from __future__ import annotations
+
+import torch
+
+from ._abi import check, lib
+from .ops import _nhwc, _stream, new_nhwc
+
+
+def pack_weights(kernel_hwio: torch.Tensor) -> torch.Tensor:
+    """HWIO (3,3,Cin,Cout) -> packed [2][9][Cout][Cin_pad] (tf32-exact hi plane + residual lo plane)."""
+    if kernel_hwio.dim() != 4 or kernel_hwio.shape[:2] != (3, 3) or not kernel_hwio.is_cuda \
+            or kernel_hwio.dtype != torch.float32 or not kernel_hwio.is_contiguous():
+        raise ValueError("pack_weights: kernel must be a contiguous CUDA float32 HWIO (3,3,Cin,Cout) tensor")
+    cin, cout = kernel_hwio.shape[2], kernel_hwio.shape[3]
+    nbytes = lib().pwc_conv3x3_packed_bytes(cin, cout)
+    out = torch.empty(nbytes // 4, dtype=torch.float32, device=kernel_hwio.device)
+    check(lib().pwc_conv3x3_pack_weights(kernel_hwio.data_ptr(), out.data_ptr(), cin, cout, _stream()),
+          "pwc_conv3x3_pack_weights")
+    return out
+
+
+def conv3x3_tc(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, alpha: float = 1.0, n_split: int = 3,
+               out=None):
+    """Stride-1 3x3 SAME conv + bias + leaky on tcgen05 (n_split=1: TF32, 3: 3xTF32 fp32-class)."""
+    B, H, W, C, x_cs = _nhwc(x, "x")
+    if C != cin:
+        raise ValueError(f"conv3x3_tc: x has {C} channels, weights expect {cin}")
+    if bias.shape != (cout,) or not bias.is_cuda or bias.dtype != torch.float32:
+        raise ValueError("conv3x3_tc: bias must be CUDA float32 (Cout,)")
+    if w_packed.numel() * 4 != lib().pwc_conv3x3_packed_bytes(cin, cout):
+        raise ValueError("conv3x3_tc: w_packed has the wrong size for (Cin, Cout)")
+    if out is None:
+        out = new_nhwc(B, H, W, cout, x.device)
+    Bo, Ho, Wo, Co, y_cs = _nhwc(out, "out")
+    if (Bo, Ho, Wo, Co) != (B, H, W, cout):
+        raise ValueError("conv3x3_tc: out shape mismatch")
+    check(lib().pwc_conv3x3_tc_fwd(x.data_ptr(), x_cs, w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(), y_cs,
+                                   B, H, W, cin, cout, dilation, float(alpha), n_split, _stream()), "pwc_conv3x3_tc_fwd")
+    return out

@@ -207,3 +207,44 @@ def test_host_layer_rejects_bad_inputs(P):
         P.ops.cost_volume(torch.zeros(1, 8, 8, 32), torch.zeros(1, 8, 8, 32))
     with pytest.raises(P.ops.PwcError):   # C not a multiple of 4 -> PWC_E_ALIGN from the C entry point
         P.ops.cost_volume(torch.zeros(1, 8, 8, 30, device="cuda"), torch.zeros(1, 8, 8, 30, device="cuda"))
+
+
+TC_CASES = [
+    # (B, H, W, Cin, channel stride, Cout, dilation)
+    (1, 8, 16, 32, 32, 32, 1),
+    (2, 14, 32, 128, 128, 128, 1),
+    (1, 28, 64, 147, 148, 128, 1),      # estimator conv 0 at level 4: ragged K (147 -> zero-filled to 160)
+    (1, 7, 16, 273, 276, 128, 1),       # coarsest level: 7 rows in an 8-row tile
+    (1, 28, 64, 128, 128, 96, 2),
+    (1, 24, 40, 96, 96, 64, 16),        # dilation 16: taps mostly outside the image (TMA zero fill)
+    (2, 9, 21, 64, 64, 32, 4),          # ragged tiles in x and y
+    (1, 16, 32, 192, 192, 192, 1),      # N = 192 (TMEM allocation 256 columns)
+]
+
+
+@pytest.mark.parametrize("n_split,tol", [(3, 3e-5), (1, 1e-2)])
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv3x3_tcgen05_matches_oracle(P, case, n_split, tol):
+    """tcgen05 implicit-GEMM conv vs the oracle's fp32 conv.  3xTF32 must be fp32-class (3e-5 max-abs on
+    O(1) outputs); plain TF32 (operands truncated to 10 mantissa bits by the hardware) within 1e-2."""
+    from pwcnet_b200 import ops_tc
+    B, H, W, Cin, cs, Cout, dil = case
+    buf = _rand((B, H, W, cs), 1)
+    k = _rand((3, 3, Cin, Cout), 2, scale=1.0 / np.sqrt(9 * Cin))
+    b = _rand((Cout,), 3, scale=0.1)
+    x = buf[..., :Cin]
+    ref = O.leaky_relu(O.conv2d_same(torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(k), torch.from_numpy(b), 1, dil), 0.1).numpy()
+    wp = ops_tc.pack_weights(_cuda(k))
+    out = ops_tc.conv3x3_tc(_cuda(buf)[..., :Cin], wp, _cuda(b), Cin, Cout, dilation=dil, alpha=0.1, n_split=n_split)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=tol, rtol=0)
+
+
+def test_conv3x3_tcgen05_writes_only_its_slot(P):
+    from pwcnet_b200 import ops_tc
+    B, H, W, Cin, Cout = 1, 12, 20, 64, 32
+    x = _rand((B, H, W, Cin), 1); k = _rand((3, 3, Cin, Cout), 2, 0.05); b = _rand((Cout,), 3, 0.1)
+    out = torch.full((B, H, W, 40), 9.0, device="cuda")
+    ops_tc.conv3x3_tc(_cuda(x), ops_tc.pack_weights(_cuda(k)), _cuda(b), Cin, Cout, alpha=1.0, n_split=3, out=out[..., 4:36])
+    ref = O.conv2d_same(torch.from_numpy(x), torch.from_numpy(k), torch.from_numpy(b)).numpy()
+    np.testing.assert_allclose(out[..., 4:36].cpu().numpy(), ref, atol=2e-5)
+    assert (out[..., :4] == 9.0).all() and (out[..., 36:] == 9.0).all()
