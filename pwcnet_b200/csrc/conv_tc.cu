@@ -24,6 +24,7 @@
 // warps 2..5 = A_lo converter during the main loop, then epilogue (TMEM lane quadrant = warp % 4).
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace pwc {
 
@@ -43,6 +44,8 @@ struct TcParams {
     int stages;
     int tmem_cols;
     int n_main;       // number of main accumulators the K loop rotates over
+    int cluster;      // CTAs per cluster sharing the weight tiles by TMA multicast (1, 2 or 4)
+    int total_tiles;  // real tiles; CTAs beyond it are padding (run the pipeline, store nothing)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -77,6 +80,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -139,8 +159,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
     // tile coordinates
     int t = blockIdx.x;
+    const bool real_tile = t < p.total_tiles;
     const int tx = t % p.tiles_x; t /= p.tiles_x;
-    const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
+    const int ty = t % p.tiles_y; const int b = t / p.tiles_y;   // b == B for padding CTAs: TMA zero-fills
+    const int CS = p.cluster;
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << CS) - 1);
     const int x0 = tx * TC_TW, y0 = ty * TC_TH;
     const int KT = 9 * p.kchunks;
 
@@ -153,7 +177,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int s = 0; s < S; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_conv + 8 * s, 128);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, CS);
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -164,6 +188,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base_slot;
 
@@ -182,8 +207,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const uint32_t st = base + s * p.stage_bytes;
                 mbar_expect_tx(bar_full + 8 * s, tx_bytes);
                 tma_load_4d(st, &tmX, bar_full + 8 * s, kc * TC_BK, x0 + (kx - 1) * p.dil, y0 + (ky - 1) * p.dil, b);
-                tma_load_3d(st + off_b, &tmW, bar_full + 8 * s, kc * TC_BK, 0, tap);
-                if (NSPLIT == 3) tma_load_3d(st + off_blo, &tmW, bar_full + 8 * s, kc * TC_BK, 0, 9 + tap);
+                if (CS == 1) {
+                    tma_load_3d(st + off_b, &tmW, bar_full + 8 * s, kc * TC_BK, 0, tap);
+                    if (NSPLIT == 3) tma_load_3d(st + off_blo, &tmW, bar_full + 8 * s, kc * TC_BK, 0, 9 + tap);
+                } else {
+                    // this CTA fetches rows [crank*N/CS, (crank+1)*N/CS) of the weight tile once and multicasts
+                    // them into every CTA of the cluster (same smem offset, each CTA's own full barrier)
+                    const int nrow = p.Cout / CS;
+                    const uint32_t sl = crank * nrow * 128;
+                    tma_load_3d_mc(st + off_b + sl, &tmW, bar_full + 8 * s, kc * TC_BK, crank * nrow, tap, cmask);
+                    if (NSPLIT == 3) tma_load_3d_mc(st + off_blo + sl, &tmW, bar_full + 8 * s, kc * TC_BK, crank * nrow, 9 + tap, cmask);
+                }
             }
         }
     } else if (warp == 1) {
@@ -217,7 +251,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     for (int k = 0; k < TC_BK / 8; ++k)
                         tc_mma_tf32(d_corr, make_desc_sw128(st + k * 32), make_desc_sw128(st + off_blo + k * 32), idesc, 1u);
                 }
-                tc_commit(bar_empty + 8 * s);     // frees the stage when these MMAs have read it
+                if (CS == 1) tc_commit(bar_empty + 8 * s);     // frees the stage when these MMAs have read it
+                else tc_commit_mc(bar_empty + 8 * s, cmask);   // ... in every CTA of the cluster (its producer multicasts into ours)
             }
             tc_commit(bar_acc);                   // accumulator complete
         }
@@ -249,7 +284,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int q = warp & 3;                    // TMEM lane quadrant this warp may access
         const int m = q * 32 + lane;               // accumulator row = pixel within the tile
         const int oy = y0 + m / TC_TW, ox = x0 + (m % TC_TW);
-        const bool valid = oy < p.H && ox < p.W;
+        const bool valid = real_tile && oy < p.H && ox < p.W;
         float* yrow = p.y + (((size_t)b * p.H + oy) * p.W + ox) * p.y_cs;
         const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y);
         const int n_acc = p.n_main + (NSPLIT == 3 ? 1 : 0);
@@ -284,6 +319,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();   // no CTA may exit while peers can still arrive on its barriers
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(p.tmem_cols));
     }
@@ -357,6 +393,15 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     PWC_REQUIRE(enc != nullptr, PWC_E_NOTBUILT, "conv3x3_tc: cuTensorMapEncodeTiled not available from the driver");
 
     const int cpad = cin_pad(Cin);
+    const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH;
+    const long long tiles = (long long)tiles_x * tiles_y * B;
+    PWC_REQUIRE(tiles < (1LL << 30), PWC_E_BADARG, "conv3x3_tc: too many tiles");
+    // CTAs per cluster that share each weight tile through TMA multicast (cuts the L2->SM weight traffic).
+    // PWC_TC_CLUSTER=2|4 enables it.
+    int cluster = 1;   // measured on B200: multicast (2: -4%, 4: -13%) does not pay, the kernel is not L2-bound
+    if (const char* e = getenv("PWC_TC_CLUSTER")) cluster = atoi(e);
+    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
+    while (cluster > 1 && (Cout / cluster) % 8 != 0) cluster /= 2;
     CUtensorMap tmX, tmW;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -371,7 +416,7 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     {
         cuuint64_t dims[3] = {(cuuint64_t)cpad, (cuuint64_t)Cout, 18};
         cuuint64_t strides[2] = {(cuuint64_t)cpad * 4, (cuuint64_t)Cout * cpad * 4};
-        cuuint32_t box[3] = {TC_BK, (cuuint32_t)Cout, 1};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)(Cout / cluster), 1};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)w_packed, dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -380,7 +425,8 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     }
     TcParams p{};
     p.bias = bias; p.y = y; p.y_cs = y_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dil = dilation;
-    p.tiles_x = (W + TC_TW - 1) / TC_TW; p.tiles_y = (H + TC_TH - 1) / TC_TH;
+    p.tiles_x = tiles_x; p.tiles_y = tiles_y;
+    p.cluster = cluster; p.total_tiles = (int)tiles;
     p.kchunks = cpad / TC_BK;
     p.alpha = alpha;
     p.b_bytes = Cout * 128;
@@ -401,19 +447,21 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     while (cols < (p.n_main + (n_split == 3 ? 1 : 0)) * Cout) cols *= 2;
     p.tmem_cols = cols;
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-    const long long tiles = (long long)p.tiles_x * p.tiles_y * B;
-    PWC_REQUIRE(tiles < (1LL << 31), PWC_E_BADARG, "conv3x3_tc: too many tiles");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e;
-    if (n_split == 3) {
-        e = cudaFuncSetAttribute(conv3x3_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-        conv3x3_tc_kernel<3><<<(unsigned)tiles, TC_THREADS, smem, st>>>(tmX, tmW, p);
-    } else {
-        e = cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-        conv3x3_tc_kernel<1><<<(unsigned)tiles, TC_THREADS, smem, st>>>(tmX, tmW, p);
-    }
+    auto kern = n_split == 3 ? conv3x3_tc_kernel<3> : conv3x3_tc_kernel<1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((tiles + cluster - 1) / cluster * cluster), 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p);
+    if (e != cudaSuccess) { set_error("conv3x3_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     PWC_CHECK_LAUNCH("conv3x3_tc_kernel");
     return 0;
 }

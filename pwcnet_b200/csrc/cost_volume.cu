@@ -9,15 +9,18 @@
 // HBM-bound by design: f0 and f1 are read once (the f1 halo re-reads hit L2), the 81-channel
 // result is written once, straight into the estimator's concat buffer.
 //
-// Tiling (R = 4): a CTA owns a TY x TX = 7 x 32 output tile.  Per 32-channel chunk it stages the
-// f0 tile and the (TY+8) x (TX+8) f1 halo tile in shared memory (the halo pixels are bilinearly
-// gathered from f1 on the fly in the fused variant, zero outside the image = the reference's
-// zero padding).  Each thread owns one (row y, vertical shift v, 8-pixel x strip) item and keeps
-// an 8 x 9 accumulator tile in registers: per 4 channels it issues 8 + 16 LDS.128 for 288 FMAs.
-// Lanes of a warp enumerate (y, v) for the same strip, so the f0 loads hit <= 4 and the f1 loads
-// <= 12 distinct 16-byte rows per instruction (shared-memory broadcast), which keeps the kernel
-// FMA-issue bound rather than LDS bound.  Results are transposed through shared memory so the
-// 81 channels of a pixel leave as one contiguous 324-byte run.
+// Tiling (R = 4): a CTA (128 threads) owns a TY x TX = 6 x 32 output tile.  Per 32-channel chunk it
+// stages the f0 tile and the (TY+8) x (TX+8) f1 halo tile in shared memory (cp.async with zero fill
+// outside the image = the reference's zero padding; in the fused variant the halo pixels are
+// bilinearly gathered from f1 on the fly).  Work decomposition: all (row y, vertical shift v) pairs
+// that read the SAME f1 row r = y + v are grouped, and a thread owns one f1 row r, two consecutive
+// output rows (y, y+1) of that group and an 8-pixel strip: 2 x 8 x 9 = 144 accumulators.  Per 4
+// channels it issues 16 (f1 row, shared by both output rows) + 2 x 8 (f0) LDS.128 for 576 FMAs,
+// i.e. 4.5 FMAs per shared-memory word: above the 4.0 needed to be FMA-bound rather than LDS-bound
+// (an LDS.128 costs four shared-memory wavefronts whatever the lane addresses are).  The 30 work items
+// of a strip fill one warp; lanes of a quarter-warp touch distinct bank groups (rows padded by 16 B).
+// Results are transposed through shared memory so the 81 channels of a pixel leave as one contiguous
+// 324-byte run.
 #include "common.cuh"
 
 namespace pwc {
@@ -26,19 +29,20 @@ constexpr int CV_R = 4;
 constexpr int CV_D = 2 * CV_R + 1;     // 9
 constexpr int CV_ND = CV_D * CV_D;     // 81
 static_assert(CV_ND == 81, "r=4 kernel");
-constexpr int CV_TY = 7;
+constexpr int CV_TY = 6;
 constexpr int CV_TX = 32;
 constexpr int CV_SX = 8;               // strip width (pixels per thread)
 constexpr int CV_CH = 32;              // channels per chunk
-constexpr int CV_HY = CV_TY + 2 * CV_R;   // 15
+constexpr int CV_HY = CV_TY + 2 * CV_R;   // 14
 constexpr int CV_HX = CV_TX + 2 * CV_R;   // 40
 constexpr int CV_F0_ROW = CV_TX * CV_CH + 4;   // floats; +4 -> rows land in distinct 16B bank groups
 constexpr int CV_F1_ROW = CV_HX * CV_CH + 4;
-constexpr int CV_F0_FLOATS = CV_TY * CV_F0_ROW;
+constexpr int CV_F0_FLOATS = (CV_TY + 1) * CV_F0_ROW;   // +1 row: single items read a dummy second row
 constexpr int CV_F1_FLOATS = CV_HY * CV_F1_ROW;
 constexpr int CV_OPIX = 84;                    // smem floats per output pixel (81 padded to 16B multiple)
 constexpr int CV_OROW = CV_TX * CV_OPIX + 8;   // + 8 floats: de-phase rows across banks
-constexpr int CV_THREADS = 256;
+constexpr int CV_THREADS = 128;                // 4 warps = 4 strips of 8 pixels
+constexpr int CV_ITEMS = 30;                   // (f1 row, output row pair) items per strip for TY = 6
 constexpr int CV_SMEM_BYTES = (CV_F0_FLOATS + CV_F1_FLOATS) * 4;
 static_assert(CV_TY * CV_OROW <= CV_F1_FLOATS, "output staging must fit in the f1 halo buffer");
 
@@ -85,6 +89,29 @@ __device__ __forceinline__ float4 sample_f1(const CvParams& p, const float* f1b,
     return r;
 }
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;   // src-size 0 -> 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+// item -> (f1 halo row index 0..13, first output row ya, rows n in {1,2}); items sorted by f1 row
+__device__ __forceinline__ void cv_item(int item, int& r_idx, int& ya, int& n) {
+    int cnt = 0;
+    r_idx = 0; ya = 0; n = 0;
+#pragma unroll 1
+    for (int r = 0; r < CV_HY; ++r) {
+        const int ylo = max(0, r - 2 * CV_R), yhi = min(CV_TY - 1, r);   // |(r - 4) - y| <= 4
+        const int rows = yhi - ylo + 1, items = (rows + 1) >> 1;
+        if (item < cnt + items) {
+            const int j = item - cnt;
+            r_idx = r; ya = ylo + 2 * j; n = min(2, yhi - ya + 1);
+            return;
+        }
+        cnt += items;
+    }
+}
+
 // WARP: 0 = f1 used as is, 1 = bilinear, 2 = nearest
 template <int WARP>
 __global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvParams p) {
@@ -98,78 +125,101 @@ __global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvP
     const float* f1b = p.f1 + (size_t)b * p.H * p.W * p.f1_cs;
     const float* flowb = WARP ? p.flow + (size_t)b * p.H * p.W * p.flow_cs : nullptr;
 
-    // work item of this thread
-    const int warp = tid >> 5, lane = tid & 31;
-    const int xs = warp >> 1;                       // strip 0..3
-    const int item = (warp & 1) * 32 + lane;        // 0..63, 63 idle
-    const bool active = item < CV_TY * CV_D;
-    const int iy = active ? item / CV_D : 0;        // output row in tile
-    const int iv = active ? item % CV_D : 0;        // vertical shift index 0..8 (v = iv - 4)
+    // work item of this thread: strip = warp, item = lane
+    const int xs = tid >> 5, lane = tid & 31;
+    int r_idx, ya, n_rows;
+    cv_item(lane < CV_ITEMS ? lane : 0, r_idx, ya, n_rows);
+    if (lane >= CV_ITEMS) n_rows = 0;
 
-    float acc[CV_SX][CV_D];
+    float acc0[CV_SX][CV_D], acc1[CV_SX][CV_D];
 #pragma unroll
     for (int i = 0; i < CV_SX; ++i)
 #pragma unroll
-        for (int j = 0; j < CV_D; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < CV_D; ++j) { acc0[i][j] = 0.f; acc1[i][j] = 0.f; }
 
     for (int c0 = 0; c0 < p.C; c0 += CV_CH) {
         const int nch4 = min(CV_CH, p.C - c0) >> 2;   // float4 groups valid in this chunk
         if (c0) __syncthreads();
-        // ---- stage f0 tile (and optionally copy it out to the concat slot)
+        // ---- stage the f0 tile
         for (int e = tid; e < CV_TY * CV_TX * (CV_CH / 4); e += CV_THREADS) {
             const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e >> 8;
             const int gy = y0 + py, gx = x0 + px;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gy < p.H && gx < p.W && k < nch4) {
-                v = ldg4(f0b + ((size_t)gy * p.W + gx) * p.f0_cs + c0 + 4 * k);
-                if (p.f0_copy)
-                    *reinterpret_cast<float4*>(p.f0_copy + (((size_t)b * p.H + gy) * p.W + gx) * p.f0_copy_cs + c0 + 4 * k) = v;
-            }
-            *reinterpret_cast<float4*>(f0s + py * CV_F0_ROW + px * CV_CH + 4 * k) = v;
+            const bool ok = gy < p.H && gx < p.W && k < nch4;
+            const float* src = ok ? f0b + ((size_t)gy * p.W + gx) * p.f0_cs + c0 + 4 * k : f0b;
+            cp_async16(f0s + py * CV_F0_ROW + px * CV_CH + 4 * k, src, ok);
         }
-        // ---- stage f1 halo tile (warped on the fly), zeros outside the image
+        // ---- stage the f1 halo tile (warped on the fly in the fused variants), zeros outside the image
         for (int e = tid; e < CV_HY * CV_HX * (CV_CH / 4); e += CV_THREADS) {
             const int k = e & 7, pix = e >> 3;
             const int py = pix / CV_HX, px = pix - py * CV_HX;
             const int gy = y0 + py - CV_R, gx = x0 + px - CV_R;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && k < nch4)
-                v = sample_f1<WARP>(p, f1b, flowb, gy, gx, c0 + 4 * k);
-            *reinterpret_cast<float4*>(f1s + py * CV_F1_ROW + px * CV_CH + 4 * k) = v;
+            const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && k < nch4;
+            float* dst = f1s + py * CV_F1_ROW + px * CV_CH + 4 * k;
+            if (WARP == 0) {
+                const float* src = ok ? f1b + ((size_t)gy * p.W + gx) * p.f1_cs + c0 + 4 * k : f1b;
+                cp_async16(dst, src, ok);
+            } else {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) v = sample_f1<WARP>(p, f1b, flowb, gy, gx, c0 + 4 * k);
+                *reinterpret_cast<float4*>(dst) = v;
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // ---- correlate
-        const float* a_base = f0s + iy * CV_F0_ROW + xs * CV_SX * CV_CH;
-        const float* b_base = f1s + (iy + iv) * CV_F1_ROW + xs * CV_SX * CV_CH;
+        // ---- optional copy of the staged f0 tile into the estimator's concat slot
+        if (p.f0_copy) {
+            for (int e = tid; e < CV_TY * CV_TX * (CV_CH / 4); e += CV_THREADS) {
+                const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e >> 8;
+                const int gy = y0 + py, gx = x0 + px;
+                if (gy < p.H && gx < p.W && k < nch4)
+                    *reinterpret_cast<float4*>(p.f0_copy + (((size_t)b * p.H + gy) * p.W + gx) * p.f0_copy_cs + c0 + 4 * k) =
+                        *reinterpret_cast<const float4*>(f0s + py * CV_F0_ROW + px * CV_CH + 4 * k);
+            }
+        }
+        // ---- correlate: f1 row r against output rows ya (v = r - ya) and ya + 1 (v - 1)
+        const float* a0_base = f0s + ya * CV_F0_ROW + xs * CV_SX * CV_CH;
+        const float* a1_base = a0_base + CV_F0_ROW;
+        const float* f_base = f1s + r_idx * CV_F1_ROW + xs * CV_SX * CV_CH;
 #pragma unroll 1
         for (int k = 0; k < CV_CH / 4; ++k) {
-            float4 a[CV_SX];
+            float4 f[CV_D];   // sliding window over the f1 row: columns i .. i+8
 #pragma unroll
-            for (int i = 0; i < CV_SX; ++i) a[i] = *reinterpret_cast<const float4*>(a_base + i * CV_CH + 4 * k);
+            for (int q = 0; q < CV_D; ++q) f[q] = *reinterpret_cast<const float4*>(f_base + q * CV_CH + 4 * k);
 #pragma unroll
-            for (int q = 0; q < CV_SX + 2 * CV_R; ++q) {
-                const float4 f = *reinterpret_cast<const float4*>(b_base + q * CV_CH + 4 * k);
+            for (int i = 0; i < CV_SX; ++i) {
+                const float4 a0 = *reinterpret_cast<const float4*>(a0_base + i * CV_CH + 4 * k);
+                const float4 a1 = *reinterpret_cast<const float4*>(a1_base + i * CV_CH + 4 * k);
+                // component-major order: 18 independent FMAs between two updates of the same accumulator
 #pragma unroll
-                for (int i = 0; i < CV_SX; ++i) {
-                    const int j = q - i;   // horizontal shift index: f1 column (x + i) + (j - 4) + 4 = q
-                    if (j >= 0 && j < CV_D) {
-                        acc[i][j] = fmaf(a[i].x, f.x, acc[i][j]);
-                        acc[i][j] = fmaf(a[i].y, f.y, acc[i][j]);
-                        acc[i][j] = fmaf(a[i].z, f.z, acc[i][j]);
-                        acc[i][j] = fmaf(a[i].w, f.w, acc[i][j]);
-                    }
-                }
+                for (int j = 0; j < CV_D; ++j) { const float fx = f[(i + j) % CV_D].x; acc0[i][j] = fmaf(a0.x, fx, acc0[i][j]); acc1[i][j] = fmaf(a1.x, fx, acc1[i][j]); }
+#pragma unroll
+                for (int j = 0; j < CV_D; ++j) { const float fy = f[(i + j) % CV_D].y; acc0[i][j] = fmaf(a0.y, fy, acc0[i][j]); acc1[i][j] = fmaf(a1.y, fy, acc1[i][j]); }
+#pragma unroll
+                for (int j = 0; j < CV_D; ++j) { const float fz = f[(i + j) % CV_D].z; acc0[i][j] = fmaf(a0.z, fz, acc0[i][j]); acc1[i][j] = fmaf(a1.z, fz, acc1[i][j]); }
+#pragma unroll
+                for (int j = 0; j < CV_D; ++j) { const float fw = f[(i + j) % CV_D].w; acc0[i][j] = fmaf(a0.w, fw, acc0[i][j]); acc1[i][j] = fmaf(a1.w, fw, acc1[i][j]); }
+                if (i + 1 < CV_SX)   // column i leaves the window, column i + 9 enters
+                    f[i % CV_D] = *reinterpret_cast<const float4*>(f_base + (i + CV_D) * CV_CH + 4 * k);
             }
         }
     }
     __syncthreads();   // everyone is done reading f1s -> reuse it as the output staging tile
     float* outs = f1s;
-    if (active) {
+    const int iv0 = r_idx - ya;   // vertical shift index (v + 4) of row ya; row ya + 1 has iv0 - 1
+    if (n_rows >= 1) {
 #pragma unroll
         for (int i = 0; i < CV_SX; ++i)
 #pragma unroll
             for (int j = 0; j < CV_D; ++j)
-                outs[iy * CV_OROW + (xs * CV_SX + i) * CV_OPIX + iv * CV_D + j] = leaky(acc[i][j] * p.inv_c, p.alpha);
+                outs[ya * CV_OROW + (xs * CV_SX + i) * CV_OPIX + iv0 * CV_D + j] = leaky(acc0[i][j] * p.inv_c, p.alpha);
+    }
+    if (n_rows == 2) {
+#pragma unroll
+        for (int i = 0; i < CV_SX; ++i)
+#pragma unroll
+            for (int j = 0; j < CV_D; ++j)
+                outs[(ya + 1) * CV_OROW + (xs * CV_SX + i) * CV_OPIX + (iv0 - 1) * CV_D + j] = leaky(acc1[i][j] * p.inv_c, p.alpha);
     }
     __syncthreads();
     // ---- contiguous 324-byte runs per pixel
