@@ -64,9 +64,10 @@ int pwc_conv3x3_fwd(const float* x, int x_cs, const float* w_hwio, const float* 
 /* Same function on the tcgen05 tensor cores (implicit GEMM, TMA-staged taps, TMEM accumulators).
  * w_packed: [9][Cout_pad][Cin_pad] fp32 (tap-major, K contiguous) produced by
  * pwc_conv3x3_pack_weights; n_split = 1 (TF32) or 3 (3xTF32 error-compensated, fp32-class).
- * Requires stride 1, x 16-byte aligned, x_cs % 4 == 0, Cout % 16 == 0, Cout <= 256. */
+ * Requires stride 1 or 2, Cin == 16 or Cin >= 32, x 16-byte aligned, x_cs % 4 == 0, Cout % 16 == 0,
+ * Cout <= 256. */
 int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packed, const float* bias,
-                       float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int dilation,
+                       float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int stride, int dilation,
                        float alpha, int n_split, void* stream);
 /* bytes needed for w_packed (hi and lo planes) */
 long long pwc_conv3x3_packed_bytes(int Cin, int Cout);

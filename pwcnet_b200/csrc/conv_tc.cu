@@ -30,16 +30,17 @@ namespace pwc {
 
 constexpr int TC_BM = 128;        // pixels per CTA
 constexpr int TC_TW = 16, TC_TH = 8;
-constexpr int TC_BK = 32;         // channels per stage (128 bytes = swizzle span)
 constexpr int TC_THREADS = 192;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 
 struct TcParams {
     const float* bias; float* y;
     int y_cs, B, H, W, Cin, Cout, dil;
+    int OH, OW, stride, pad_t, pad_l;   // TF SAME geometry (stride 1 or 2)
+    int bk;                             // channels per pipeline stage: 32 (128B swizzle) or 16 (64B swizzle, Cin == 16)
+    int a_bytes;                        // 128 * bk * 4
     int tiles_x, tiles_y, kchunks;
     float alpha;
-    int b_bytes;      // Cout * 128
+    int b_bytes;      // Cout * bk * 4
     int stage_bytes;  // per-stage smem
     int stages;
     int tmem_cols;
@@ -112,14 +113,15 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+// K-major swizzled operand tile: rows of `bk*4` bytes (128B swizzle for bk = 32, 64B swizzle for bk = 16),
+// 8-row swizzle atoms packed back to back (1024 / 512 bytes apart).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int bk) {
     uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
-    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: next 8-row atom
-    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);                    // start address
+    d |= (uint64_t)1 << 16;                                     // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((bk == 32 ? 1024 : 512) >> 4) << 32;        // stride byte offset: next 8-row atom
+    d |= (uint64_t)1 << 46;                                     // descriptor version (Blackwell)
+    d |= (uint64_t)(bk == 32 ? 2 : 4) << 61;                    // SWIZZLE_128B / SWIZZLE_64B
     return d;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -141,7 +143,7 @@ __device__ __forceinline__ float tf32_residual(float x) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int NSPLIT>
+template <int NSPLIT, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -169,8 +171,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int KT = 9 * p.kchunks;
 
     // per-stage layout: [A raw 16K][A lo 16K (NSPLIT==3)][B hi][B lo (NSPLIT==3)]
-    const uint32_t off_alo = TC_A_BYTES;
-    const uint32_t off_b = (NSPLIT == 3 ? 2 : 1) * TC_A_BYTES;
+    constexpr uint32_t A_BYTES = TC_BM * BK * 4;
+    constexpr uint32_t off_alo = A_BYTES;
+    constexpr uint32_t off_b = (NSPLIT == 3 ? 2 : 1) * A_BYTES;
     const uint32_t off_blo = off_b + p.b_bytes;
 
     if (threadIdx.x == 0) {
@@ -197,7 +200,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-            const uint32_t tx_bytes = TC_A_BYTES + (NSPLIT == 3 ? 2 : 1) * p.b_bytes;
+            const uint32_t tx_bytes = A_BYTES + (NSPLIT == 3 ? 2 : 1) * p.b_bytes;
             for (int it = 0; it < KT; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (it / S) & 1;
@@ -206,17 +209,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const int ky = tap / 3, kx = tap - ky * 3;
                 const uint32_t st = base + s * p.stage_bytes;
                 mbar_expect_tx(bar_full + 8 * s, tx_bytes);
-                tma_load_4d(st, &tmX, bar_full + 8 * s, kc * TC_BK, x0 + (kx - 1) * p.dil, y0 + (ky - 1) * p.dil, b);
+                tma_load_4d(st, &tmX, bar_full + 8 * s, kc * BK, x0 * p.stride - p.pad_l + kx * p.dil, y0 * p.stride - p.pad_t + ky * p.dil, b);
                 if (CS == 1) {
-                    tma_load_3d(st + off_b, &tmW, bar_full + 8 * s, kc * TC_BK, 0, tap);
-                    if (NSPLIT == 3) tma_load_3d(st + off_blo, &tmW, bar_full + 8 * s, kc * TC_BK, 0, 9 + tap);
+                    tma_load_3d(st + off_b, &tmW, bar_full + 8 * s, kc * BK, 0, tap);
+                    if (NSPLIT == 3) tma_load_3d(st + off_blo, &tmW, bar_full + 8 * s, kc * BK, 0, 9 + tap);
                 } else {
                     // this CTA fetches rows [crank*N/CS, (crank+1)*N/CS) of the weight tile once and multicasts
                     // them into every CTA of the cluster (same smem offset, each CTA's own full barrier)
                     const int nrow = p.Cout / CS;
-                    const uint32_t sl = crank * nrow * 128;
-                    tma_load_3d_mc(st + off_b + sl, &tmW, bar_full + 8 * s, kc * TC_BK, crank * nrow, tap, cmask);
-                    if (NSPLIT == 3) tma_load_3d_mc(st + off_blo + sl, &tmW, bar_full + 8 * s, kc * TC_BK, crank * nrow, 9 + tap, cmask);
+                    const uint32_t sl = crank * nrow * BK * 4;
+                    tma_load_3d_mc(st + off_b + sl, &tmW, bar_full + 8 * s, kc * BK, crank * nrow, tap, cmask);
+                    if (NSPLIT == 3) tma_load_3d_mc(st + off_blo + sl, &tmW, bar_full + 8 * s, kc * BK, crank * nrow, 9 + tap, cmask);
                 }
             }
         }
@@ -225,6 +228,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            // upper descriptor word: stride byte offset (next 8-row atom), version 1, swizzle mode
+            const uint64_t desc_hi = ((uint64_t)((BK == 32 ? 1024 : 512) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(BK == 32 ? 2 : 4) << 61);
             for (int it = 0; it < KT; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (it / S) & 1;
@@ -237,19 +242,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 // (|corr| ~ 2^-11 |D|, its truncation error is negligible); the epilogue sums them in fp32.
                 const int am = it % p.n_main;
                 const uint32_t d_main = tmem_acc + am * p.Cout;
+                // descriptors differ only in the 14-bit start-address field: build the low words once per
+                // stage and step them by 32 bytes (>> 4 = 2) per K = 8 slice -- the single issuing thread
+                // must spend well under the MMA's ~64 cycles on address arithmetic
+                const uint32_t a_lo = ((st >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t alo_lo = (((st + off_alo) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t b_lo = (((st + off_b) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t blo_lo = (((st + off_blo) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k)
-                    tc_mma_tf32(d_main, make_desc_sw128(st + k * 32), make_desc_sw128(st + off_b + k * 32), idesc,
-                                (it >= p.n_main || k > 0) ? 1u : 0u);
+                for (int k = 0; k < BK / 8; ++k)
+                    tc_mma_tf32(d_main, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (it >= p.n_main || k > 0) ? 1u : 0u);
                 if (NSPLIT == 3) {
                     const uint32_t d_corr = tmem_acc + p.n_main * p.Cout;
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k)
-                        tc_mma_tf32(d_corr, make_desc_sw128(st + off_alo + k * 32), make_desc_sw128(st + off_b + k * 32), idesc,
-                                    (it | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 8; ++k)
+                        tc_mma_tf32(d_corr, desc_hi | (alo_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (it | k) != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k)
-                        tc_mma_tf32(d_corr, make_desc_sw128(st + k * 32), make_desc_sw128(st + off_blo + k * 32), idesc, 1u);
+                    for (int k = 0; k < BK / 8; ++k)
+                        tc_mma_tf32(d_corr, desc_hi | (a_lo + 2 * k), desc_hi | (blo_lo + 2 * k), idesc, 1u);
                 }
                 if (CS == 1) tc_commit(bar_empty + 8 * s);     // frees the stage when these MMAs have read it
                 else tc_commit_mc(bar_empty + 8 * s, cmask);   // ... in every CTA of the cluster (its producer multicasts into ours)
@@ -267,7 +277,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const float4* a = reinterpret_cast<const float4*>(base_ptr + (size_t)s * p.stage_bytes);
                 float4* alo = reinterpret_cast<float4*>(base_ptr + (size_t)s * p.stage_bytes + off_alo);
 #pragma unroll
-                for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+                for (int i = 0; i < (int)(A_BYTES / 16 / 128); ++i) {
                     const float4 v = a[ct + 128 * i];
                     float4 l;
                     l.x = tf32_residual(v.x); l.y = tf32_residual(v.y);
@@ -284,24 +294,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int q = warp & 3;                    // TMEM lane quadrant this warp may access
         const int m = q * 32 + lane;               // accumulator row = pixel within the tile
         const int oy = y0 + m / TC_TW, ox = x0 + (m % TC_TW);
-        const bool valid = real_tile && oy < p.H && ox < p.W;
-        float* yrow = p.y + (((size_t)b * p.H + oy) * p.W + ox) * p.y_cs;
+        const bool valid = real_tile && oy < p.OH && ox < p.OW;
+        float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs;
         const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y);
         const int n_acc = p.n_main + (NSPLIT == 3 ? 1 : 0);
         for (int n0 = 0; n0 < p.Cout; n0 += 16) {
-            uint32_t r[16];
-            float acc[16];
-            // smallest-magnitude accumulator (the correction) first
-            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (n_acc - 1) * p.Cout + n0, r);
+            // issue the loads of all accumulators (n_acc <= 4), wait once, then sum in fp32:
+            // correction (last, smallest) + main n_main-1 .. 1 first, main 0 last
+            uint32_t r[4][16];
+            const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + n0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                if (a < n_acc) tmem_ld16(tbase + a * p.Cout, r[a]);
             tmem_ld_wait();
+            float acc[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
-            for (int a = n_acc - 2; a >= 0; --a) {
-                tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + a * p.Cout + n0, r);
-                tmem_ld_wait();
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
-            }
+            for (int a = 3; a >= 0; --a)
+                if (a < n_acc) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[a][j]);
+                }
             if (valid) {
                 float v[16];
 #pragma unroll
@@ -359,7 +373,8 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static inline int cin_pad(int Cin) { return (Cin + TC_BK - 1) / TC_BK * TC_BK; }
+static inline int tc_bk(int Cin) { return Cin >= 32 ? 32 : 16; }
+static inline int cin_pad(int Cin) { const int bk = tc_bk(Cin); return (Cin + bk - 1) / bk * bk; }
 
 }  // namespace pwc
 
@@ -378,22 +393,28 @@ extern "C" int pwc_conv3x3_pack_weights(const float* w_hwio, float* w_packed, in
 }
 
 extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packed, const float* bias,
-                                  float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int dilation,
+                                  float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int stride, int dilation,
                                   float alpha, int n_split, void* stream) {
     using namespace pwc;
+    PWC_REQUIRE(stride == 1 || stride == 2, PWC_E_BADARG, "conv3x3_tc: stride must be 1 or 2");
     PWC_REQUIRE(x && w_packed && bias && y, PWC_E_BADARG, "conv3x3_tc: null pointer");
     PWC_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && dilation >= 1, PWC_E_BADARG, "conv3x3_tc: bad dims");
     PWC_REQUIRE(n_split == 1 || n_split == 3, PWC_E_BADARG, "conv3x3_tc: n_split must be 1 or 3");
     PWC_REQUIRE(Cout % 16 == 0 && Cout <= 256, PWC_E_BADARG, "conv3x3_tc: Cout must be a multiple of 16, <= 256");
-    PWC_REQUIRE(Cin >= TC_BK, PWC_E_BADARG, "conv3x3_tc: Cin must be >= 32");
+    PWC_REQUIRE(Cin == 16 || Cin >= 32, PWC_E_BADARG, "conv3x3_tc: Cin must be 16 or >= 32");
     PWC_REQUIRE(x_cs >= Cin && y_cs >= Cout, PWC_E_BADARG, "conv3x3_tc: channel stride smaller than channel count");
     PWC_REQUIRE(aligned16(x) && (x_cs % 4 == 0) && aligned16(w_packed), PWC_E_ALIGN,
                 "conv3x3_tc: x / w_packed must be 16-byte aligned and x_cs a multiple of 4");
     EncodeTiledFn enc = get_encode();
     PWC_REQUIRE(enc != nullptr, PWC_E_NOTBUILT, "conv3x3_tc: cuTensorMapEncodeTiled not available from the driver");
 
-    const int cpad = cin_pad(Cin);
-    const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH;
+    const int cpad = cin_pad(Cin), bk = tc_bk(Cin);
+    // TF 'SAME': out = ceil(in / s); pad_before = max((out-1)*s + 2*d + 1 - in, 0) / 2
+    const int OH = (H + stride - 1) / stride, OW = (W + stride - 1) / stride;
+    int pad_t = ((OH - 1) * stride + 2 * dilation + 1 - H); pad_t = pad_t > 0 ? pad_t / 2 : 0;
+    int pad_l = ((OW - 1) * stride + 2 * dilation + 1 - W); pad_l = pad_l > 0 ? pad_l / 2 : 0;
+    const int tiles_x = (OW + TC_TW - 1) / TC_TW, tiles_y = (OH + TC_TH - 1) / TC_TH;
+    const CUtensorMapSwizzle swz = bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const long long tiles = (long long)tiles_x * tiles_y * B;
     PWC_REQUIRE(tiles < (1LL << 30), PWC_E_BADARG, "conv3x3_tc: too many tiles");
     // CTAs per cluster that share each weight tile through TMA multicast (cuts the L2->SM weight traffic).
@@ -406,20 +427,21 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)x_cs * 4, (cuuint64_t)W * x_cs * 4, (cuuint64_t)H * W * x_cs * 4};
-        cuuint32_t box[4] = {TC_BK, TC_TW, TC_TH, 1};
-        cuuint32_t es[4] = {1, 1, 1, 1};
+        // with element strides s the box spans TW*s x TH*s input pixels and delivers TW x TH of them
+        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(TC_TW * stride), (cuuint32_t)(TC_TH * stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         PWC_REQUIRE(r == CUDA_SUCCESS, PWC_E_BADARG, "conv3x3_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)cpad, (cuuint64_t)Cout, 18};
         cuuint64_t strides[2] = {(cuuint64_t)cpad * 4, (cuuint64_t)Cout * cpad * 4};
-        cuuint32_t box[3] = {TC_BK, (cuuint32_t)(Cout / cluster), 1};
+        cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(Cout / cluster), 1};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)w_packed, dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         PWC_REQUIRE(r == CUDA_SUCCESS, PWC_E_BADARG, "conv3x3_tc: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
     }
@@ -427,14 +449,18 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     p.bias = bias; p.y = y; p.y_cs = y_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dil = dilation;
     p.tiles_x = tiles_x; p.tiles_y = tiles_y;
     p.cluster = cluster; p.total_tiles = (int)tiles;
-    p.kchunks = cpad / TC_BK;
+    p.OH = OH; p.OW = OW; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
+    p.bk = bk; p.a_bytes = TC_BM * bk * 4;
+    p.kchunks = cpad / bk;
     p.alpha = alpha;
-    p.b_bytes = Cout * 128;
-    p.stage_bytes = (n_split == 3 ? 2 : 1) * (TC_A_BYTES + p.b_bytes);
+    p.b_bytes = Cout * bk * 4;
+    p.stage_bytes = (n_split == 3 ? 2 : 1) * (p.a_bytes + p.b_bytes);
     p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
     const int budget = 220 * 1024;
     p.stages = budget / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
+    const int kt = 9 * p.kchunks;
+    if (kt <= 18 && p.stages > 4) p.stages = 4;   // short K loops: keep smem small so several CTAs share an SM
     PWC_REQUIRE(p.stages >= 2, PWC_E_BADARG, "conv3x3_tc: tile does not fit in shared memory");
     // TMEM columns: n_main main accumulators (+1 correction accumulator for 3xTF32), N columns each
     p.n_main = 1;
@@ -448,7 +474,8 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     p.tmem_cols = cols;
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     cudaStream_t st = (cudaStream_t)stream;
-    auto kern = n_split == 3 ? conv3x3_tc_kernel<3> : conv3x3_tc_kernel<1>;
+    auto kern = n_split == 3 ? (bk == 32 ? conv3x3_tc_kernel<3, 32> : conv3x3_tc_kernel<3, 16>)
+                             : (bk == 32 ? conv3x3_tc_kernel<1, 32> : conv3x3_tc_kernel<1, 16>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     cudaLaunchConfig_t cfg{};

@@ -216,17 +216,17 @@ class PWCDCNet(object):
         cin, cout = k.shape[2], k.shape[3]
         if self.precision == "cudnn":
             return self._conv_cudnn(x, k, b, out, stride, dilation, alpha, residual)
-        if self.precision in ("3xtf32", "tf32") and stride == 1 and residual is None and cout % 16 == 0 \
-                and cin >= 32 and cout <= 256 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
-            return self._conv_tc(x, scope, k, b, out, dilation, alpha)
+        if self.precision in ("3xtf32", "tf32") and stride in (1, 2) and residual is None and cout % 16 == 0 \
+                and (cin == 16 or cin >= 32) and cout <= 256 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
+            return self._conv_tc(x, scope, k, b, out, dilation, alpha, stride)
         return ops.conv3x3(x, k, b, stride=stride, dilation=dilation, alpha=alpha, residual=residual, out=out)
 
-    def _conv_tc(self, x, scope, k, b, out, dilation, alpha):
+    def _conv_tc(self, x, scope, k, b, out, dilation, alpha, stride=1):
         from . import ops_tc
         if scope not in self._packed:
             self._packed[scope] = ops_tc.pack_weights(k)
         return ops_tc.conv3x3_tc(x, self._packed[scope], b, k.shape[2], k.shape[3], dilation=dilation, alpha=alpha,
-                                 n_split=3 if self.precision == "3xtf32" else 1, out=out)
+                                 n_split=3 if self.precision == "3xtf32" else 1, out=out, stride=stride)
 
     @staticmethod
     def _conv_cudnn(x, k, b, out, stride, dilation, alpha, residual):

@@ -21,8 +21,8 @@ def pack_weights(kernel_hwio: torch.Tensor) -> torch.Tensor:
 
 
 def conv3x3_tc(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, alpha: float = 1.0, n_split: int = 3,
-               out=None):
-    """Stride-1 3x3 SAME conv + bias + leaky on tcgen05 (n_split=1: TF32, 3: 3xTF32 fp32-class)."""
+               out=None, stride: int = 1):
+    """3x3 SAME conv (stride 1 or 2) + bias + leaky on tcgen05 (n_split=1: TF32, 3: 3xTF32 fp32-class)."""
     B, H, W, C, x_cs = _nhwc(x, "x")
     if C != cin:
         raise ValueError(f"conv3x3_tc: x has {C} channels, weights expect {cin}")
@@ -30,11 +30,12 @@ def conv3x3_tc(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, alpha:
         raise ValueError("conv3x3_tc: bias must be CUDA float32 (Cout,)")
     if w_packed.numel() * 4 != lib().pwc_conv3x3_packed_bytes(cin, cout):
         raise ValueError("conv3x3_tc: w_packed has the wrong size for (Cin, Cout)")
+    OH, OW = -(-H // stride), -(-W // stride)
     if out is None:
-        out = new_nhwc(B, H, W, cout, x.device)
+        out = new_nhwc(B, OH, OW, cout, x.device)
     Bo, Ho, Wo, Co, y_cs = _nhwc(out, "out")
-    if (Bo, Ho, Wo, Co) != (B, H, W, cout):
+    if (Bo, Ho, Wo, Co) != (B, OH, OW, cout):
         raise ValueError("conv3x3_tc: out shape mismatch")
     check(lib().pwc_conv3x3_tc_fwd(x.data_ptr(), x_cs, w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(), y_cs,
-                                   B, H, W, cin, cout, dilation, float(alpha), n_split, _stream()), "pwc_conv3x3_tc_fwd")
+                                   B, H, W, cin, cout, stride, dilation, float(alpha), n_split, _stream()), "pwc_conv3x3_tc_fwd")
     return out

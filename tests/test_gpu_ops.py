@@ -210,8 +210,13 @@ def test_host_layer_rejects_bad_inputs(P):
 
 
 TC_CASES = [
-    # (B, H, W, Cin, channel stride, Cout, dilation)
+    # (B, H, W, Cin, channel stride, Cout, dilation[, stride])
     (1, 8, 16, 32, 32, 32, 1),
+    (2, 32, 48, 16, 16, 16, 1),          # Cin = 16: 64-byte swizzle path (pyramid level 1)
+    (2, 32, 48, 16, 16, 32, 1, 2),       # stride 2 through TMA element strides, asymmetric SAME (0 before, 1 after)
+    (1, 28, 64, 64, 64, 96, 1, 2),
+    (1, 15, 17, 32, 32, 64, 1, 2),       # odd sizes: SAME pads 1 before / 1 after
+    (2, 14, 32, 128, 128, 192, 1, 2),
     (2, 14, 32, 128, 128, 128, 1),
     (1, 28, 64, 147, 148, 128, 1),      # estimator conv 0 at level 4: ragged K (147 -> zero-filled to 160)
     (1, 7, 16, 273, 276, 128, 1),       # coarsest level: 7 rows in an 8-row tile
@@ -228,14 +233,17 @@ def test_conv3x3_tcgen05_matches_oracle(P, case, n_split, tol):
     """tcgen05 implicit-GEMM conv vs the oracle's fp32 conv.  3xTF32 must be fp32-class (3e-5 max-abs on
     O(1) outputs); plain TF32 (operands truncated to 10 mantissa bits by the hardware) within 1e-2."""
     from pwcnet_b200 import ops_tc
-    B, H, W, Cin, cs, Cout, dil = case
+    B, H, W, Cin, cs, Cout, dil = case[:7]
+    stride = case[7] if len(case) > 7 else 1
     buf = _rand((B, H, W, cs), 1)
     k = _rand((3, 3, Cin, Cout), 2, scale=1.0 / np.sqrt(9 * Cin))
     b = _rand((Cout,), 3, scale=0.1)
     x = buf[..., :Cin]
-    ref = O.leaky_relu(O.conv2d_same(torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(k), torch.from_numpy(b), 1, dil), 0.1).numpy()
+    ref = O.leaky_relu(O.conv2d_same(torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(k), torch.from_numpy(b), stride, dil), 0.1).numpy()
     wp = ops_tc.pack_weights(_cuda(k))
-    out = ops_tc.conv3x3_tc(_cuda(buf)[..., :Cin], wp, _cuda(b), Cin, Cout, dilation=dil, alpha=0.1, n_split=n_split)
+    out = ops_tc.conv3x3_tc(_cuda(buf)[..., :Cin], wp, _cuda(b), Cin, Cout, dilation=dil, alpha=0.1, n_split=n_split,
+                            stride=stride)
+    assert out.shape == ref.shape
     np.testing.assert_allclose(out.cpu().numpy(), ref, atol=tol, rtol=0)
 
 
