@@ -143,7 +143,7 @@ __device__ __forceinline__ float tf32_residual(float x) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int NSPLIT, int BK>
+template <int NSPLIT, int BK, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -167,13 +167,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int CS = p.cluster;
     const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
     const uint16_t cmask = (uint16_t)((1u << CS) - 1);
-    const int x0 = tx * TC_TW, y0 = ty * TC_TH;
+    const int x0 = tx * TC_TW, y0 = ty * TC_TH * MT;   // MT vertically stacked 16x8 pixel tiles share each weight tile
     const int KT = 9 * p.kchunks;
 
     // per-stage layout: [A raw 16K][A lo 16K (NSPLIT==3)][B hi][B lo (NSPLIT==3)]
     constexpr uint32_t A_BYTES = TC_BM * BK * 4;
-    constexpr uint32_t off_alo = A_BYTES;
-    constexpr uint32_t off_b = (NSPLIT == 3 ? 2 : 1) * A_BYTES;
+    constexpr uint32_t off_alo = MT * A_BYTES;
+    constexpr uint32_t off_b = (NSPLIT == 3 ? 2 : 1) * MT * A_BYTES;
     const uint32_t off_blo = off_b + p.b_bytes;
 
     if (threadIdx.x == 0) {
@@ -200,7 +200,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-            const uint32_t tx_bytes = A_BYTES + (NSPLIT == 3 ? 2 : 1) * p.b_bytes;
+            const uint32_t tx_bytes = MT * A_BYTES + (NSPLIT == 3 ? 2 : 1) * p.b_bytes;
             for (int it = 0; it < KT; ++it) {
                 const int s = it % S;
                 const uint32_t ph = (it / S) & 1;
@@ -209,7 +209,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const int ky = tap / 3, kx = tap - ky * 3;
                 const uint32_t st = base + s * p.stage_bytes;
                 mbar_expect_tx(bar_full + 8 * s, tx_bytes);
-                tma_load_4d(st, &tmX, bar_full + 8 * s, kc * BK, x0 * p.stride - p.pad_l + kx * p.dil, y0 * p.stride - p.pad_t + ky * p.dil, b);
+#pragma unroll
+                for (int t = 0; t < MT; ++t)
+                    tma_load_4d(st + t * A_BYTES, &tmX, bar_full + 8 * s, kc * BK, x0 * p.stride - p.pad_l + kx * p.dil,
+                                (y0 + t * TC_TH) * p.stride - p.pad_t + ky * p.dil, b);
                 if (CS == 1) {
                     tma_load_3d(st + off_b, &tmW, bar_full + 8 * s, kc * BK, 0, tap);
                     if (NSPLIT == 3) tma_load_3d(st + off_blo, &tmW, bar_full + 8 * s, kc * BK, 0, 9 + tap);
@@ -241,25 +244,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 // n_main TMEM accumulators, the two small correction products go to their own accumulator
                 // (|corr| ~ 2^-11 |D|, its truncation error is negligible); the epilogue sums them in fp32.
                 const int am = it % p.n_main;
-                const uint32_t d_main = tmem_acc + am * p.Cout;
+                const int n_acc = p.n_main + (NSPLIT == 3 ? 1 : 0);
                 // descriptors differ only in the 14-bit start-address field: build the low words once per
                 // stage and step them by 32 bytes (>> 4 = 2) per K = 8 slice -- the single issuing thread
                 // must spend well under the MMA's ~64 cycles on address arithmetic
-                const uint32_t a_lo = ((st >> 4) & 0x3FFF) | (1u << 16);
-                const uint32_t alo_lo = (((st + off_alo) >> 4) & 0x3FFF) | (1u << 16);
                 const uint32_t b_lo = (((st + off_b) >> 4) & 0x3FFF) | (1u << 16);
                 const uint32_t blo_lo = (((st + off_blo) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k)
-                    tc_mma_tf32(d_main, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (it >= p.n_main || k > 0) ? 1u : 0u);
-                if (NSPLIT == 3) {
-                    const uint32_t d_corr = tmem_acc + p.n_main * p.Cout;
+                for (int t = 0; t < MT; ++t) {
+                    const uint32_t a_lo = (((st + t * A_BYTES) >> 4) & 0x3FFF) | (1u << 16);
+                    const uint32_t alo_lo = (((st + off_alo + t * A_BYTES) >> 4) & 0x3FFF) | (1u << 16);
+                    const uint32_t d_main = tmem_acc + (t * n_acc + am) * p.Cout;
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k)
-                        tc_mma_tf32(d_corr, desc_hi | (alo_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32(d_main, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (it >= p.n_main || k > 0) ? 1u : 0u);
+                    if (NSPLIT == 3) {
+                        const uint32_t d_corr = tmem_acc + (t * n_acc + p.n_main) * p.Cout;
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)
-                        tc_mma_tf32(d_corr, desc_hi | (a_lo + 2 * k), desc_hi | (blo_lo + 2 * k), idesc, 1u);
+                        for (int k = 0; k < BK / 8; ++k)
+                            tc_mma_tf32(d_corr, desc_hi | (alo_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k)
+                            tc_mma_tf32(d_corr, desc_hi | (a_lo + 2 * k), desc_hi | (blo_lo + 2 * k), idesc, 1u);
+                    }
                 }
                 if (CS == 1) tc_commit(bar_empty + 8 * s);     // frees the stage when these MMAs have read it
                 else tc_commit_mc(bar_empty + 8 * s, cmask);   // ... in every CTA of the cluster (its producer multicasts into ours)
@@ -277,7 +284,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const float4* a = reinterpret_cast<const float4*>(base_ptr + (size_t)s * p.stage_bytes);
                 float4* alo = reinterpret_cast<float4*>(base_ptr + (size_t)s * p.stage_bytes + off_alo);
 #pragma unroll
-                for (int i = 0; i < (int)(A_BYTES / 16 / 128); ++i) {
+                for (int i = 0; i < (int)(MT * A_BYTES / 16 / 128); ++i) {
                     const float4 v = a[ct + 128 * i];
                     float4 l;
                     l.x = tf32_residual(v.x); l.y = tf32_residual(v.y);
@@ -292,41 +299,44 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait(bar_acc, 0);
         tc_fence_after();
         const int q = warp & 3;                    // TMEM lane quadrant this warp may access
-        const int m = q * 32 + lane;               // accumulator row = pixel within the tile
-        const int oy = y0 + m / TC_TW, ox = x0 + (m % TC_TW);
-        const bool valid = real_tile && oy < p.OH && ox < p.OW;
-        float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs;
+        const int m = q * 32 + lane;               // accumulator row = pixel within the 16x8 tile
         const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y);
         const int n_acc = p.n_main + (NSPLIT == 3 ? 1 : 0);
-        for (int n0 = 0; n0 < p.Cout; n0 += 16) {
-            // issue the loads of all accumulators (n_acc <= 4), wait once, then sum in fp32:
-            // correction (last, smallest) + main n_main-1 .. 1 first, main 0 last
-            uint32_t r[4][16];
-            const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + n0;
+#pragma unroll 1
+        for (int t = 0; t < MT; ++t) {
+            const int oy = y0 + t * TC_TH + m / TC_TW, ox = x0 + (m % TC_TW);
+            const bool valid = real_tile && oy < p.OH && ox < p.OW;
+            float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs;
+            for (int n0 = 0; n0 < p.Cout; n0 += 16) {
+                // issue the loads of all accumulators (n_acc <= 4), wait once, then sum in fp32:
+                // correction (last, smallest) + main n_main-1 .. 1 first, main 0 last
+                uint32_t r[4][16];
+                const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + t * n_acc * p.Cout + n0;
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-                if (a < n_acc) tmem_ld16(tbase + a * p.Cout, r[a]);
-            tmem_ld_wait();
-            float acc[16];
+                for (int a = 0; a < 4; ++a)
+                    if (a < n_acc) tmem_ld16(tbase + a * p.Cout, r[a]);
+                tmem_ld_wait();
+                float acc[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                for (int j = 0; j < 16; ++j) acc[j] = 0.f;
 #pragma unroll
-            for (int a = 3; a >= 0; --a)
-                if (a < n_acc) {
+                for (int a = 3; a >= 0; --a)
+                    if (a < n_acc) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[a][j]);
-                }
-            if (valid) {
-                float v[16];
+                        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[a][j]);
+                    }
+                if (valid) {
+                    float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = leaky(acc[j] + __ldg(p.bias + n0 + j), p.alpha);
-                if (vec) {
+                    for (int j = 0; j < 16; ++j) v[j] = leaky(acc[j] + __ldg(p.bias + n0 + j), p.alpha);
+                    if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) yrow[n0 + j] = v[j];
+                        for (int j = 0; j < 16; ++j) yrow[n0 + j] = v[j];
+                    }
                 }
             }
         }
@@ -408,12 +418,21 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     EncodeTiledFn enc = get_encode();
     PWC_REQUIRE(enc != nullptr, PWC_E_NOTBUILT, "conv3x3_tc: cuTensorMapEncodeTiled not available from the driver");
 
-    const int cpad = cin_pad(Cin), bk = tc_bk(Cin);
+    const int cpad = cin_pad(Cin);
     // TF 'SAME': out = ceil(in / s); pad_before = max((out-1)*s + 2*d + 1 - in, 0) / 2
     const int OH = (H + stride - 1) / stride, OW = (W + stride - 1) / stride;
     int pad_t = ((OH - 1) * stride + 2 * dilation + 1 - H); pad_t = pad_t > 0 ? pad_t / 2 : 0;
     int pad_l = ((OW - 1) * stride + 2 * dilation + 1 - W); pad_l = pad_l > 0 ? pad_l / 2 : 0;
-    const int tiles_x = (OW + TC_TW - 1) / TC_TW, tiles_y = (OH + TC_TH - 1) / TC_TH;
+    // M tiles per CTA: two vertically stacked 16x8 tiles reuse every weight tile twice (the kernel is bound by
+    // bytes delivered into the SM, not by L2 or the tensor pipe) when TMEM has room for both accumulator sets.
+    // Measured on B200 (profiles/r01_tc_probe_mt.log): +17% in tf32 mode, -5% in 3xtf32 mode (shared-memory
+    // bandwidth, not delivered bytes, is the limiter there), so it is opt-in via PWC_TC_MT=2.
+    int mt = 1;
+    if (const char* e = getenv("PWC_TC_MT")) mt = (atoi(e) == 2 && Cout <= 128 && OH > TC_TH) ? 2 : 1;
+    // K slice per stage: 16 channels when two 128-wide tiles would leave too few pipeline stages
+    int bk = tc_bk(Cin);
+    if (mt == 2 && n_split == 3 && Cout > 64) bk = 16;
+    const int tiles_x = (OW + TC_TW - 1) / TC_TW, tiles_y = (OH + TC_TH * mt - 1) / (TC_TH * mt);
     const CUtensorMapSwizzle swz = bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const long long tiles = (long long)tiles_x * tiles_y * B;
     PWC_REQUIRE(tiles < (1LL << 30), PWC_E_BADARG, "conv3x3_tc: too many tiles");
@@ -454,28 +473,36 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     p.kchunks = cpad / bk;
     p.alpha = alpha;
     p.b_bytes = Cout * bk * 4;
-    p.stage_bytes = (n_split == 3 ? 2 : 1) * (p.a_bytes + p.b_bytes);
+    p.stage_bytes = (n_split == 3 ? 2 : 1) * (mt * p.a_bytes + p.b_bytes);
     p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
     const int budget = 220 * 1024;
     p.stages = budget / p.stage_bytes;
     if (p.stages > 8) p.stages = 8;
     const int kt = 9 * p.kchunks;
-    if (kt <= 18 && p.stages > 4) p.stages = 4;   // short K loops: keep smem small so several CTAs share an SM
+    // short K loops are dominated by per-tile prologue/epilogue latency: keep smem small so that 3-4 CTAs share
+    // an SM and overlap each other's fill and drain phases
+    if (kt <= 18) { int cap = (56 * 1024) / p.stage_bytes; if (cap < 2) cap = 2; if (p.stages > cap) p.stages = cap; }
+    if (const char* e = getenv("PWC_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 8 && v * p.stage_bytes <= budget) p.stages = v; }
     PWC_REQUIRE(p.stages >= 2, PWC_E_BADARG, "conv3x3_tc: tile does not fit in shared memory");
     // TMEM columns: n_main main accumulators (+1 correction accumulator for 3xTF32), N columns each
-    p.n_main = 1;
-    if (n_split == 3) {
-        p.n_main = 512 / Cout - 1;
-        if (p.n_main > 3) p.n_main = 3;
-        PWC_REQUIRE(p.n_main >= 1, PWC_E_BADARG, "conv3x3_tc: Cout too large for the 3xTF32 accumulator layout");
-    }
+    const int extra = n_split == 3 ? 1 : 0;
+    p.n_main = 512 / (mt * Cout) - extra;
+    if (p.n_main > 3) p.n_main = 3;
+    if (n_split == 1) p.n_main = 1;
+    PWC_REQUIRE(p.n_main >= 1, PWC_E_BADARG, "conv3x3_tc: Cout too large for the accumulator layout");
     int cols = 32;
-    while (cols < (p.n_main + (n_split == 3 ? 1 : 0)) * Cout) cols *= 2;
+    while (cols < mt * (p.n_main + extra) * Cout) cols *= 2;
     p.tmem_cols = cols;
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     cudaStream_t st = (cudaStream_t)stream;
-    auto kern = n_split == 3 ? (bk == 32 ? conv3x3_tc_kernel<3, 32> : conv3x3_tc_kernel<3, 16>)
-                             : (bk == 32 ? conv3x3_tc_kernel<1, 32> : conv3x3_tc_kernel<1, 16>);
+    void (*kern)(const CUtensorMap, const CUtensorMap, const TcParams);
+    if (n_split == 3) {
+        if (mt == 2) kern = bk == 32 ? conv3x3_tc_kernel<3, 32, 2> : conv3x3_tc_kernel<3, 16, 2>;
+        else kern = bk == 32 ? conv3x3_tc_kernel<3, 32, 1> : conv3x3_tc_kernel<3, 16, 1>;
+    } else {
+        if (mt == 2) kern = bk == 32 ? conv3x3_tc_kernel<1, 32, 2> : conv3x3_tc_kernel<1, 16, 2>;
+        else kern = bk == 32 ? conv3x3_tc_kernel<1, 32, 1> : conv3x3_tc_kernel<1, 16, 1>;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     cudaLaunchConfig_t cfg{};
