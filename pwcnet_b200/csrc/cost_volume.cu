@@ -44,6 +44,8 @@ constexpr int CV_OROW = CV_TX * CV_OPIX + 8;   // + 8 floats: de-phase rows acro
 constexpr int CV_THREADS = 128;                // 4 warps = 4 strips of 8 pixels
 constexpr int CV_ITEMS = 30;                   // (f1 row, output row pair) items per strip for TY = 6
 constexpr int CV_SMEM_BYTES = (CV_F0_FLOATS + CV_F1_FLOATS) * 4;
+constexpr int CV_TAPS_WORDS = CV_HY * CV_HX * 6;   // fused variants: per halo pixel 4 tap offsets + 2 fractions
+constexpr int CV_SMEM_BYTES_FUSED = CV_SMEM_BYTES + CV_TAPS_WORDS * 4;
 static_assert(CV_TY * CV_OROW <= CV_F1_FLOATS, "output staging must fit in the f1 halo buffer");
 
 struct CvParams {
@@ -137,6 +139,42 @@ __global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvP
 #pragma unroll
         for (int j = 0; j < CV_D; ++j) { acc0[i][j] = 0.f; acc1[i][j] = 0.f; }
 
+    // Fused variants: per halo pixel, resolve the flow once into 4 clamped tap offsets and the two
+    // fractional weights (modules.py:107-123); the per-chunk gather below then has a single level of
+    // dependent loads.  oy0 < 0 marks a halo pixel outside the image (zero padding of the cost volume).
+    int* taps = reinterpret_cast<int*>(smem + CV_F0_FLOATS + CV_F1_FLOATS);
+    if (WARP != 0) {
+        for (int pix = tid; pix < CV_HY * CV_HX; pix += CV_THREADS) {
+            const int py = pix / CV_HX, px = pix - py * CV_HX;
+            const int gy = y0 + py - CV_R, gx = x0 + px - CV_R;
+            int oy0 = -1, oy1 = 0, ox0 = 0, ox1 = 0;
+            float ty = 0.f, tx = 0.f;
+            if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+                const float* fl = flowb + ((size_t)gy * p.W + gx) * p.flow_cs;
+                const float fx = __ldg(fl) * p.flow_scale, fy = __ldg(fl + 1) * p.flow_scale;
+                int iy0, iy1, ix0, ix1;
+                if (WARP == 2) {   // nearest: tf.cast(flow, int32) truncates toward zero (modules.py:85)
+                    iy0 = iy1 = min(max(gy + (int)fy, 0), p.H - 1);
+                    ix0 = ix1 = min(max(gx + (int)fx, 0), p.W - 1);
+                } else {
+                    const float fx0 = floorf(fx), fy0 = floorf(fy);
+                    const float wl = (float)(p.W - 1), hl = (float)(p.H - 1);
+                    iy0 = (int)fminf(fmaxf((float)gy + fy0, 0.f), hl);
+                    iy1 = (int)fminf(fmaxf((float)gy + (fy0 + 1.f), 0.f), hl);
+                    ix0 = (int)fminf(fmaxf((float)gx + fx0, 0.f), wl);
+                    ix1 = (int)fminf(fmaxf((float)gx + (fx0 + 1.f), 0.f), wl);
+                    ty = fy - fy0; tx = fx - fx0;   // exact; (f0 + 1) - f == 1 - t after one rounding
+                }
+                oy0 = iy0 * p.W * p.f1_cs; oy1 = iy1 * p.W * p.f1_cs;
+                ox0 = ix0 * p.f1_cs; ox1 = ix1 * p.f1_cs;
+            }
+            int* t = taps + pix * 6;
+            t[0] = oy0; t[1] = oy1; t[2] = ox0; t[3] = ox1;
+            t[4] = __float_as_int(ty); t[5] = __float_as_int(tx);
+        }
+        __syncthreads();
+    }
+
     for (int c0 = 0; c0 < p.C; c0 += CV_CH) {
         const int nch4 = min(CV_CH, p.C - c0) >> 2;   // float4 groups valid in this chunk
         if (c0) __syncthreads();
@@ -149,19 +187,37 @@ __global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvP
             cp_async16(f0s + py * CV_F0_ROW + px * CV_CH + 4 * k, src, ok);
         }
         // ---- stage the f1 halo tile (warped on the fly in the fused variants), zeros outside the image
-        for (int e = tid; e < CV_HY * CV_HX * (CV_CH / 4); e += CV_THREADS) {
-            const int k = e & 7, pix = e >> 3;
-            const int py = pix / CV_HX, px = pix - py * CV_HX;
-            const int gy = y0 + py - CV_R, gx = x0 + px - CV_R;
-            const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && k < nch4;
-            float* dst = f1s + py * CV_F1_ROW + px * CV_CH + 4 * k;
-            if (WARP == 0) {
+        if (WARP == 0) {
+            for (int e = tid; e < CV_HY * CV_HX * (CV_CH / 4); e += CV_THREADS) {
+                const int k = e & 7, pix = e >> 3;
+                const int py = pix / CV_HX, px = pix - py * CV_HX;
+                const int gy = y0 + py - CV_R, gx = x0 + px - CV_R;
+                const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && k < nch4;
                 const float* src = ok ? f1b + ((size_t)gy * p.W + gx) * p.f1_cs + c0 + 4 * k : f1b;
-                cp_async16(dst, src, ok);
-            } else {
+                cp_async16(f1s + py * CV_F1_ROW + px * CV_CH + 4 * k, src, ok);
+            }
+        } else {
+            const float* f1c = f1b + c0;
+#pragma unroll 2
+            for (int e = tid; e < CV_HY * CV_HX * (CV_CH / 4); e += CV_THREADS) {
+                const int k = e & 7, pix = e >> 3;
+                const int py = pix / CV_HX, px = pix - py * CV_HX;
+                const int* t = taps + pix * 6;
+                const int oy0 = t[0];
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok) v = sample_f1<WARP>(p, f1b, flowb, gy, gx, c0 + 4 * k);
-                *reinterpret_cast<float4*>(dst) = v;
+                if (oy0 >= 0 && k < nch4) {
+                    const int oy1 = t[1], ox0 = t[2], ox1 = t[3];
+                    const float ty = __int_as_float(t[4]), tx = __int_as_float(t[5]);
+                    const float4 a = ldg4(f1c + oy0 + ox0 + 4 * k), bq = ldg4(f1c + oy0 + ox1 + 4 * k);
+                    const float4 d = ldg4(f1c + oy1 + ox0 + 4 * k), g = ldg4(f1c + oy1 + ox1 + 4 * k);
+                    const float sy = 1.f - ty, sx = 1.f - tx;
+                    const float c00 = sy * sx, c01 = sy * tx, c10 = ty * sx, c11 = ty * tx;
+                    v.x = c00 * a.x + c01 * bq.x + c10 * d.x + c11 * g.x;
+                    v.y = c00 * a.y + c01 * bq.y + c10 * d.y + c11 * g.y;
+                    v.z = c00 * a.z + c01 * bq.z + c10 * d.z + c11 * g.z;
+                    v.w = c00 * a.w + c01 * bq.w + c10 * d.w + c11 * g.w;
+                }
+                *reinterpret_cast<float4*>(f1s + py * CV_F1_ROW + px * CV_CH + 4 * k) = v;
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -295,9 +351,10 @@ static int launch_cv(CvParams p, int search_range, cudaStream_t st) {
     if (search_range == CV_R) {
         dim3 grid((p.W + CV_TX - 1) / CV_TX, (p.H + CV_TY - 1) / CV_TY, p.B);
         auto kern = !p.flow ? cost_volume_r4_kernel<0> : (p.warp_type == 0 ? cost_volume_r4_kernel<1> : cost_volume_r4_kernel<2>);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES);
+        const int smem_bytes = p.flow ? CV_SMEM_BYTES_FUSED : CV_SMEM_BYTES;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) { set_error("cost_volume: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-        kern<<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(p);
+        kern<<<grid, CV_THREADS, smem_bytes, st>>>(p);
         PWC_CHECK_LAUNCH("cost_volume_r4_kernel");
     } else {
         const size_t total = (size_t)p.B * p.H * p.W * nd;

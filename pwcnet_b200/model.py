@@ -356,19 +356,35 @@ class PWCDCNet(object):
         if i0.shape != i1.shape:
             raise ValueError(f"images_0 {tuple(i0.shape)} and images_1 {tuple(i1.shape)} differ in shape")
         B, H, W, C = i0.shape
+        self._check_shape(B, H, W, C)
+        p = self.plan(B, H, W)
+        p.im[:B].copy_(i0, non_blocking=True)
+        p.im[B:].copy_(i1, non_blocking=True)
+        self._launch(p)
+        flows_pyramid = list(p.flows)
+        if with_features:
+            pyramid_0 = [p.pyr[self.num_levels - 1 - l][2][:B] for l in range(self.num_levels)]
+            return p.flows_final, flows_pyramid, pyramid_0
+        return p.flows_final, flows_pyramid
+
+    def _check_shape(self, B, H, W, C=3) -> None:
         m = 2 ** self.num_levels
         if C != 3 or H % m or W % m or min(B, H, W) <= 0:
             raise ValueError(f"images must be (B,H,W,3) with H, W multiples of {m} (test.py:13-17 crops to /64); "
-                             f"got {tuple(i0.shape)}")
+                             f"got {(B, H, W, C)}")
+
+    def plan(self, B, H, W) -> _Plan:
+        """Workspace (buffers + CUDA graph) for one input shape; created on first use."""
         key = (B, H, W)
         p = self._plans.get(key)
         if p is None:
             p = self._plans[key] = self._make_plan(B, H, W)
-        p.im[:B].copy_(i0, non_blocking=True)
-        p.im[B:].copy_(i1, non_blocking=True)
+        return p
+
+    def _launch(self, p: _Plan) -> None:
         if self.use_cuda_graph and self.precision != "cudnn":
             if p.graph is None:
-                self._forward(p)                      # warm-up (also sets kernel attributes)
+                self._forward(p)                      # warm-up (also sets kernel attributes, packs weights)
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
@@ -377,11 +393,14 @@ class PWCDCNet(object):
             p.graph.replay()
         else:
             self._forward(p)
-        flows_pyramid = list(p.flows)
-        if with_features:
-            pyramid_0 = [p.pyr[self.num_levels - 1 - l][2][:B] for l in range(self.num_levels)]
-            return p.flows_final, flows_pyramid, pyramid_0
-        return p.flows_final, flows_pyramid
+
+    def _run_device(self, images_2b, B, H, W):
+        """Forward on a device tensor (2B,H,W,3) holding images_0 then images_1 (used by InferenceStream)."""
+        self._check_shape(B, H, W, images_2b.shape[3])
+        p = self.plan(B, H, W)
+        p.im.copy_(images_2b, non_blocking=True)
+        self._launch(p)
+        return p.flows_final, list(p.flows)
 
     def _as_input(self, a, name):
         if isinstance(a, np.ndarray):

@@ -1,0 +1,105 @@
+"""Host<->device pipelining for throughput inference through the public model API.
+
+`PWCDCNet.__call__` on host arrays is synchronous in effect (H2D, forward, then the caller's D2H).
+`InferenceStream` keeps `depth` requests in flight: the H2D copy of request i+1 (copy engine, its own
+stream) and the D2H copy of request i-1 overlap the forward of request i, so end-to-end throughput is
+max(compute, PCIe) instead of their sum.  Inputs come from (pinned) host memory every request and the
+results land in pinned host buffers: same data movement as the synchronous call.
+
+    stream = InferenceStream(model, depth=2)
+    tickets = [stream.submit(im0, im1) for ...]      # host float32 (B,H,W,3) arrays / tensors
+    flows_final, flows_pyramid = stream.collect(ticket)   # torch CPU tensors (pinned), valid until the slot is reused
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+
+class InferenceStream:
+    def __init__(self, model, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.model = model
+        self.depth = depth
+        self.dev = model.device
+        self.s_in = torch.cuda.Stream(device=self.dev)
+        self.s_out = torch.cuda.Stream(device=self.dev)
+        self._slots = None
+        self._shape = None
+        self._next = 0
+        self._pending = {}
+
+    def _alloc(self, B, H, W):
+        plan = self.model.plan(B, H, W)
+        outs = [plan.flows_final] + list(plan.flows)
+        self._slots = []
+        for _ in range(self.depth):
+            self._slots.append(dict(
+                in_dev=torch.empty((2 * B, H, W, 3), dtype=torch.float32, device=self.dev),
+                out_dev=[torch.empty_like(t) for t in outs],
+                out_host=[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs],
+                ev_in=torch.cuda.Event(), ev_taken=torch.cuda.Event(), ev_fwd=torch.cuda.Event(),
+                ev_out=torch.cuda.Event(), used=False, ticket=None))
+        self._shape = (B, H, W)
+
+    @staticmethod
+    def _host(a, name):
+        if isinstance(a, np.ndarray):
+            if a.dtype != np.float32:
+                raise TypeError(f"{name}: dtype must be float32")
+            a = torch.from_numpy(np.ascontiguousarray(a))
+        if not isinstance(a, torch.Tensor) or a.is_cuda or a.dtype != torch.float32 or a.dim() != 4:
+            raise TypeError(f"{name}: expected a float32 host array/tensor of shape (B,H,W,3)")
+        return a
+
+    def submit(self, images_0, images_1) -> int:
+        i0, i1 = self._host(images_0, "images_0"), self._host(images_1, "images_1")
+        if i0.shape != i1.shape:
+            raise ValueError("images_0 and images_1 differ in shape")
+        B, H, W, _ = i0.shape
+        if self._shape != (B, H, W):
+            self.drain()
+            self._alloc(B, H, W)
+        ticket = self._next
+        self._next += 1
+        sl = self._slots[ticket % self.depth]
+        if sl["used"] and sl["ticket"] in self._pending:
+            raise RuntimeError(f"slot still holds uncollected ticket {sl['ticket']}: collect() it first (depth={self.depth})")
+        cur = torch.cuda.current_stream(self.dev)
+        # ---- H2D on the input stream (waits until the previous user of this slot was consumed)
+        with torch.cuda.stream(self.s_in):
+            if sl["used"]:
+                self.s_in.wait_event(sl["ev_taken"])
+            sl["in_dev"][:B].copy_(i0, non_blocking=True)
+            sl["in_dev"][B:].copy_(i1, non_blocking=True)
+            sl["ev_in"].record(self.s_in)
+        # ---- forward on the caller's stream
+        cur.wait_event(sl["ev_in"])
+        flows_final, pyr = self.model._run_device(sl["in_dev"], B, H, W)
+        sl["ev_taken"].record(cur)
+        if sl["used"]:
+            cur.wait_event(sl["ev_out"])            # previous D2H out of this slot's staging has finished
+        for d, s in zip(sl["out_dev"], [flows_final] + list(pyr)):
+            d.copy_(s, non_blocking=True)
+        sl["ev_fwd"].record(cur)
+        # ---- D2H on the output stream
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(sl["ev_fwd"])
+            for h, d in zip(sl["out_host"], sl["out_dev"]):
+                h.copy_(d, non_blocking=True)
+            sl["ev_out"].record(self.s_out)
+        sl["used"], sl["ticket"] = True, ticket
+        self._pending[ticket] = sl
+        return ticket
+
+    def collect(self, ticket: int) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        sl = self._pending.pop(ticket)
+        sl["ev_out"].synchronize()
+        return sl["out_host"][0], sl["out_host"][1:]
+
+    def drain(self):
+        for t in list(self._pending):
+            self.collect(t)
