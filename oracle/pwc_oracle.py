@@ -7,16 +7,21 @@ CUDA path in `pwcnet_b200/` can be checked against it.  Only `tests/`,
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs
 may import it; the product package never does.
 
-PARITY STATUS: the reference cannot run here (TensorFlow 1.8 is not installable,
-no network) and ships no tests or golden vectors, so this oracle is NOT pinned by
-outputs of the reference program itself.  It is pinned by
-  (1) the saved TF-1.8 GraphDef of the reference (`*.ckpt.meta`) executed node by
-      node by `oracle/tf_graph_interp.py` on the trained checkpoint weights
-      (fixtures in tests/golden/, generated by oracle/make_golden.py), and
-  (2) hand-derived known-answer tests for every TF-1.8 kernel semantic
-      (asymmetric SAME padding, legacy bilinear resize, clamp-not-zero warp,
-      cost-volume channel order) in tests/test_oracle.py.
-See DESIGN.md "Oracle".
+PARITY STATUS: TensorFlow 1.8 is not installable here (no cp312 wheel, no network) and the reference
+ships no tests or golden vectors, so this oracle cannot be pinned by running the reference program.
+It is pinned, in decreasing strength, by
+  (1) the reference's OWN serialized computation: the TF-1.8 GraphDef it saved next to its checkpoints
+      (`model_250.ckpt.meta`, forward + loss graphs built from model.py / modules.py / losses.py) is
+      executed node by node by `oracle/tf_graph_interp.py` (a TensorFlow-free interpreter of the 30 op
+      types that occur); this oracle matches it to 3e-7 (glorot weights), 4e-5 on 14-px flows and 2e-6
+      with the trained checkpoint; the outputs are the fixtures in tests/golden/ (oracle/make_golden.py);
+  (2) an end-to-end semantic check with the reference's trained checkpoint (recovers a known synthetic
+      translation) and
+  (3) hand-derived known-answer tests for every TF-1.8 kernel semantic (asymmetric SAME padding, legacy
+      bilinear resize, clamp-not-zero warp, cost-volume channel order) in tests/test_oracle.py.
+What remains unpinned: the numpy/torch kernels inside the interpreter restate TF's op kernels (Conv2D,
+ResizeBilinear, GatherNd, ...) from their documented semantics, they are not TF's binaries.
+See DESIGN.md "Oracle and parity".
 
 All tensors are NHWC.  Conv kernels are HWIO.  `W` is a dict name -> array keyed by
 the reference's checkpoint variable names (pwcdcnet/<scope>/conv2d[_i]/{kernel,bias}).

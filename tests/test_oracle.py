@@ -158,12 +158,54 @@ def test_config1_shapes_and_golden():
     ff, pyr = O.pwcdcnet_forward(W, im0, im1)
     assert ff.shape == (1, 64, 128, 2)
     assert [tuple(p.shape) for p in pyr] == [(1, 1, 2, 2), (1, 2, 4, 2), (1, 4, 8, 2), (1, 8, 16, 2), (1, 16, 32, 2)]
+    # golden = the reference's own saved GraphDef executed node by node (oracle/make_golden.py)
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "config1_glorot_seed2.npz"))
-    np.testing.assert_allclose(ff.numpy(), gold["flows_final"], atol=2e-6)
+    assert "reference GraphDef" in str(gold["source"])
+    np.testing.assert_allclose(ff.numpy(), gold["flows_final"], atol=5e-6)
     for l, p in enumerate(pyr):
         np.testing.assert_allclose(p.numpy(), gold[f"pyr{l}"], atol=2e-6)
     gt = np.random.default_rng(1).normal(0, 5, (1, 64, 128, 2)).astype(np.float32)
     assert O.EPE(torch.from_numpy(gt), ff).item() == pytest.approx(float(gold["epe"]), rel=1e-5)
+
+
+def test_hot_weights_vs_reference_graph_golden():
+    """Flows up to 14 px (warp / clamp / residual paths live): oracle vs the reference GraphDef's outputs,
+    including the serialized loss graph (multiscale loss, + 4e-4 * sum l2_loss(var), EPE)."""
+    W = O.glorot_weights(7, gain=1.4, bias_scale=0.02)
+    im0, im1 = O.synthetic_pair(2, 64, 128, 3, shift=(5, -3))
+    gt = np.random.default_rng(1).normal(0, 5, (2, 64, 128, 2)).astype(np.float32)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "hot_seed7_64x128.npz"))
+    loss, epe, ff, pyr = O.training_loss({k: torch.from_numpy(v) for k, v in W.items()}, im0, im1, gt)
+    assert np.abs(gold["flows_final"]).max() > 10
+    np.testing.assert_allclose(ff.numpy(), gold["flows_final"], atol=2e-4)
+    for l, p in enumerate(pyr):
+        np.testing.assert_allclose(p.numpy(), gold[f"pyr{l}"], atol=1e-5)
+    assert loss.item() == pytest.approx(float(gold["total_loss"]), rel=1e-5)
+    assert O.multiscale_loss(torch.from_numpy(gt), pyr, O.DEFAULT_LOSS_WEIGHTS).item() == pytest.approx(float(gold["loss"]), rel=1e-5)
+    assert epe.item() == pytest.approx(float(gold["epe"]), rel=1e-5)
+
+
+@pytest.mark.skipif(not os.path.exists(REF + "/model_250epochs_ft_Final/model_250.ckpt.meta"),
+                    reason="reference GraphDef not mounted (only in the build container)")
+def test_reference_graphdef_live_with_trained_checkpoint():
+    """Execute the reference's saved GraphDef with its trained weights and compare the oracle, live."""
+    from oracle import tf_graph_interp as G
+    from pwcnet_b200.checkpoint import load_checkpoint
+    ck = REF + "/model_250epochs_ft_Final/model_250.ckpt"
+    W = load_checkpoint(ck)
+    im0, im1 = O.synthetic_pair(1, 64, 128, 0, shift=(3, -2))
+    ff, pyr, _ = G.run_reference_graph(ck + ".meta", W, np.stack([im0, im1], 1))
+    rff, rpyr = O.pwcdcnet_forward(W, im0, im1)
+    np.testing.assert_allclose(rff.numpy(), ff, atol=2e-5)
+    for a, b in zip(rpyr, pyr):
+        np.testing.assert_allclose(a.numpy(), b, atol=2e-6)
+    # graph-level facts the restatement relies on
+    g = G.Graph(ck + ".meta")
+    assert float(g.attr("pwcdcnet/mul_6/y", "value")) == 20.0                        # model.py:127
+    assert [float(g.attr(f"pwcdcnet/mul{'_' + str(i) if i else ''}/y", "value")) for i in range(4)] == [0.625, 1.25, 2.5, 5.0]
+    assert g.attr("pwcdcnet/ResizeBilinear", "align_corners") in (None, False)
+    assert g.attr("pwcdcnet/fp_extractor/conv2d/Conv2D", "padding") == b"SAME"
+    assert g.attr("pwcdcnet/fp_extractor/conv2d/Conv2D", "strides") == [1, 2, 2, 1]
 
 
 def test_piecewise_lr_and_adam():
