@@ -83,7 +83,7 @@ class _Plan:
 class PWCDCNet(object):
     def __init__(self, num_levels=6, search_range=4, warp_type='bilinear', use_dc=False,
                  output_level=4, name='pwcdcnet', *, device=None, weights=None, seed=0,
-                 precision=None, use_cuda_graph=True):
+                 precision=None, use_cuda_graph=True, fuse_warp=False):
         self.num_levels = num_levels
         self.s_range = search_range
         self.warp_type = warp_type
@@ -100,6 +100,7 @@ class PWCDCNet(object):
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.precision = precision
         self.use_cuda_graph = use_cuda_graph
+        self.fuse_warp = fuse_warp
         if not torch.cuda.is_available():
             raise PwcError("PWCDCNet needs a CUDA device: the compute path is sm_100a CUDA only (no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -263,7 +264,7 @@ class PWCDCNet(object):
             C = PYRAMID_FILTERS[l]
             p.pyr.append([torch.empty((2 * B, h, w, C), dtype=torch.float32, device=dev) for _ in range(3)])
         pre_total = sum(ESTIMATOR_FILTERS) if self.use_dc else 0
-        p.S, p.tmp, p.flows = [], [], []
+        p.S, p.tmp, p.flows, p.f1w = [], [], [], []
         for l, lv in enumerate(self._lv):
             ph, pw = p.pyr[self.num_levels - 1 - l][2].shape[1:3]
             is_out = l == self.output_level
@@ -278,6 +279,7 @@ class PWCDCNet(object):
                 last = torch.zeros((B, ph, pw, ESTIMATOR_FILTERS[-1] + (4 if is_out else 0)), dtype=torch.float32, device=dev)
                 p.tmp.append(tmps + [last])
             p.flows.append(torch.empty((B, ph, pw, 2), dtype=torch.float32, device=dev))
+            p.f1w.append(torch.empty((B, ph, pw, lv["C"]), dtype=torch.float32, device=dev) if l and not self.fuse_warp else None)
         ph, pw = p.flows[-1].shape[1:3]
         p.ctx = [torch.empty((B, ph, pw, f), dtype=torch.float32, device=dev) for f in CONTEXT_FILTERS[:-1]]
         up = 2 ** (self.num_levels - self.output_level)
@@ -306,9 +308,14 @@ class PWCDCNet(object):
             flow_up = X[..., lv["off_flow"]:lv["off_flow"] + 2] if l else None
             if l == 0:
                 ops.cost_volume(f0, f1, self.s_range, 0.1, out=cv, f0_copy=f0slot)
-            else:
+            elif self.fuse_warp:
                 ops.warp_cost_volume(f0, f1, flow_up, self.scales[l], self.warp_type, self.s_range, 0.1,
                                      out=cv, f0_copy=f0slot)
+            else:
+                # measured on B200: warp kernel + unfused cost volume (15 + 89 us at level 4, B=8) beats the
+                # fused kernel (150 us), whose on-the-fly gather is latency-bound with 2 CTAs/SM
+                f1w = ops.warp(f1, flow_up, self.scales[l], self.warp_type, out=p.f1w[l])
+                ops.cost_volume(f0, f1w, self.s_range, 0.1, out=cv, f0_copy=f0slot)
             is_out = l == self.output_level
             # ---- estimator convs (modules.py:266-274)
             if self.use_dc:
@@ -419,6 +426,7 @@ class PWCDCNet(object):
         """Number of kernel launches of ours in one forward (for bench.py's gpu_launches)."""
         n = 3 * self.num_levels                      # pyramid (both images batched)
         n += (self.output_level + 1) * (1 + len(ESTIMATOR_FILTERS) + 1)   # cv + estimator convs + head
+        n += 0 if self.fuse_warp else self.output_level              # stand-alone warp kernels
         n += self.output_level * 2                    # up-sampling of flows and features
         n += len(CONTEXT_FILTERS) + 1                 # context + final x4 resize
         return n
