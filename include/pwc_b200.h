@@ -73,6 +73,16 @@ int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packed, const fl
 long long pwc_conv3x3_packed_bytes(int Cin, int Cout);
 int pwc_conv3x3_pack_weights(const float* w_hwio, float* w_packed, int Cin, int Cout, void* stream);
 
+/* Same function with the "3 x fp16, scaled residual" split (x = h + l * 2^-11, h/l fp16; tcgen05 kind::f16,
+ * fp32 accumulation in TMEM): fp32-class accuracy at half the MMA instructions of 3xTF32.  Requires
+ * |x|, |w| < 65504.  w_packed: [2][9][Cout][Cin_pad32] fp16 from pwc_conv3x3_pack_weights_f16.
+ * Requires stride 1 or 2, Cin >= 16, Cout % 16 == 0, Cout <= 256, x 16-byte aligned, x_cs % 4 == 0. */
+int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_packed, const float* bias,
+                           float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int stride, int dilation,
+                           float alpha, void* stream);
+long long pwc_conv3x3_packed_bytes_f16(int Cin, int Cout);
+int pwc_conv3x3_pack_weights_f16(const float* w_hwio, void* w_packed, int Cin, int Cout, void* stream);
+
 /* tf.image.resize_bilinear(x,(OH,OW)) with align_corners=False as in TF 1.8 (no half-pixel
  * offset; modules.py:283-284, model.py:127), result multiplied by `mul` (model.py:127 "*20."). */
 int pwc_resize_bilinear_fwd(const float* x, int x_cs, float* y, int y_cs, int B, int H, int W, int C,

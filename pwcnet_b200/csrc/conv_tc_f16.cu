@@ -1,0 +1,385 @@
+// 3x3 convolution on tcgen05 with the error-compensated "3 x fp16, scaled residual" scheme (fp32-class).
+//
+// Same implicit GEMM / pipeline as conv_tc.cu (replaces the same reference node groups,
+// modules.py:62-67, 266-274, 306-323), but the operands are split as
+//        x = h + l * 2^-11,   h = fp16_rn(x),   l = fp16_rn((x - h) * 2^11)
+// (Ootomo & Yokota's residual scaling keeps l out of the fp16 subnormal range), and
+//        D = A_h.W_h  +  2^-11 * (A_l.W_h + A_h.W_l)
+// is accumulated in two fp32 TMEM accumulator groups with tcgen05.mma.kind::f16 (K = 16 per instruction).
+// h.h products are exact in fp32 (11 x 11 bits); the representation error of h + l/2048 is 2^-23 |x|, the
+// dropped l.l term 2^-22: fp32-class results, like 3xTF32, at HALF the MMA instructions (6 instead of 12 per
+// 32-channel slice) and 2/3 of the shared-memory operand traffic -- on B200 the tf32 variant is bound by
+// shared-memory bandwidth (UMMA operand reads + the converter + TMA writes), not by the tensor pipe.
+//
+// Stage layout: [A raw fp32 16K (TMA, 128B swizzle) | A_h fp16 8K | A_l fp16 8K | W_h fp16 N*64 | W_l fp16 N*64];
+// the fp16 tiles are K-major with 64-byte rows (64B swizzle).  The four converter/epilogue warps turn the
+// raw fp32 tile into A_h / A_l between TMA arrival and MMA issue; weights are split once on the host side
+// of the ABI (pwc_conv3x3_pack_weights_f16).  fp16 range: |x| < 65504 is required (activations and weights
+// of this network are O(1e-3 .. 1e2)); values that overflow saturate to inf like any fp16 path would.
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+#include <cstdlib>
+
+namespace pwc {
+
+constexpr int F16_BM = 128, F16_TW = 16, F16_TH = 8, F16_BK = 32, F16_THREADS = 192;
+constexpr uint32_t F16_A_RAW = F16_BM * F16_BK * 4;   // 16 KB
+constexpr uint32_t F16_A_HALF = F16_BM * F16_BK * 2;  // 8 KB
+constexpr float F16_SCALE = 2048.f, F16_INV_SCALE = 1.f / 2048.f;
+
+struct F16Params {
+    const float* bias; float* y;
+    int y_cs, B, H, W, Cin, Cout, dil;
+    int OH, OW, stride, pad_t, pad_l;
+    int tiles_x, tiles_y, kchunks, total_tiles;
+    float alpha;
+    int b_bytes;       // Cout * 64 (one fp16 weight tile)
+    int stage_bytes, stages, tmem_cols, n_main, prefetch;
+    unsigned long long* dbg;   // optional per-CTA timeline (clock64), 8 slots per CTA; nullptr in production
+};
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(F16_THREADS, 1)
+conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const F16Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    __shared__ __align__(8) uint64_t bars[3 * 8 + 1];   // full[8], conv[8], empty[8], acc_full
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 72 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[8]), bar_empty = smem_u32(&bars[16]);
+    const uint32_t bar_acc = smem_u32(&bars[24]);
+
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
+    const int x0 = tx * F16_TW, y0 = ty * F16_TH;
+    const int KT = 9 * p.kchunks;
+
+    constexpr uint32_t off_ah = F16_A_RAW, off_al = F16_A_RAW + F16_A_HALF, off_bh = F16_A_RAW + 2 * F16_A_HALF;
+    const uint32_t off_bl = off_bh + p.b_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 128);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();   // setup done
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+            const uint32_t tx_bytes = F16_A_RAW + 2 * p.b_bytes;
+            const int PF = p.prefetch;   // stages of L2 prefetch distance for the activation boxes
+            for (int it = 0; it < PF && it < KT; ++it) {
+                const int tap = it / p.kchunks, kc = it - tap * p.kchunks, ky = tap / 3, kx = tap - ky * 3;
+                tma_prefetch_4d(&tmX, kc * F16_BK, x0 * p.stride - p.pad_l + kx * p.dil, y0 * p.stride - p.pad_t + ky * p.dil, b);
+            }
+            for (int it = 0; it < KT; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                if (it + PF < KT) {
+                    const int itp = it + PF;
+                    const int tap = itp / p.kchunks, kc = itp - tap * p.kchunks, ky = tap / 3, kx = tap - ky * 3;
+                    tma_prefetch_4d(&tmX, kc * F16_BK, x0 * p.stride - p.pad_l + kx * p.dil, y0 * p.stride - p.pad_t + ky * p.dil, b);
+                }
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const uint32_t st = base + s * p.stage_bytes;
+                if (dbg && it >= 8 && it < 24) dbg[8 + (it - 8)] = clock64();
+                mbar_expect_tx(bar_full + 8 * s, tx_bytes);
+                tma_load_4d(st, &tmX, bar_full + 8 * s, kc * F16_BK, x0 * p.stride - p.pad_l + kx * p.dil,
+                            y0 * p.stride - p.pad_t + ky * p.dil, b);
+                tma_load_3d(st + off_bh, &tmW, bar_full + 8 * s, kc * F16_BK, 0, tap);
+                tma_load_3d(st + off_bl, &tmW, bar_full + 8 * s, kc * F16_BK, 0, 9 + tap);
+            }
+            if (dbg) dbg[2] = clock64();   // last TMA issued
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // kind::f16: D = f32 (bit 4), A = B = F16 (format 0), K-major, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(F16_BM >> 4) << 24);
+            // 64-byte-row K-major tiles: 8-row atoms 512 bytes apart, SWIZZLE_64B (layout type 4)
+            const uint64_t desc_hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+            const uint32_t d_corr = tmem_acc + p.n_main * p.Cout;
+            for (int it = 0; it < KT; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                mbar_wait(bar_conv + 8 * s, ph);
+                if (dbg && it == 0) dbg[3] = clock64();   // first stage converted
+                if (dbg && it >= 8 && it < 24) dbg[56 + (it - 8)] = clock64();
+                tc_fence_after();
+                const uint32_t st = base + s * p.stage_bytes;
+                const uint32_t ah = (((st + off_ah) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t al = (((st + off_al) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t bh = (((st + off_bh) >> 4) & 0x3FFF) | (1u << 16);
+                const uint32_t bl = (((st + off_bl) >> 4) & 0x3FFF) | (1u << 16);
+                const int am = it % p.n_main;
+                const uint32_t d_main = tmem_acc + am * p.Cout;
+#pragma unroll
+                for (int k = 0; k < F16_BK / 16; ++k)   // K = 16 fp16 = 32 bytes per instruction
+                    tc_mma_f16(d_main, desc_hi | (ah + 2 * k), desc_hi | (bh + 2 * k), idesc, (it >= p.n_main || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < F16_BK / 16; ++k)
+                    tc_mma_f16(d_corr, desc_hi | (al + 2 * k), desc_hi | (bh + 2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < F16_BK / 16; ++k)
+                    tc_mma_f16(d_corr, desc_hi | (ah + 2 * k), desc_hi | (bl + 2 * k), idesc, 1u);
+                tc_commit(bar_empty + 8 * s);
+            }
+            tc_commit(bar_acc);
+            if (dbg) dbg[4] = clock64();   // last MMA issued
+        }
+    } else {
+        // ===================== converter, then epilogue =====================
+        const int ct = threadIdx.x - 64;   // 0..127
+        for (int it = 0; it < KT; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            if (dbg && ct == 0 && it >= 8 && it < 24) dbg[24 + (it - 8)] = clock64();
+            const uint8_t* stp = base_ptr + (size_t)s * p.stage_bytes;
+            const float4* a = reinterpret_cast<const float4*>(stp);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int chunk = ct + 128 * i;          // physical 16-byte chunk of the raw tile
+                const int m = chunk >> 3;                 // pixel row 0..127
+                const int lk = (chunk & 7) ^ (m & 7);     // logical 4-channel group (undo the 128B swizzle)
+                const float4 v = a[chunk];
+                const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn((v.x - f01.x) * F16_SCALE, (v.y - f01.y) * F16_SCALE);
+                const __half2 l23 = __floats2half2_rn((v.z - f23.x) * F16_SCALE, (v.w - f23.y) * F16_SCALE);
+                // destination in the 64-byte-row, 64B-swizzled fp16 tile: 16-byte chunk j = lk >> 1, half lk & 1
+                const uint32_t off = m * 64 + ((((lk >> 1) ^ ((m >> 1) & 3))) << 4) + ((lk & 1) << 3);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(const_cast<uint8_t*>(stp) + off_ah + off) = hv;
+                *reinterpret_cast<uint2*>(const_cast<uint8_t*>(stp) + off_al + off) = lv;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (dbg && ct == 0 && it >= 8 && it < 24) dbg[40 + (it - 8)] = clock64();
+            mbar_arrive(bar_conv + 8 * s);
+        }
+        // ---- epilogue
+        mbar_wait(bar_acc, 0);
+        if (dbg && ct == 0) dbg[5] = clock64();   // accumulator complete
+        tc_fence_after();
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int oy = y0 + m / F16_TW, ox = x0 + (m % F16_TW);
+        const bool valid = oy < p.OH && ox < p.OW;
+        float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs;
+        const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y);
+        for (int n0 = 0; n0 < p.Cout; n0 += 16) {
+            uint32_t r[4][16];
+            const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + n0;
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2)
+                if (a2 <= p.n_main) tmem_ld16(tbase + a2 * p.Cout, r[a2]);
+            tmem_ld_wait();
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int a2 = 3; a2 >= 0; --a2) {
+                if (a2 == p.n_main) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[a2][j]) * F16_INV_SCALE;   // correction group
+                } else if (a2 < p.n_main) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[a2][j]);
+                }
+            }
+            if (valid) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = leaky(acc[j] + __ldg(p.bias + n0 + j), p.alpha);
+                if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) yrow[n0 + j] = v[j];
+                }
+            }
+        }
+    }
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();   // epilogue stores issued
+    __syncwarp();   // lanes 1..31 of the producer / MMA warps wait for their lane 0 before the block barrier
+    tc_fence_before();
+    __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[7] = clock64();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(p.tmem_cols));
+    }
+}
+
+// HWIO (3,3,Cin,Cout) fp32 -> [2][9][Cout][Cin_pad] fp16: plane 0 = h, plane 1 = l (scaled residual).
+__global__ void pack_weights_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cin, int Cout, int Cin_pad) {
+    const size_t total = (size_t)9 * Cout * Cin_pad;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = idx % Cin_pad; size_t r = idx / Cin_pad;
+        const int n = r % Cout; const int tap = r / Cout;
+        __half h = __float2half_rn(0.f), l = h;
+        if (c < Cin) {
+            const float v = w[((size_t)tap * Cin + c) * Cout + n];
+            h = __float2half_rn(v);
+            l = __float2half_rn((v - __half2float(h)) * F16_SCALE);
+        }
+        out[idx] = h;
+        out[total + idx] = l;
+    }
+}
+
+static inline int f16_cin_pad(int Cin) { return (Cin + F16_BK - 1) / F16_BK * F16_BK; }
+
+}  // namespace pwc
+
+extern "C" long long pwc_conv3x3_packed_bytes_f16(int Cin, int Cout) {
+    if (Cin <= 0 || Cout <= 0) return 0;
+    return 2LL * 9 * Cout * pwc::f16_cin_pad(Cin) * 2;
+}
+
+extern "C" int pwc_conv3x3_pack_weights_f16(const float* w_hwio, void* w_packed, int Cin, int Cout, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(w_hwio && w_packed, PWC_E_BADARG, "pack_weights_f16: null pointer");
+    PWC_REQUIRE(Cin > 0 && Cout > 0, PWC_E_BADARG, "pack_weights_f16: bad dims");
+    pack_weights_f16_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(w_hwio, (__half*)w_packed, Cin, Cout, f16_cin_pad(Cin));
+    PWC_CHECK_LAUNCH("pack_weights_f16_kernel");
+    return 0;
+}
+
+extern "C" int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_packed, const float* bias,
+                                      float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int stride, int dilation,
+                                      float alpha, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(x && w_packed && bias && y, PWC_E_BADARG, "conv3x3_tc_f16: null pointer");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && dilation >= 1, PWC_E_BADARG, "conv3x3_tc_f16: bad dims");
+    PWC_REQUIRE(stride == 1 || stride == 2, PWC_E_BADARG, "conv3x3_tc_f16: stride must be 1 or 2");
+    PWC_REQUIRE(Cout % 16 == 0 && Cout <= 256, PWC_E_BADARG, "conv3x3_tc_f16: Cout must be a multiple of 16, <= 256");
+    PWC_REQUIRE(Cin >= 16, PWC_E_BADARG, "conv3x3_tc_f16: Cin must be >= 16");
+    PWC_REQUIRE(x_cs >= Cin && y_cs >= Cout, PWC_E_BADARG, "conv3x3_tc_f16: channel stride smaller than channel count");
+    PWC_REQUIRE(aligned16(x) && (x_cs % 4 == 0) && aligned16(w_packed), PWC_E_ALIGN,
+                "conv3x3_tc_f16: x / w_packed must be 16-byte aligned and x_cs a multiple of 4");
+    EncodeTiledFn enc = get_encode();
+    PWC_REQUIRE(enc != nullptr, PWC_E_NOTBUILT, "conv3x3_tc_f16: cuTensorMapEncodeTiled not available from the driver");
+
+    const int cpad = f16_cin_pad(Cin);
+    const int OH = (H + stride - 1) / stride, OW = (W + stride - 1) / stride;
+    int pad_t = ((OH - 1) * stride + 2 * dilation + 1 - H); pad_t = pad_t > 0 ? pad_t / 2 : 0;
+    int pad_l = ((OW - 1) * stride + 2 * dilation + 1 - W); pad_l = pad_l > 0 ? pad_l / 2 : 0;
+    const int tiles_x = (OW + F16_TW - 1) / F16_TW, tiles_y = (OH + F16_TH - 1) / F16_TH;
+    const long long tiles = (long long)tiles_x * tiles_y * B;
+    PWC_REQUIRE(tiles < (1LL << 30), PWC_E_BADARG, "conv3x3_tc_f16: too many tiles");
+    CUtensorMap tmX, tmW;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)x_cs * 4, (cuuint64_t)W * x_cs * 4, (cuuint64_t)H * W * x_cs * 4};
+        cuuint32_t box[4] = {F16_BK, (cuuint32_t)(F16_TW * stride), (cuuint32_t)(F16_TH * stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PWC_REQUIRE(r == CUDA_SUCCESS, PWC_E_BADARG, "conv3x3_tc_f16: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)cpad, (cuuint64_t)Cout, 18};
+        cuuint64_t strides[2] = {(cuuint64_t)cpad * 2, (cuuint64_t)Cout * cpad * 2};
+        cuuint32_t box[3] = {F16_BK, (cuuint32_t)Cout, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)w_packed, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PWC_REQUIRE(r == CUDA_SUCCESS, PWC_E_BADARG, "conv3x3_tc_f16: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
+    }
+    F16Params p{};
+    p.bias = bias; p.y = y; p.y_cs = y_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dil = dilation;
+    p.OH = OH; p.OW = OW; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
+    p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.total_tiles = (int)tiles;
+    p.kchunks = cpad / F16_BK;
+    p.alpha = alpha;
+    p.b_bytes = Cout * 64;
+    p.stage_bytes = (int)(F16_A_RAW + 2 * F16_A_HALF) + 2 * p.b_bytes;
+    p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
+    // Occupancy beats pipeline depth here (measured, profiles/r01_f16_occupancy.log: 2 CTAs/SM with 2 stages each
+    // are 1.38x faster than 1 CTA with 4 stages): a CTA's prologue (descriptor fetch, first TMA latency) and
+    // epilogue (TMEM drain + stores, ~15% of its life) overlap the other CTA's main loop.  So: <= 110 KB of
+    // shared memory and <= 256 TMEM columns per CTA; short K loops (pyramid layers) get 3 CTAs per SM.
+    const int budget = 220 * 1024;
+    const int kt = 9 * p.kchunks;
+    p.stages = ((kt <= 18 ? 72 : 110) * 1024) / p.stage_bytes;
+    if (p.stages < 2) p.stages = 2;
+    if (p.stages > 4) p.stages = 4;
+    if (const char* e = getenv("PWC_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 8 && v * p.stage_bytes <= budget) p.stages = v; }
+    PWC_REQUIRE(p.stages >= 2, PWC_E_BADARG, "conv3x3_tc_f16: tile does not fit in shared memory");
+    p.prefetch = 0;   // L2 prefetch of upcoming activation boxes: measured no gain (profiles/r01_f16_prefetch.log)
+    if (const char* e = getenv("PWC_TC_PREFETCH")) p.prefetch = atoi(e);
+    p.n_main = 256 / Cout - 1;   // main accumulators the K loop rotates over (+1 correction accumulator)
+    if (p.n_main > 3) p.n_main = 3;
+    if (p.n_main < 1) p.n_main = 1;
+    if (const char* e = getenv("PWC_TC_NMAIN")) { int v = atoi(e); if (v >= 1 && v <= p.n_main) p.n_main = v; }
+    PWC_REQUIRE(p.n_main >= 1, PWC_E_BADARG, "conv3x3_tc_f16: Cout too large for the accumulator layout");
+    int cols = 32;
+    while (cols < (p.n_main + 1) * Cout) cols *= 2;
+    p.tmem_cols = cols;
+    static unsigned long long* dbg_buf = nullptr;
+    if (getenv("PWC_TC_DEBUG")) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 72 * 8 * 65536);
+        p.dbg = tiles <= 65536 ? dbg_buf : nullptr;
+    }
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("conv3x3_tc_f16: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    conv3x3_tc_f16_kernel<<<(unsigned)tiles, F16_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, p);
+    PWC_CHECK_LAUNCH("conv3x3_tc_f16_kernel");
+    if (p.dbg) {   // debugging aid only (synchronises!): print the timeline of a few CTAs
+        cudaStreamSynchronize((cudaStream_t)stream);
+        unsigned long long h[8 * 4];
+        const long long ids[4] = {0, 147, tiles / 2, tiles - 1};
+        for (int i = 0; i < 4; ++i) cudaMemcpy(h + 8 * i, p.dbg + 72 * ids[i], 64, cudaMemcpyDeviceToHost);
+        {
+            unsigned long long d[72];
+            cudaMemcpy(d, p.dbg + 72 * ids[2], 72 * 8, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[tc_f16 dbg] cta %lld per-stage (it: tma_issue full conv_done mma_start), clk from start\n", ids[2]);
+            for (int i = 0; i < 16; ++i)
+                fprintf(stderr, "   it %2d: %6llu %6llu %6llu %6llu\n", i + 8, d[8 + i] - d[0], d[24 + i] - d[0], d[40 + i] - d[0], d[56 + i] - d[0]);
+        }
+        for (int i = 0; i < 4; ++i) {
+            unsigned long long* t = h + 8 * i;
+            fprintf(stderr, "[tc_f16 dbg] cta %lld KT=%d S=%d: setup %llu | lastTMA %llu | firstConv %llu | lastMMAissue %llu | accDone %llu | epiDone %llu | end %llu (clk from start)\n",
+                    ids[i], 9 * p.kchunks, p.stages, t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0], t[6] - t[0], t[7] - t[0]);
+        }
+    }
+    return 0;
+}

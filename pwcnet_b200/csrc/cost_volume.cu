@@ -31,7 +31,10 @@ constexpr int CV_D = 2 * CV_R + 1;     // 9
 constexpr int CV_ND = CV_D * CV_D;     // 81
 static_assert(CV_ND == 81, "r=4 kernel");
 constexpr int CV_TY = 6;
-constexpr int CV_TX = 32;
+#ifndef PWC_CV_TX
+#define PWC_CV_TX 32
+#endif
+constexpr int CV_TX = PWC_CV_TX;
 constexpr int CV_SX = 8;               // strip width (pixels per thread)
 constexpr int CV_CH = 32;              // channels per chunk
 constexpr int CV_HY = CV_TY + 2 * CV_R;   // 14
@@ -42,7 +45,8 @@ constexpr int CV_F0_FLOATS = (CV_TY + 1) * CV_F0_ROW;   // +1 row: single items 
 constexpr int CV_F1_FLOATS = CV_HY * CV_F1_ROW;
 constexpr int CV_OPIX = 84;                    // smem floats per output pixel (81 padded to 16B multiple)
 constexpr int CV_OROW = CV_TX * CV_OPIX + 8;   // + 8 floats: de-phase rows across banks
-constexpr int CV_THREADS = 128;                // 4 warps = 4 strips of 8 pixels
+constexpr int CV_THREADS = 32 * (CV_TX / CV_SX);   // one warp per 8-pixel strip
+constexpr int CV_CTAS_PER_SM = CV_TX == 32 ? 2 : 4;
 constexpr int CV_ITEMS = 30;                   // (f1 row, output row pair) items per strip for TY = 6
 constexpr int CV_SMEM_BYTES = (CV_F0_FLOATS + CV_F1_FLOATS) * 4;
 constexpr int CV_TAPS_WORDS = CV_HY * CV_HX * 6;   // fused variants: per halo pixel 4 tap offsets + 2 fractions
@@ -117,7 +121,7 @@ __device__ __forceinline__ void cv_item(int item, int& r_idx, int& ya, int& n) {
 
 // WARP: 0 = f1 used as is, 1 = bilinear, 2 = nearest
 template <int WARP>
-__global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvParams p) {
+__global__ void __launch_bounds__(CV_THREADS, CV_CTAS_PER_SM) cost_volume_r4_kernel(const CvParams p) {
     extern __shared__ __align__(16) float smem[];
     float* f0s = smem;
     float* f1s = smem + CV_F0_FLOATS;
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvP
         if (c0) __syncthreads();
         // ---- stage the f0 tile
         for (int e = tid; e < CV_TY * CV_TX * (CV_CH / 4); e += CV_THREADS) {
-            const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e >> 8;
+            const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e / (CV_TX * 8);
             const int gy = y0 + py, gx = x0 + px;
             const bool ok = gy < p.H && gx < p.W && k < nch4;
             const float* src = ok ? f0b + ((size_t)gy * p.W + gx) * p.f0_cs + c0 + 4 * k : f0b;
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvP
         // ---- optional copy of the staged f0 tile into the estimator's concat slot
         if (p.f0_copy) {
             for (int e = tid; e < CV_TY * CV_TX * (CV_CH / 4); e += CV_THREADS) {
-                const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e >> 8;
+                const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e / (CV_TX * 8);
                 const int gy = y0 + py, gx = x0 + px;
                 if (gy < p.H && gx < p.W && k < nch4)
                     *reinterpret_cast<float4*>(p.f0_copy + (((size_t)b * p.H + gy) * p.W + gx) * p.f0_copy_cs + c0 + 4 * k) =
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvP
     constexpr int UNITS = 21;   // 20 float4 + 1 scalar
     for (int e = tid; e < CV_TY * CV_TX * UNITS; e += CV_THREADS) {
         const int pix = e / UNITS, u = e - pix * UNITS;
-        const int py = pix >> 5, px = pix & 31;
+        const int py = pix / CV_TX, px = pix % CV_TX;
         const int gy = y0 + py, gx = x0 + px;
         if (gy >= p.H || gx >= p.W) continue;
         const float* s = outs + py * CV_OROW + px * CV_OPIX + 4 * u;
@@ -311,6 +315,7 @@ __global__ void __launch_bounds__(CV_THREADS, 2) cost_volume_r4_kernel(const CvP
 // MEASURED (profiles/r01_cost_volume_ws_ncu.txt): 130 us vs 89 us for the 2-CTA/SM kernel above -- with a
 // single compute warp per sub-partition every LDS->FFMA latency is exposed (IPC 0.3); kept opt-in
 // (PWC_CV_WS=1) as the starting point for a two-consumer-group version.
+static_assert(true, "");
 constexpr int WS_THREADS = 256;
 constexpr int WS_STAGE_FLOATS = CV_F0_FLOATS + CV_F1_FLOATS;
 constexpr int WS_SMEM_BYTES = 2 * WS_STAGE_FLOATS * 4 + 64;
@@ -470,7 +475,7 @@ cost_volume_r4_ws_kernel(const CvParams p, const int tiles_x, const int tiles_y,
                 if (p.f0_copy) {
                     const int c0 = c * CV_CH, nch4 = min(CV_CH, p.C - c0) >> 2;
                     for (int e = stid; e < CV_TY * CV_TX * 8; e += 64) {
-                        const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e >> 8;
+                        const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e / (CV_TX * 8);
                         const int gy = y0 + py, gx = x0 + px;
                         if (gy < p.H && gx < p.W && k < nch4)
                             *reinterpret_cast<float4*>(p.f0_copy + (((size_t)b * p.H + gy) * p.W + gx) * p.f0_copy_cs + c0 + 4 * k) =
@@ -480,7 +485,7 @@ cost_volume_r4_ws_kernel(const CvParams p, const int tiles_x, const int tiles_y,
                 if (c == n_chunks - 1) {
                     const float* outs = f0s + CV_F0_FLOATS;
                     for (int pix = stid >> 1; pix < CV_TY * CV_TX; pix += 32) {   // two threads per pixel
-                        const int py = pix >> 5, px = pix & 31;
+                        const int py = pix / CV_TX, px = pix % CV_TX;
                         const int gy = y0 + py, gx = x0 + px;
                         if (gy >= p.H || gx >= p.W) continue;
                         const float* s = outs + py * CV_OROW + px * CV_OPIX;

@@ -29,8 +29,8 @@ from . import ops
 from ._abi import PwcError
 from .modules import (CONTEXT_DILATIONS, CONTEXT_FILTERS, ESTIMATOR_FILTERS, PYRAMID_FILTERS)
 
-PRECISIONS = ("fp32", "3xtf32", "tf32", "cudnn")
-DEFAULT_PRECISION = "3xtf32"
+PRECISIONS = ("fp32", "3xf16", "3xtf32", "tf32", "cudnn")
+DEFAULT_PRECISION = "3xf16"
 
 
 def _round_up(a: int, m: int) -> int:
@@ -217,6 +217,13 @@ class PWCDCNet(object):
         cin, cout = k.shape[2], k.shape[3]
         if self.precision == "cudnn":
             return self._conv_cudnn(x, k, b, out, stride, dilation, alpha, residual)
+        if self.precision == "3xf16" and stride in (1, 2) and residual is None and cout % 16 == 0 \
+                and cin >= 16 and cout <= 256 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
+            from . import ops_tc
+            if scope not in self._packed:
+                self._packed[scope] = ops_tc.pack_weights_f16(k)
+            return ops_tc.conv3x3_tc_f16(x, self._packed[scope], b, cin, cout, dilation=dilation, alpha=alpha, out=out,
+                                         stride=stride)
         if self.precision in ("3xtf32", "tf32") and stride in (1, 2) and residual is None and cout % 16 == 0 \
                 and (cin == 16 or cin >= 32) and cout <= 256 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
             return self._conv_tc(x, scope, k, b, out, dilation, alpha, stride)

@@ -39,3 +39,38 @@ def conv3x3_tc(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, alpha:
     check(lib().pwc_conv3x3_tc_fwd(x.data_ptr(), x_cs, w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(), y_cs,
                                    B, H, W, cin, cout, stride, dilation, float(alpha), n_split, _stream()), "pwc_conv3x3_tc_fwd")
     return out
+
+
+def pack_weights_f16(kernel_hwio: torch.Tensor) -> torch.Tensor:
+    """HWIO (3,3,Cin,Cout) fp32 -> packed fp16 [2][9][Cout][Cin_pad32] (h plane + scaled-residual l plane)."""
+    if kernel_hwio.dim() != 4 or kernel_hwio.shape[:2] != (3, 3) or not kernel_hwio.is_cuda \
+            or kernel_hwio.dtype != torch.float32 or not kernel_hwio.is_contiguous():
+        raise ValueError("pack_weights_f16: kernel must be a contiguous CUDA float32 HWIO (3,3,Cin,Cout) tensor")
+    cin, cout = kernel_hwio.shape[2], kernel_hwio.shape[3]
+    nbytes = lib().pwc_conv3x3_packed_bytes_f16(cin, cout)
+    out = torch.empty(nbytes // 2, dtype=torch.float16, device=kernel_hwio.device)
+    check(lib().pwc_conv3x3_pack_weights_f16(kernel_hwio.data_ptr(), out.data_ptr(), cin, cout, _stream()),
+          "pwc_conv3x3_pack_weights_f16")
+    return out
+
+
+def conv3x3_tc_f16(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, alpha: float = 1.0, out=None,
+                   stride: int = 1):
+    """3x3 SAME conv (stride 1 or 2) + bias + leaky on tcgen05 kind::f16 with the 3 x fp16 scaled-residual split."""
+    B, H, W, C, x_cs = _nhwc(x, "x")
+    if C != cin:
+        raise ValueError(f"conv3x3_tc_f16: x has {C} channels, weights expect {cin}")
+    if bias.shape != (cout,) or not bias.is_cuda or bias.dtype != torch.float32:
+        raise ValueError("conv3x3_tc_f16: bias must be CUDA float32 (Cout,)")
+    if w_packed.dtype != torch.float16 or w_packed.numel() * 2 != lib().pwc_conv3x3_packed_bytes_f16(cin, cout):
+        raise ValueError("conv3x3_tc_f16: w_packed has the wrong dtype/size for (Cin, Cout)")
+    OH, OW = -(-H // stride), -(-W // stride)
+    if out is None:
+        out = new_nhwc(B, OH, OW, cout, x.device)
+    Bo, Ho, Wo, Co, y_cs = _nhwc(out, "out")
+    if (Bo, Ho, Wo, Co) != (B, OH, OW, cout):
+        raise ValueError("conv3x3_tc_f16: out shape mismatch")
+    check(lib().pwc_conv3x3_tc_f16_fwd(x.data_ptr(), x_cs, w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(), y_cs,
+                                       B, H, W, cin, cout, stride, dilation, float(alpha), _stream()),
+          "pwc_conv3x3_tc_f16_fwd")
+    return out

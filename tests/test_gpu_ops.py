@@ -256,3 +256,31 @@ def test_conv3x3_tcgen05_writes_only_its_slot(P):
     ref = O.conv2d_same(torch.from_numpy(x), torch.from_numpy(k), torch.from_numpy(b)).numpy()
     np.testing.assert_allclose(out[..., 4:36].cpu().numpy(), ref, atol=2e-5)
     assert (out[..., :4] == 9.0).all() and (out[..., 36:] == 9.0).all()
+
+
+@pytest.mark.parametrize("case", TC_CASES + [(1, 28, 64, 34, 36, 128, 1), (2, 14, 32, 128, 128, 128, 1)])
+def test_conv3x3_tcgen05_f16x3_matches_oracle(P, case):
+    """tcgen05 kind::f16 conv with the 3 x fp16 scaled-residual split (the default path): fp32-class,
+    max-abs 2e-5 on O(1) outputs vs the oracle's fp32 conv."""
+    from pwcnet_b200 import ops_tc
+    B, H, W, Cin, cs, Cout, dil = case[:7]
+    stride = case[7] if len(case) > 7 else 1
+    buf = _rand((B, H, W, cs), 1)
+    k = _rand((3, 3, Cin, Cout), 2, scale=1.0 / np.sqrt(9 * Cin))
+    b = _rand((Cout,), 3, scale=0.1)
+    x = buf[..., :Cin]
+    ref = O.leaky_relu(O.conv2d_same(torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(k), torch.from_numpy(b), stride, dil), 0.1).numpy()
+    out = ops_tc.conv3x3_tc_f16(_cuda(buf)[..., :Cin], ops_tc.pack_weights_f16(_cuda(k)), _cuda(b), Cin, Cout, dilation=dil,
+                                alpha=0.1, stride=stride)
+    assert out.shape == ref.shape
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=2e-5, rtol=0)
+
+
+def test_conv3x3_f16x3_small_and_large_magnitudes(P):
+    """The scaled residual keeps accuracy relative to the data scale from 1e-3 to 1e2."""
+    from pwcnet_b200 import ops_tc
+    for scale in (1e-3, 1.0, 1e2):
+        x = _rand((1, 16, 32, 64), 1, scale); k = _rand((3, 3, 64, 64), 2, 1.0 / 24); b = np.zeros(64, np.float32)
+        ref = O.conv2d_same(torch.from_numpy(x), torch.from_numpy(k), torch.from_numpy(b)).numpy()
+        out = ops_tc.conv3x3_tc_f16(_cuda(x), ops_tc.pack_weights_f16(_cuda(k)), _cuda(b), 64, 64, alpha=1.0)
+        np.testing.assert_allclose(out.cpu().numpy(), ref, atol=2e-5 * scale, rtol=0)
