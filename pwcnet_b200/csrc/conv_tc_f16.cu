@@ -22,19 +22,22 @@
 
 namespace pwc {
 
-constexpr int F16_BM = 128, F16_TW = 16, F16_TH = 8, F16_BK = 32, F16_THREADS = 192;
+constexpr int F16_BM = 128, F16_TW = 16, F16_TH = 8, F16_BK = 32;
+constexpr int F16_CONV_THREADS = 256;                 // 8 converter warps (the fp32 -> fp16 hi/lo split is the
+                                                      // per-stage bottleneck with 4: ~1000 clk per 16 KB tile)
+constexpr int F16_THREADS = 64 + F16_CONV_THREADS;    // + TMA producer warp + MMA warp
 constexpr uint32_t F16_A_RAW = F16_BM * F16_BK * 4;   // 16 KB
 constexpr uint32_t F16_A_HALF = F16_BM * F16_BK * 2;  // 8 KB
 constexpr float F16_SCALE = 2048.f, F16_INV_SCALE = 1.f / 2048.f;
 
 struct F16Params {
-    const float* bias; float* y;
+    const float* bias; float* y; const uint8_t* w;
     int y_cs, B, H, W, Cin, Cout, dil;
     int OH, OW, stride, pad_t, pad_l;
     int tiles_x, tiles_y, kchunks, total_tiles;
     float alpha;
     int b_bytes;       // Cout * 64 (one fp16 weight tile)
-    int stage_bytes, stages, tmem_cols, n_main, prefetch;
+    int stage_bytes, stages, tmem_cols, n_main, prefetch, shift;
     unsigned long long* dbg;   // optional per-CTA timeline (clock64), 8 slots per CTA; nullptr in production
 };
 
@@ -47,8 +50,8 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-__global__ void __launch_bounds__(F16_THREADS, 1)
-conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const F16Params p) {
+__global__ void __launch_bounds__(F16_THREADS, 2)
+conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -57,7 +60,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
-    unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 72 : nullptr;
+    unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 80 : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[8]), bar_empty = smem_u32(&bars[16]);
     const uint32_t bar_acc = smem_u32(&bars[24]);
@@ -68,13 +71,16 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int x0 = tx * F16_TW, y0 = ty * F16_TH;
     const int KT = 9 * p.kchunks;
 
-    constexpr uint32_t off_ah = F16_A_RAW, off_al = F16_A_RAW + F16_A_HALF, off_bh = F16_A_RAW + 2 * F16_A_HALF;
+    // (p.shift: experiment knob -- start the fp16 A tiles `shift` bytes into their 512-byte swizzle atom to test that
+    //  UMMA and the converter agree on an ABSOLUTE-address swizzle; 1 KB of slack follows the A_l tile)
+    const uint32_t off_ah = F16_A_RAW + p.shift, off_al = F16_A_RAW + F16_A_HALF + p.shift;
+    constexpr uint32_t off_bh = F16_A_RAW + 2 * F16_A_HALF + 1024;
     const uint32_t off_bl = off_bh + p.b_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, 128);
+            mbar_init(bar_conv + 8 * s, F16_CONV_THREADS);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
@@ -94,7 +100,6 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         // ===================== TMA producer =====================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
             const uint32_t tx_bytes = F16_A_RAW + 2 * p.b_bytes;
             const int PF = p.prefetch;   // stages of L2 prefetch distance for the activation boxes
             for (int it = 0; it < PF && it < KT; ++it) {
@@ -117,8 +122,8 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 mbar_expect_tx(bar_full + 8 * s, tx_bytes);
                 tma_load_4d(st, &tmX, bar_full + 8 * s, kc * F16_BK, x0 * p.stride - p.pad_l + kx * p.dil,
                             y0 * p.stride - p.pad_t + ky * p.dil, b);
-                tma_load_3d(st + off_bh, &tmW, bar_full + 8 * s, kc * F16_BK, 0, tap);
-                tma_load_3d(st + off_bl, &tmW, bar_full + 8 * s, kc * F16_BK, 0, 9 + tap);
+                // [h tile | l tile] of this (tap, slice): one linear bulk copy
+                bulk_load_1d(st + off_bh, p.w + (size_t)it * 2 * p.b_bytes, 2 * p.b_bytes, bar_full + 8 * s);
             }
             if (dbg) dbg[2] = clock64();   // last TMA issued
         }
@@ -160,17 +165,18 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
     } else {
         // ===================== converter, then epilogue =====================
-        const int ct = threadIdx.x - 64;   // 0..127
+        const int ct = threadIdx.x - 64;   // 0..255
         for (int it = 0; it < KT; ++it) {
             const int s = it % S;
             const uint32_t ph = (it / S) & 1;
             mbar_wait(bar_full + 8 * s, ph);
             if (dbg && ct == 0 && it >= 8 && it < 24) dbg[24 + (it - 8)] = clock64();
+            if (dbg && ct == 0 && it == 12) dbg[72] = clock64();
             const uint8_t* stp = base_ptr + (size_t)s * p.stage_bytes;
             const float4* a = reinterpret_cast<const float4*>(stp);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int chunk = ct + 128 * i;          // physical 16-byte chunk of the raw tile
+            for (int i = 0; i < 1024 / F16_CONV_THREADS; ++i) {
+                const int chunk = ct + F16_CONV_THREADS * i;   // physical 16-byte chunk of the raw tile
                 const int m = chunk >> 3;                 // pixel row 0..127
                 const int lk = (chunk & 7) ^ (m & 7);     // logical 4-channel group (undo the 128B swizzle)
                 const float4 v = a[chunk];
@@ -179,58 +185,58 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 const __half2 l01 = __floats2half2_rn((v.x - f01.x) * F16_SCALE, (v.y - f01.y) * F16_SCALE);
                 const __half2 l23 = __floats2half2_rn((v.z - f23.x) * F16_SCALE, (v.w - f23.y) * F16_SCALE);
                 // destination in the 64-byte-row, 64B-swizzled fp16 tile: 16-byte chunk j = lk >> 1, half lk & 1
-                const uint32_t off = m * 64 + ((((lk >> 1) ^ ((m >> 1) & 3))) << 4) + ((lk & 1) << 3);
+                const uint32_t row = p.shift + m * 64;   // byte offset of the row inside the 1024-aligned tile region
+                const uint32_t off = m * 64 + ((((lk >> 1) ^ ((row >> 7) & 3))) << 4) + ((lk & 1) << 3);
                 uint2 hv, lv;
                 hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
                 lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
                 *reinterpret_cast<uint2*>(const_cast<uint8_t*>(stp) + off_ah + off) = hv;
                 *reinterpret_cast<uint2*>(const_cast<uint8_t*>(stp) + off_al + off) = lv;
             }
+            if (dbg && ct == 0 && it == 12) dbg[73] = clock64();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (dbg && ct == 0 && it == 12) dbg[74] = clock64();
             if (dbg && ct == 0 && it >= 8 && it < 24) dbg[40 + (it - 8)] = clock64();
             mbar_arrive(bar_conv + 8 * s);
+            if (dbg && ct == 0 && it == 12) dbg[75] = clock64();
         }
-        // ---- epilogue
-        mbar_wait(bar_acc, 0);
-        if (dbg && ct == 0) dbg[5] = clock64();   // accumulator complete
-        tc_fence_after();
-        const int q = warp & 3;
-        const int m = q * 32 + lane;
-        const int oy = y0 + m / F16_TW, ox = x0 + (m % F16_TW);
-        const bool valid = oy < p.OH && ox < p.OW;
-        float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs;
-        const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y);
-        for (int n0 = 0; n0 < p.Cout; n0 += 16) {
-            uint32_t r[4][16];
-            const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + n0;
+        // ---- epilogue: warps 2..5 (TMEM lane quadrant = warp % 4); the other converter warps are done
+        if (warp < 6) {
+            mbar_wait(bar_acc, 0);
+            if (dbg && ct == 0) dbg[5] = clock64();   // accumulator complete
+            tc_fence_after();
+            const int q = warp & 3;
+            const int m = q * 32 + lane;
+            const int oy = y0 + m / F16_TW, ox = x0 + (m % F16_TW);
+            const bool valid = oy < p.OH && ox < p.OW;
+            float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs;
+            const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y);
+            for (int n0 = 0; n0 < p.Cout; n0 += 16) {
+                const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + n0;
+                uint32_t r[16];
+                float acc[16];
+                // correction group first (scaled by 2^-11), then the main accumulators, main 0 last
+                tmem_ld16(tbase + p.n_main * p.Cout, r);
+                tmem_ld_wait();
 #pragma unroll
-            for (int a2 = 0; a2 < 4; ++a2)
-                if (a2 <= p.n_main) tmem_ld16(tbase + a2 * p.Cout, r[a2]);
-            tmem_ld_wait();
-            float acc[16];
+                for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]) * F16_INV_SCALE;
+                for (int a2 = p.n_main - 1; a2 >= 0; --a2) {
+                    tmem_ld16(tbase + a2 * p.Cout, r);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#pragma unroll
-            for (int a2 = 3; a2 >= 0; --a2) {
-                if (a2 == p.n_main) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[a2][j]) * F16_INV_SCALE;   // correction group
-                } else if (a2 < p.n_main) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[a2][j]);
+                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
                 }
-            }
-            if (valid) {
-                float v[16];
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = leaky(acc[j] + __ldg(p.bias + n0 + j), p.alpha);
-                if (vec) {
+                    for (int j = 0; j < 16; ++j) acc[j] = leaky(acc[j] + __ldg(p.bias + n0 + j), p.alpha);
+                    if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) yrow[n0 + j] = v[j];
+                        for (int j = 0; j < 16; ++j) yrow[n0 + j] = acc[j];
+                    }
                 }
             }
         }
@@ -245,9 +251,13 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
 }
 
-// HWIO (3,3,Cin,Cout) fp32 -> [2][9][Cout][Cin_pad] fp16: plane 0 = h, plane 1 = l (scaled residual).
+// HWIO (3,3,Cin,Cout) fp32 -> fp16 weight tiles stored as SHARED-MEMORY IMAGES: for every (tap, 32-channel slice)
+// one contiguous block [h tile | l tile], each tile Cout rows x 64 bytes with the 64-byte swizzle already applied
+// (16-byte chunk j of row n sits at chunk j ^ ((n >> 1) & 3)).  A pipeline stage then needs ONE linear
+// cp.async.bulk of 2*Cout*64 bytes instead of two tensor boxes with 64-byte rows (measured 265 vs 415 clk / 16 KB).
 __global__ void pack_weights_f16_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cin, int Cout, int Cin_pad) {
     const size_t total = (size_t)9 * Cout * Cin_pad;
+    const int kchunks = Cin_pad / F16_BK;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int c = idx % Cin_pad; size_t r = idx / Cin_pad;
         const int n = r % Cout; const int tap = r / Cout;
@@ -257,8 +267,11 @@ __global__ void pack_weights_f16_kernel(const float* __restrict__ w, __half* __r
             h = __float2half_rn(v);
             l = __float2half_rn((v - __half2float(h)) * F16_SCALE);
         }
-        out[idx] = h;
-        out[total + idx] = l;
+        const int kc = c / F16_BK, cc = c % F16_BK;
+        const size_t tile = ((size_t)(tap * kchunks + kc) * 2) * Cout * F16_BK;          // halfs
+        const size_t off = (size_t)n * F16_BK + ((((cc >> 3) ^ ((n >> 1) & 3))) << 3) + (cc & 7);
+        out[tile + off] = h;
+        out[tile + (size_t)Cout * F16_BK + off] = l;
     }
 }
 
@@ -302,7 +315,7 @@ extern "C" int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_pa
     const int tiles_x = (OW + F16_TW - 1) / F16_TW, tiles_y = (OH + F16_TH - 1) / F16_TH;
     const long long tiles = (long long)tiles_x * tiles_y * B;
     PWC_REQUIRE(tiles < (1LL << 30), PWC_E_BADARG, "conv3x3_tc_f16: too many tiles");
-    CUtensorMap tmX, tmW;
+    CUtensorMap tmX;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)x_cs * 4, (cuuint64_t)W * x_cs * 4, (cuuint64_t)H * W * x_cs * 4};
@@ -313,24 +326,16 @@ extern "C" int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_pa
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         PWC_REQUIRE(r == CUDA_SUCCESS, PWC_E_BADARG, "conv3x3_tc_f16: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
     }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)cpad, (cuuint64_t)Cout, 18};
-        cuuint64_t strides[2] = {(cuuint64_t)cpad * 2, (cuuint64_t)Cout * cpad * 2};
-        cuuint32_t box[3] = {F16_BK, (cuuint32_t)Cout, 1};
-        cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)w_packed, dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        PWC_REQUIRE(r == CUDA_SUCCESS, PWC_E_BADARG, "conv3x3_tc_f16: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
-    }
     F16Params p{};
-    p.bias = bias; p.y = y; p.y_cs = y_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dil = dilation;
+    p.bias = bias; p.y = y; p.w = (const uint8_t*)w_packed; p.y_cs = y_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dil = dilation;
     p.OH = OH; p.OW = OW; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
     p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.total_tiles = (int)tiles;
     p.kchunks = cpad / F16_BK;
     p.alpha = alpha;
     p.b_bytes = Cout * 64;
-    p.stage_bytes = (int)(F16_A_RAW + 2 * F16_A_HALF) + 2 * p.b_bytes;
+    p.stage_bytes = (int)(F16_A_RAW + 2 * F16_A_HALF) + 1024 + 2 * p.b_bytes;
+    p.shift = 0;
+    if (const char* e = getenv("PWC_TC_SHIFT")) p.shift = atoi(e) & 0x3C0;
     p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
     // Occupancy beats pipeline depth here (measured, profiles/r01_f16_occupancy.log: 2 CTAs/SM with 2 stages each
     // are 1.38x faster than 1 CTA with 4 stages): a CTA's prologue (descriptor fetch, first TMA latency) and
@@ -355,22 +360,23 @@ extern "C" int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_pa
     p.tmem_cols = cols;
     static unsigned long long* dbg_buf = nullptr;
     if (getenv("PWC_TC_DEBUG")) {
-        if (!dbg_buf) cudaMalloc(&dbg_buf, 72 * 8 * 65536);
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 80 * 8 * 65536);
         p.dbg = tiles <= 65536 ? dbg_buf : nullptr;
     }
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc_f16: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    conv3x3_tc_f16_kernel<<<(unsigned)tiles, F16_THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, p);
+    conv3x3_tc_f16_kernel<<<(unsigned)tiles, F16_THREADS, smem, (cudaStream_t)stream>>>(tmX, p);
     PWC_CHECK_LAUNCH("conv3x3_tc_f16_kernel");
     if (p.dbg) {   // debugging aid only (synchronises!): print the timeline of a few CTAs
         cudaStreamSynchronize((cudaStream_t)stream);
         unsigned long long h[8 * 4];
         const long long ids[4] = {0, 147, tiles / 2, tiles - 1};
-        for (int i = 0; i < 4; ++i) cudaMemcpy(h + 8 * i, p.dbg + 72 * ids[i], 64, cudaMemcpyDeviceToHost);
+        for (int i = 0; i < 4; ++i) cudaMemcpy(h + 8 * i, p.dbg + 80 * ids[i], 64, cudaMemcpyDeviceToHost);
         {
-            unsigned long long d[72];
-            cudaMemcpy(d, p.dbg + 72 * ids[2], 72 * 8, cudaMemcpyDeviceToHost);
+            unsigned long long d[80];
+            cudaMemcpy(d, p.dbg + 80 * ids[2], 80 * 8, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[tc_f16 dbg] converter thread 0, it 12: full->stores issued %llu clk, fence %llu clk, arrive %llu clk\n", d[73] - d[72], d[74] - d[73], d[75] - d[74]);
             fprintf(stderr, "[tc_f16 dbg] cta %lld per-stage (it: tma_issue full conv_done mma_start), clk from start\n", ids[2]);
             for (int i = 0; i < 16; ++i)
                 fprintf(stderr, "   it %2d: %6llu %6llu %6llu %6llu\n", i + 8, d[8 + i] - d[0], d[24 + i] - d[0], d[40 + i] - d[0], d[56 + i] - d[0]);
