@@ -21,7 +21,7 @@
 // of a strip fill one warp; lanes of a quarter-warp touch distinct bank groups (rows padded by 16 B).
 // Results are transposed through shared memory so the 81 channels of a pixel leave as one contiguous
 // 324-byte run.
-#include "common.cuh"
+#include "cost_volume.cuh"
 #include <cstdlib>
 
 namespace pwc {
@@ -53,14 +53,6 @@ constexpr int CV_TAPS_WORDS = CV_HY * CV_HX * 6;   // fused variants: per halo p
 constexpr int CV_SMEM_BYTES_FUSED = CV_SMEM_BYTES + CV_TAPS_WORDS * 4;
 static_assert(CV_TY * CV_OROW <= CV_F1_FLOATS, "output staging must fit in the f1 halo buffer");
 
-struct CvParams {
-    const float* f0; const float* f1; const float* flow;
-    float* out; float* f0_copy;
-    int f0_cs, f1_cs, flow_cs, out_cs, f0_copy_cs;
-    int B, H, W, C;
-    float flow_scale, alpha, inv_c;
-    int warp_type;   // 0 bilinear, 1 nearest
-};
 
 // Bilinear / nearest sample of 4 channels of f1 at pixel (y,x) displaced by the flow there.
 // Index clamping and weights follow modules.py:107-137 (clamped taps, un-clamped weights).
@@ -303,210 +295,6 @@ __global__ void __launch_bounds__(CV_THREADS, CV_CTAS_PER_SM) cost_volume_r4_ker
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Persistent, warp-specialised variant of the unfused kernel (the level-2 roofline kernel).
-//   warps 0-3 : compute  (one per SM sub-partition; the same 2 x 8 x 9 register tile as above)
-//   warps 4-5 : producers (cp.async the next tile's f0 / f1 halo into the other shared-memory buffer,
-//               completion signalled with cp.async.mbarrier.arrive)
-//   warps 6-7 : storers  (drain the transposed result tile -- staged in the consumed f1 buffer -- to
-//               global memory as contiguous 324-byte runs, copy f0 to the concat slot, free the buffer)
-// Compute warps therefore execute almost only FFMA + LDS; loads of tile i+1 and stores of tile i-1
-// overlap the arithmetic of tile i.  One CTA per SM, tiles strided over the grid.
-// MEASURED (profiles/r01_cost_volume_ws_ncu.txt): 130 us vs 89 us for the 2-CTA/SM kernel above -- with a
-// single compute warp per sub-partition every LDS->FFMA latency is exposed (IPC 0.3); kept opt-in
-// (PWC_CV_WS=1) as the starting point for a two-consumer-group version.
-static_assert(true, "");
-constexpr int WS_THREADS = 256;
-constexpr int WS_STAGE_FLOATS = CV_F0_FLOATS + CV_F1_FLOATS;
-constexpr int WS_SMEM_BYTES = 2 * WS_STAGE_FLOATS * 4 + 64;
-
-__device__ __forceinline__ void ws_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void ws_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void ws_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WS_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra WS_DONE;\n\t"
-        "bra WS_WAIT;\n\t"
-        "WS_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-
-__global__ void __launch_bounds__(WS_THREADS, 1)
-cost_volume_r4_ws_kernel(const CvParams p, const int tiles_x, const int tiles_y, const int total_tiles) {
-    extern __shared__ __align__(16) float smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * WS_STAGE_FLOATS);
-    const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(&bars[0]);    // [2]
-    const uint32_t bar_done = (uint32_t)__cvta_generic_to_shared(&bars[2]);    // [2]
-    const uint32_t bar_empty = (uint32_t)__cvta_generic_to_shared(&bars[4]);   // [2]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int b = 0; b < 2; ++b) {
-            ws_mbar_init(bar_full + 8 * b, 64);     // one cp.async-arrive per producer thread
-            ws_mbar_init(bar_done + 8 * b, 128);    // compute threads
-            ws_mbar_init(bar_empty + 8 * b, 64);    // storer threads
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int n_chunks = (p.C + CV_CH - 1) / CV_CH;
-
-    if (warp >= 4 && warp < 6) {
-        // =========================== producers ===========================
-        const int pt = tid - 128;   // 0..63
-        int st = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-            const int x0 = tx * CV_TX, y0 = ty * CV_TY;
-            const float* f0b = p.f0 + (size_t)b * p.H * p.W * p.f0_cs;
-            const float* f1b = p.f1 + (size_t)b * p.H * p.W * p.f1_cs;
-            for (int c0 = 0; c0 < p.C; c0 += CV_CH, ++st) {
-                const int buf = st & 1;
-                ws_mbar_wait(bar_empty + 8 * buf, ((st >> 1) & 1) ^ 1);
-                float* f0s = smem + buf * WS_STAGE_FLOATS;
-                float* f1s = f0s + CV_F0_FLOATS;
-                const int nch4 = min(CV_CH, p.C - c0) >> 2;
-                for (int py = 0; py < CV_TY; ++py) {
-                    const int gy = y0 + py;
-                    const float* row = f0b + (size_t)gy * p.W * p.f0_cs + c0;
-                    for (int e = pt; e < CV_TX * 8; e += 64) {
-                        const int k = e & 7, px = e >> 3, gx = x0 + px;
-                        const bool ok = gy < p.H && gx < p.W && k < nch4;
-                        cp_async16(f0s + py * CV_F0_ROW + px * CV_CH + 4 * k, ok ? row + (size_t)gx * p.f0_cs + 4 * k : f0b, ok);
-                    }
-                }
-                for (int py = 0; py < CV_HY; ++py) {
-                    const int gy = y0 + py - CV_R;
-                    const bool rowok = gy >= 0 && gy < p.H;
-                    const float* row = f1b + (size_t)(rowok ? gy : 0) * p.W * p.f1_cs + c0;
-                    for (int e = pt; e < CV_HX * 8; e += 64) {
-                        const int k = e & 7, px = e >> 3, gx = x0 + px - CV_R;
-                        const bool ok = rowok && gx >= 0 && gx < p.W && k < nch4;
-                        cp_async16(f1s + py * CV_F1_ROW + px * CV_CH + 4 * k, ok ? row + (size_t)gx * p.f1_cs + 4 * k : f1b, ok);
-                    }
-                }
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8 * buf) : "memory");
-            }
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp < 4) {
-        // =========================== compute ===========================
-        const int xs = warp;
-        int r_idx, ya, n_rows;
-        cv_item(lane < CV_ITEMS ? lane : 0, r_idx, ya, n_rows);
-        if (lane >= CV_ITEMS) n_rows = 0;
-        const int iv0 = r_idx - ya;
-        int st = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            float acc0[CV_SX][CV_D], acc1[CV_SX][CV_D];
-#pragma unroll
-            for (int i = 0; i < CV_SX; ++i)
-#pragma unroll
-                for (int j = 0; j < CV_D; ++j) { acc0[i][j] = 0.f; acc1[i][j] = 0.f; }
-            for (int c = 0; c < n_chunks; ++c, ++st) {
-                const int buf = st & 1;
-                ws_mbar_wait(bar_full + 8 * buf, (st >> 1) & 1);
-                const float* f0s = smem + buf * WS_STAGE_FLOATS;
-                const float* f1s = f0s + CV_F0_FLOATS;
-                const float* a0_base = f0s + ya * CV_F0_ROW + xs * CV_SX * CV_CH;
-                const float* a1_base = a0_base + CV_F0_ROW;
-                const float* f_base = f1s + r_idx * CV_F1_ROW + xs * CV_SX * CV_CH;
-#pragma unroll 1
-                for (int k = 0; k < CV_CH / 4; ++k) {
-                    float4 f[CV_D];
-#pragma unroll
-                    for (int q = 0; q < CV_D; ++q) f[q] = *reinterpret_cast<const float4*>(f_base + q * CV_CH + 4 * k);
-#pragma unroll
-                    for (int i = 0; i < CV_SX; ++i) {
-                        const float4 a0 = *reinterpret_cast<const float4*>(a0_base + i * CV_CH + 4 * k);
-                        const float4 a1 = *reinterpret_cast<const float4*>(a1_base + i * CV_CH + 4 * k);
-#pragma unroll
-                        for (int j = 0; j < CV_D; ++j) { const float fx = f[(i + j) % CV_D].x; acc0[i][j] = fmaf(a0.x, fx, acc0[i][j]); acc1[i][j] = fmaf(a1.x, fx, acc1[i][j]); }
-#pragma unroll
-                        for (int j = 0; j < CV_D; ++j) { const float fy = f[(i + j) % CV_D].y; acc0[i][j] = fmaf(a0.y, fy, acc0[i][j]); acc1[i][j] = fmaf(a1.y, fy, acc1[i][j]); }
-#pragma unroll
-                        for (int j = 0; j < CV_D; ++j) { const float fz = f[(i + j) % CV_D].z; acc0[i][j] = fmaf(a0.z, fz, acc0[i][j]); acc1[i][j] = fmaf(a1.z, fz, acc1[i][j]); }
-#pragma unroll
-                        for (int j = 0; j < CV_D; ++j) { const float fw = f[(i + j) % CV_D].w; acc0[i][j] = fmaf(a0.w, fw, acc0[i][j]); acc1[i][j] = fmaf(a1.w, fw, acc1[i][j]); }
-                        if (i + 1 < CV_SX)
-                            f[i % CV_D] = *reinterpret_cast<const float4*>(f_base + (i + CV_D) * CV_CH + 4 * k);
-                    }
-                }
-                if (c == n_chunks - 1) {
-                    // all four strips must be done with this buffer before it becomes the output staging tile
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    float* outs = smem + buf * WS_STAGE_FLOATS + CV_F0_FLOATS;
-                    if (n_rows >= 1) {
-#pragma unroll
-                        for (int i = 0; i < CV_SX; ++i)
-#pragma unroll
-                            for (int j = 0; j < CV_D; ++j)
-                                outs[ya * CV_OROW + (xs * CV_SX + i) * CV_OPIX + iv0 * CV_D + j] = leaky(acc0[i][j] * p.inv_c, p.alpha);
-                    }
-                    if (n_rows == 2) {
-#pragma unroll
-                        for (int i = 0; i < CV_SX; ++i)
-#pragma unroll
-                            for (int j = 0; j < CV_D; ++j)
-                                outs[(ya + 1) * CV_OROW + (xs * CV_SX + i) * CV_OPIX + (iv0 - 1) * CV_D + j] = leaky(acc1[i][j] * p.inv_c, p.alpha);
-                    }
-                }
-                ws_mbar_arrive(bar_done + 8 * buf);
-            }
-        }
-    } else {
-        // =========================== storers ===========================
-        const int stid = tid - 192;   // 0..63
-        const bool vec = ((p.out_cs & 3) == 0) && aligned16(p.out);
-        int st = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-            const int x0 = tx * CV_TX, y0 = ty * CV_TY;
-            for (int c = 0; c < n_chunks; ++c, ++st) {
-                const int buf = st & 1;
-                ws_mbar_wait(bar_done + 8 * buf, (st >> 1) & 1);
-                const float* f0s = smem + buf * WS_STAGE_FLOATS;
-                if (p.f0_copy) {
-                    const int c0 = c * CV_CH, nch4 = min(CV_CH, p.C - c0) >> 2;
-                    for (int e = stid; e < CV_TY * CV_TX * 8; e += 64) {
-                        const int k = e & 7, px = (e >> 3) & (CV_TX - 1), py = e / (CV_TX * 8);
-                        const int gy = y0 + py, gx = x0 + px;
-                        if (gy < p.H && gx < p.W && k < nch4)
-                            *reinterpret_cast<float4*>(p.f0_copy + (((size_t)b * p.H + gy) * p.W + gx) * p.f0_copy_cs + c0 + 4 * k) =
-                                *reinterpret_cast<const float4*>(f0s + py * CV_F0_ROW + px * CV_CH + 4 * k);
-                    }
-                }
-                if (c == n_chunks - 1) {
-                    const float* outs = f0s + CV_F0_FLOATS;
-                    for (int pix = stid >> 1; pix < CV_TY * CV_TX; pix += 32) {   // two threads per pixel
-                        const int py = pix / CV_TX, px = pix % CV_TX;
-                        const int gy = y0 + py, gx = x0 + px;
-                        if (gy >= p.H || gx >= p.W) continue;
-                        const float* s = outs + py * CV_OROW + px * CV_OPIX;
-                        float* g = p.out + (((size_t)b * p.H + gy) * p.W + gx) * p.out_cs;
-                        const int half = stid & 1;
-                        if (vec) {
-#pragma unroll
-                            for (int u = 0; u < 10; ++u)
-                                *reinterpret_cast<float4*>(g + 4 * (2 * u + half)) = *reinterpret_cast<const float4*>(s + 4 * (2 * u + half));
-                            if (half == 0) g[80] = s[80];
-                        } else {
-                            for (int u = half; u < 81; u += 2) g[u] = s[u];
-                        }
-                    }
-                }
-                ws_mbar_arrive(bar_empty + 8 * buf);
-            }
-        }
-    }
-}
-
 // Generic search range (reference ctor arg search_range, model.py:88): one thread per output
 // value.  Only used when search_range != 4; not tuned.
 __global__ void cost_volume_generic_kernel(const CvParams p, int r) {
@@ -557,14 +345,11 @@ static int launch_cv(CvParams p, int search_range, cudaStream_t st) {
     p.inv_c = 1.0f / (float)p.C;
     const int nd = (2 * search_range + 1) * (2 * search_range + 1);
     PWC_REQUIRE(p.out_cs >= nd, PWC_E_BADARG, "cost_volume: out_cs < (2r+1)^2");
-    if (search_range == CV_R && !p.flow && getenv("PWC_CV_WS")) {   // opt-in: measured slower (130 vs 89 us), see header
-        const int tiles_x = (p.W + CV_TX - 1) / CV_TX, tiles_y = (p.H + CV_TY - 1) / CV_TY;
-        const int total = tiles_x * tiles_y * p.B;
-        cudaError_t e = cudaFuncSetAttribute(cost_volume_r4_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("cost_volume: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-        cost_volume_r4_ws_kernel<<<total < 148 ? total : 148, WS_THREADS, WS_SMEM_BYTES, st>>>(p, tiles_x, tiles_y, total);
-        PWC_CHECK_LAUNCH("cost_volume_r4_ws_kernel");
-    } else if (search_range == CV_R) {
+    if (search_range == CV_R && !p.flow && !getenv("PWC_CV_LEGACY")) {
+        const int rc = launch_cv_tma(p, st);   // TMA-pipelined kernel; falls through when the arguments do not fit it
+        if (rc != CV_TMA_UNSUPPORTED) return rc;
+    }
+    if (search_range == CV_R) {
         dim3 grid((p.W + CV_TX - 1) / CV_TX, (p.H + CV_TY - 1) / CV_TY, p.B);
         auto kern = !p.flow ? cost_volume_r4_kernel<0> : (p.warp_type == 0 ? cost_volume_r4_kernel<1> : cost_volume_r4_kernel<2>);
         const int smem_bytes = p.flow ? CV_SMEM_BYTES_FUSED : CV_SMEM_BYTES;

@@ -28,7 +28,8 @@ def _cuda(a):
 
 # the five pyramid levels of a 448x1024 pair scaled down, plus ragged / tiny / odd shapes
 CV_SHAPES = [(2, 7, 16, 192), (1, 14, 32, 128), (1, 28, 64, 96), (1, 56, 128, 64), (1, 112, 256, 32),
-             (2, 5, 9, 16), (1, 1, 2, 32), (3, 13, 45, 36), (1, 9, 40, 4)]
+             (2, 5, 9, 16), (1, 1, 2, 32), (3, 13, 45, 36), (1, 9, 40, 4),
+             (3, 13, 45, 48), (2, 30, 70, 16), (1, 8, 33, 64), (1, 15, 100, 32)]
 
 
 @pytest.mark.parametrize("shape", CV_SHAPES)

@@ -8,12 +8,13 @@ import pwcnet_b200 as P
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 fused = len(sys.argv) > 3 and sys.argv[3] == "fused"
+slot = len(sys.argv) > 3 and sys.argv[3] == "slot"   # write into the 148-wide concat buffer of level 2, as the model does
 h, w, C = 112, 256, 32
 g = torch.Generator(device="cuda").manual_seed(0)
 f0 = torch.randn((B, h, w, C), device="cuda", generator=g)
 f1 = torch.randn((B, h, w, C), device="cuda", generator=g)
 flow = torch.randn((B, h, w, 2), device="cuda", generator=g) * 3
-cv = torch.empty((B, h, w, 81), device="cuda")
+cv = torch.empty((B, h, w, 148), device="cuda")[..., :81] if slot else torch.empty((B, h, w, 81), device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 def run():
     if fused:
@@ -32,4 +33,4 @@ for _ in range(iters):
 alg = 4 * h * w * (2 * C + 81 + (2 if fused else 0)) * B
 import statistics
 us = statistics.mean(ts)
-print(f"cost_volume level-2 B={B} fused={fused}: {us:.1f} us/launch (min {min(ts):.1f}), {alg/us/1e3:.0f} GB/s algorithmic, frac of 6550 = {alg/us/1e3/6550:.3f}")
+print(f"cost_volume level-2 B={B} fused={fused} slot={slot}: {us:.1f} us/launch (min {min(ts):.1f}), {alg/us/1e3:.0f} GB/s algorithmic, frac of 6550 = {alg/us/1e3/6550:.3f}")
