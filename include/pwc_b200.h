@@ -96,6 +96,74 @@ int pwc_lploss_level_fwd(const float* gt, int H, int W, const float* fs, int fs_
 /* losses.py:11-13 EPE: acc[0] += (1/(B*H*W)) * sum || gt - flows ||_2 */
 int pwc_epe_fwd(const float* gt, const float* flows, int B, int H, int W, float* acc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Backward pass / training step (train.py:65-92; the node groups TF-1.8 autodiff built).
+ * Gradient tensors have the shape and channel-stride conventions of the activations they belong to.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Conv2DBackpropInput of pwc_conv3x3_fwd.  H, W, Cin describe dx (the conv INPUT), dy is (B,OH,OW,Cout) with
+ * the SAME-padding output size.  new = sum_{tap,co} dy * w;  if mask != NULL new *= (mask > 0 ? 1 : mask_alpha)
+ * (LeakyReluGrad of the layer that produced the conv input; mask = that layer's output);
+ * dx = accumulate ? dx + new : new. */
+int pwc_conv3x3_dgrad(const float* dy, int dy_cs, const float* w_hwio, float* dx, int dx_cs,
+                      const float* mask, int mask_cs, float mask_alpha, int accumulate,
+                      int B, int H, int W, int Cin, int Cout, int stride, int dilation, void* stream);
+
+/* Conv2DBackpropFilter + BiasAddGrad: dw[tap, map(ci), co] += sum x * dy and db[co] += sum dy (db may be NULL).
+ * cin_map (device int32[Cin], may be NULL) maps the channel order of x (a concat buffer in internal order,
+ * DESIGN.md section 2) to the input-channel index of the reference kernel (-1 = padding channel, skipped);
+ * dw_cin = number of input channels of dw.  Accumulates with atomics: zero dw/db before the first call. */
+int pwc_conv3x3_wgrad(const float* x, int x_cs, const float* dy, int dy_cs, float* dw, float* db,
+                      const int* cin_map, int dw_cin, int B, int H, int W, int Cin, int Cout,
+                      int stride, int dilation, void* stream);
+
+/* LeakyReluGrad in place: g *= (y > 0 ? 1 : alpha), y = the activation OUTPUT (modules.py:63). */
+int pwc_leaky_bwd(float* g, int g_cs, const float* y, int y_cs, long long n_pix, int C, float alpha, void* stream);
+
+/* dst += scale * src over n_pix pixels x C channels (gradient fan-in of residual adds and concat slots). */
+int pwc_add_strided(float* dst, int dst_cs, const float* src, int src_cs, long long n_pix, int C, float scale,
+                    void* stream);
+
+/* Gradient of pwc_cost_volume_fwd (modules.py:164-204).  g = gradient w.r.t. the cost volume OUTPUT, cv = that
+ * output (for the leaky slope).  df0 += d/df0 (+ g_f0slot if not NULL: the gradient that arrived through the
+ * f0 copy in the concat buffer); df1 = d/df1 (accumulate_f1 != 0: +=). */
+int pwc_cost_volume_bwd(const float* g, int g_cs, const float* cv, int cv_cs, const float* f0, int f0_cs,
+                        const float* f1, int f1_cs, const float* g_f0slot, int gs_cs,
+                        float* df0, int df0_cs, float* df1, int df1_cs, int accumulate_f1,
+                        int B, int H, int W, int C, int search_range, float alpha, void* stream);
+
+/* Gradient of pwc_warp_fwd (modules.py:83-137): dx += scatter of the weighted taps (atomics; zero/initialise
+ * dx first); dflow (may be NULL) += flow_scale * d/d(flow*flow_scale), through the bilinear weights only. */
+int pwc_warp_bwd(const float* x, int x_cs, const float* flow, int flow_cs, float flow_scale, int warp_type,
+                 const float* g, int g_cs, float* dx, int dx_cs, float* dflow, int dflow_cs,
+                 int B, int H, int W, int C, void* stream);
+
+/* ResizeBilinearGrad of pwc_resize_bilinear_fwd: dx (B,H,W,C) += adjoint applied to g (B,OH,OW,C) * mul. */
+int pwc_resize_bilinear_bwd(const float* g, int g_cs, float* dx, int dx_cs, int B, int H, int W, int C,
+                            int OH, int OW, float mul, void* stream);
+
+/* Gradient of pwc_lploss_level_fwd w.r.t. fs: gfs (=|+=) weight/B * d||gt_s - fs||_ord / dfs. */
+int pwc_lploss_level_bwd(const float* gt, int H, int W, const float* fs, int fs_cs, int h, int w, int B,
+                         float gt_div, float weight, int ord, float* gfs, int gfs_cs, int accumulate,
+                         void* stream);
+
+/* train.py:74,89: g = grad*grad_scale + gamma*var (l2_loss regulariser); tf.train.AdamOptimizer update with
+ * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) read from the device float lr_t_dev (so a captured graph can be
+ * replayed for every step); var -= lr_t * m / (sqrt(v) + eps). */
+int pwc_adam_step(float* var, const float* grad, float* m, float* v, long long n, const float* lr_t_dev,
+                  float beta1, float beta2, float eps, float gamma, float grad_scale, void* stream);
+
+/* acc[0] += scale * sum x^2 (tf.nn.l2_loss with scale = 0.5, train.py:74). */
+int pwc_sumsq(const float* x, long long n, float scale, float* acc, void* stream);
+
+/* w_dst[tap, i, co] = perm[i] >= 0 ? w_src[tap, perm[i], co] : 0 -- internal-channel-order kernel of a concat
+ * layer from the reference-order kernel (perm: device int32[cin_dst]). */
+int pwc_permute_cin(const float* w_src, float* w_dst, const int* perm, int cin_dst, int cin_src, int cout,
+                    void* stream);
+
+/* w_rot[ky,kx,co,ci] = w[2-ky,2-kx,ci,co]: with it, pwc_conv3x3_*_fwd(dy, w_rot, stride 1) IS the dgrad. */
+int pwc_conv3x3_rot_weights(const float* w_hwio, float* w_rot, int Cin, int Cout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ _f32p = C.c_void_p
 _i = C.c_int
 _f = C.c_float
 _vp = C.c_void_p
+_ll = C.c_longlong
 
 # name -> (restype, argtypes); must list every symbol include/pwc_b200.h declares
 SIGNATURES = {
@@ -33,6 +34,19 @@ SIGNATURES = {
     "pwc_resize_bilinear_fwd": (_i, [_f32p, _i, _f32p, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "pwc_lploss_level_fwd": (_i, [_f32p, _i, _i, _f32p, _i, _i, _i, _i, _f, _f, _i, _f32p, _vp]),
     "pwc_epe_fwd": (_i, [_f32p, _f32p, _i, _i, _i, _f32p, _vp]),
+    "pwc_conv3x3_dgrad": (_i, [_f32p, _i, _f32p, _f32p, _i, _f32p, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "pwc_conv3x3_wgrad": (_i, [_f32p, _i, _f32p, _i, _f32p, _f32p, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "pwc_leaky_bwd": (_i, [_f32p, _i, _f32p, _i, _ll, _i, _f, _vp]),
+    "pwc_add_strided": (_i, [_f32p, _i, _f32p, _i, _ll, _i, _f, _vp]),
+    "pwc_cost_volume_bwd": (_i, [_f32p, _i, _f32p, _i, _f32p, _i, _f32p, _i, _f32p, _i, _f32p, _i, _f32p, _i, _i,
+                                 _i, _i, _i, _i, _i, _f, _vp]),
+    "pwc_warp_bwd": (_i, [_f32p, _i, _f32p, _i, _f, _i, _f32p, _i, _f32p, _i, _f32p, _i, _i, _i, _i, _i, _vp]),
+    "pwc_resize_bilinear_bwd": (_i, [_f32p, _i, _f32p, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "pwc_lploss_level_bwd": (_i, [_f32p, _i, _i, _f32p, _i, _i, _i, _i, _f, _f, _i, _f32p, _i, _i, _vp]),
+    "pwc_adam_step": (_i, [_f32p, _f32p, _f32p, _f32p, _ll, _f32p, _f, _f, _f, _f, _f, _vp]),
+    "pwc_sumsq": (_i, [_f32p, _ll, _f, _f32p, _vp]),
+    "pwc_permute_cin": (_i, [_f32p, _f32p, _vp, _i, _i, _i, _vp]),
+    "pwc_conv3x3_rot_weights": (_i, [_f32p, _f32p, _i, _i, _vp]),
 }
 
 _lib = None

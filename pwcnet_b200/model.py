@@ -128,19 +128,33 @@ class PWCDCNet(object):
 
     def load_weights(self, weights) -> None:
         """weights: dict name -> array in the reference's checkpoint naming, or the prefix of a TF
-        checkpoint written by the reference (e.g. '.../model_250.ckpt')."""
+        checkpoint written by the reference (e.g. '.../model_250.ckpt').
+
+        All variables live in ONE flat fp32 buffer (`self.flat`, creation order kernel, bias, kernel, ...;
+        5 029 868 floats for the default net) and `self.params[name]` are views into it, so the optimizer
+        update and the gradient all-reduce of a training step are single launches over flat buffers."""
         if isinstance(weights, str):
             from .checkpoint import load_checkpoint
             weights = load_checkpoint(weights, self.name)
-        for scope, cin, cout in self._table:
-            for sfx, shape in (("/kernel", (3, 3, cin, cout)), ("/bias", (cout,))):
-                if scope + sfx not in weights:
-                    raise KeyError(f"weights lack variable {scope + sfx}")
-                a = weights[scope + sfx]
-                t = a.detach().to(torch.float32) if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a, np.float32))
-                if tuple(t.shape) != shape:
-                    raise ValueError(f"{scope + sfx}: shape {tuple(t.shape)} != expected {shape}")
-                self.params[scope + sfx] = t.to(self.device).contiguous()
+        if not self.params:
+            shapes = []
+            for scope, cin, cout in self._table:
+                shapes += [(scope + "/kernel", (3, 3, cin, cout)), (scope + "/bias", (cout,))]
+            total = sum(int(np.prod(sh)) for _, sh in shapes)
+            self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+            off = 0
+            for name, sh in shapes:
+                n = int(np.prod(sh))
+                self.params[name] = self.flat[off:off + n].view(sh)
+                off += n
+        for name, dst in self.params.items():
+            if name not in weights:
+                raise KeyError(f"weights lack variable {name}")
+            a = weights[name]
+            t = a.detach().to(torch.float32) if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a, np.float32))
+            if tuple(t.shape) != tuple(dst.shape):
+                raise ValueError(f"{name}: shape {tuple(t.shape)} != expected {tuple(dst.shape)}")
+            dst.copy_(t)
         self._prepare()
 
     def state_dict(self) -> Dict[str, np.ndarray]:
@@ -182,33 +196,45 @@ class PWCDCNet(object):
         # context input, internal order [features stack | flows(2) | pad(2)], reference [flows, features]
         self._ctx_perm = [(-1 if r < 0 else 2 + r) for r in prev_stack_perm] + [0, 1, -1, -1]
 
-    @staticmethod
-    def _permute_kernel(k: torch.Tensor, perm: Sequence[int]) -> torch.Tensor:
-        perm_t = torch.tensor(perm, device=k.device, dtype=torch.long)
-        valid = perm_t >= 0
-        out = torch.zeros((3, 3, len(perm), k.shape[3]), dtype=k.dtype, device=k.device)
-        out[:, :, valid, :] = k[:, :, perm_t[valid], :]
-        return out.contiguous()
-
     def _prepare(self) -> None:
-        """Derive the kernels the launches use (internal channel order; packed tensor-core form)."""
-        self._k: Dict[str, torch.Tensor] = {}
+        """Derive the kernels the launches use (internal channel order; packed tensor-core form).  Derived
+        tensors are allocated once and refreshed IN PLACE, so captured CUDA graphs stay valid when the
+        weights change (every training step)."""
+        from . import ops_bwd
         n = self.name
-        for scope, cin, cout in self._table:
-            self._k[scope] = self.params[scope + "/kernel"]
-        for l, lv in enumerate(self._lv):
-            pre = 0
-            for i in range(len(ESTIMATOR_FILTERS) + 1):
-                scope = f"{n}/optflow_{l}/conv2d" + (f"_{i}" if i else "")
-                if i == 0 or self.use_dc:
-                    perm = list(range(pre)) + [(-1 if r < 0 else pre + r) for r in lv["perm"]]
-                    self._k[scope] = self._permute_kernel(self.params[scope + "/kernel"], perm)
-                if self.use_dc and i < len(ESTIMATOR_FILTERS):
-                    pre += ESTIMATOR_FILTERS[i]
-        self._k[f"{n}/context/conv2d"] = self._permute_kernel(self.params[f"{n}/context/conv2d/kernel"], self._ctx_perm)
-        self._packed: Dict[str, torch.Tensor] = {}
-        for plan in self._plans.values():
-            plan.graph = None   # weights changed -> re-capture
+        if not hasattr(self, "_k"):
+            self._k: Dict[str, torch.Tensor] = {}
+            self._packed: Dict[str, torch.Tensor] = {}
+            self._cin_perm: Dict[str, torch.Tensor] = {}     # scope -> CUDA int32 internal->reference channel map
+            for scope, cin, cout in self._table:
+                self._k[scope] = self.params[scope + "/kernel"]
+            perms = {}
+            for l, lv in enumerate(self._lv):
+                pre = 0
+                for i in range(len(ESTIMATOR_FILTERS) + 1):
+                    scope = f"{n}/optflow_{l}/conv2d" + (f"_{i}" if i else "")
+                    if i == 0 or self.use_dc:
+                        perms[scope] = list(range(pre)) + [(-1 if r < 0 else pre + r) for r in lv["perm"]]
+                    if self.use_dc and i < len(ESTIMATOR_FILTERS):
+                        pre += ESTIMATOR_FILTERS[i]
+            perms[f"{n}/context/conv2d"] = self._ctx_perm
+            for scope, perm in perms.items():
+                cout = self.params[scope + "/kernel"].shape[3]
+                self._cin_perm[scope] = torch.tensor(perm, dtype=torch.int32, device=self.device)
+                self._k[scope] = torch.zeros((3, 3, len(perm), cout), dtype=torch.float32, device=self.device)
+        for scope, perm in self._cin_perm.items():
+            ops_bwd.permute_cin(self.params[scope + "/kernel"], self._k[scope], perm)
+        from . import ops_tc
+        for key, packed in self._packed.items():
+            scope = key.split("#")[0]
+            if key.endswith("#rot"):
+                continue   # owned by the trainer
+            if packed.dtype == torch.float16:
+                ops_tc.pack_weights_f16(self._k[scope], out=packed)
+            else:
+                ops_tc.pack_weights(self._k[scope], out=packed)
+
+    refresh_derived = _prepare
 
     # ------------------------------------------------------------------ conv dispatch
     def _conv(self, x, scope, out, stride=1, dilation=1, alpha=0.1, residual=None):

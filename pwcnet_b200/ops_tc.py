@@ -7,14 +7,17 @@ from ._abi import check, lib
 from .ops import _nhwc, _stream, new_nhwc
 
 
-def pack_weights(kernel_hwio: torch.Tensor) -> torch.Tensor:
+def pack_weights(kernel_hwio: torch.Tensor, out=None) -> torch.Tensor:
     """HWIO (3,3,Cin,Cout) -> packed [2][9][Cout][Cin_pad] (tf32-exact hi plane + residual lo plane)."""
     if kernel_hwio.dim() != 4 or kernel_hwio.shape[:2] != (3, 3) or not kernel_hwio.is_cuda \
             or kernel_hwio.dtype != torch.float32 or not kernel_hwio.is_contiguous():
         raise ValueError("pack_weights: kernel must be a contiguous CUDA float32 HWIO (3,3,Cin,Cout) tensor")
     cin, cout = kernel_hwio.shape[2], kernel_hwio.shape[3]
     nbytes = lib().pwc_conv3x3_packed_bytes(cin, cout)
-    out = torch.empty(nbytes // 4, dtype=torch.float32, device=kernel_hwio.device)
+    if out is None:
+        out = torch.empty(nbytes // 4, dtype=torch.float32, device=kernel_hwio.device)
+    elif out.dtype != torch.float32 or out.numel() * 4 != nbytes or not out.is_contiguous():
+        raise ValueError("pack_weights: out has the wrong dtype/size")
     check(lib().pwc_conv3x3_pack_weights(kernel_hwio.data_ptr(), out.data_ptr(), cin, cout, _stream()),
           "pwc_conv3x3_pack_weights")
     return out
@@ -41,14 +44,17 @@ def conv3x3_tc(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, alpha:
     return out
 
 
-def pack_weights_f16(kernel_hwio: torch.Tensor) -> torch.Tensor:
+def pack_weights_f16(kernel_hwio: torch.Tensor, out=None) -> torch.Tensor:
     """HWIO (3,3,Cin,Cout) fp32 -> packed fp16 [2][9][Cout][Cin_pad32] (h plane + scaled-residual l plane)."""
     if kernel_hwio.dim() != 4 or kernel_hwio.shape[:2] != (3, 3) or not kernel_hwio.is_cuda \
             or kernel_hwio.dtype != torch.float32 or not kernel_hwio.is_contiguous():
         raise ValueError("pack_weights_f16: kernel must be a contiguous CUDA float32 HWIO (3,3,Cin,Cout) tensor")
     cin, cout = kernel_hwio.shape[2], kernel_hwio.shape[3]
     nbytes = lib().pwc_conv3x3_packed_bytes_f16(cin, cout)
-    out = torch.empty(nbytes // 2, dtype=torch.float16, device=kernel_hwio.device)
+    if out is None:
+        out = torch.empty(nbytes // 2, dtype=torch.float16, device=kernel_hwio.device)
+    elif out.dtype != torch.float16 or out.numel() * 2 != nbytes or not out.is_contiguous():
+        raise ValueError("pack_weights_f16: out has the wrong dtype/size")
     check(lib().pwc_conv3x3_pack_weights_f16(kernel_hwio.data_ptr(), out.data_ptr(), cin, cout, _stream()),
           "pwc_conv3x3_pack_weights_f16")
     return out

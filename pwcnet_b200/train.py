@@ -1,0 +1,265 @@
+"""Training step of the reference (train.py:65-92) on the B200 compute path.
+
+    trainer = Trainer(model, lr=1e-4, gamma=4e-4, weights=[0.32, 0.08, 0.02, 0.01, 0.005])
+    loss, loss_ms, epe = trainer.step(images_0, images_1, flows_gt)      # one sess.run([optimizer, loss, epe])
+
+What the reference's graph does per step, and what runs here instead:
+  * forward PWCDCNet (model.py:95-134)                    -> model's forward launches (activations stay in the plan)
+  * loss = multiscale_loss + gamma * sum_v l2_loss(v) over all 110 variables incl. biases (train.py:66-75),
+    epe = EPE(flows_gt, flows_final) (train.py:77)         -> fused loss kernels
+  * tf.gradients (37k-node backward graph)    -> `Trainer.backward`: ~190 launches of the kernels in
+    csrc/backward.cu over gradient buffers that mirror the activation buffers; no autograd
+  * data parallel: one all-reduce (sum) of the flat fp32 gradient (20.1 MB) over NCCL per step
+  * AdamOptimizer.minimize, lr = piecewise_constant(global_step, [200k,250k,300k,350k,4M], lr/2^i)
+    (train.py:82-89), global_step += 1 afterwards (train.py:91-92) -> one Adam launch over the flat buffers
+  * the derived kernels (internal channel order, packed tensor-core tiles) are refreshed in place
+
+Only `use_dc=False` (every BASELINE config and every reference checkpoint) is trainable here."""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops, ops_bwd
+from ._abi import PwcError
+from .model import PWCDCNet
+from .modules import CONTEXT_DILATIONS, CONTEXT_FILTERS, ESTIMATOR_FILTERS
+
+DEFAULT_LOSS_WEIGHTS = [0.32, 0.08, 0.02, 0.01, 0.005]          # train.py:220-222
+LR_BOUNDARIES = [200000, 250000, 300000, 350000, 4000000]       # train.py:83
+
+
+def piecewise_lr(step: int, lr: float = 1e-4, boundaries: Sequence[int] = LR_BOUNDARIES) -> float:
+    """tf.train.piecewise_constant(global_step, boundaries, [lr/2^i]) (train.py:82-85): value i applies for
+    boundaries[i-1] < step <= boundaries[i]."""
+    for i, b in enumerate(boundaries):
+        if step <= b:
+            return lr / (2 ** i)
+    return lr / (2 ** len(boundaries))
+
+
+class _Grads:
+    """Gradient buffers mirroring one forward plan (one flat allocation, zeroed once per step)."""
+    pass
+
+
+class Trainer(object):
+    def __init__(self, model: PWCDCNet, lr: float = 1e-4, gamma: float = 4e-4,
+                 weights: Sequence[float] = DEFAULT_LOSS_WEIGHTS, beta1: float = 0.9, beta2: float = 0.999,
+                 eps: float = 1e-8, lr_boundaries: Sequence[int] = LR_BOUNDARIES, process_group=None,
+                 global_step: int = 0):
+        if model.use_dc:
+            raise NotImplementedError("Trainer: use_dc=True is inference-only in this build (no reference checkpoint "
+                                      "or BASELINE config trains it)")
+        if model.fuse_warp:
+            raise PwcError("Trainer needs the warped features in memory: construct the model with fuse_warp=False")
+        if model.precision == "cudnn":
+            raise PwcError("Trainer: the cuDNN baseline arm has no backward path")
+        if len(weights) != model.output_level + 1:
+            raise ValueError(f"need {model.output_level + 1} loss weights (one per pyramid flow), got {len(weights)}")
+        self.model = model
+        self.lr, self.gamma = float(lr), float(gamma)
+        self.loss_weights = [float(w) for w in weights]
+        self.beta1, self.beta2, self.eps = float(beta1), float(beta2), float(eps)
+        self.lr_boundaries = list(lr_boundaries)
+        self.global_step = int(global_step)            # train.py:81
+        self.pg = process_group
+        dev = model.device
+        n = model.flat.numel()
+        self.grad_flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)      # <var>/Adam
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)      # <var>/Adam_1
+        self.grads: Dict[str, torch.Tensor] = {}
+        off = 0
+        for name in model.var_names:
+            t = model.params[name]
+            self.grads[name] = self.grad_flat[off:off + t.numel()].view(t.shape)
+            off += t.numel()
+        self._lr_t = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._scalars = torch.zeros(3, dtype=torch.float32, device=dev)   # multiscale loss, l2 term, epe
+        self._gbufs: Dict[tuple, _Grads] = {}
+
+    # ------------------------------------------------------------------ gradient workspace
+    def _grad_buffers(self, p) -> _Grads:
+        key = (p.B, p.H, p.W)
+        g = self._gbufs.get(key)
+        if g is not None:
+            return g
+        acts: List[torch.Tensor] = []
+        for lev in p.pyr:
+            acts += lev
+        for l in range(len(p.S)):
+            acts += [p.S[l]] + list(p.tmp[l]) + [p.flows[l]] + ([p.f1w[l]] if p.f1w[l] is not None else [])
+        acts += list(p.ctx)
+        total = sum(a.numel() for a in acts)
+        g = _Grads()
+        g.flat = torch.zeros(total, dtype=torch.float32, device=self.model.device)
+        off = 0
+        views = []
+        for a in acts:
+            views.append(g.flat[off:off + a.numel()].view(a.shape))
+            off += a.numel()
+        it = iter(views)
+        g.pyr = [[next(it) for _ in lev] for lev in p.pyr]
+        g.S, g.tmp, g.flows, g.f1w = [], [], [], []
+        for l in range(len(p.S)):
+            g.S.append(next(it))
+            g.tmp.append([next(it) for _ in p.tmp[l]])
+            g.flows.append(next(it))
+            g.f1w.append(next(it) if p.f1w[l] is not None else None)
+        g.ctx = [next(it) for _ in p.ctx]
+        self._gbufs[key] = g
+        return g
+
+    # ------------------------------------------------------------------ one layer
+    def _conv_bwd(self, scope, x, dy, gx, stride=1, dilation=1, mask=None, accumulate=False):
+        """wgrad + bias grad into the flat gradient, then dgrad into gx (skipped when gx is None)."""
+        m = self.model
+        ops_bwd.conv3x3_wgrad(x, dy, self.grads[scope + "/kernel"], self.grads[scope + "/bias"], stride=stride,
+                              dilation=dilation, cin_map=m._cin_perm.get(scope))
+        if gx is not None:
+            ops_bwd.conv3x3_dgrad(dy, m._k[scope], gx, stride=stride, dilation=dilation, mask=mask, mask_alpha=0.1,
+                                  accumulate=accumulate)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, p, flows_gt) -> None:
+        """Gradient of multiscale_loss(flows_gt, flows_pyramid) w.r.t. every variable -> self.grad_flat
+        (the regulariser's gradient gamma*var is added inside the Adam kernel)."""
+        m = self.model
+        n, B, nd, L = m.name, p.B, m._nd, m.output_level
+        nest = len(ESTIMATOR_FILTERS)
+        nf = ESTIMATOR_FILTERS[-1]
+        g = self._grad_buffers(p)
+        g.flat.zero_()
+        self.grad_flat.zero_()
+        for l in range(L + 1):
+            ops_bwd.lploss_level_bwd(flows_gt, p.flows[l], self.loss_weights[l], g.flows[l], gt_div=20.0, ord=2)
+
+        for l in range(L, -1, -1):
+            lv = m._lv[l]
+            lev = m.num_levels - 1 - l
+            S, gS = p.S[l], g.S[l]
+            feats, gfeats = p.tmp[l][-1][..., 0:nf], g.tmp[l][-1][..., 0:nf]
+            flow_slot_g = gS[..., lv["off_flow"]:lv["off_flow"] + 2] if l else None
+            head = f"{n}/optflow_{l}/conv2d_{nest}"
+            if l == L:
+                # ---- context network (modules.py:304-326): flows_out = flow_slot + conv6(...conv0([features, flows]))
+                Cbuf, gCbuf = p.tmp[l][-1], g.tmp[l][-1]            # [features nf | flows 2 | pad 2]
+                nctx = len(CONTEXT_FILTERS)
+                for i in range(nctx - 1, 0, -1):
+                    scope = f"{n}/context/conv2d_{i}"
+                    dy = g.flows[l] if i == nctx - 1 else g.ctx[i]
+                    self._conv_bwd(scope, p.ctx[i - 1], dy, g.ctx[i - 1], dilation=CONTEXT_DILATIONS[i], mask=p.ctx[i - 1])
+                ops_bwd.add_(gCbuf[..., nf:nf + 2], g.flows[l])     # residual `flows + x` (modules.py:326)
+                self._conv_bwd(f"{n}/context/conv2d", Cbuf[..., 0:nf + 4], g.ctx[0], gCbuf[..., 0:nf + 4],
+                               dilation=CONTEXT_DILATIONS[0], accumulate=True)
+                dy_head = gCbuf[..., nf:nf + 2]
+            else:
+                dy_head = g.flows[l]
+            # ---- flow head (no activation) + residual flows_up (modules.py:274-277)
+            self._conv_bwd(head, feats, dy_head, gfeats, accumulate=True)
+            if l:
+                ops_bwd.add_(flow_slot_g, dy_head)
+            ops_bwd.leaky_bwd(gfeats, feats, 0.1)
+            # ---- estimator convs (modules.py:266-270)
+            for i in range(nest - 1, 0, -1):
+                scope = f"{n}/optflow_{l}/conv2d_{i}"
+                fi = ESTIMATOR_FILTERS[i]
+                self._conv_bwd(scope, p.tmp[l][i - 1], g.tmp[l][i][..., 0:fi], g.tmp[l][i - 1], mask=p.tmp[l][i - 1])
+            self._conv_bwd(f"{n}/optflow_{l}/conv2d", S, g.tmp[l][0], gS, accumulate=True)
+            # ---- concat slots: cost volume (+ f0 copy), warp, x2 up-sampling (model.py:106-112, modules.py:262-285)
+            F, gF = p.pyr[lev][2], g.pyr[lev][2]
+            f0, f1 = F[:B], F[B:]
+            g_cv, cv = gS[..., 0:nd], S[..., 0:nd]
+            g_f0 = gS[..., lv["off_f0"]:lv["off_f0"] + lv["C"]]
+            if l == 0:
+                ops_bwd.cost_volume_bwd(g_cv, cv, f0, f1, gF[:B], gF[B:], g_f0slot=g_f0, accumulate_f1=True,
+                                        search_range=m.s_range)
+            else:
+                ops_bwd.cost_volume_bwd(g_cv, cv, f0, p.f1w[l], gF[:B], g.f1w[l], g_f0slot=g_f0, accumulate_f1=False,
+                                        search_range=m.s_range)
+                flow_up = S[..., lv["off_flow"]:lv["off_flow"] + 2]
+                ops_bwd.warp_bwd(f1, flow_up, g.f1w[l], gF[B:], dflow=flow_slot_g, flow_scale=m.scales[l],
+                                 warp_type=m.warp_type)
+                ops_bwd.resize_bilinear_bwd(flow_slot_g, g.flows[l - 1])
+                ops_bwd.resize_bilinear_bwd(gS[..., lv["off_feat"]:lv["off_feat"] + nf], g.tmp[l - 1][-1][..., 0:nf])
+
+        # ---- feature pyramid, both images as one batch of 2B (modules.py:49-71)
+        for lev in range(m.num_levels - 1, -1, -1):
+            def scope(j, lev=lev):
+                idx = 3 * lev + j
+                return f"{n}/fp_extractor/conv2d" + (f"_{idx}" if idx else "")
+            ops_bwd.leaky_bwd(g.pyr[lev][2], p.pyr[lev][2], 0.1)
+            self._conv_bwd(scope(2), p.pyr[lev][1], g.pyr[lev][2], g.pyr[lev][1], mask=p.pyr[lev][1])
+            self._conv_bwd(scope(1), p.pyr[lev][0], g.pyr[lev][1], g.pyr[lev][0], mask=p.pyr[lev][0])
+            if lev:
+                self._conv_bwd(scope(0), p.pyr[lev - 1][2], g.pyr[lev][0], g.pyr[lev - 1][2], stride=2, accumulate=True)
+            else:
+                self._conv_bwd(scope(0), p.im, g.pyr[lev][0], None, stride=2)
+
+    # ------------------------------------------------------------------ losses
+    def _losses(self, p, flows_gt) -> None:
+        s = self._scalars
+        s.zero_()
+        for w, fs in zip(self.loss_weights, p.flows):
+            ops.lploss_level(flows_gt, fs, w, s[0:1], gt_div=20.0, ord=2)     # losses.py:15-31
+        ops_bwd.sumsq(self.model.flat, s[1:2], 0.5)                           # train.py:74
+        ops.epe(flows_gt, p.flows_final, s[2:3])                              # train.py:77
+
+    # ------------------------------------------------------------------ step
+    def lr_t(self, t: int) -> float:
+        """Learning rate TF's Adam applies at its t-th update: lr(global_step) * sqrt(1-b2^t)/(1-b1^t)."""
+        lr = piecewise_lr(self.global_step, self.lr, self.lr_boundaries)
+        return lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+
+    def forward_backward(self, images_0, images_1, flows_gt):
+        m = self.model
+        i0, i1 = m._as_input(images_0, "images_0"), m._as_input(images_1, "images_1")
+        if i0.shape != i1.shape:
+            raise ValueError("images_0 and images_1 differ in shape")
+        B, H, W, C = i0.shape
+        m._check_shape(B, H, W, C)
+        gt = flows_gt if isinstance(flows_gt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(flows_gt))
+        if gt.dtype != torch.float32 or tuple(gt.shape) != (B, H, W, 2):
+            raise ValueError(f"flows_gt must be float32 (B,H,W,2) = {(B, H, W, 2)}, got {tuple(gt.shape)} {gt.dtype}")
+        gt = gt.to(m.device, non_blocking=True).contiguous()
+        p = m.plan(B, H, W)
+        p.im[:B].copy_(i0, non_blocking=True)
+        p.im[B:].copy_(i1, non_blocking=True)
+        m._launch(p)
+        self._losses(p, gt)
+        self.backward(p, gt)
+        return p
+
+    def step(self, images_0, images_1, flows_gt):
+        """One optimisation step (train.py:143-147).  Returns (loss, multiscale_loss, epe) as 0-dim CUDA tensors;
+        with a process group the three scalars are averaged over ranks like the gradient."""
+        from .parallel import allreduce_gradients
+        self.forward_backward(images_0, images_1, flows_gt)
+        world = allreduce_gradients(self.grad_flat, self._scalars, self.pg)      # the one data-path collective
+        t = self.global_step + 1
+        self._lr_t.fill_(self.lr_t(t))
+        ops_bwd.adam_step(self.model.flat, self.grad_flat, self.m, self.v, self._lr_t, self.beta1, self.beta2, self.eps,
+                          gamma=self.gamma, grad_scale=1.0 / world)
+        self.global_step += 1                                                         # train.py:91-92
+        self.model.refresh_derived()
+        s = self._scalars
+        return s[0] + self.gamma * s[1], s[0].clone(), s[2].clone()
+
+    def launches_per_step(self) -> int:
+        """Kernel launches of ours in one training step (forward + losses + backward + update)."""
+        m = self.model
+        L = m.output_level
+        n_conv = len(m._table)
+        fwd = m.launches_per_forward()
+        losses = (L + 1) + 2
+        bwd = (L + 1)                                   # loss gradients
+        bwd += 2 * n_conv - 1                           # wgrad per layer, dgrad per layer but the first
+        bwd += 1 + (L + 1) + L                          # residual adds
+        bwd += (L + 1) + m.num_levels                   # stand-alone leaky'
+        bwd += (L + 1) + 3 * L                          # cost volume, warp, 2 x resize
+        upd = 1 + len(m._cin_perm) + len(m._packed)
+        return fwd + losses + bwd + upd
