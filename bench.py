@@ -129,18 +129,162 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_oracle_train_pairs_per_s(n_steps: int, h: int, w: int, warm: int = 1):
+    """One reference training step (train.py:65-92) on the CPU oracle: forward, multiscale loss + regulariser,
+    autograd backward, TF-Adam over the 110 variables; one pair per step (bounded sample)."""
+    import torch
+    from oracle import pwc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    W0 = O.glorot_weights(2)
+    Wt = {k: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in W0.items()}
+    M = {k: np.zeros_like(v) for k, v in W0.items()}
+    V = {k: np.zeros_like(v) for k, v in W0.items()}
+    im0, im1 = O.synthetic_pair(1, h, w, 0)
+    gt = np.random.default_rng(1).normal(0, 5, (1, h, w, 2)).astype(np.float32)
+    times = []
+    for t in range(1, warm + n_steps + 1):
+        t0 = time.perf_counter()
+        total, epe, _, _ = O.training_loss(Wt, im0, im1, gt)
+        total.backward()
+        with torch.no_grad():
+            for k, v in Wt.items():
+                nv, M[k], V[k] = O.adam_step_tf(v.numpy(), v.grad.numpy(), M[k], V[k], t, O.piecewise_lr(t - 1))
+                v.copy_(torch.from_numpy(nv)); v.grad = None
+        if t > warm:
+            times.append(time.perf_counter() - t0)
+    return 1.0 / float(np.mean(times)), cores, times
+
+
+TRAIN_H, TRAIN_W = 384, 1024   # factor_crop(436x1024, 64) (test.py:13-17): the Sintel shape the reference can execute
+TRAIN_METRIC = "training image-pairs/sec at 384x1024 (Sintel shape cropped to /64)"
+
+
+def run_train_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n = max(min(args.steps, 5), 1)
+    pps, cores, times = cpu_oracle_train_pairs_per_s(n, TRAIN_H, TRAIN_W, warm=1)
+    line = {"impl": "reference", "metric": TRAIN_METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+            "warmup": 1, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "PWCDCNet training step 384x1024 (BASELINE config 5)", "sample": "each step = 1 pair"},
+            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n} training steps on one 384x1024 pair, restated reference + torch autograd on CPU"},
+            "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_train(args):
+    """BASELINE config 5: PWCNet training step, batch 8/GPU, synthetic Sintel-shape pairs + random GT flow,
+    multiscale L2 loss + regulariser, TF-Adam, NCCL all-reduce of the flat gradient at N > 1."""
+    import torch
+    import torch.distributed as dist
+    import pwcnet_b200 as P
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev); dist.barrier(); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    B, h, w = args.batch, TRAIN_H, TRAIN_W
+    precision = args.precision or P.model.DEFAULT_PRECISION
+    model = P.PWCDCNet(weights=P.glorot_init(2), precision=precision, device=dev)
+    trainer = P.Trainer(model, lr=1e-4, gamma=4e-4)
+    rng = np.random.default_rng(2000 + rank)
+    host0 = torch.from_numpy(rng.random((B, h, w, 3), dtype=np.float32)).pin_memory()
+    host1 = torch.from_numpy(rng.random((B, h, w, 3), dtype=np.float32)).pin_memory()
+    hostg = torch.from_numpy(rng.normal(0, 5, (B, h, w, 2)).astype(np.float32)).pin_memory()
+    dev0, dev1, devg = host0.to(dev), host1.to(dev), hostg.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        trainer.step(dev0, dev1, devg)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s, e in ev:
+        flush.fill_(1)
+        s.record()
+        out = trainer.step(dev0, dev1, devg)
+        e.record()
+    barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    # e2e: pinned host batch in, loss/EPE scalars back on the host, every step
+    res_host = torch.empty(3, dtype=torch.float32).pin_memory()
+    def e2e_step():
+        loss, lms, epe = trainer.step(host0, host1, hostg)
+        res_host.copy_(torch.stack([loss, lms, epe]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    total_pairs = B * world * args.steps
+    if rank == 0:
+        cpu_baseline = None
+        if not args.no_cpu_baseline:
+            pps, cores, _ = cpu_oracle_train_pairs_per_s(3, h, w)
+            cpu_baseline = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "3 training steps on one 384x1024 pair; restated reference + torch autograd on CPU"}
+        line = {"metric": TRAIN_METRIC, "value": total_pairs / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else precision + " forward, f32 backward",
+                "data": "synthetic",
+                "config": {"workload": "PWCDCNet(use_dc=False) training step (forward, multiscale L2 loss + 4e-4 l2 regulariser, "
+                                       "backward, gradient all-reduce, TF-Adam), batch=%d synthetic 384x1024 pairs + random GT "
+                                       "flow per GPU (BASELINE config 5; 436x1024 is not divisible by 64)" % B,
+                           "global_batch": B * world, "parallelism": f"dp{world} (one NCCL all-reduce of the 20.1 MB flat gradient per step)",
+                           "l2": "256 MiB write between timed iterations"},
+                "e2e": {"value": total_pairs / (e2e_ms * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": int(host0.numel() + host1.numel() + hostg.numel()) * 4, "d2h_bytes_per_step": 12,
+                        "what": "Trainer.step on pinned host images + GT flow; loss, multiscale loss and EPE copied back"},
+                "gpu_launches": args.steps * trainer.launches_per_step(), "clocks": clocks,
+                "loss": float(out[0].item()), "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer = the headline metric (default); train = BASELINE config 5")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "tf32", "cudnn"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "3xf16", "3xtf32", "tf32", "cudnn"])
     ap.add_argument("--cpu-pairs", type=int, default=20, help="pairs timed for cpu_baseline (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.mode == "train":
+        return run_train_reference(args) if args.impl == "reference" else run_train(args)
     if args.impl == "reference":
         return run_reference(args)
 

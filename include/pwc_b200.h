@@ -161,8 +161,17 @@ int pwc_sumsq(const float* x, long long n, float scale, float* acc, void* stream
 int pwc_permute_cin(const float* w_src, float* w_dst, const int* perm, int cin_dst, int cin_src, int cout,
                     void* stream);
 
-/* w_rot[ky,kx,co,ci] = w[2-ky,2-kx,ci,co]: with it, pwc_conv3x3_*_fwd(dy, w_rot, stride 1) IS the dgrad. */
-int pwc_conv3x3_rot_weights(const float* w_hwio, float* w_rot, int Cin, int Cout, void* stream);
+/* w_rot[ky,kx,co,j] = w[2-ky,2-kx,ci_begin+j,co] (j < ci_count; zero for ci_count <= j < ci_pad): with it,
+ * pwc_conv3x3_*_fwd(dy, w_rot, stride 1) IS the dgrad for input channels [ci_begin, ci_begin+ci_count). */
+int pwc_conv3x3_rot_weights(const float* w_hwio, float* w_rot, int Cin, int Cout, int ci_begin, int ci_count,
+                            int ci_pad, void* stream);
+
+/* Conv2DBackpropInput of a stride-1 conv on tcgen05 (3 x fp16 split, fp32-class): dx[..., :Cdx] (=|+=)
+ * conv(dy, w_rot) [* leaky'(mask)].  w_rot_packed = pwc_conv3x3_pack_weights_f16(pwc_conv3x3_rot_weights(w),
+ * Cin = Cdy, Cout = Cdx_pad); Cdx_pad % 16 == 0, Cdx_pad <= 256, Cdy >= 16. */
+int pwc_conv3x3_tc_f16_dgrad(const float* dy, int dy_cs, const void* w_rot_packed, float* dx, int dx_cs,
+                             const float* mask, int mask_cs, float mask_alpha, int accumulate,
+                             int B, int H, int W, int Cdy, int Cdx, int Cdx_pad, int dilation, void* stream);
 
 #ifdef __cplusplus
 }

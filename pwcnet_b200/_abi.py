@@ -46,7 +46,8 @@ SIGNATURES = {
     "pwc_adam_step": (_i, [_f32p, _f32p, _f32p, _f32p, _ll, _f32p, _f, _f, _f, _f, _f, _vp]),
     "pwc_sumsq": (_i, [_f32p, _ll, _f, _f32p, _vp]),
     "pwc_permute_cin": (_i, [_f32p, _f32p, _vp, _i, _i, _i, _vp]),
-    "pwc_conv3x3_rot_weights": (_i, [_f32p, _f32p, _i, _i, _vp]),
+    "pwc_conv3x3_rot_weights": (_i, [_f32p, _f32p, _i, _i, _i, _i, _i, _vp]),
+    "pwc_conv3x3_tc_f16_dgrad": (_i, [_f32p, _i, _f32p, _f32p, _i, _f32p, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -474,13 +474,15 @@ __global__ void permute_cin_kernel(const float* __restrict__ src, float* __restr
     }
 }
 
-// w_rot[ky,kx,co,ci] = w[2-ky,2-kx,ci,co]: the kernel with which a stride-1 SAME conv of dy gives dx.
-__global__ void rot_weights_kernel(const float* __restrict__ w, float* __restrict__ w_rot, int cin, int cout) {
-    const size_t total = (size_t)9 * cin * cout;
+// w_rot[ky,kx,co,j] = w[2-ky,2-kx,ci_begin+j,co] for j < ci_count, 0 for ci_count <= j < ci_pad: the kernel with
+// which a stride-1 SAME conv of dy gives dx[..., ci_begin : ci_begin+ci_count].
+__global__ void rot_weights_kernel(const float* __restrict__ w, float* __restrict__ w_rot, int cin, int cout,
+                                   int ci_begin, int ci_count, int ci_pad) {
+    const size_t total = (size_t)9 * ci_pad * cout;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int ci = idx % cin; const size_t r = idx / cin;
+        const int j = idx % ci_pad; const size_t r = idx / ci_pad;
         const int co = r % cout; const int tap = r / cout;
-        w_rot[idx] = __ldg(w + ((size_t)(8 - tap) * cin + ci) * cout + co);
+        w_rot[idx] = j < ci_count ? __ldg(w + ((size_t)(8 - tap) * cin + ci_begin + j) * cout + co) : 0.f;
     }
 }
 
@@ -652,9 +654,13 @@ extern "C" int pwc_permute_cin(const float* w_src, float* w_dst, const int* perm
     return 0;
 }
 
-extern "C" int pwc_conv3x3_rot_weights(const float* w_hwio, float* w_rot, int Cin, int Cout, void* stream) {
+extern "C" int pwc_conv3x3_rot_weights(const float* w_hwio, float* w_rot, int Cin, int Cout, int ci_begin, int ci_count,
+                                       int ci_pad, void* stream) {
     PWC_REQUIRE(w_hwio && w_rot && Cin > 0 && Cout > 0, PWC_E_BADARG, "rot_weights: bad arguments");
-    rot_weights_kernel<<<grid_for((size_t)9 * Cin * Cout, 256), 256, 0, (cudaStream_t)stream>>>(w_hwio, w_rot, Cin, Cout);
+    PWC_REQUIRE(ci_begin >= 0 && ci_count > 0 && ci_begin + ci_count <= Cin && ci_pad >= ci_count, PWC_E_BADARG,
+                "rot_weights: bad channel range");
+    rot_weights_kernel<<<grid_for((size_t)9 * ci_pad * Cout, 256), 256, 0, (cudaStream_t)stream>>>(w_hwio, w_rot, Cin, Cout,
+                                                                                                 ci_begin, ci_count, ci_pad);
     PWC_CHECK_LAUNCH("rot_weights_kernel");
     return 0;
 }

@@ -413,16 +413,22 @@ extern "C" int pwc_conv3x3_tc_fwd(const float* x, int x_cs, const float* w_packe
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)((tiles + cluster - 1) / cluster * cluster), 1, 1);
-    cfg.blockDim = dim3(TC_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p);
+    if (cluster == 1) {
+        // plain launch: cudaLaunchKernelEx with a cluster attribute fails under ncu while a CUDA graph is being captured
+        kern<<<(unsigned)tiles, TC_THREADS, smem, st>>>(tmX, tmW, p);
+        e = cudaGetLastError();
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)((tiles + cluster - 1) / cluster * cluster), 1, 1);
+        cfg.blockDim = dim3(TC_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p);
+    }
     if (e != cudaSuccess) { set_error("conv3x3_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     PWC_CHECK_LAUNCH("conv3x3_tc_kernel");
     return 0;

@@ -39,6 +39,10 @@ struct F16Params {
     int b_bytes;       // Cout * 64 (one fp16 weight tile)
     int stage_bytes, stages, tmem_cols, n_main, prefetch, shift;
     unsigned long long* dbg;   // optional per-CTA timeline (clock64), 8 slots per CTA; nullptr in production
+    // dgrad use (pwc_conv3x3_tc_f16_dgrad): bias may be null, stores are limited to the first cout_valid channels
+    // (Cout is the MMA N, padded to a multiple of 16), the result is multiplied by leaky'(mask) and optionally
+    // accumulated into y
+    const float* mask; int mask_cs; float mask_alpha; int accumulate; int cout_valid;
 };
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -210,7 +214,9 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
             const int oy = y0 + m / F16_TW, ox = x0 + (m % F16_TW);
             const bool valid = oy < p.OH && ox < p.OW;
             float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs;
-            const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y);
+            const float* mrow = p.mask ? p.mask + (((size_t)b * p.OH + oy) * p.OW + ox) * p.mask_cs : nullptr;
+            const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y) && ((p.cout_valid & 3) == 0) &&
+                             (!p.mask || (((p.mask_cs & 3) == 0) && aligned16(p.mask)));
             for (int n0 = 0; n0 < p.Cout; n0 += 16) {
                 const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + n0;
                 uint32_t r[16];
@@ -227,15 +233,35 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                     for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
                 }
                 if (valid) {
+                    if (p.bias) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = leaky(acc[j] + __ldg(p.bias + n0 + j), p.alpha);
+                        for (int j = 0; j < 16; ++j) acc[j] += __ldg(p.bias + n0 + j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = leaky(acc[j], p.alpha);
                     if (vec) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                        for (int j = 0; j < 16; j += 4) {
+                            if (n0 + j >= p.cout_valid) break;
+                            float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                            if (mrow) {
+                                const float4 m = ldg4(mrow + n0 + j);
+                                v.x *= m.x > 0.f ? 1.f : p.mask_alpha; v.y *= m.y > 0.f ? 1.f : p.mask_alpha;
+                                v.z *= m.z > 0.f ? 1.f : p.mask_alpha; v.w *= m.w > 0.f ? 1.f : p.mask_alpha;
+                            }
+                            float4* dst = reinterpret_cast<float4*>(yrow + n0 + j);
+                            if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                            *dst = v;
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) yrow[n0 + j] = acc[j];
+                        for (int j = 0; j < 16; ++j) {
+                            if (n0 + j >= p.cout_valid) break;
+                            float v = acc[j];
+                            if (mrow) v *= __ldg(mrow + n0 + j) > 0.f ? 1.f : p.mask_alpha;
+                            if (p.accumulate) v += yrow[n0 + j];
+                            yrow[n0 + j] = v;
+                        }
                     }
                 }
             }
@@ -293,16 +319,21 @@ extern "C" int pwc_conv3x3_pack_weights_f16(const float* w_hwio, void* w_packed,
     return 0;
 }
 
-extern "C" int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_packed, const float* bias,
-                                      float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int stride, int dilation,
-                                      float alpha, void* stream) {
+namespace pwc {
+struct F16Extra { const float* mask; int mask_cs; float mask_alpha; int accumulate; int cout_valid; };
+}
+
+static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const float* bias,
+                           float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int stride, int dilation,
+                           float alpha, const pwc::F16Extra& ex, void* stream) {
     using namespace pwc;
-    PWC_REQUIRE(x && w_packed && bias && y, PWC_E_BADARG, "conv3x3_tc_f16: null pointer");
+    PWC_REQUIRE(x && w_packed && y, PWC_E_BADARG, "conv3x3_tc_f16: null pointer");
     PWC_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && dilation >= 1, PWC_E_BADARG, "conv3x3_tc_f16: bad dims");
     PWC_REQUIRE(stride == 1 || stride == 2, PWC_E_BADARG, "conv3x3_tc_f16: stride must be 1 or 2");
     PWC_REQUIRE(Cout % 16 == 0 && Cout <= 256, PWC_E_BADARG, "conv3x3_tc_f16: Cout must be a multiple of 16, <= 256");
     PWC_REQUIRE(Cin >= 16, PWC_E_BADARG, "conv3x3_tc_f16: Cin must be >= 16");
-    PWC_REQUIRE(x_cs >= Cin && y_cs >= Cout, PWC_E_BADARG, "conv3x3_tc_f16: channel stride smaller than channel count");
+    PWC_REQUIRE(x_cs >= Cin && y_cs >= ex.cout_valid && ex.cout_valid > 0 && ex.cout_valid <= Cout, PWC_E_BADARG,
+                "conv3x3_tc_f16: channel stride smaller than channel count");
     PWC_REQUIRE(aligned16(x) && (x_cs % 4 == 0) && aligned16(w_packed), PWC_E_ALIGN,
                 "conv3x3_tc_f16: x / w_packed must be 16-byte aligned and x_cs a multiple of 4");
     EncodeTiledFn enc = get_encode();
@@ -332,6 +363,7 @@ extern "C" int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_pa
     p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.total_tiles = (int)tiles;
     p.kchunks = cpad / F16_BK;
     p.alpha = alpha;
+    p.mask = ex.mask; p.mask_cs = ex.mask_cs; p.mask_alpha = ex.mask_alpha; p.accumulate = ex.accumulate; p.cout_valid = ex.cout_valid;
     p.b_bytes = Cout * 64;
     p.stage_bytes = (int)(F16_A_RAW + 2 * F16_A_HALF) + 1024 + 2 * p.b_bytes;
     p.shift = 0;
@@ -388,4 +420,23 @@ extern "C" int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_pa
         }
     }
     return 0;
+}
+
+extern "C" int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_packed, const float* bias,
+                                      float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int stride, int dilation,
+                                      float alpha, void* stream) {
+    PWC_REQUIRE(bias, PWC_E_BADARG, "conv3x3_tc_f16: null pointer");
+    const pwc::F16Extra ex{nullptr, 0, 1.f, 0, Cout};
+    return launch_conv_f16(x, x_cs, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, stride, dilation, alpha, ex, stream);
+}
+
+// Conv2DBackpropInput of a STRIDE-1 conv on the tensor cores: a SAME conv of dy with the 180-degree-rotated,
+// transposed kernel (pwc_conv3x3_rot_weights + pwc_conv3x3_pack_weights_f16).  Cdx_pad is the MMA N (multiple
+// of 16, the rotated kernel is zero-padded to it), only the first Cdx channels are stored.
+extern "C" int pwc_conv3x3_tc_f16_dgrad(const float* dy, int dy_cs, const void* w_rot_packed, float* dx, int dx_cs,
+                                        const float* mask, int mask_cs, float mask_alpha, int accumulate,
+                                        int B, int H, int W, int Cdy, int Cdx, int Cdx_pad, int dilation, void* stream) {
+    PWC_REQUIRE(!mask || mask_cs >= Cdx, PWC_E_BADARG, "conv3x3_tc_f16_dgrad: mask channel stride smaller than Cdx");
+    const pwc::F16Extra ex{mask, mask_cs, mask_alpha, accumulate, Cdx};
+    return launch_conv_f16(dy, dy_cs, w_rot_packed, nullptr, dx, dx_cs, B, H, W, Cdy, Cdx_pad, 1, dilation, 1.f, ex, stream);
 }

@@ -20,6 +20,7 @@ legacy x2 up-sampling are epilogues or slot writes.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -99,7 +100,8 @@ class PWCDCNet(object):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.precision = precision
-        self.use_cuda_graph = use_cuda_graph
+        # PWC_NO_GRAPH=1: eager launches (ncu cannot profile the tf32 16-channel kernel as a graph node: LaunchFailed)
+        self.use_cuda_graph = use_cuda_graph and not os.environ.get("PWC_NO_GRAPH")
         self.fuse_warp = fuse_warp
         if not torch.cuda.is_available():
             raise PwcError("PWCDCNet needs a CUDA device: the compute path is sm_100a CUDA only (no CPU fallback)")

@@ -166,10 +166,37 @@ def permute_cin(w_src, w_dst, perm):
     return w_dst
 
 
-def rot_weights(w, out=None):
-    """(3,3,Cin,Cout) -> (3,3,Cout,Cin) rotated by 180 degrees: the stride-1 dgrad kernel."""
+def rot_weights(w, out=None, ci_begin: int = 0, ci_count=None, ci_pad=None):
+    """(3,3,Cin,Cout) -> (3,3,Cout,ci_pad): rotated by 180 degrees and transposed, restricted to input channels
+    [ci_begin, ci_begin+ci_count) and zero-padded to ci_pad: the stride-1 dgrad kernel for that channel range."""
     cin, cout = w.shape[2], w.shape[3]
+    ci_count = cin - ci_begin if ci_count is None else ci_count
+    ci_pad = ci_count if ci_pad is None else ci_pad
     if out is None:
-        out = torch.empty((3, 3, cout, cin), dtype=torch.float32, device=w.device)
-    check(lib().pwc_conv3x3_rot_weights(w.data_ptr(), out.data_ptr(), cin, cout, _stream()), "pwc_conv3x3_rot_weights")
+        out = torch.empty((3, 3, cout, ci_pad), dtype=torch.float32, device=w.device)
+    elif tuple(out.shape) != (3, 3, cout, ci_pad) or not out.is_contiguous():
+        raise ValueError("rot_weights: out shape mismatch")
+    check(lib().pwc_conv3x3_rot_weights(w.data_ptr(), out.data_ptr(), cin, cout, ci_begin, ci_count, ci_pad, _stream()),
+          "pwc_conv3x3_rot_weights")
     return out
+
+
+def conv3x3_tc_f16_dgrad(dy, w_rot_packed, dx, cdx_pad: int, dilation: int = 1, mask=None, mask_alpha: float = 0.1,
+                         accumulate: bool = False):
+    """Stride-1 dgrad on tcgen05: dx (=|+=) conv(dy, w_rot) [* leaky'(mask)]; w_rot_packed from
+    ops_tc.pack_weights_f16(rot_weights(kernel, ci_pad=cdx_pad))."""
+    B, H, W, Cdx, dx_cs = _nhwc(dx, "dx")
+    Bo, OH, OW, Cdy, dy_cs = _nhwc(dy, "dy")
+    if (Bo, OH, OW) != (B, H, W):
+        raise ValueError("conv3x3_tc_f16_dgrad: stride-1 only, dy and dx must have the same spatial shape")
+    if w_rot_packed.dtype != torch.float16 or w_rot_packed.numel() * 2 != lib().pwc_conv3x3_packed_bytes_f16(Cdy, cdx_pad):
+        raise ValueError("conv3x3_tc_f16_dgrad: w_rot_packed has the wrong dtype/size")
+    m_cs = 0
+    if mask is not None:
+        Bm, Hm, Wm, Cm, m_cs = _nhwc(mask, "mask")
+        if (Bm, Hm, Wm, Cm) != (B, H, W, Cdx):
+            raise ValueError("conv3x3_tc_f16_dgrad: mask shape mismatch")
+    check(lib().pwc_conv3x3_tc_f16_dgrad(dy.data_ptr(), dy_cs, w_rot_packed.data_ptr(), dx.data_ptr(), dx_cs, _ptr(mask), m_cs,
+                                         float(mask_alpha), int(accumulate), B, H, W, Cdy, Cdx, cdx_pad, dilation, _stream()),
+          "pwc_conv3x3_tc_f16_dgrad")
+    return dx

@@ -50,7 +50,7 @@ class Trainer(object):
     def __init__(self, model: PWCDCNet, lr: float = 1e-4, gamma: float = 4e-4,
                  weights: Sequence[float] = DEFAULT_LOSS_WEIGHTS, beta1: float = 0.9, beta2: float = 0.999,
                  eps: float = 1e-8, lr_boundaries: Sequence[int] = LR_BOUNDARIES, process_group=None,
-                 global_step: int = 0):
+                 global_step: int = 0, tc_dgrad: Optional[bool] = None):
         if model.use_dc:
             raise NotImplementedError("Trainer: use_dc=True is inference-only in this build (no reference checkpoint "
                                       "or BASELINE config trains it)")
@@ -81,6 +81,8 @@ class Trainer(object):
         self._lr_t = torch.zeros(1, dtype=torch.float32, device=dev)
         self._scalars = torch.zeros(3, dtype=torch.float32, device=dev)   # multiscale loss, l2 term, epe
         self._gbufs: Dict[tuple, _Grads] = {}
+        self._parts: Dict[str, list] = {}
+        self.tc_dgrad = model.precision == "3xf16" if tc_dgrad is None else bool(tc_dgrad)
 
     # ------------------------------------------------------------------ gradient workspace
     def _grad_buffers(self, p) -> _Grads:
@@ -120,9 +122,40 @@ class Trainer(object):
         m = self.model
         ops_bwd.conv3x3_wgrad(x, dy, self.grads[scope + "/kernel"], self.grads[scope + "/bias"], stride=stride,
                               dilation=dilation, cin_map=m._cin_perm.get(scope))
-        if gx is not None:
-            ops_bwd.conv3x3_dgrad(dy, m._k[scope], gx, stride=stride, dilation=dilation, mask=mask, mask_alpha=0.1,
+        if gx is None:
+            return
+        k = m._k[scope]
+        if self.tc_dgrad and stride == 1 and k.shape[3] >= 16 and dy.stride(2) % 4 == 0 and dy.data_ptr() % 16 == 0:
+            # stride-1 dgrad == SAME conv of dy with the rotated kernel: runs on the tcgen05 forward kernel
+            # (3 x fp16 split, fp32-class).  dx channel ranges wider than 256 / not a multiple of 16 are split / padded.
+            from . import ops_tc
+            for c0, cnt, pad, rot, packed in self._dgrad_parts(scope):
+                ops_bwd.rot_weights(k, out=rot, ci_begin=c0, ci_count=cnt, ci_pad=pad)
+                ops_tc.pack_weights_f16(rot, out=packed)
+                ops_bwd.conv3x3_tc_f16_dgrad(dy, packed, gx[..., c0:c0 + cnt], pad, dilation=dilation,
+                                             mask=None if mask is None else mask[..., c0:c0 + cnt], mask_alpha=0.1,
+                                             accumulate=accumulate)
+        else:
+            ops_bwd.conv3x3_dgrad(dy, k, gx, stride=stride, dilation=dilation, mask=mask, mask_alpha=0.1,
                                   accumulate=accumulate)
+
+    def _dgrad_parts(self, scope):
+        parts = self._parts.get(scope)
+        if parts is None:
+            from ._abi import lib
+            k = self.model._k[scope]
+            cdx, cdy = k.shape[2], k.shape[3]
+            n_parts = -(-cdx // 256)
+            size = (-(-cdx // n_parts) + 15) // 16 * 16
+            parts = []
+            for c0 in range(0, cdx, size):
+                cnt = min(size, cdx - c0)
+                pad = (cnt + 15) // 16 * 16
+                rot = torch.empty((3, 3, cdy, pad), dtype=torch.float32, device=k.device)
+                packed = torch.empty(lib().pwc_conv3x3_packed_bytes_f16(cdy, pad) // 2, dtype=torch.float16, device=k.device)
+                parts.append((c0, cnt, pad, rot, packed))
+            self._parts[scope] = parts
+        return parts
 
     # ------------------------------------------------------------------ backward
     def backward(self, p, flows_gt) -> None:

@@ -123,6 +123,36 @@ def test_rot_weights_turns_forward_conv_into_dgrad(P):
     assert krot.shape == (3, 3, Cout, Cin)
     via_fwd = P.ops.conv3x3(_cuda(dy), krot, torch.zeros(Cin, device="cuda"), dilation=d, alpha=1.0)
     _close(via_fwd, dx, name="rot")
+    part = ops_bwd.rot_weights(_cuda(k), ci_begin=8, ci_count=20, ci_pad=32)
+    assert torch.equal(part[..., :20], krot[..., 8:28]) and float(part[..., 20:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("case", [(2, 9, 13, 32, 32, 1), (1, 11, 18, 36, 128, 2), (1, 20, 40, 96, 64, 8), (1, 10, 12, 148, 128, 1),
+                                  (1, 7, 16, 276, 128, 1), (2, 16, 16, 16, 16, 1), (1, 12, 20, 128, 96, 16)])
+def test_tc_dgrad_matches_cuda_core_dgrad(P, case):
+    """Stride-1 dgrad on tcgen05 (rotated kernel, 3 x fp16 split) vs the exact fp32 dgrad kernel: channel counts
+    that are not multiples of 16, wider than 256 (split in parts), leaky mask, accumulation, slot views."""
+    from pwcnet_b200 import ops_bwd, ops_tc
+    B, H, W, Cdx, Cdy, d = case
+    k = _cuda(_rand((3, 3, Cdx, Cdy), 2, 0.1))
+    dy = _cuda(_rand((B, H, W, Cdy), 4))
+    mask = _cuda(_rand((B, H, W, Cdx), 5))
+    prev = _rand((B, H, W, Cdx), 6)
+    ref = _cuda(prev)
+    ops_bwd.conv3x3_dgrad(dy, k, ref, dilation=d, mask=mask, accumulate=True)
+    buf = torch.zeros((B, H, W, Cdx + 8), device="cuda")
+    got = buf[..., 4:4 + Cdx]
+    got.copy_(_cuda(prev))
+    n_parts = -(-Cdx // 256)
+    size = (-(-Cdx // n_parts) + 15) // 16 * 16
+    for c0 in range(0, Cdx, size):
+        cnt = min(size, Cdx - c0)
+        pad = (cnt + 15) // 16 * 16
+        packed = ops_tc.pack_weights_f16(ops_bwd.rot_weights(k, ci_begin=c0, ci_count=cnt, ci_pad=pad))
+        ops_bwd.conv3x3_tc_f16_dgrad(dy, packed, got[..., c0:c0 + cnt], pad, dilation=d, mask=mask[..., c0:c0 + cnt],
+                                     accumulate=True)
+    _close(got, ref, rel=2e-5, name="tc dgrad")
+    assert float(buf[..., :4].abs().max()) == 0 and float(buf[..., 4 + Cdx:].abs().max()) == 0
 
 
 @pytest.mark.parametrize("shape", [(2, 7, 16, 192), (1, 14, 32, 128), (1, 28, 64, 32), (2, 5, 9, 16), (1, 1, 2, 32), (1, 13, 21, 36)])
@@ -235,7 +265,7 @@ def _oracle_grads(W, im0, im1, gt, gamma=0.0):
     return float(total), float(epe), {k: v.grad.numpy() for k, v in Wt.items()}
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xf16"])
+@pytest.mark.parametrize("precision", ["fp32", "3xf16"])   # 3xf16: tcgen05 forward AND stride-1 dgrad
 def test_network_gradients_match_oracle_autograd(P, precision):
     """All 110 gradient tensors of the multiscale loss at 64x128 with 'hot' weights (flows of several pixels, so
     the warp's flow gradient, border clamping and the three flow routes between levels are all live)."""
