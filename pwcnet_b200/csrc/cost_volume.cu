@@ -346,7 +346,15 @@ static int launch_cv(CvParams p, int search_range, cudaStream_t st) {
     const int nd = (2 * search_range + 1) * (2 * search_range + 1);
     PWC_REQUIRE(p.out_cs >= nd, PWC_E_BADARG, "cost_volume: out_cs < (2r+1)^2");
     if (search_range == CV_R && !p.flow && !getenv("PWC_CV_LEGACY")) {
-        const int rc = launch_cv_tma(p, st);   // TMA-pipelined kernel; falls through when the arguments do not fit it
+        // PWC_CV_KERNEL=tc selects the tcgen05 band-GEMM kernel (cost_volume_tc.cu, C % 32 == 0): parity-green but
+        // measured slower than the TMA-pipelined CUDA-core kernel (77-109 vs 57 us at level 2, B = 8) because it is
+        // bound by shared-memory bandwidth; default = tma.  Each falls through when it does not fit.
+        const char* sel = getenv("PWC_CV_KERNEL");
+        if (sel && sel[0] == 't' && sel[1] == 'c') {
+            const int rc = launch_cv_tc(p, st);
+            if (rc != CV_TMA_UNSUPPORTED) return rc;
+        }
+        const int rc = launch_cv_tma(p, st);
         if (rc != CV_TMA_UNSUPPORTED) return rc;
     }
     if (search_range == CV_R) {

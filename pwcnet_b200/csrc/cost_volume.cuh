@@ -17,5 +17,7 @@ struct CvParams {
 // CV_TMA_UNSUPPORTED when the arguments need the generic kernels of cost_volume.cu.
 constexpr int CV_TMA_UNSUPPORTED = -1000;
 int launch_cv_tma(const CvParams& p, cudaStream_t st);
+// tcgen05 band-GEMM r = 4 kernel (cost_volume_tc.cu), same contract.
+int launch_cv_tc(const CvParams& p, cudaStream_t st);
 
 }  // namespace pwc

@@ -41,6 +41,27 @@ def test_cost_volume_matches_oracle(P, shape):
     np.testing.assert_allclose(out, ref, atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("shape", [(2, 7, 16, 192), (1, 28, 64, 96), (1, 112, 256, 32), (3, 13, 45, 64), (1, 9, 17, 32), (2, 30, 70, 32)])
+@pytest.mark.parametrize("slot", [False, True])
+def test_cost_volume_tcgen05_variant_matches_oracle(P, shape, slot, monkeypatch):
+    """The opt-in tensor-core band-GEMM kernel (PWC_CV_KERNEL=tc, 3 x fp16 split, fp32-class): dense output and
+    the 81-channel slot of a wider concat buffer with the f0 copy, ragged tiles, all five level widths."""
+    import os
+    monkeypatch.setenv("PWC_CV_KERNEL", "tc")
+    os.environ["PWC_CV_KERNEL"] = "tc"
+    f0, f1 = _rand(shape, 1), _rand(shape, 2)
+    ref = O.cost_volume(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy()
+    B, H, W, C = shape
+    if slot:
+        buf = torch.full((B, H, W, 84 + C), 7.0, device="cuda")
+        out = P.ops.cost_volume(_cuda(f0), _cuda(f1), 4, out=buf[..., :81], f0_copy=buf[..., 84:84 + C])
+        np.testing.assert_array_equal(buf[..., 84:].cpu().numpy(), f0)
+        assert float((buf[..., 81:84] - 7.0).abs().max()) == 0
+    else:
+        out = P.ops.cost_volume(_cuda(f0), _cuda(f1), 4)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
+
+
 def test_cost_volume_all_81_displacements_at_corners(P):
     """Adversarial: impulses in the four corners; every displacement channel must pick exactly the
     reference's (v outer, h inner) neighbour and zero-pad outside the image."""
