@@ -282,6 +282,50 @@ class Trainer(object):
         s = self._scalars
         return s[0] + self.gamma * s[1], s[0].clone(), s[2].clone()
 
+    # ------------------------------------------------------------------ checkpoints (train.py:95-99,166)
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        """Everything tf.train.Saver stores for the reference's training graph, under the same names: the 110
+        variables, their Adam slots `<var>/Adam` (m) and `<var>/Adam_1` (v), `Variable` (global_step, int32),
+        `beta1_power`, `beta2_power`."""
+        m = self.model
+        sd = m.state_dict()
+        off = 0
+        mh, vh = self.m.cpu().numpy(), self.v.cpu().numpy()
+        for name in m.var_names:
+            t = m.params[name]
+            n = t.numel()
+            sd[name + "/Adam"] = mh[off:off + n].reshape(tuple(t.shape)).copy()
+            sd[name + "/Adam_1"] = vh[off:off + n].reshape(tuple(t.shape)).copy()
+            off += n
+        sd["Variable"] = np.array(self.global_step, np.int32)
+        sd["beta1_power"] = np.array(self.beta1 ** (self.global_step + 1), np.float32)   # TF stores beta^(t+1) after t updates
+        sd["beta2_power"] = np.array(self.beta2 ** (self.global_step + 1), np.float32)
+        return sd
+
+    def load_state_dict(self, sd) -> None:
+        """Inverse of state_dict(); `sd` may also be the prefix of a checkpoint written by the reference's
+        tf.train.Saver (e.g. 'model_250.ckpt'): weights, Adam moments and global_step are resumed."""
+        if isinstance(sd, str):
+            from .checkpoint import load_checkpoint, read_scalar
+            prefix = sd
+            sd = load_checkpoint(prefix, self.model.name, include_slots=True)
+            sd["Variable"] = read_scalar(prefix, "Variable")
+        m = self.model
+        m.load_weights({k: sd[k] for k in m.var_names})
+        off = 0
+        for name in m.var_names:
+            n = m.params[name].numel()
+            for buf, sfx in ((self.m, "/Adam"), (self.v, "/Adam_1")):
+                if name + sfx in sd:
+                    buf[off:off + n].copy_(torch.from_numpy(np.ascontiguousarray(sd[name + sfx], np.float32)).reshape(-1))
+            off += n
+        if "Variable" in sd:
+            self.global_step = int(np.asarray(sd["Variable"]).reshape(-1)[0])
+
+    def save(self, path: str) -> None:
+        """Per-epoch checkpoint (train.py:164-166) as a .npz with the reference's variable names."""
+        np.savez(path, **self.state_dict())
+
     def launches_per_step(self) -> int:
         """Kernel launches of ours in one training step (forward + losses + backward + update)."""
         m = self.model
