@@ -321,6 +321,10 @@ extern "C" int pwc_conv3x3_pack_weights_f16(const float* w_hwio, void* w_packed,
 
 namespace pwc {
 struct F16Extra { const float* mask; int mask_cs; float mask_alpha; int accumulate; int cout_valid; };
+// conv_tc_halo.cu: halo-resident variant for stride 1, dilation 1, wide rows, Cout <= 128
+int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
+                     int B, int H, int W, int Cin, int Cout, float alpha, const float* mask, int mask_cs,
+                     float mask_alpha, int accumulate, int cout_valid, cudaStream_t st);
 }
 
 static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const float* bias,
@@ -338,6 +342,17 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
                 "conv3x3_tc_f16: x / w_packed must be 16-byte aligned and x_cs a multiple of 4");
     EncodeTiledFn enc = get_encode();
     PWC_REQUIRE(enc != nullptr, PWC_E_NOTBUILT, "conv3x3_tc_f16: cuTensorMapEncodeTiled not available from the driver");
+    {
+        // halo-resident kernel (conv_tc_halo.cu): one 3 x 130 pixel box per 32-channel slice instead of nine shifted
+        // tiles; rows of at least 96 pixels keep its 128-pixel row tiles mostly full.  PWC_CONV_HALO=0 disables it.
+        const char* he = getenv("PWC_CONV_HALO");
+        const int halo_on = he ? atoi(he) : 1;
+        if (halo_on && stride == 1 && dilation == 1 && W >= 96 && Cout <= 128) {
+            const int rc = launch_conv_halo(x, x_cs, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, alpha, ex.mask, ex.mask_cs,
+                                            ex.mask_alpha, ex.accumulate, ex.cout_valid, (cudaStream_t)stream);
+            if (rc != -1000) return rc;
+        }
+    }
 
     const int cpad = f16_cin_pad(Cin);
     const int OH = (H + stride - 1) / stride, OW = (W + stride - 1) / stride;

@@ -1,0 +1,344 @@
+// 3x3 stride-1 dilation-1 convolution on tcgen05 with a HALO-RESIDENT activation tile (3 x fp16 split, fp32-class).
+//
+// Same function and numerics as conv_tc_f16.cu (tf.layers.Conv2D(filters,(3,3),1,'same') + bias + leaky,
+// modules.py:62-67, 266-274, 306-323; also Conv2DBackpropInput through pwc_conv3x3_tc_f16_dgrad), other data flow.
+// conv_tc_f16.cu streams nine shifted copies of every activation tile through TMA and the fp32->fp16 converter;
+// measured, it moves ~86 B/clk/SM through shared memory and is bound by exactly that (tensor pipe ~45 % busy).  Here
+//   * a tile is 128 consecutive pixels of ONE image row; per 32-channel slice the producer loads the 3 x 130 pixel
+//     halo box once (TMA, 128B swizzle, out-of-bounds zero fill = SAME padding), and the converter warps split each
+//     pixel row (128 B of fp32) IN PLACE into [h: 32 x fp16 | l: 32 x fp16 scaled by 2^11] -- 390 rows instead of
+//     9 x 128;
+//   * the A operand of tap (ky, kx) is the same shared-memory tile read through a descriptor whose start address
+//     is shifted by (ky*130 + kx) pixel rows (the swizzle is a function of the absolute shared-memory address);
+//   * with Cout <= 128 the [W_h | W_l] weight tiles of a tap form ONE N = 2*Cout operand: A_h x [W_h|W_l] yields the
+//     main and the first correction accumulator in one instruction (A_h is read once instead of twice), A_l x W_h
+//     accumulates into the correction columns: 2 MMAs and 20 KB of operand reads per K = 16 step instead of 3 / 24 KB;
+//   * the CTA is persistent with two accumulator sets in TMEM, so the epilogue of tile i overlaps the MMAs of
+//     tile i + 1; weights stream through their own 4-deep ring from the packed images of pwc_conv3x3_pack_weights_f16.
+// Shared-memory traffic per 32-channel slice of a tile drops from ~1008 KB to ~650 KB.
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+#include <cstdlib>
+
+namespace pwc {
+
+constexpr int HL_M = 128;                          // output pixels per tile (one row segment)
+constexpr int HL_BW = HL_M + 2, HL_BH = 3;         // halo box
+constexpr int HL_ROWS = HL_BW * HL_BH;             // 390 pixel rows of 128 bytes
+constexpr int HL_BK = 32;
+constexpr uint32_t HL_ACT_TX = HL_ROWS * 128;      // 49920 bytes per TMA box
+constexpr uint32_t HL_ACT_STAGE = 49 * 1024;       // 50176
+constexpr int HL_ACT_STAGES = 2, HL_W_STAGES = 4;
+constexpr int HL_CONV_THREADS = 256;
+constexpr int HL_THREADS = 64 + 128 + HL_CONV_THREADS + 32;   // act TMA, MMA, 4 epilogue, 8 converter, weight producer
+constexpr float HL_SCALE = 2048.f, HL_INV_SCALE = 1.f / 2048.f;
+
+struct HaloParams {
+    const float* bias; float* y; const uint8_t* w;
+    const float* mask;
+    int y_cs, mask_cs, B, H, W, Cin, Cout, cout_valid;
+    int tiles_x, total_tiles, kchunks;
+    int b_bytes;          // Cout * 64: one fp16 weight tile (h or l) of a (tap, slice)
+    int w_stage_bytes;    // 2 * b_bytes rounded up to 1024
+    int accumulate, desc_mode;
+    float alpha, mask_alpha;
+};
+
+__device__ __forceinline__ void hl_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    // barriers: act_full[2], act_conv[2], act_empty[2], w_full[4], w_empty[4], acc_full[2], acc_empty[2]
+    __shared__ __align__(8) uint64_t bars[3 * HL_ACT_STAGES + 2 * HL_W_STAGES + 4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aconv = smem_u32(&bars[2]), bar_aempty = smem_u32(&bars[4]);
+    const uint32_t bar_wfull = smem_u32(&bars[6]), bar_wempty = smem_u32(&bars[10]);
+    const uint32_t bar_accf = smem_u32(&bars[14]), bar_acce = smem_u32(&bars[16]);
+    const uint32_t w_base = base + HL_ACT_STAGES * HL_ACT_STAGE;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HL_ACT_STAGES; ++s) {
+            mbar_init(bar_afull + 8 * s, 1);
+            mbar_init(bar_aconv + 8 * s, HL_CONV_THREADS);
+            mbar_init(bar_aempty + 8 * s, 1);
+        }
+        for (int s = 0; s < HL_W_STAGES; ++s) {
+            mbar_init(bar_wfull + 8 * s, 1);
+            mbar_init(bar_wempty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_accf + 8 * a, 1);
+            mbar_init(bar_acce + 8 * a, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+    const int KC = p.kchunks;
+    const int tiles_per_img = p.tiles_x * p.H;
+
+    if (warp == 0) {
+        // ===================== activation producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+            int it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+                const int y = r / p.tiles_x, x0 = (r - y * p.tiles_x) * HL_M;
+                for (int c = 0; c < KC; ++c, ++it) {
+                    const int s = it & 1;
+                    mbar_wait(bar_aempty + 8 * s, ((it >> 1) & 1) ^ 1);
+                    mbar_expect_tx(bar_afull + 8 * s, HL_ACT_TX);
+                    tma_load_4d(base + s * HL_ACT_STAGE, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - 1, y - 1, b);
+                }
+            }
+        }
+    } else if (warp == 14) {
+        // ===================== weight producer: [W_h | W_l] image of every (slice, tap), one bulk copy each =====================
+        if (lane == 0) {
+            int wt = 0;
+            const uint32_t bytes = 2 * p.b_bytes;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                for (int c = 0; c < KC; ++c) {
+                    for (int tap = 0; tap < 9; ++tap, ++wt) {
+                        const int s = wt & (HL_W_STAGES - 1);
+                        mbar_wait(bar_wempty + 8 * s, ((wt / HL_W_STAGES) & 1) ^ 1);
+                        mbar_expect_tx(bar_wfull + 8 * s, bytes);
+                        bulk_load_1d(w_base + s * p.w_stage_bytes, p.w + (size_t)(tap * KC + c) * bytes, bytes, bar_wfull + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const bool wide = p.Cout <= 128;   // [W_h | W_l] as one N = 2*Cout operand
+            const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
+            const uint32_t idesc_w = (1u << 4) | ((uint32_t)((2 * p.Cout) >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
+            // A: K-major rows of 128 bytes ([h | l]), 128B swizzle, 8-row groups 1024 bytes apart
+            const uint64_t adesc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            // B: K-major rows of 64 bytes, 64B swizzle, 8-row groups 512 bytes apart
+            const uint64_t bdesc_hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+            int it = 0, wt = 0, tcount = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+                const int a = tcount & 1, u = tcount >> 1;
+                if (u > 0) {                       // the epilogue has drained this accumulator set
+                    mbar_wait(bar_acce + 8 * a, (u - 1) & 1);
+                    tc_fence_after();
+                }
+                const uint32_t d_main = tmem_acc + a * 256, d_corr = d_main + p.Cout;
+                for (int c = 0; c < KC; ++c, ++it) {
+                    const int s = it & 1;
+                    mbar_wait(bar_aconv + 8 * s, (it >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t ast = base + s * HL_ACT_STAGE;
+                    for (int tap = 0; tap < 9; ++tap, ++wt) {
+                        const int ws = wt & (HL_W_STAGES - 1);
+                        mbar_wait(bar_wfull + 8 * ws, (wt / HL_W_STAGES) & 1);
+                        tc_fence_after();
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const uint32_t aaddr = ast + (uint32_t)(ky * HL_BW + kx) * 128;
+                        uint64_t ad = adesc_hi | (uint64_t)(((aaddr >> 4) & 0x3FFF) | (1u << 16));
+                        if (p.desc_mode == 1) ad |= (uint64_t)((aaddr >> 7) & 7) << 49;   // matrix base offset
+                        const uint32_t wst = w_base + ws * p.w_stage_bytes;
+                        const uint64_t bh = bdesc_hi | (uint64_t)(((wst >> 4) & 0x3FFF) | (1u << 16));
+                        const uint64_t bl = bdesc_hi | (uint64_t)((((wst + p.b_bytes) >> 4) & 0x3FFF) | (1u << 16));
+                        const uint32_t first = (c | tap) == 0 ? 0u : 1u;
+                        if (wide) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)   // A_h x [W_h | W_l] -> main | corr
+                                hl_mma(d_main, ad + 2 * k, bh + 2 * k, idesc_w, (first | k) ? 1u : 0u);
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)   // A_l x W_h -> corr
+                                hl_mma(d_corr, ad + 4 + 2 * k, bh + 2 * k, idesc_n, 1u);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) hl_mma(d_main, ad + 2 * k, bh + 2 * k, idesc_n, (first | k) ? 1u : 0u);
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) hl_mma(d_corr, ad + 4 + 2 * k, bh + 2 * k, idesc_n, (first | k) ? 1u : 0u);
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) hl_mma(d_corr, ad + 2 * k, bl + 2 * k, idesc_n, 1u);
+                        }
+                        tc_commit(bar_wempty + 8 * ws);
+                    }
+                    tc_commit(bar_aempty + 8 * s);
+                }
+                tc_commit(bar_accf + 8 * a);
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        int tcount = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+            const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+            const int y = r / p.tiles_x, x = (r - y * p.tiles_x) * HL_M + m;
+            const int a = tcount & 1, u = tcount >> 1;
+            mbar_wait(bar_accf + 8 * a, u & 1);
+            tc_fence_after();
+            const bool valid = x < p.W;
+            const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+            float* yrow = p.y + pix * p.y_cs;
+            const float* mrow = p.mask ? p.mask + pix * p.mask_cs : nullptr;
+            const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y) && ((p.cout_valid & 3) == 0) &&
+                             (!p.mask || (((p.mask_cs & 3) == 0) && aligned16(p.mask)));
+            const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + a * 256;
+            for (int n0 = 0; n0 < p.Cout; n0 += 16) {
+                uint32_t rm[16], rc[16];
+                tmem_ld16(tbase + p.Cout + n0, rc);
+                tmem_ld16(tbase + n0, rm);
+                tmem_ld_wait();
+                float acc[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rc[j]) * HL_INV_SCALE + __uint_as_float(rm[j]);
+                if (valid) {
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] += __ldg(p.bias + n0 + j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = leaky(acc[j], p.alpha);
+                    if (vec) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            if (n0 + j >= p.cout_valid) break;
+                            float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                            if (mrow) {
+                                const float4 mk = ldg4(mrow + n0 + j);
+                                v.x *= mk.x > 0.f ? 1.f : p.mask_alpha; v.y *= mk.y > 0.f ? 1.f : p.mask_alpha;
+                                v.z *= mk.z > 0.f ? 1.f : p.mask_alpha; v.w *= mk.w > 0.f ? 1.f : p.mask_alpha;
+                            }
+                            float4* dst = reinterpret_cast<float4*>(yrow + n0 + j);
+                            if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                            *dst = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (n0 + j >= p.cout_valid) break;
+                            float v = acc[j];
+                            if (mrow) v *= __ldg(mrow + n0 + j) > 0.f ? 1.f : p.mask_alpha;
+                            if (p.accumulate) v += yrow[n0 + j];
+                            yrow[n0 + j] = v;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acce + 8 * a);
+        }
+    } else {
+        // ===================== converters (warps 6..13): fp32 pixel row -> [h | l * 2^11] fp16, in place =====================
+        const int ct = threadIdx.x - 192;   // 0..255
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int c = 0; c < KC; ++c, ++it) {
+                const int s = it & 1;
+                mbar_wait(bar_afull + 8 * s, (it >> 1) & 1);
+                uint8_t* stp = base_ptr + (size_t)s * HL_ACT_STAGE;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int R = ct + rr * HL_CONV_THREADS;
+                    if (R < HL_ROWS) {
+                        uint8_t* row = stp + (size_t)R * 128;
+                        const int sw = R & 7;              // 128B swizzle: logical 16-byte chunk j sits at chunk j ^ (R & 7)
+                        float4 v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
+                        uint4 hq[4], lq[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 a = v[2 * j], bq = v[2 * j + 1];
+                            const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+                            const __half2 h2 = __floats2half2_rn(bq.x, bq.y), h3 = __floats2half2_rn(bq.z, bq.w);
+                            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+                            const __half2 l0 = __floats2half2_rn((a.x - f0.x) * HL_SCALE, (a.y - f0.y) * HL_SCALE);
+                            const __half2 l1 = __floats2half2_rn((a.z - f1.x) * HL_SCALE, (a.w - f1.y) * HL_SCALE);
+                            const __half2 l2 = __floats2half2_rn((bq.x - f2.x) * HL_SCALE, (bq.y - f2.y) * HL_SCALE);
+                            const __half2 l3 = __floats2half2_rn((bq.z - f3.x) * HL_SCALE, (bq.w - f3.y) * HL_SCALE);
+                            hq[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                               *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+                            lq[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1),
+                                               *reinterpret_cast<const uint32_t*>(&l2), *reinterpret_cast<const uint32_t*>(&l3));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = hq[j];
+                            *reinterpret_cast<uint4*>(row + (((j + 4) ^ sw) << 4)) = lq[j];
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(bar_aconv + 8 * s);
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512));
+    }
+}
+
+// Returns CONV_HALO_UNSUPPORTED when the arguments need the streaming kernel of conv_tc_f16.cu.
+int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
+                     int B, int H, int W, int Cin, int Cout, float alpha, const float* mask, int mask_cs,
+                     float mask_alpha, int accumulate, int cout_valid, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc || Cout > 128 || (Cout & 7)) return -1000;   // two accumulator sets of 2*Cout columns must fit 512
+    CUtensorMap tmX;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)x_cs * 4, (cuuint64_t)W * x_cs * 4, (cuuint64_t)H * W * x_cs * 4};
+        cuuint32_t box[4] = {HL_BK, HL_BW, HL_BH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return PWC_E_BADARG; }
+    }
+    HaloParams p{};
+    p.bias = bias; p.y = y; p.w = (const uint8_t*)w_packed; p.mask = mask;
+    p.y_cs = y_cs; p.mask_cs = mask_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.cout_valid = cout_valid;
+    p.tiles_x = (W + HL_M - 1) / HL_M;
+    const long long tiles = (long long)p.tiles_x * H * B;
+    if (tiles >= (1ll << 30)) return -1000;
+    p.total_tiles = (int)tiles;
+    p.kchunks = (Cin + HL_BK - 1) / HL_BK;
+    p.b_bytes = Cout * 64;
+    p.w_stage_bytes = (2 * p.b_bytes + 1023) / 1024 * 1024;
+    p.accumulate = accumulate; p.alpha = alpha; p.mask_alpha = mask_alpha;
+    p.desc_mode = 0;
+    if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
+    const size_t smem = (size_t)HL_ACT_STAGES * HL_ACT_STAGE + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024;
+    if (smem > 227 * 1024) return -1000;
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("conv3x3_tc_halo: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
+    conv3x3_tc_halo_kernel<<<grid, HL_THREADS, smem, st>>>(tmX, p);
+    PWC_CHECK_LAUNCH("conv3x3_tc_halo_kernel");
+    return 0;
+}
+
+}  // namespace pwc

@@ -246,12 +246,13 @@ class PWCDCNet(object):
         if self.precision == "cudnn":
             return self._conv_cudnn(x, k, b, out, stride, dilation, alpha, residual)
         if self.precision == "3xf16" and cin == 16 and stride in (1, 2) and residual is None and cout % 16 == 0 \
-                and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
-            # 16-channel inputs (pyramid level 1): the tf32 kernel has a native 16-channel K slice (the fp16
-            # kernel would zero-pad K to 32); measured 353 vs 518 us at 224x512x16 images
+                and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0 and not (stride == 1 and dilation == 1 and x.shape[2] >= 96):
+            # 16-channel inputs (pyramid level 1): the tf32 kernel has a native 16-channel K slice (the streaming fp16
+            # kernel would zero-pad K to 32; measured 353 vs 518 us at 224x512x16 images).  Stride-1 layers on wide
+            # rows take the halo-resident fp16 kernel instead (281 us).
             return self._conv_tc(x, scope + "#tf32", k, b, out, dilation, alpha, stride, n_split=3)
         if self.precision == "3xf16" and stride in (1, 2) and residual is None and cout % 16 == 0 \
-                and cin >= 32 and cout <= 256 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
+                and cin >= 16 and cout <= 256 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
             from . import ops_tc
             if scope not in self._packed:
                 self._packed[scope] = ops_tc.pack_weights_f16(k)

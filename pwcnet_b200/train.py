@@ -96,14 +96,16 @@ class Trainer(object):
         for l in range(len(p.S)):
             acts += [p.S[l]] + list(p.tmp[l]) + [p.flows[l]] + ([p.f1w[l]] if p.f1w[l] is not None else [])
         acts += list(p.ctx)
-        total = sum(a.numel() for a in acts)
+        def al(n):   # every view starts on a 256-byte boundary (vector loads / TMA need 16)
+            return (n + 63) // 64 * 64
+        total = sum(al(a.numel()) for a in acts)
         g = _Grads()
         g.flat = torch.zeros(total, dtype=torch.float32, device=self.model.device)
         off = 0
         views = []
         for a in acts:
             views.append(g.flat[off:off + a.numel()].view(a.shape))
-            off += a.numel()
+            off += al(a.numel())
         it = iter(views)
         g.pyr = [[next(it) for _ in lev] for lev in p.pyr]
         g.S, g.tmp, g.flows, g.f1w = [], [], [], []
