@@ -323,7 +323,7 @@ namespace pwc {
 struct F16Extra { const float* mask; int mask_cs; float mask_alpha; int accumulate; int cout_valid; };
 // conv_tc_halo.cu: halo-resident variant for stride 1, dilation 1, wide rows, Cout <= 128
 int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
-                     int B, int H, int W, int Cin, int Cout, float alpha, const float* mask, int mask_cs,
+                     int B, int H, int W, int Cin, int Cout, int dilation, float alpha, const float* mask, int mask_cs,
                      float mask_alpha, int accumulate, int cout_valid, cudaStream_t st);
 }
 
@@ -343,12 +343,12 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     EncodeTiledFn enc = get_encode();
     PWC_REQUIRE(enc != nullptr, PWC_E_NOTBUILT, "conv3x3_tc_f16: cuTensorMapEncodeTiled not available from the driver");
     {
-        // halo-resident kernel (conv_tc_halo.cu): one 3 x 130 pixel box per 32-channel slice instead of nine shifted
+        // halo-resident kernel (conv_tc_halo.cu): one 3 x (128+2d) pixel box per 32-channel slice instead of nine shifted
         // tiles; rows of at least 96 pixels keep its 128-pixel row tiles mostly full.  PWC_CONV_HALO=0 disables it.
         const char* he = getenv("PWC_CONV_HALO");
         const int halo_on = he ? atoi(he) : 1;
-        if (halo_on && stride == 1 && dilation == 1 && W >= 96 && Cout <= 128) {
-            const int rc = launch_conv_halo(x, x_cs, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, alpha, ex.mask, ex.mask_cs,
+        if (halo_on && stride == 1 && dilation <= 16 && W >= 96 && Cout <= 128) {
+            const int rc = launch_conv_halo(x, x_cs, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, dilation, alpha, ex.mask, ex.mask_cs,
                                             ex.mask_alpha, ex.accumulate, ex.cout_valid, (cudaStream_t)stream);
             if (rc != -1000) return rc;
         }

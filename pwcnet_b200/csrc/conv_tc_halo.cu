@@ -4,12 +4,13 @@
 // modules.py:62-67, 266-274, 306-323; also Conv2DBackpropInput through pwc_conv3x3_tc_f16_dgrad), other data flow.
 // conv_tc_f16.cu streams nine shifted copies of every activation tile through TMA and the fp32->fp16 converter;
 // measured, it moves ~86 B/clk/SM through shared memory and is bound by exactly that (tensor pipe ~45 % busy).  Here
-//   * a tile is 128 consecutive pixels of ONE image row; per 32-channel slice the producer loads the 3 x 130 pixel
-//     halo box once (TMA, 128B swizzle, out-of-bounds zero fill = SAME padding), and the converter warps split each
-//     pixel row (128 B of fp32) IN PLACE into [h: 32 x fp16 | l: 32 x fp16 scaled by 2^11] -- 390 rows instead of
-//     9 x 128;
+//   * a tile is 128 consecutive pixels of ONE image row; per 32-channel slice the producer loads the 3 x (128+2d)
+//     pixel halo box once (rows y-d, y, y+d through the TMA traversal stride; 128B swizzle, out-of-bounds zero fill =
+//     SAME padding), and the converter warps split each pixel row (128 B of fp32) IN PLACE into
+//     [h: 32 x fp16 | l: 32 x fp16 scaled by 2^11] -- 390 rows (d = 1) instead of 9 x 128;
 //   * the A operand of tap (ky, kx) is the same shared-memory tile read through a descriptor whose start address
-//     is shifted by (ky*130 + kx) pixel rows (the swizzle is a function of the absolute shared-memory address);
+//     is shifted by (ky*(128+2d) + kx*d) pixel rows (the swizzle is a function of the absolute shared-memory
+//     address: measured, no descriptor base offset is needed);
 //   * with Cout <= 128 the [W_h | W_l] weight tiles of a tap form ONE N = 2*Cout operand: A_h x [W_h|W_l] yields the
 //     main and the first correction accumulator in one instruction (A_h is read once instead of twice), A_l x W_h
 //     accumulates into the correction columns: 2 MMAs and 20 KB of operand reads per K = 16 step instead of 3 / 24 KB;
@@ -23,11 +24,8 @@
 namespace pwc {
 
 constexpr int HL_M = 128;                          // output pixels per tile (one row segment)
-constexpr int HL_BW = HL_M + 2, HL_BH = 3;         // halo box
-constexpr int HL_ROWS = HL_BW * HL_BH;             // 390 pixel rows of 128 bytes
+constexpr int HL_BH = 3;                           // halo box: 3 rows (y-d, y, y+d) x (128 + 2d) pixels
 constexpr int HL_BK = 32;
-constexpr uint32_t HL_ACT_TX = HL_ROWS * 128;      // 49920 bytes per TMA box
-constexpr uint32_t HL_ACT_STAGE = 49 * 1024;       // 50176
 constexpr int HL_ACT_STAGES = 2, HL_W_STAGES = 4;
 constexpr int HL_CONV_THREADS = 256;
 constexpr int HL_THREADS = 64 + 128 + HL_CONV_THREADS + 32;   // act TMA, MMA, 4 epilogue, 8 converter, weight producer
@@ -41,6 +39,9 @@ struct HaloParams {
     int b_bytes;          // Cout * 64: one fp16 weight tile (h or l) of a (tap, slice)
     int w_stage_bytes;    // 2 * b_bytes rounded up to 1024
     int accumulate, desc_mode;
+    int dil, bw;          // dilation d; box width 128 + 2d (pixel rows of one box row)
+    int row_loads;        // 1: one box with row traversal stride d (d <= 8); 3: one single-row box per row (d > 8)
+    int act_stage;        // bytes per activation stage (3 * bw * 128 rounded up to 1024)
     float alpha, mask_alpha;
 };
 
@@ -66,7 +67,8 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
     const uint32_t bar_afull = smem_u32(&bars[0]), bar_aconv = smem_u32(&bars[2]), bar_aempty = smem_u32(&bars[4]);
     const uint32_t bar_wfull = smem_u32(&bars[6]), bar_wempty = smem_u32(&bars[10]);
     const uint32_t bar_accf = smem_u32(&bars[14]), bar_acce = smem_u32(&bars[16]);
-    const uint32_t w_base = base + HL_ACT_STAGES * HL_ACT_STAGE;
+    const uint32_t w_base = base + HL_ACT_STAGES * p.act_stage;
+    const int n_rows = HL_BH * p.bw;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < HL_ACT_STAGES; ++s) {
@@ -106,8 +108,15 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                 for (int c = 0; c < KC; ++c, ++it) {
                     const int s = it & 1;
                     mbar_wait(bar_aempty + 8 * s, ((it >> 1) & 1) ^ 1);
-                    mbar_expect_tx(bar_afull + 8 * s, HL_ACT_TX);
-                    tma_load_4d(base + s * HL_ACT_STAGE, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - 1, y - 1, b);
+                    mbar_expect_tx(bar_afull + 8 * s, (uint32_t)n_rows * 128);
+                    if (p.row_loads == 1) {
+                        tma_load_4d(base + s * p.act_stage, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - p.dil, y - p.dil, b);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < HL_BH; ++r)
+                            tma_load_4d(base + s * p.act_stage + r * p.bw * 128, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - p.dil,
+                                        y + (r - 1) * p.dil, b);
+                    }
                 }
             }
         }
@@ -149,13 +158,13 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                     const int s = it & 1;
                     mbar_wait(bar_aconv + 8 * s, (it >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t ast = base + s * HL_ACT_STAGE;
+                    const uint32_t ast = base + s * p.act_stage;
                     for (int tap = 0; tap < 9; ++tap, ++wt) {
                         const int ws = wt & (HL_W_STAGES - 1);
                         mbar_wait(bar_wfull + 8 * ws, (wt / HL_W_STAGES) & 1);
                         tc_fence_after();
                         const int ky = tap / 3, kx = tap - ky * 3;
-                        const uint32_t aaddr = ast + (uint32_t)(ky * HL_BW + kx) * 128;
+                        const uint32_t aaddr = ast + (uint32_t)(ky * p.bw + kx * p.dil) * 128;
                         uint64_t ad = adesc_hi | (uint64_t)(((aaddr >> 4) & 0x3FFF) | (1u << 16));
                         if (p.desc_mode == 1) ad |= (uint64_t)((aaddr >> 7) & 7) << 49;   // matrix base offset
                         const uint32_t wst = w_base + ws * p.w_stage_bytes;
@@ -255,11 +264,11 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
             for (int c = 0; c < KC; ++c, ++it) {
                 const int s = it & 1;
                 mbar_wait(bar_afull + 8 * s, (it >> 1) & 1);
-                uint8_t* stp = base_ptr + (size_t)s * HL_ACT_STAGE;
+                uint8_t* stp = base_ptr + (size_t)s * p.act_stage;
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int R = ct + rr * HL_CONV_THREADS;
-                    if (R < HL_ROWS) {
+                    if (R < n_rows) {
                         uint8_t* row = stp + (size_t)R * 128;
                         const int sw = R & 7;              // 128B swizzle: logical 16-byte chunk j sits at chunk j ^ (R & 7)
                         float4 v[8];
@@ -303,16 +312,20 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
 
 // Returns CONV_HALO_UNSUPPORTED when the arguments need the streaming kernel of conv_tc_f16.cu.
 int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
-                     int B, int H, int W, int Cin, int Cout, float alpha, const float* mask, int mask_cs,
+                     int B, int H, int W, int Cin, int Cout, int dilation, float alpha, const float* mask, int mask_cs,
                      float mask_alpha, int accumulate, int cout_valid, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
-    if (!enc || Cout > 128 || (Cout & 7)) return -1000;   // two accumulator sets of 2*Cout columns must fit 512
+    if (!enc || Cout > 128 || (Cout & 7) || dilation < 1 || dilation > 16) return -1000;   // two accumulator sets of 2*Cout columns must fit 512
     CUtensorMap tmX;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)x_cs * 4, (cuuint64_t)W * x_cs * 4, (cuuint64_t)H * W * x_cs * 4};
-        cuuint32_t box[4] = {HL_BK, HL_BW, HL_BH, 1};
-        cuuint32_t es[4] = {1, 1, 1, 1};
+        // rows y-d, y, y+d through the traversal stride of the row dimension (TMA allows strides up to 8); larger
+        // dilations use one single-row box per row (their row pitch (128+2d)*128 B must keep the 1024-byte swizzle phase)
+        const bool strided = dilation <= 8;
+        if (!strided && (((HL_M + 2 * dilation) * 128) & 1023)) return -1000;
+        cuuint32_t box[4] = {HL_BK, (cuuint32_t)(HL_M + 2 * dilation), (cuuint32_t)(strided ? HL_BH * dilation : 1), 1};
+        cuuint32_t es[4] = {1, 1, (cuuint32_t)(strided ? dilation : 1), 1};
         CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -329,9 +342,11 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.b_bytes = Cout * 64;
     p.w_stage_bytes = (2 * p.b_bytes + 1023) / 1024 * 1024;
     p.accumulate = accumulate; p.alpha = alpha; p.mask_alpha = mask_alpha;
+    p.dil = dilation; p.bw = HL_M + 2 * dilation; p.row_loads = dilation <= 8 ? 1 : HL_BH;
+    p.act_stage = (HL_BH * p.bw * 128 + 1023) / 1024 * 1024;
     p.desc_mode = 0;
     if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
-    const size_t smem = (size_t)HL_ACT_STAGES * HL_ACT_STAGE + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024;
+    const size_t smem = (size_t)HL_ACT_STAGES * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024;
     if (smem > 227 * 1024) return -1000;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc_halo: smem attr: %s", cudaGetErrorString(e)); return (int)e; }

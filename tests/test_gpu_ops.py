@@ -298,6 +298,38 @@ def test_conv3x3_tcgen05_f16x3_matches_oracle(P, case):
     np.testing.assert_allclose(out.cpu().numpy(), ref, atol=2e-5, rtol=0)
 
 
+HALO_CASES = [  # rows of >= 96 pixels, stride 1, Cout <= 128 take the halo-resident kernel (conv_tc_halo.cu)
+    # (B, H, W, Cin, channel stride, Cout, dilation)
+    (1, 4, 128, 32, 32, 32, 1), (1, 9, 130, 32, 32, 16, 1), (2, 14, 256, 128, 128, 128, 1), (1, 7, 200, 147, 148, 128, 1),
+    (1, 5, 96, 64, 64, 64, 1), (2, 6, 300, 16, 16, 16, 1), (1, 3, 512, 96, 96, 48, 1), (1, 2, 128, 34, 36, 128, 1),
+    (1, 9, 130, 32, 32, 32, 2), (2, 20, 256, 128, 128, 128, 4), (1, 30, 200, 128, 128, 96, 8), (1, 40, 256, 96, 96, 64, 16),
+    (1, 5, 100, 64, 64, 32, 16), (3, 1, 97, 32, 32, 16, 1),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv3x3_halo_resident_kernel_matches_oracle_and_streaming_kernel(P, case, monkeypatch):
+    """Halo-resident tcgen05 conv: one 3 x (128+2d) box per channel slice, shifted A descriptors, persistent CTA.
+    Must agree with the oracle's fp32 conv (2e-5 max-abs on O(1) outputs) and with the streaming kernel, and write
+    only its channel slot."""
+    from pwcnet_b200 import ops_tc
+    B, H, W, Cin, cs, Cout, dil = case
+    buf = _rand((B, H, W, cs), 1)
+    k = _rand((3, 3, Cin, Cout), 2, scale=1.0 / np.sqrt(9 * Cin))
+    b = _rand((Cout,), 3, scale=0.1)
+    x = buf[..., :Cin]
+    ref = O.leaky_relu(O.conv2d_same(torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(k), torch.from_numpy(b), 1, dil), 0.1).numpy()
+    wp = ops_tc.pack_weights_f16(_cuda(k))
+    monkeypatch.setenv("PWC_CONV_HALO", "1")
+    out = torch.full((B, H, W, Cout + 8), 9.0, device="cuda")
+    ops_tc.conv3x3_tc_f16(_cuda(buf)[..., :Cin], wp, _cuda(b), Cin, Cout, dilation=dil, alpha=0.1, out=out[..., 4:4 + Cout])
+    np.testing.assert_allclose(out[..., 4:4 + Cout].cpu().numpy(), ref, atol=2e-5, rtol=0)
+    assert (out[..., :4] == 9.0).all() and (out[..., 4 + Cout:] == 9.0).all()
+    monkeypatch.setenv("PWC_CONV_HALO", "0")
+    stream = ops_tc.conv3x3_tc_f16(_cuda(buf)[..., :Cin], wp, _cuda(b), Cin, Cout, dilation=dil, alpha=0.1)
+    np.testing.assert_allclose(out[..., 4:4 + Cout].cpu().numpy(), stream.cpu().numpy(), atol=2e-5, rtol=0)
+
+
 def test_conv3x3_f16x3_small_and_large_magnitudes(P):
     """The scaled residual keeps accuracy relative to the data scale from 1e-3 to 1e2."""
     from pwcnet_b200 import ops_tc
