@@ -152,93 +152,231 @@ struct WgradParams {
     int vec_x, vec_dy;
 };
 
-constexpr int WG_BM = 64, WG_BN = 64, WG_BK = 16, WG_THREADS = 256;
+constexpr int WG_BK = 8, WG_THREADS = 256;
 
 // dw[tap,ci,co] += sum_{output pixels} x[pixel shifted by tap, ci] * dy[pixel, co]:  per tap a GEMM with
-// M = Cin, N = Cout, K = pixels.  CTA = (pixel chunk, 64x64 tile of (ci,co), tap); both operands are staged in
-// their natural channel-contiguous layout, 4x4 register tile per thread, atomic accumulation into dw.
-// CTAs of tap 0 / ci-tile 0 also reduce the bias gradient db[co] += sum dy[pixel, co].
-__global__ void __launch_bounds__(WG_THREADS) conv3x3_wgrad_kernel(const WgradParams p) {
-    __shared__ __align__(16) float As[WG_BK][WG_BM];
-    __shared__ __align__(16) float Bs[WG_BK][WG_BN];
+// M = Cin, N = Cout, K = pixels.  CTA = (pixel chunk, TM x TN tile of (ci,co), tap); both operands are staged in
+// their natural channel-contiguous layout (8 pixels per stage, the next stage is fetched into registers while the
+// current one is multiplied), (TM/16) x (TN/16) register tile per thread (8x8 for the 128-channel layers: 64 FMAs per
+// four LDS.128), atomic accumulation into dw.  CTAs of tap 0 / ci-tile 0 also reduce db[co] += sum dy[pixel, co].
+template <int TM, int TN>
+__global__ void __launch_bounds__(WG_THREADS, 2) conv3x3_wgrad_kernel(const WgradParams p) {
+    constexpr int BK = (TM == 64 && TN == 64) ? 16 : WG_BK;   // pixels per stage: every thread loads one float4 per operand
+    constexpr int RM = TM / 16, RN = TN / 16;         // register tile (4 or 8 per dimension), split in halves of 4
+    __shared__ __align__(16) float As[BK][TM];
+    __shared__ __align__(16) float Bs[BK][TN];
 
     const int tid = threadIdx.x;
     const int tap = blockIdx.z, ky = tap / 3, kx = tap - ky * 3;
-    const int ci0 = (blockIdx.y % p.ci_tiles) * WG_BM, co0 = (blockIdx.y / p.ci_tiles) * WG_BN;
+    const int ci0 = (blockIdx.y % p.ci_tiles) * TM, co0 = (blockIdx.y / p.ci_tiles) * TN;
     const long long p_begin = (long long)blockIdx.x * p.chunk;
     const long long p_end = p_begin + p.chunk < p.total ? p_begin + p.chunk : p.total;
-    const int lk = tid >> 4, lc = (tid & 15) * 4;
+    // loader roles: pixel lk of the stage, four channels starting at la (x) / lb (dy)
+    const int lk = tid / (TM / 4) < BK ? tid / (TM / 4) : 0, la = (tid % (TM / 4)) * 4;
+    const bool a_role = tid < BK * (TM / 4);
+    const int lkb = tid / (TN / 4) < BK ? tid / (TN / 4) : 0, lb = (tid % (TN / 4)) * 4;
+    const bool b_role = tid < BK * (TN / 4);
     const int tm = tid >> 4, tn = tid & 15;
     const bool do_bias = p.db != nullptr && tap == 0 && ci0 == 0;
 
-    float acc[4][4];
+    float acc[RM][RN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
     float bsum = 0.f;
 
-    for (long long p0 = p_begin; p0 < p_end; p0 += WG_BK) {
-        const long long pix = p0 + lk;
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
-        if (pix < p_end) {
-            const int ox = (int)(pix % p.OW); const long long row = pix / p.OW;
-            const int oy = (int)(row % p.OH); const int b = (int)(row / p.OH);
-            const float* dyp = p.dy + (size_t)pix * p.dy_cs;
-            const int co = co0 + lc;
-            if (p.vec_dy && co + 3 < p.Cout) bv = ldg4(dyp + co);
-            else {
-                if (co + 0 < p.Cout) bv.x = __ldg(dyp + co + 0);
-                if (co + 1 < p.Cout) bv.y = __ldg(dyp + co + 1);
-                if (co + 2 < p.Cout) bv.z = __ldg(dyp + co + 2);
-                if (co + 3 < p.Cout) bv.w = __ldg(dyp + co + 3);
-            }
-            const int iy = oy * p.stride - p.pad_t + ky * p.dil, ix = ox * p.stride - p.pad_l + kx * p.dil;
-            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-                const float* xp = p.x + (((size_t)b * p.H + iy) * p.W + ix) * p.x_cs;
-                const int ci = ci0 + lc;
-                if (p.vec_x && ci + 3 < p.Cin) av = ldg4(xp + ci);
+    auto fetch = [&](long long p0, float4& av, float4& bv) {
+        av = make_float4(0.f, 0.f, 0.f, 0.f); bv = av;
+        if (b_role) {
+            const long long pix = p0 + lkb;
+            if (pix < p_end) {
+                const float* dyp = p.dy + (size_t)pix * p.dy_cs;
+                const int co = co0 + lb;
+                if (p.vec_dy && co + 3 < p.Cout) bv = ldg4(dyp + co);
                 else {
-                    if (ci + 0 < p.Cin) av.x = __ldg(xp + ci + 0);
-                    if (ci + 1 < p.Cin) av.y = __ldg(xp + ci + 1);
-                    if (ci + 2 < p.Cin) av.z = __ldg(xp + ci + 2);
-                    if (ci + 3 < p.Cin) av.w = __ldg(xp + ci + 3);
+                    if (co + 0 < p.Cout) bv.x = __ldg(dyp + co + 0);
+                    if (co + 1 < p.Cout) bv.y = __ldg(dyp + co + 1);
+                    if (co + 2 < p.Cout) bv.z = __ldg(dyp + co + 2);
+                    if (co + 3 < p.Cout) bv.w = __ldg(dyp + co + 3);
                 }
             }
         }
-        *reinterpret_cast<float4*>(&As[lk][lc]) = av;
-        *reinterpret_cast<float4*>(&Bs[lk][lc]) = bv;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < WG_BK; ++k) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][tm * 4]);
-            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tn * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        if (a_role) {
+            const long long pix = p0 + lk;
+            if (pix < p_end) {
+                const int ox = (int)(pix % p.OW); const long long row = pix / p.OW;
+                const int oy = (int)(row % p.OH); const int b = (int)(row / p.OH);
+                const int iy = oy * p.stride - p.pad_t + ky * p.dil, ix = ox * p.stride - p.pad_l + kx * p.dil;
+                if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                    const float* xp = p.x + (((size_t)b * p.H + iy) * p.W + ix) * p.x_cs;
+                    const int ci = ci0 + la;
+                    if (p.vec_x && ci + 3 < p.Cin) av = ldg4(xp + ci);
+                    else {
+                        if (ci + 0 < p.Cin) av.x = __ldg(xp + ci + 0);
+                        if (ci + 1 < p.Cin) av.y = __ldg(xp + ci + 1);
+                        if (ci + 2 < p.Cin) av.z = __ldg(xp + ci + 2);
+                        if (ci + 3 < p.Cin) av.w = __ldg(xp + ci + 3);
+                    }
+                }
+            }
         }
-        if (do_bias && tid < WG_BN) {
+    };
+
+    float4 av, bv;
+    fetch(p_begin, av, bv);
+    for (long long p0 = p_begin; p0 < p_end; p0 += BK) {
+        if (a_role) *reinterpret_cast<float4*>(&As[lk][la]) = av;
+        if (b_role) *reinterpret_cast<float4*>(&Bs[lkb][lb]) = bv;
+        __syncthreads();
+        if (p0 + BK < p_end) fetch(p0 + BK, av, bv);     // in flight during the multiply
 #pragma unroll
-            for (int k = 0; k < WG_BK; ++k) bsum += Bs[k][tid];
+        for (int k = 0; k < BK; ++k) {
+            float a[RM], bb[RN];
+#pragma unroll
+            for (int h = 0; h < RM / 4; ++h) {
+                const float4 t4 = *reinterpret_cast<const float4*>(&As[k][h * (TM / 2) + tm * 4]);
+                a[4 * h] = t4.x; a[4 * h + 1] = t4.y; a[4 * h + 2] = t4.z; a[4 * h + 3] = t4.w;
+            }
+#pragma unroll
+            for (int h = 0; h < RN / 4; ++h) {
+                const float4 t4 = *reinterpret_cast<const float4*>(&Bs[k][h * (TN / 2) + tn * 4]);
+                bb[4 * h] = t4.x; bb[4 * h + 1] = t4.y; bb[4 * h + 2] = t4.z; bb[4 * h + 3] = t4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        if (do_bias && tid < TN) {
+#pragma unroll
+            for (int k = 0; k < BK; ++k) bsum += Bs[k][tid];
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ci = ci0 + tm * 4 + i;
+    for (int i = 0; i < RM; ++i) {
+        const int ci = ci0 + (i >> 2) * (TM / 2) + tm * 4 + (i & 3);
         if (ci >= p.Cin) continue;
         const int dst = p.cin_map ? __ldg(p.cin_map + ci) : ci;
         if (dst < 0) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int co = co0 + tn * 4 + j;
+        for (int j = 0; j < RN; ++j) {
+            const int co = co0 + (j >> 2) * (TN / 2) + tn * 4 + (j & 3);
             if (co < p.Cout) atomicAdd(p.dw + ((size_t)tap * p.dw_cin + dst) * p.Cout + co, acc[i][j]);
         }
     }
-    if (do_bias && tid < WG_BN && co0 + tid < p.Cout) atomicAdd(p.db + co0 + tid, bsum);
+    if (do_bias && tid < TN && co0 + tid < p.Cout) atomicAdd(p.db + co0 + tid, bsum);
+}
+
+// Small-channel wgrad (Cin <= 32 and Cout <= 32, dilation 1: the first two pyramid levels and the 2-channel flow
+// heads).  These layers are memory/latency-bound, so one persistent CTA handles ALL nine taps of a 4 x 32 output tile
+// from one shared-memory patch of x and one tile of dy (each input byte is read once instead of nine times), keeps
+// its (tap, 4 ci, 4 co) register tiles across all of its tiles and issues its atomics once at the end.
+constexpr int WS_TW = 32, WS_TH = 4, WS_PIX = WS_TW * WS_TH, WS_ITEMS = 3;
+__global__ void __launch_bounds__(256) conv3x3_wgrad_small_kernel(const WgradParams p, int tiles_x, int tiles_y, int n_tiles) {
+    extern __shared__ __align__(16) float ws_smem[];
+    const int C4i = (p.Cin + 3) >> 2, C4o = (p.Cout + 3) >> 2, Cip = C4i * 4, Cop = C4o * 4;
+    const int prow = (WS_TH - 1) * p.stride + 3, pcol = (WS_TW - 1) * p.stride + 3;
+    float* patch = ws_smem;                              // [prow][pcol][Cip]
+    float* dys = ws_smem + prow * pcol * Cip;            // [WS_PIX][Cop]
+    const int tid = threadIdx.x;
+    const int n_items = 9 * C4i * C4o;
+    int xoff[WS_ITEMS], doff[WS_ITEMS];                  // per item: patch offset of its tap / channel group, dy offset
+    bool live[WS_ITEMS];
+    float acc[WS_ITEMS][4][4];
+#pragma unroll
+    for (int j = 0; j < WS_ITEMS; ++j) {
+        const int item = tid + 256 * j;
+        live[j] = item < n_items;
+        const int it = live[j] ? item : 0;
+        const int tap = it / (C4i * C4o), rem = it - tap * (C4i * C4o);
+        const int ci4 = rem / C4o, co4 = rem - ci4 * C4o;
+        xoff[j] = ((tap / 3) * pcol + (tap % 3)) * Cip + ci4 * 4;
+        doff[j] = co4 * 4;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[j][a][b] = 0.f;
+    }
+    float bsum = 0.f;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+        const int oy0 = ty * WS_TH, ox0 = tx * WS_TW;
+        const int iy0 = oy0 * p.stride - p.pad_t, ix0 = ox0 * p.stride - p.pad_l;
+        __syncthreads();                                 // previous tile fully consumed
+        const float* xb = p.x + (size_t)b * p.H * p.W * p.x_cs;
+        for (int e = tid; e < prow * pcol * C4i; e += 256) {
+            const int c4 = e % C4i, px = (e / C4i) % pcol, py = e / (C4i * pcol);
+            const int iy = iy0 + py, ix = ix0 + px;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                const float* xp = xb + ((size_t)iy * p.W + ix) * p.x_cs + 4 * c4;
+                if (p.vec_x && 4 * c4 + 3 < p.Cin) v = ldg4(xp);
+                else {
+                    if (4 * c4 + 0 < p.Cin) v.x = __ldg(xp + 0);
+                    if (4 * c4 + 1 < p.Cin) v.y = __ldg(xp + 1);
+                    if (4 * c4 + 2 < p.Cin) v.z = __ldg(xp + 2);
+                    if (4 * c4 + 3 < p.Cin) v.w = __ldg(xp + 3);
+                }
+            }
+            *reinterpret_cast<float4*>(patch + (py * pcol + px) * Cip + 4 * c4) = v;
+        }
+        for (int e = tid; e < WS_PIX * C4o; e += 256) {
+            const int c4 = e % C4o, pp = e / C4o;
+            const int oy = oy0 + (pp >> 5), ox = ox0 + (pp & 31);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (oy < p.OH && ox < p.OW) {
+                const float* dp = p.dy + (((size_t)b * p.OH + oy) * p.OW + ox) * p.dy_cs + 4 * c4;
+                if (p.vec_dy && 4 * c4 + 3 < p.Cout) v = ldg4(dp);
+                else {
+                    if (4 * c4 + 0 < p.Cout) v.x = __ldg(dp + 0);
+                    if (4 * c4 + 1 < p.Cout) v.y = __ldg(dp + 1);
+                    if (4 * c4 + 2 < p.Cout) v.z = __ldg(dp + 2);
+                    if (4 * c4 + 3 < p.Cout) v.w = __ldg(dp + 3);
+                }
+            }
+            *reinterpret_cast<float4*>(dys + pp * Cop + 4 * c4) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < WS_ITEMS; ++j) {
+            if (!live[j]) continue;
+            const float* xq = patch + xoff[j];
+            const float* dq = dys + doff[j];
+#pragma unroll 4
+            for (int pp = 0; pp < WS_PIX; ++pp) {
+                const float4 xv = *reinterpret_cast<const float4*>(xq + (((pp >> 5) * p.stride) * pcol + (pp & 31) * p.stride) * Cip);
+                const float4 dv = *reinterpret_cast<const float4*>(dq + pp * Cop);
+                const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) acc[j][a][b2] = fmaf(xa[a], da[b2], acc[j][a][b2]);
+            }
+        }
+        if (p.db && tid < p.Cout) {
+            for (int pp = 0; pp < WS_PIX; ++pp) bsum += dys[pp * Cop + tid];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < WS_ITEMS; ++j) {
+        if (!live[j]) continue;
+        const int item = tid + 256 * j;
+        const int tap = item / (C4i * C4o), rem = item - tap * (C4i * C4o);
+        const int ci4 = rem / C4o, co4 = rem - ci4 * C4o;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int ci = ci4 * 4 + a;
+            if (ci >= p.Cin) continue;
+#pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2) {
+                const int co = co4 * 4 + b2;
+                if (co < p.Cout) atomicAdd(p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + co, acc[j][a][b2]);
+            }
+        }
+    }
+    if (p.db && tid < p.Cout) atomicAdd(p.db + tid, bsum);
 }
 
 // ------------------------------------------------------------------------------------- element-wise helpers
@@ -529,21 +667,43 @@ extern "C" int pwc_conv3x3_wgrad(const float* x, int x_cs, const float* dy, int 
     same_pad_b(H, stride, dilation, &p.OH, &p.pad_t);
     same_pad_b(W, stride, dilation, &p.OW, &p.pad_l);
     p.total = (long long)B * p.OH * p.OW;
-    p.ci_tiles = (Cin + WG_BM - 1) / WG_BM;
-    const int co_tiles = (Cout + WG_BN - 1) / WG_BN;
+    p.vec_x = aligned16(x) && (x_cs % 4 == 0);
+    p.vec_dy = aligned16(dy) && (dy_cs % 4 == 0);
+    if (Cin <= 32 && Cout <= 32 && dilation == 1 && stride <= 2 && !cin_map) {
+        const int tiles_x = (p.OW + WS_TW - 1) / WS_TW, tiles_y = (p.OH + WS_TH - 1) / WS_TH;
+        const long long n_tiles = (long long)tiles_x * tiles_y * B;
+        if (n_tiles < (1ll << 30)) {
+            const int Cip = (Cin + 3) / 4 * 4, Cop = (Cout + 3) / 4 * 4;
+            const int prow = (WS_TH - 1) * stride + 3, pcol = (WS_TW - 1) * stride + 3;
+            const size_t smem = ((size_t)prow * pcol * Cip + (size_t)WS_PIX * Cop) * 4;
+            cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("conv3x3_wgrad_small: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+            const int grid = (int)(n_tiles < 148 * 2 ? n_tiles : 148 * 2);
+            conv3x3_wgrad_small_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, tiles_x, tiles_y, (int)n_tiles);
+            PWC_CHECK_LAUNCH("conv3x3_wgrad_small_kernel");
+            return 0;
+        }
+    }
+    // 128-wide tiles (8 registers per dimension) unless the 64-wide tiling pads noticeably less
+    auto pick = [](int c) { const int p128 = (c + 127) / 128 * 128, p64 = (c + 63) / 64 * 64; return p128 * 100 <= p64 * 115 ? 128 : 64; };
+    const int TM = pick(Cin), TN = pick(Cout);
+    p.ci_tiles = (Cin + TM - 1) / TM;
+    const int co_tiles = (Cout + TN - 1) / TN;
     const int tiles = p.ci_tiles * co_tiles;
     PWC_REQUIRE(tiles <= 65535, PWC_E_BADARG, "conv3x3_wgrad: too many channel tiles");
-    // ~8 CTAs per SM in total; every CTA reduces at least 64 pixels
-    long long chunks = (148LL * 8 + tiles * 9 - 1) / (tiles * 9);
+    // ~6 CTAs per SM in total; every CTA reduces at least 64 pixels
+    long long chunks = (148LL * 6 + tiles * 9 - 1) / (tiles * 9);
     const long long max_chunks = (p.total + 63) / 64;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
-    p.chunk = ((p.total + chunks - 1) / chunks + WG_BK - 1) / WG_BK * WG_BK;
+    p.chunk = ((p.total + chunks - 1) / chunks + 15) / 16 * 16;
     chunks = (p.total + p.chunk - 1) / p.chunk;
-    p.vec_x = aligned16(x) && (x_cs % 4 == 0);
-    p.vec_dy = aligned16(dy) && (dy_cs % 4 == 0);
     dim3 grid((unsigned)chunks, tiles, 9);
-    conv3x3_wgrad_kernel<<<grid, WG_THREADS, 0, (cudaStream_t)stream>>>(p);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (TM == 128 && TN == 128) conv3x3_wgrad_kernel<128, 128><<<grid, WG_THREADS, 0, st>>>(p);
+    else if (TM == 128) conv3x3_wgrad_kernel<128, 64><<<grid, WG_THREADS, 0, st>>>(p);
+    else if (TN == 128) conv3x3_wgrad_kernel<64, 128><<<grid, WG_THREADS, 0, st>>>(p);
+    else conv3x3_wgrad_kernel<64, 64><<<grid, WG_THREADS, 0, st>>>(p);
     PWC_CHECK_LAUNCH("conv3x3_wgrad_kernel");
     return 0;
 }

@@ -50,13 +50,22 @@ __global__ void warp_kernel(const float* __restrict__ x, int x_cs, const float* 
 }
 
 // Legacy TF-1.8 bilinear resize: src = dst * in/out (no half-pixel offset), hi = min(lo+1, in-1).
-// One thread per output scalar (C is 2 or 32 here; channel-fastest so accesses coalesce).
+// One thread per (output pixel, V-channel vector), V = 4 / 2 / 1 by alignment: the four taps and the store are
+// single 16 / 8 / 4-byte accesses (C is 2 or 32 here).
+template <int V> struct VecT;
+template <> struct VecT<4> { typedef float4 type; };
+template <> struct VecT<2> { typedef float2 type; };
+template <> struct VecT<1> { typedef float type; };
+
+template <int V>
 __global__ void resize_bilinear_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int y_cs,
                                        int B, int H, int W, int C, int OH, int OW, float sy, float sx, float mul) {
-    const size_t total = (size_t)B * OH * OW * C;
+    typedef typename VecT<V>::type vec_t;
+    const int CV = C / V;
+    const size_t total = (size_t)B * OH * OW * CV;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int c = idx % C;
-        size_t pix = idx / C;
+        const int c = (int)(idx % CV) * V;
+        size_t pix = idx / CV;
         const int ox = pix % OW; const size_t row = pix / OW;
         const int oy = row % OH; const int b = row / OH;
         const float fy = (float)oy * sy, fx = (float)ox * sx;
@@ -64,11 +73,21 @@ __global__ void resize_bilinear_kernel(const float* __restrict__ x, int x_cs, fl
         const int yhi = min(ylo + 1, H - 1), xhi = min(xlo + 1, W - 1);
         const float yl = fy - (float)ylo, xl = fx - (float)xlo;
         const float* xb = x + (size_t)b * H * W * x_cs + c;
-        const float tl = __ldg(xb + ((size_t)ylo * W + xlo) * x_cs), tr = __ldg(xb + ((size_t)ylo * W + xhi) * x_cs);
-        const float bl = __ldg(xb + ((size_t)yhi * W + xlo) * x_cs), br = __ldg(xb + ((size_t)yhi * W + xhi) * x_cs);
-        const float top = tl + (tr - tl) * xl;
-        const float bot = bl + (br - bl) * xl;
-        y[pix * y_cs + c] = (top + (bot - top) * yl) * mul;
+        const vec_t tlv = __ldg(reinterpret_cast<const vec_t*>(xb + ((size_t)ylo * W + xlo) * x_cs));
+        const vec_t trv = __ldg(reinterpret_cast<const vec_t*>(xb + ((size_t)ylo * W + xhi) * x_cs));
+        const vec_t blv = __ldg(reinterpret_cast<const vec_t*>(xb + ((size_t)yhi * W + xlo) * x_cs));
+        const vec_t brv = __ldg(reinterpret_cast<const vec_t*>(xb + ((size_t)yhi * W + xhi) * x_cs));
+        const float* tl = reinterpret_cast<const float*>(&tlv); const float* tr = reinterpret_cast<const float*>(&trv);
+        const float* bl = reinterpret_cast<const float*>(&blv); const float* br = reinterpret_cast<const float*>(&brv);
+        vec_t ov;
+        float* o = reinterpret_cast<float*>(&ov);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float top = tl[j] + (tr[j] - tl[j]) * xl;
+            const float bot = bl[j] + (br[j] - bl[j]) * xl;
+            o[j] = (top + (bot - top) * yl) * mul;
+        }
+        *reinterpret_cast<vec_t*>(y + pix * y_cs + c) = ov;
     }
 }
 
@@ -130,11 +149,17 @@ extern "C" int pwc_resize_bilinear_fwd(const float* x, int x_cs, float* y, int y
     using namespace pwc;
     PWC_REQUIRE(x && y, PWC_E_BADARG, "resize: null pointer");
     PWC_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, PWC_E_BADARG, "resize: bad dims");
-    const size_t total = (size_t)B * OH * OW * C;
-    const int blocks = (int)((total + 255) / 256 < (size_t)148 * 16 ? (total + 255) / 256 : (size_t)148 * 16);
     // TF computes the scale in float32: in / out
     const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
-    resize_bilinear_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y);
+    const int V = ((C & 3) == 0 && (x_cs & 3) == 0 && (y_cs & 3) == 0 && (al & 15) == 0) ? 4
+                : ((C & 1) == 0 && (x_cs & 1) == 0 && (y_cs & 1) == 0 && (al & 7) == 0) ? 2 : 1;
+    const size_t total = (size_t)B * OH * OW * (C / V);
+    const int blocks = (int)((total + 255) / 256 < (size_t)148 * 32 ? (total + 255) / 256 : (size_t)148 * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (V == 4) resize_bilinear_kernel<4><<<blocks, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
+    else if (V == 2) resize_bilinear_kernel<2><<<blocks, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
+    else resize_bilinear_kernel<1><<<blocks, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
     PWC_CHECK_LAUNCH("resize_bilinear_kernel");
     return 0;
 }
