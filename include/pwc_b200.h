@@ -173,6 +173,28 @@ int pwc_conv3x3_tc_f16_dgrad(const float* dy, int dy_cs, const void* w_rot_packe
                              const float* mask, int mask_cs, float mask_alpha, int accumulate,
                              int B, int H, int W, int Cdy, int Cdx, int Cdx_pad, int dilation, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Cost volume from pre-split fp16 operands (the pipeline's fast path; cost_volume_tcs.cu).
+ * A "split" tensor holds, per pixel and 32-channel slice, the 128-byte row [h: 32 x fp16 | l: 32 x fp16] with
+ * h = fp16(x), l = fp16(x - h): the same bytes as the fp32 row, dense (B,H,W,2C) fp16.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* scale * x (fp32, channel stride x_cs) -> split tensor `out`; if copy != NULL the UNSCALED x is also copied to `copy`
+ * (fp32, channel stride copy_cs: the f0 slot of the estimator's concat buffer, modules.py:262).  C % 32 == 0.
+ * The pipeline passes scale = 1/C for f0, so the mean over channels (modules.py:181) costs nothing later. */
+int pwc_split_f16_fwd(const float* x, int x_cs, void* out, float* copy, int copy_cs, long long n_pix, int C,
+                      float scale, void* stream);
+
+/* pwc_warp_fwd (WarpingLayer, modules.py:83-154) writing its result as a split tensor.  C % 32 == 0. */
+int pwc_warp_split_fwd(const float* x, int x_cs, const float* flow, int flow_cs, float flow_scale, int warp_type,
+                       void* out, int B, int H, int W, int C, void* stream);
+
+/* pwc_cost_volume_fwd for search_range 4 on tcgen05 from split operands f0s, f1s (modules.py:164-204):
+ * out[b,y,x,(v+4)*9+(h+4)] = leaky_alpha(scale * sum_c f0s[b,y,x,c] f1s[b,y+v,x+h,c]); scale = 1/C, or 1 when f0s was
+ * produced with scale 1/C.  fp32-class (3 x fp16 products, fp32 accumulation). */
+int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float* out, int out_cs,
+                              int B, int H, int W, int C, float scale, float alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

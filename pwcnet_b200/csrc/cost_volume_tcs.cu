@@ -1,0 +1,429 @@
+// Cost volume, search range 4, on tcgen05 from PRE-SPLIT fp16 operands (sm_100a) -- the pipeline's level kernel.
+//
+//   out[b,y,x,(v+4)*9+(h+4)] = leaky( (1/C) * sum_c f0[b,y,x,c] * f1[b,y+v,x+h,c] ),  zero outside the image
+//   (CostVolumeLayer.__call__ / get_cost, reference modules.py:164-204).
+//
+// Same band GEMM as cost_volume_tc.cu (f0 patch 16 x 8 = 128 rows against the 24 x 16 f1 patch = 2 x 192 columns,
+// 3 x fp16 split x = h + l in ONE fp32 TMEM accumulator), but the operands arrive already split: the producers
+// (pwc_split_f16_fwd for pyramid features, pwc_warp_split_fwd for warped features) write, per pixel and 32-channel
+// slice, the 128-byte row [h: 32 x fp16 | l: 32 x fp16] -- the same bytes as the fp32 row, and exactly the K-major
+// UMMA operand row.  That removes the in-kernel converter pass, which was a third of the shared-memory traffic and
+// competed with the tensor core's operand fetches (profiles/r01_cost_volume_tc_timeline.log).  Pipeline:
+//   warp 0   TMA producer: f0 box {64 x fp16, 16, 8}, f1 box {64 x fp16, 24, 16} at (x0-4, y0-4), 128B swizzle,
+//            out-of-bounds zero fill = the reference's zero padding; 2 stages of 64 KB
+//   warp 1   MMA issuer: per slice 2 halves x 6 x tcgen05.mma (M128 N192 K16): h.h + l.h + h.l
+//   warps 2..17  epilogue: four warps per TMEM lane quadrant (2 accumulator halves x 2 column ranges) read the
+//            accumulator (lane = pixel), scatter the 9 x 9 band into the quadrant's shared-memory slab
+//            [32 pixels][81], then each warp streams 8 pixels x 324 bytes to HBM.  A half is handed back to the MMA
+//            warp as soon as its 8 warps have drained it.
+// Measured (profiles/r01_cost_volume_split.log): 54 us at B = 8 (0.38 of the HBM roofline), 169 us at B = 32 (0.48).
+// The MMAs are no longer the limit (1/3 of them changes nothing); the band scatter is: it is instruction-issue
+// bound at ~3 instructions per accumulator element read (60 x 16 x 32 lane-elements per tile, 21 % useful), and the
+// accumulator cannot be double-buffered (2 x 384 columns > 512).  Variants that were built and measured slower:
+// three 128-column pieces over a 4-slot TMEM ring with scale/leaky in the scatter (76 us), per-pixel bulk copies
+// (76 us) or one TMA tensor store per quadrant (126 us) for the output -- stores queue behind the tile loads in the
+// SM's TMA engine.
+#include "cost_volume.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+#include <cstdlib>
+
+namespace pwc {
+
+constexpr int S_TW = 16, S_TH = 8, S_FW = S_TW + 8, S_FH = S_TH + 8;
+constexpr int S_M = S_TW * S_TH;                   // 128
+constexpr int S_NH = S_FW * (S_FH / 2);            // 192 columns per accumulator half
+constexpr uint32_t S_F0_BYTES = S_M * 128;         // 16 KB
+constexpr uint32_t S_F1_BYTES = 2 * S_NH * 128;    // 48 KB
+constexpr uint32_t S_STAGE_BYTES = S_F0_BYTES + S_F1_BYTES;
+constexpr int S_STAGES = 2;
+constexpr int S_EPI_WARPS = 16;
+constexpr int S_THREADS = 64 + S_EPI_WARPS * 32;   // 576
+constexpr int S_SLAB_PITCH = 84;
+constexpr uint32_t S_SLAB_BYTES = 4 * 32 * S_SLAB_PITCH * 4;
+constexpr uint32_t S_SMEM_BYTES = S_STAGES * S_STAGE_BYTES + S_SLAB_BYTES + 1024;
+
+struct CvSplitParams {
+    float* out;
+    int out_cs, B, H, W, kchunks;
+    int tiles_x, tiles_y, total_tiles;
+    float alpha, scale;
+    int vec;
+    unsigned long long* dbg;   // optional timeline (clock64), 64 slots per CTA: 8 events x 8 tiles
+};
+
+#define S_DBG(ev, tile) do { if (dbg && (tile) < 8) dbg[(ev) * 8 + (tile)] = clock64(); } while (0)
+
+__device__ __forceinline__ void s_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Band extraction of six 16-column chunks [J0, J0+6) of accumulator half HB: register i of chunk j holds D[m, n],
+// n = HB*192 + 16j + i, i.e. f1 patch pixel (fy, fx) = (HB*8 + (16j+i)/24, (16j+i)%24) -- compile-time after
+// unrolling; the lane's pixel (py, px) decides whether it is inside the 9x9 window and where it goes in the slab row.
+// Kept to three instructions per element: measured, this scatter is instruction-issue bound (applying scale / leaky
+// here instead of in the output loop made the kernel 2.4x slower).
+template <int HB, int J0>
+__device__ __forceinline__ void s_scatter(uint32_t taddr, float* slab_lane, int py, int px, int q) {
+    const uint32_t rowmask = 0x1FFu << py, colmask = 0x1FFu << px;
+#pragma unroll
+    for (int j = J0; j < J0 + 6; ++j) {
+        const int fylo = HB * 8 + (16 * j) / S_FW, fyhi = HB * 8 + (16 * j + 15) / S_FW;
+        if (fyhi < 2 * q || fylo > 2 * q + 9) continue;   // no lane of this warp (py in {2q, 2q+1}) needs the chunk
+        uint32_t r[16];
+        tmem_ld16(taddr + 16 * j, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int n = 16 * j + i;
+            const int fy = HB * 8 + n / S_FW, fx = n % S_FW;
+            if (((rowmask >> fy) & (colmask >> fx)) & 1u) slab_lane[fy * 9 + fx] = __uint_as_float(r[i]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+cost_volume_split_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1, const CvSplitParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    __shared__ __align__(8) uint64_t bars[2 * S_STAGES + 4];   // full[2], empty[2], acc_full[2], acc_empty[2]
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[S_STAGES]);
+    const uint32_t bar_accf = smem_u32(&bars[2 * S_STAGES]), bar_acce = smem_u32(&bars[2 * S_STAGES + 2]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(bar_accf + 8 * h, 1);
+            mbar_init(bar_acce + 8 * h, 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+    const int KC = p.kchunks;
+    unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f0) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f1) : "memory");
+            int it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * S_TW, y0 = ty * S_TH;
+                for (int c = 0; c < KC; ++c, ++it) {
+                    const int s = it % S_STAGES;
+                    mbar_wait(bar_empty + 8 * s, ((it / S_STAGES) & 1) ^ 1);
+                    S_DBG(0, it);
+                    const uint32_t st = base + s * S_STAGE_BYTES;
+                    mbar_expect_tx(bar_full + 8 * s, S_STAGE_BYTES);
+                    tma_load_4d(st, &tm_f0, bar_full + 8 * s, c * 64, x0, y0, b);
+                    tma_load_4d(st + S_F0_BYTES, &tm_f1, bar_full + 8 * s, c * 64, x0 - 4, y0 - 4, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(S_NH >> 3) << 17) | ((uint32_t)(S_M >> 4) << 24);
+            const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            int it = 0, tcount = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+                for (int c = 0; c < KC; ++c, ++it) {
+                    const int s = it % S_STAGES;
+                    mbar_wait(bar_full + 8 * s, (it / S_STAGES) & 1);
+                    S_DBG(1, it);
+                    tc_fence_after();
+                    const uint32_t st = base + s * S_STAGE_BYTES;
+                    const uint32_t a0 = ((st >> 4) & 0x3FFF) | (1u << 16);
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {
+                        if (c == 0 && tcount > 0) {   // the epilogue of the previous tile has drained this half
+                            mbar_wait(bar_acce + 8 * hb, (tcount - 1) & 1);
+                            tc_fence_after();
+                        }
+                        if (hb == 1) S_DBG(2, it);
+                        const uint32_t b0 = (((st + S_F0_BYTES + hb * S_NH * 128) >> 4) & 0x3FFF) | (1u << 16);
+                        const uint32_t d = tmem_acc + hb * S_NH;
+                        // k-steps of 32 bytes inside the 128-byte row: 0,1 = h (channels 0-15, 16-31), 2,3 = l
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) s_mma(d, desc_hi | (a0 + 2 * k), desc_hi | (b0 + 2 * k), idesc, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) s_mma(d, desc_hi | (a0 + 4 + 2 * k), desc_hi | (b0 + 2 * k), idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) s_mma(d, desc_hi | (a0 + 2 * k), desc_hi | (b0 + 4 + 2 * k), idesc, 1u);
+                        if (c == KC - 1) tc_commit(bar_accf + 8 * hb);
+                    }
+                    tc_commit(bar_empty + 8 * s);
+                    S_DBG(3, it);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..17) =====================
+        // TMEM lane quadrant q = warp % 4 (hardware rule).  e = (warp - 2) / 4 in 0..3: accumulator half hb = e >> 1,
+        // column range ch = e & 1 (16-column chunks [6 ch, 6 ch + 6) of the half).
+        const int q = warp & 3, e = (warp - 2) >> 2, hb = e >> 1, ch = e & 1;
+        const int py = 2 * q + (lane >> 4), px = lane & 15;
+        float* slab = reinterpret_cast<float*>(base_ptr + S_STAGES * S_STAGE_BYTES) + q * 32 * S_SLAB_PITCH;
+        float* slab_lane = slab + lane * S_SLAB_PITCH - (py * 9 + px);
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + hb * S_NH;
+        const int cs = p.out_cs;
+        const float scale = p.scale, alpha = p.alpha;
+        int tcount = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+            const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+            const int x0 = tx * S_TW, y0 = ty * S_TH;
+            mbar_wait(bar_accf + 8 * hb, tcount & 1);
+            if (lane == 0 && q == 2 && ch == 0) S_DBG(4 + hb, tcount);   // warps 2 (half A) and 10 (half B)
+            tc_fence_after();
+            if (hb == 0) { if (ch == 0) s_scatter<0, 0>(taddr, slab_lane, py, px, q); else s_scatter<0, 6>(taddr, slab_lane, py, px, q); }
+            else         { if (ch == 0) s_scatter<1, 0>(taddr, slab_lane, py, px, q); else s_scatter<1, 6>(taddr, slab_lane, py, px, q); }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acce + 8 * hb);
+            if (warp == 2 && lane == 0) S_DBG(6, tcount);
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");     // the whole band of the quadrant is in the slab
+            // ---- slab -> HBM: the quadrant owns image rows y0+2q, y0+2q+1 (16 pixels each); this warp writes
+            // eight pixels: row e >> 1, columns 8 (e & 1) .. +7.  scale and the leaky slope are applied here, on the 81
+            // useful values per pixel.
+            const int yy = y0 + 2 * q + (e >> 1), xs = x0 + 8 * (e & 1);
+            if (yy < p.H && xs < p.W) {
+                float* orow = p.out + (((size_t)b * p.H + yy) * p.W + xs) * cs;
+                const float* srow = slab + (e * 8) * S_SLAB_PITCH;
+                const int npx = min(8, p.W - xs);
+                if (p.vec) {
+                    // 8 pixels x (20 float4 + 1 scalar) = 168 units; lane handles u = lane + 32 m
+                    int pix = lane / 21, k = lane - pix * 21;
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) {
+                        if (pix < npx) {
+                            const float* src = srow + pix * S_SLAB_PITCH + 4 * k;
+                            float* dst = orow + pix * cs + 4 * k;
+                            if (k < 20) {
+                                float4 v = *reinterpret_cast<const float4*>(src);
+                                v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+                                v.x = fmaxf(v.x, alpha * v.x); v.y = fmaxf(v.y, alpha * v.y);
+                                v.z = fmaxf(v.z, alpha * v.z); v.w = fmaxf(v.w, alpha * v.w);
+                                *reinterpret_cast<float4*>(dst) = v;
+                            } else {
+                                const float v = *src * scale;
+                                *dst = fmaxf(v, alpha * v);
+                            }
+                        }
+                        k += 11; pix += 1;                  // u += 32 = 21 + 11
+                        if (k >= 21) { k -= 21; pix += 1; }
+                    }
+                } else {
+                    int pix = 0, k = lane;                  // 8 pixels x 81 scalars
+#pragma unroll 3
+                    for (int m = 0; m < 21; ++m) {
+                        if (pix < npx) {
+                            const float v = srow[pix * S_SLAB_PITCH + k] * scale;
+                            orow[pix * cs + k] = fmaxf(v, alpha * v);
+                        }
+                        k += 32;
+                        if (k >= 81) { k -= 81; pix += 1; }
+                    }
+                }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");     // the slab is rewritten by the next tile's scatter
+            if (warp == 2 && lane == 0) S_DBG(7, tcount);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512));
+    }
+}
+
+// fp32 NHWC -> split rows: per pixel and 32-channel slice [h: 32 x fp16 | l: 32 x fp16], h = fp16(x), l = fp16(x - h);
+// optionally also copies x to a second fp32 destination (the estimator's concat slot, modules.py:262).
+__global__ void split_f16_kernel(const float* __restrict__ x, int x_cs, __half* __restrict__ out, float* __restrict__ copy,
+                                 int copy_cs, size_t n_pix, int C, float scale) {
+    const int C8 = C >> 3;
+    const size_t total = n_pix * C8;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % C8; const size_t pix = idx / C8;
+        float4 a = ldg4(x + pix * x_cs + 8 * g), bq = ldg4(x + pix * x_cs + 8 * g + 4);
+        if (copy) {
+            *reinterpret_cast<float4*>(copy + pix * copy_cs + 8 * g) = a;
+            *reinterpret_cast<float4*>(copy + pix * copy_cs + 8 * g + 4) = bq;
+        }
+        a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;        // (the copy stays unscaled)
+        bq.x *= scale; bq.y *= scale; bq.z *= scale; bq.w *= scale;
+        const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+        const __half2 h2 = __floats2half2_rn(bq.x, bq.y), h3 = __floats2half2_rn(bq.z, bq.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+        const __half2 l0 = __floats2half2_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2half2_rn(a.z - f1.x, a.w - f1.y);
+        const __half2 l2 = __floats2half2_rn(bq.x - f2.x, bq.y - f2.y), l3 = __floats2half2_rn(bq.z - f3.x, bq.w - f3.y);
+        // 8 channels = 16 bytes of h and 16 bytes of l inside slice g / 4
+        __half* row = out + pix * (size_t)(2 * C) + (g >> 2) * 64 + (g & 3) * 8;
+        *reinterpret_cast<uint4*>(row) = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                    *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+        *reinterpret_cast<uint4*>(row + 32) = make_uint4(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1),
+                                                         *reinterpret_cast<const uint32_t*>(&l2), *reinterpret_cast<const uint32_t*>(&l3));
+    }
+}
+
+// WarpingLayer (modules.py:99-154) writing split rows: one thread per (pixel, 8 channels).
+template <bool NEAREST>
+__global__ void warp_split_kernel(const float* __restrict__ x, int x_cs, const float* __restrict__ flow, int flow_cs,
+                                  float flow_scale, __half* __restrict__ out, int B, int H, int W, int C) {
+    const int C8 = C >> 3;
+    const size_t total = (size_t)B * H * W * C8;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % C8; const size_t pix = idx / C8;
+        const int px = pix % W; const size_t rowi = pix / W;
+        const int py = rowi % H; const size_t b = rowi / H;
+        const float* fl = flow + pix * flow_cs;
+        const float fx = __ldg(fl) * flow_scale, fy = __ldg(fl + 1) * flow_scale;
+        const float* xb = x + b * H * W * x_cs + 8 * g;
+        float r[8];
+        if (NEAREST) {
+            const int ix = min(max(px + (int)fx, 0), W - 1), iy = min(max(py + (int)fy, 0), H - 1);
+            const float4 a = ldg4(xb + ((size_t)iy * W + ix) * x_cs), c = ldg4(xb + ((size_t)iy * W + ix) * x_cs + 4);
+            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = c.x; r[5] = c.y; r[6] = c.z; r[7] = c.w;
+        } else {
+            const float fx0 = floorf(fx), fy0 = floorf(fy), fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+            const float wl = (float)(W - 1), hl = (float)(H - 1);
+            const int gy0 = (int)fminf(fmaxf((float)py + fy0, 0.f), hl), gy1 = (int)fminf(fmaxf((float)py + fy1, 0.f), hl);
+            const int gx0 = (int)fminf(fmaxf((float)px + fx0, 0.f), wl), gx1 = (int)fminf(fmaxf((float)px + fx1, 0.f), wl);
+            const float c00 = (fy1 - fy) * (fx1 - fx), c01 = (fy1 - fy) * (fx - fx0);
+            const float c10 = (fy - fy0) * (fx1 - fx), c11 = (fy - fy0) * (fx - fx0);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const float4 a = ldg4(xb + ((size_t)gy0 * W + gx0) * x_cs + 4 * hh), bq = ldg4(xb + ((size_t)gy0 * W + gx1) * x_cs + 4 * hh);
+                const float4 d = ldg4(xb + ((size_t)gy1 * W + gx0) * x_cs + 4 * hh), ee = ldg4(xb + ((size_t)gy1 * W + gx1) * x_cs + 4 * hh);
+                // same expression order as warp_kernel (warp_resize_loss.cu): results are bit-identical
+                r[4 * hh + 0] = c00 * a.x + c01 * bq.x + c10 * d.x + c11 * ee.x;
+                r[4 * hh + 1] = c00 * a.y + c01 * bq.y + c10 * d.y + c11 * ee.y;
+                r[4 * hh + 2] = c00 * a.z + c01 * bq.z + c10 * d.z + c11 * ee.z;
+                r[4 * hh + 3] = c00 * a.w + c01 * bq.w + c10 * d.w + c11 * ee.w;
+            }
+        }
+        __half2 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __floats2half2_rn(r[2 * j], r[2 * j + 1]);
+            const float2 f = __half22float2(h[j]);
+            l[j] = __floats2half2_rn(r[2 * j] - f.x, r[2 * j + 1] - f.y);
+        }
+        __half* row = out + pix * (size_t)(2 * C) + (g >> 2) * 64 + (g & 3) * 8;
+        *reinterpret_cast<uint4*>(row) = make_uint4(*reinterpret_cast<const uint32_t*>(&h[0]), *reinterpret_cast<const uint32_t*>(&h[1]),
+                                                    *reinterpret_cast<const uint32_t*>(&h[2]), *reinterpret_cast<const uint32_t*>(&h[3]));
+        *reinterpret_cast<uint4*>(row + 32) = make_uint4(*reinterpret_cast<const uint32_t*>(&l[0]), *reinterpret_cast<const uint32_t*>(&l[1]),
+                                                         *reinterpret_cast<const uint32_t*>(&l[2]), *reinterpret_cast<const uint32_t*>(&l[3]));
+    }
+}
+
+static bool make_map_split(CUtensorMap* tm, const void* basep, int B, int H, int W, int C, int bx, int by) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)(2 * C), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t box[4] = {64, (cuuint32_t)bx, (cuuint32_t)by, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(basep), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace pwc
+
+using namespace pwc;
+
+extern "C" int pwc_split_f16_fwd(const float* x, int x_cs, void* out, float* copy, int copy_cs,
+                                 long long n_pix, int C, float scale, void* stream) {
+    PWC_REQUIRE(x && out && n_pix > 0 && C > 0, PWC_E_BADARG, "split_f16: bad arguments");
+    PWC_REQUIRE((C % 32) == 0 && (x_cs & 3) == 0 && aligned16(x) && aligned16(out) &&
+                (!copy || ((copy_cs & 3) == 0 && aligned16(copy))), PWC_E_ALIGN,
+                "split_f16: C must be a multiple of 32, strides multiples of 4, pointers 16-byte aligned");
+    const size_t total = (size_t)n_pix * (C / 8);
+    const int blocks = (int)((total + 255) / 256 < (size_t)148 * 16 ? (total + 255) / 256 : (size_t)148 * 16);
+    split_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, (__half*)out, copy, copy_cs, (size_t)n_pix, C, scale);
+    PWC_CHECK_LAUNCH("split_f16_kernel");
+    return 0;
+}
+
+extern "C" int pwc_warp_split_fwd(const float* x, int x_cs, const float* flow, int flow_cs, float flow_scale,
+                                  int warp_type, void* out, int B, int H, int W, int C, void* stream) {
+    PWC_REQUIRE(x && flow && out, PWC_E_BADARG, "warp_split: null pointer");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, PWC_E_BADARG, "warp_split: bad dims");
+    PWC_REQUIRE(warp_type == 0 || warp_type == 1, PWC_E_BADARG, "warp_split: warp_type must be 0 (bilinear) or 1 (nearest)");
+    PWC_REQUIRE((C % 32) == 0 && (x_cs & 3) == 0 && aligned16(x) && aligned16(out), PWC_E_ALIGN,
+                "warp_split: C must be a multiple of 32, x_cs a multiple of 4, x/out 16-byte aligned");
+    const size_t total = (size_t)B * H * W * (C / 8);
+    const int blocks = (int)((total + 255) / 256 < (size_t)148 * 16 ? (total + 255) / 256 : (size_t)148 * 16);
+    if (warp_type == 1) warp_split_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, flow, flow_cs, flow_scale, (__half*)out, B, H, W, C);
+    else warp_split_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, flow, flow_cs, flow_scale, (__half*)out, B, H, W, C);
+    PWC_CHECK_LAUNCH("warp_split_kernel");
+    return 0;
+}
+
+extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float* out, int out_cs,
+                                         int B, int H, int W, int C, float scale, float alpha, void* stream) {
+    PWC_REQUIRE(f0s && f1s && out, PWC_E_BADARG, "cost_volume_split: null pointer");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && out_cs >= 81 && scale > 0.f, PWC_E_BADARG, "cost_volume_split: bad dims");
+    PWC_REQUIRE((C % 32) == 0 && aligned16(f0s) && aligned16(f1s), PWC_E_ALIGN,
+                "cost_volume_split: C must be a multiple of 32 and the operands 16-byte aligned");
+    CUtensorMap tm0, tm1;
+    PWC_REQUIRE(make_map_split(&tm0, f0s, B, H, W, C, S_TW, S_TH) && make_map_split(&tm1, f1s, B, H, W, C, S_FW, S_FH),
+                PWC_E_BADARG, "cost_volume_split: cuTensorMapEncodeTiled failed");
+    CvSplitParams p{};
+    p.out = out; p.out_cs = out_cs; p.B = B; p.H = H; p.W = W; p.kchunks = C / 32;
+    p.tiles_x = (W + S_TW - 1) / S_TW; p.tiles_y = (H + S_TH - 1) / S_TH;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * B;
+    PWC_REQUIRE(tiles < (1ll << 30), PWC_E_BADARG, "cost_volume_split: too many tiles");
+    p.total_tiles = (int)tiles;
+    p.alpha = alpha; p.scale = scale;
+    p.vec = aligned16(out) && (out_cs & 3) == 0;
+    cudaError_t e = cudaFuncSetAttribute(cost_volume_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("cost_volume_split: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
+    static unsigned long long* dbg_buf = nullptr;
+    if (getenv("PWC_CV_DEBUG")) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 148 * 64 * 8);
+        cudaMemsetAsync(dbg_buf, 0, 148 * 64 * 8, (cudaStream_t)stream);
+        p.dbg = dbg_buf;
+    }
+    cost_volume_split_kernel<<<grid, S_THREADS, S_SMEM_BYTES, (cudaStream_t)stream>>>(tm0, tm1, p);
+    PWC_CHECK_LAUNCH("cost_volume_split_kernel");
+    if (p.dbg) {   // debugging aid only (synchronises): timeline of the first tiles of one CTA
+        cudaStreamSynchronize((cudaStream_t)stream);
+        static int printed = 0;
+        if (printed++ < 2) {
+            unsigned long long h[64];
+            const char* names[8] = {"tma_issue", "full_seen", "halfB_go", "mma_issued", "accA_seen", "accB_seen", "scatterA_done", "stored"};
+            cudaMemcpy(h, p.dbg + 64 * (grid / 2), 64 * 8, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[cv_split dbg] cta %d (clk from first tma issue), tiles 0..7\n", grid / 2);
+            for (int e = 0; e < 8; ++e) {
+                fprintf(stderr, "   %-14s", names[e]);
+                for (int t = 0; t < 8; ++t) fprintf(stderr, " %7lld", (long long)(h[e * 8 + t] - h[0]));
+                fprintf(stderr, "\n");
+            }
+        }
+    }
+    return 0;
+}

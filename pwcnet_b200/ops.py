@@ -179,3 +179,60 @@ def epe(flows_gt, flows, acc):
         raise ValueError("epe: flows_gt and flows must be dense tensors of the same (B,H,W,2) shape")
     check(lib().pwc_epe_fwd(flows_gt.data_ptr(), flows.data_ptr(), B, H, W, acc.data_ptr(), _stream()), "pwc_epe_fwd")
     return acc
+
+
+# ------------------------------------------------------------------ split-fp16 fast path of the cost volume
+def split_f16(x, out=None, copy=None, scale: float = 1.0):
+    """fp32 NHWC view -> split tensor (B,H,W,2C) fp16: per pixel and 32-channel slice [h | l], h = fp16(x), l = fp16(x-h).
+    `copy` (fp32 view of the same shape, e.g. the f0 slot of a concat buffer) also receives x."""
+    B, H, W, C, x_cs = _nhwc(x, "x")
+    if C % 32:
+        raise ValueError("split_f16: C must be a multiple of 32")
+    if out is None:
+        out = torch.empty((B, H, W, 2 * C), dtype=torch.float16, device=x.device)
+    elif out.dtype != torch.float16 or tuple(out.shape) != (B, H, W, 2 * C) or not out.is_contiguous():
+        raise ValueError("split_f16: out must be a contiguous fp16 (B,H,W,2C) tensor")
+    cp, cp_cs = None, 0
+    if copy is not None:
+        Bc, Hc, Wc, Cc, cp_cs = _nhwc(copy, "copy")
+        if (Bc, Hc, Wc, Cc) != (B, H, W, C):
+            raise ValueError("split_f16: copy shape mismatch")
+        cp = copy.data_ptr()
+    check(lib().pwc_split_f16_fwd(x.data_ptr(), x_cs, out.data_ptr(), cp, cp_cs, B * H * W, C, float(scale), _stream()),
+          "pwc_split_f16_fwd")
+    return out
+
+
+def warp_split(x, flow, flow_scale: float = 1.0, warp_type: str = "bilinear", out=None):
+    """WarpingLayer.__call__ (modules.py:144-154) with the result written as a split tensor."""
+    assert warp_type in ["nearest", "bilinear"]   # modules.py:149
+    B, H, W, C, x_cs = _nhwc(x, "x")
+    Bf, Hf, Wf, Cf, fl_cs = _nhwc(flow, "flow")
+    if (Bf, Hf, Wf, Cf) != (B, H, W, 2) or C % 32:
+        raise ValueError("warp_split: flow shape mismatch or C not a multiple of 32")
+    if out is None:
+        out = torch.empty((B, H, W, 2 * C), dtype=torch.float16, device=x.device)
+    elif out.dtype != torch.float16 or tuple(out.shape) != (B, H, W, 2 * C) or not out.is_contiguous():
+        raise ValueError("warp_split: out must be a contiguous fp16 (B,H,W,2C) tensor")
+    check(lib().pwc_warp_split_fwd(x.data_ptr(), x_cs, flow.data_ptr(), fl_cs, float(flow_scale), WARP_TYPES[warp_type],
+                                   out.data_ptr(), B, H, W, C, _stream()), "pwc_warp_split_fwd")
+    return out
+
+
+def cost_volume_split(f0s, f1s, alpha: float = 0.1, out=None, prescaled: bool = False):
+    """CostVolumeLayer.__call__ (modules.py:189-204, search_range 4) from split operands, on the tensor cores.
+    prescaled=True: f0s was produced by split_f16(..., scale=1/C), the kernel skips the 1/C multiply."""
+    for t, nm in ((f0s, "f0s"), (f1s, "f1s")):
+        if t.dtype != torch.float16 or t.dim() != 4 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"cost_volume_split: {nm} must be a contiguous CUDA fp16 (B,H,W,2C) split tensor")
+    if f0s.shape != f1s.shape or f0s.shape[3] % 64:
+        raise ValueError("cost_volume_split: operand shapes differ or 2C is not a multiple of 64")
+    B, H, W, C2 = f0s.shape
+    if out is None:
+        out = new_nhwc(B, H, W, 81, f0s.device)
+    Bo, Ho, Wo, Co, out_cs = _nhwc(out, "out")
+    if (Bo, Ho, Wo, Co) != (B, H, W, 81):
+        raise ValueError("cost_volume_split: out shape mismatch")
+    check(lib().pwc_cost_volume_split_fwd(f0s.data_ptr(), f1s.data_ptr(), out.data_ptr(), out_cs, B, H, W, C2 // 2,
+                                          1.0 if prescaled else 2.0 / C2, float(alpha), _stream()), "pwc_cost_volume_split_fwd")
+    return out

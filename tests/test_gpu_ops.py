@@ -62,6 +62,38 @@ def test_cost_volume_tcgen05_variant_matches_oracle(P, shape, slot, monkeypatch)
     np.testing.assert_allclose(out.cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("shape", [(2, 7, 16, 192), (1, 28, 64, 96), (1, 112, 256, 32), (3, 13, 45, 64), (1, 9, 17, 32), (2, 30, 70, 32)])
+def test_cost_volume_split_pipeline_matches_oracle(P, shape):
+    """The pipeline's fast path: split producers (pwc_split_f16_fwd with the f0 slot copy, pwc_warp_split_fwd) feeding
+    the tcgen05 cost volume; result vs the oracle's warp + cost volume on fp32 (1e-5 max-abs: fp32-class)."""
+    B, H, W, C = shape
+    f0, f1 = _rand(shape, 1), _rand(shape, 2)
+    flow = _rand((B, H, W, 2), 3, 1.7)
+    ref_w = O.bilinear_warp(torch.from_numpy(f1), torch.from_numpy(flow) * 2.5)
+    ref = O.cost_volume(torch.from_numpy(f0), ref_w, 4).numpy()
+    buf = torch.full((B, H, W, 84 + C), 7.0, device="cuda")
+    f0s = P.ops.split_f16(_cuda(f0), copy=buf[..., 84:84 + C])
+    f1s = P.ops.warp_split(_cuda(f1), _cuda(flow), 2.5, "bilinear")
+    # the split tensors reproduce their fp32 source to fp32 precision: h + l
+    hl = f0s.float().view(B, H, W, C // 32, 2, 32)
+    np.testing.assert_allclose((hl[..., 0, :] + hl[..., 1, :]).reshape(B, H, W, C).cpu().numpy(), f0, atol=4e-7, rtol=1e-6)
+    np.testing.assert_array_equal(buf[..., 84:].cpu().numpy(), f0)
+    P.ops.cost_volume_split(f0s, f1s, 0.1, out=buf[..., :81])
+    np.testing.assert_allclose(buf[..., :81].cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
+    assert float((buf[..., 81:84] - 7.0).abs().max()) == 0
+    dense = P.ops.cost_volume_split(f0s, f1s, 0.1)
+    np.testing.assert_allclose(dense.cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
+    # the pipeline's form: 1/C folded into the f0 producer, the slot copy stays unscaled
+    buf2 = torch.full((B, H, W, 84 + C), 7.0, device="cuda")
+    f0p = P.ops.split_f16(_cuda(f0), copy=buf2[..., 84:84 + C], scale=1.0 / C)
+    np.testing.assert_array_equal(buf2[..., 84:].cpu().numpy(), f0)
+    P.ops.cost_volume_split(f0p, f1s, 0.1, out=buf2[..., :81], prescaled=True)
+    np.testing.assert_allclose(buf2[..., :81].cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
+    f1n = P.ops.warp_split(_cuda(f1), _cuda(flow), 2.5, "nearest")
+    refn = O.cost_volume(torch.from_numpy(f0), O.nearest_warp(torch.from_numpy(f1), torch.from_numpy(flow) * 2.5), 4).numpy()
+    np.testing.assert_allclose(P.ops.cost_volume_split(f0s, f1n, 0.1).cpu().numpy(), refn, atol=1e-5, rtol=1e-5)
+
+
 def test_cost_volume_all_81_displacements_at_corners(P):
     """Adversarial: impulses in the four corners; every displacement channel must pick exactly the
     reference's (v outer, h inner) neighbour and zero-pad outside the image."""

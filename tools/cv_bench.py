@@ -16,8 +16,15 @@ f1 = torch.randn((B, h, w, C), device="cuda", generator=g)
 flow = torch.randn((B, h, w, 2), device="cuda", generator=g) * 3
 cv = torch.empty((B, h, w, 148), device="cuda")[..., :81] if slot else torch.empty((B, h, w, 81), device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+split = len(sys.argv) > 3 and sys.argv[3] in ("split", "splitslot")
+if split:
+    if sys.argv[3] == "splitslot":
+        cv = torch.empty((B, h, w, 148), device="cuda")[..., :81]
+    f0s, f1s = P.ops.split_f16(f0, scale=1.0 / C), P.ops.split_f16(f1)
 def run():
-    if fused:
+    if split:
+        P.ops.cost_volume_split(f0s, f1s, out=cv, prescaled=True)
+    elif fused:
         P.ops.warp_cost_volume(f0, f1, flow, 5.0, out=cv)
     else:
         P.ops.cost_volume(f0, f1, out=cv)
