@@ -51,15 +51,23 @@ __global__ void __launch_bounds__(DG_THREADS) conv3x3_dgrad_kernel(const DgradPa
     __shared__ __align__(16) float As[DG_BK][DG_BM + 4];
     __shared__ __align__(16) float Bs[DG_BK][DG_BN + 4];
 
+    // For stride s the input pixels are tiled per parity class (iy % s, ix % s): every pixel of a tile then sees the
+    // same subset of taps (those with (iy + pad_t - ky*dil) % s == 0), the others are skipped instead of multiplied by 0.
     const int tid = threadIdx.x;
-    const int tiles_x = (p.W + DG_TW - 1) / DG_TW;
+    const int sub = p.stride;
+    const int n_tiles_n = (p.Cin + DG_BN - 1) / DG_BN;
+    const int par = blockIdx.y / n_tiles_n, ry = par / sub, rx = par - ry * sub;
+    const int Hs = (p.H - ry + sub - 1) / sub, Ws = (p.W - rx + sub - 1) / sub;   // pixels of this parity class
+    const int tiles_x = ((p.W + sub - 1) / sub + DG_TW - 1) / DG_TW;
     const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
     const int b = blockIdx.z;
-    const int n0 = blockIdx.y * DG_BN;
+    const int n0 = (blockIdx.y - par * n_tiles_n) * DG_BN;
     const float* dyb = p.dy + (size_t)b * p.OH * p.OW * p.dy_cs;
 
     const int lm = tid & (DG_BM - 1), lkg = tid >> 7;
-    const int l_iy = tile_y * DG_TH + (lm >> 4), l_ix = tile_x * DG_TW + (lm & 15);
+    const int l_sy = tile_y * DG_TH + (lm >> 4), l_sx = tile_x * DG_TW + (lm & 15);
+    const int l_iy = l_sy * sub + ry, l_ix = l_sx * sub + rx;
+    const bool l_ok = l_sy < Hs && l_sx < Ws;
     const int tn = tid & 15, tm = tid >> 4;
     // weight-load role (threads 0..127): input channel n = tid >> 1, four output channels 4*(tid & 1)..
     const int wn = tid >> 1, wh = tid & 1;
@@ -72,8 +80,12 @@ __global__ void __launch_bounds__(DG_THREADS) conv3x3_dgrad_kernel(const DgradPa
 
     for (int tap = 0; tap < 9; ++tap) {
         const int ky = tap / 3, kx = tap - ky * 3;
+        {   // tap parity is uniform over the CTA: skip taps that never hit an output pixel of this class
+            const int py2 = ((ry + p.pad_t - ky * p.dil) % sub + sub) % sub, px2 = ((rx + p.pad_l - kx * p.dil) % sub + sub) % sub;
+            if (py2 != 0 || px2 != 0) continue;
+        }
         const int ty = l_iy + p.pad_t - ky * p.dil, tx = l_ix + p.pad_l - kx * p.dil;
-        bool inb = l_iy < p.H && l_ix < p.W && ty >= 0 && tx >= 0 && (ty % p.stride) == 0 && (tx % p.stride) == 0;
+        bool inb = l_ok && ty >= 0 && tx >= 0;
         const int oy = ty / p.stride, ox = tx / p.stride;
         inb = inb && oy < p.OH && ox < p.OW;
         const float* dyp = dyb + ((size_t)oy * p.OW + ox) * p.dy_cs;
@@ -123,8 +135,9 @@ __global__ void __launch_bounds__(DG_THREADS) conv3x3_dgrad_kernel(const DgradPa
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = tm * 8 + i;
-        const int iy = tile_y * DG_TH + (m >> 4), ix = tile_x * DG_TW + (m & 15);
-        if (iy >= p.H || ix >= p.W) continue;
+        const int sy = tile_y * DG_TH + (m >> 4), sx = tile_x * DG_TW + (m & 15);
+        if (sy >= Hs || sx >= Ws) continue;
+        const int iy = sy * sub + ry, ix = sx * sub + rx;
         const size_t pix = ((size_t)b * p.H + iy) * p.W + ix;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -645,8 +658,10 @@ extern "C" int pwc_conv3x3_dgrad(const float* dy, int dy_cs, const float* w_hwio
     same_pad_b(W, stride, dilation, &p.OW, &p.pad_l);
     p.mask_alpha = mask_alpha; p.accumulate = accumulate;
     p.vec_dy = aligned16(dy) && (dy_cs % 4 == 0);
-    const int tiles = ((W + DG_TW - 1) / DG_TW) * ((H + DG_TH - 1) / DG_TH);
-    dim3 grid(tiles, (Cin + DG_BN - 1) / DG_BN, B);
+    PWC_REQUIRE(stride <= 8, PWC_E_BADARG, "conv3x3_dgrad: stride > 8");
+    const int Hs = (H + stride - 1) / stride, Ws = (W + stride - 1) / stride;     // largest parity class
+    const int tiles = ((Ws + DG_TW - 1) / DG_TW) * ((Hs + DG_TH - 1) / DG_TH);
+    dim3 grid(tiles, ((Cin + DG_BN - 1) / DG_BN) * stride * stride, B);
     conv3x3_dgrad_kernel<<<grid, DG_THREADS, 0, (cudaStream_t)stream>>>(p);
     PWC_CHECK_LAUNCH("conv3x3_dgrad_kernel");
     return 0;

@@ -147,7 +147,7 @@ class Trainer(object):
             from ._abi import lib
             k = self.model._k[scope]
             cdx, cdy = k.shape[2], k.shape[3]
-            n_parts = -(-cdx // 256)
+            n_parts = -(-cdx // 128)          # parts of <= 128 channels run on the halo-resident kernel
             size = (-(-cdx // n_parts) + 15) // 16 * 16
             parts = []
             for c0 in range(0, cdx, size):
