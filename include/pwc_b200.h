@@ -195,6 +195,24 @@ int pwc_warp_split_fwd(const float* x, int x_cs, const float* flow, int flow_cs,
 int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float* out, int out_cs,
                               int B, int H, int W, int C, float scale, float alpha, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Conv2DBackpropFilter on tcgen05 (wgrad_tc.cu).  Operands are first transposed to channel-major fp16 planes
+ * (h = fp16(v), l = fp16((v - h) * 2^11), each plane (B, C, H, OWp), OWp = OW rounded up to 8):
+ *   n_shift = 1 (dy):   out = [h | l] of x itself (OW = W); if db != NULL, db[c] += sum x[..., c] (BiasAddGrad);
+ *   n_shift = 3 (conv input): out = three copies [h | l], copy kx sampled at the conv's OUTPUT columns,
+ *                       copy_kx[b, c, y, ox] = x[b, y, ox*stride - pad_left + kx*dilation, c] (0 outside).
+ * pwc_tsplit_bytes gives the size of `out` (OW = output width for n_shift = 3).  C % 4 == 0.
+ * ------------------------------------------------------------------------------------------------ */
+long long pwc_tsplit_bytes(int B, int H, int OW, int C, int n_shift);
+int pwc_tsplit_f16(const float* x, int x_cs, void* out, int B, int H, int W, int C, int n_shift, int stride,
+                   int dilation, float* db, void* stream);
+
+/* dw[tap, map(ci), co] += sum x * dy from xT = pwc_tsplit_f16(conv input, n_shift 3, stride, dilation) and
+ * dyT = pwc_tsplit_f16(output gradient, n_shift 1); H, W, Cin describe the conv input; same cin_map / dw_cin meaning
+ * as pwc_conv3x3_wgrad.  stride 1 or 2, Cout % 16 == 0.  Accumulates with atomics: zero dw before the first call. */
+int pwc_conv3x3_wgrad_tc(const void* xT, const void* dyT, float* dw, const int* cin_map, int dw_cin,
+                         int B, int H, int W, int Cin, int Cout, int stride, int dilation, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

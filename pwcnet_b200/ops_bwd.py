@@ -200,3 +200,38 @@ def conv3x3_tc_f16_dgrad(dy, w_rot_packed, dx, cdx_pad: int, dilation: int = 1, 
                                          float(mask_alpha), int(accumulate), B, H, W, Cdy, Cdx, cdx_pad, dilation, _stream()),
           "pwc_conv3x3_tc_f16_dgrad")
     return dx
+
+
+def tsplit_bytes(B, H, OW, C, n_shift: int = 1) -> int:
+    return int(lib().pwc_tsplit_bytes(B, H, OW, C, n_shift))
+
+
+def tsplit(x, out=None, db=None, conv_input: bool = False, stride: int = 1, dilation: int = 1):
+    """NHWC fp32 view -> channel-major fp16 planes [h | l*2^11], each (B, C, H, OWp): the K-major operands of the
+    tensor-core wgrad.  conv_input=False: plain transpose (for dy; db += per-channel sums).  conv_input=True: three
+    copies, one per horizontal tap, sampled at the conv's output columns (see pwc_tsplit_f16)."""
+    B, H, W, C, x_cs = _nhwc(x, "x")
+    n_shift = 3 if conv_input else 1
+    OW = _same_out(W, stride) if conv_input else W
+    n = tsplit_bytes(B, H, OW, C, n_shift) // 2
+    if out is None:
+        out = torch.empty(n, dtype=torch.float16, device=x.device)
+    elif out.dtype != torch.float16 or out.numel() < n or not out.is_contiguous():
+        raise ValueError("tsplit: out must be a contiguous fp16 buffer of at least tsplit_bytes()/2 elements")
+    if db is not None and (conv_input or db.shape != (C,) or not db.is_contiguous()):
+        raise ValueError("tsplit: db must be contiguous (C,) and is only reduced by the plain transpose")
+    check(lib().pwc_tsplit_f16(x.data_ptr(), x_cs, out.data_ptr(), B, H, W, C, n_shift, stride if conv_input else 1,
+                               dilation if conv_input else 1, _ptr(db), _stream()), "pwc_tsplit_f16")
+    return out
+
+
+def conv3x3_wgrad_tc(xT, dyT, dw, in_shape, cout: int, stride: int = 1, dilation: int = 1, cin_map=None):
+    """dw += Conv2DBackpropFilter on tcgen05 from tsplit() planes; in_shape = (B, H, W, Cin) of the conv input."""
+    B, H, W, Cin = in_shape
+    if dw.dim() != 4 or dw.shape[:2] != (3, 3) or dw.shape[3] != cout or not dw.is_contiguous():
+        raise ValueError(f"conv3x3_wgrad_tc: dw must be contiguous (3,3,Cin,{cout})")
+    if cin_map is None and dw.shape[2] != Cin:
+        raise ValueError("conv3x3_wgrad_tc: dw input channels differ from x (pass cin_map for concat layers)")
+    check(lib().pwc_conv3x3_wgrad_tc(xT.data_ptr(), dyT.data_ptr(), dw.data_ptr(), _ptr(cin_map), dw.shape[2], B, H, W, Cin, cout,
+                                     stride, dilation, _stream()), "pwc_conv3x3_wgrad_tc")
+    return dw

@@ -50,7 +50,8 @@ class Trainer(object):
     def __init__(self, model: PWCDCNet, lr: float = 1e-4, gamma: float = 4e-4,
                  weights: Sequence[float] = DEFAULT_LOSS_WEIGHTS, beta1: float = 0.9, beta2: float = 0.999,
                  eps: float = 1e-8, lr_boundaries: Sequence[int] = LR_BOUNDARIES, process_group=None,
-                 global_step: int = 0, tc_dgrad: Optional[bool] = None):
+                 global_step: int = 0, tc_dgrad: Optional[bool] = None,
+                 tc_wgrad: Optional[bool] = None):
         if model.use_dc:
             raise NotImplementedError("Trainer: use_dc=True is inference-only in this build (no reference checkpoint "
                                       "or BASELINE config trains it)")
@@ -83,6 +84,8 @@ class Trainer(object):
         self._gbufs: Dict[tuple, _Grads] = {}
         self._parts: Dict[str, list] = {}
         self.tc_dgrad = model.precision == "3xf16" if tc_dgrad is None else bool(tc_dgrad)
+        self.tc_wgrad = model.precision == "3xf16" if tc_wgrad is None else bool(tc_wgrad)
+        self._tscratch = None
 
     # ------------------------------------------------------------------ gradient workspace
     def _grad_buffers(self, p) -> _Grads:
@@ -122,8 +125,22 @@ class Trainer(object):
     def _conv_bwd(self, scope, x, dy, gx, stride=1, dilation=1, mask=None, accumulate=False):
         """wgrad + bias grad into the flat gradient, then dgrad into gx (skipped when gx is None)."""
         m = self.model
-        ops_bwd.conv3x3_wgrad(x, dy, self.grads[scope + "/kernel"], self.grads[scope + "/bias"], stride=stride,
-                              dilation=dilation, cin_map=m._cin_perm.get(scope))
+        cin, cout = x.shape[3], dy.shape[3]
+        if self.tc_wgrad and cout % 16 == 0 and cin % 4 == 0 and not (cin <= 32 and cout <= 32) and stride in (1, 2) \
+                and x.stride(2) % 4 == 0 and dy.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0:
+            # tensor-core wgrad: transpose + split both operands into channel-major fp16 planes (the dy pass also
+            # reduces the bias gradient), then one GEMM launch over (tap pairs, channel tiles, row ranges)
+            B, H, W = x.shape[0], x.shape[1], x.shape[2]
+            need = max(ops_bwd.tsplit_bytes(B, H, dy.shape[2], cin, 3), ops_bwd.tsplit_bytes(B, dy.shape[1], dy.shape[2], cout)) // 2
+            if self._tscratch is None or self._tscratch[0].numel() < need:
+                self._tscratch = [torch.empty(need, dtype=torch.float16, device=x.device) for _ in range(2)]
+            xT = ops_bwd.tsplit(x, out=self._tscratch[0], conv_input=True, stride=stride, dilation=dilation)
+            dyT = ops_bwd.tsplit(dy, out=self._tscratch[1], db=self.grads[scope + "/bias"])
+            ops_bwd.conv3x3_wgrad_tc(xT, dyT, self.grads[scope + "/kernel"], (B, H, W, cin), cout, stride=stride,
+                                     dilation=dilation, cin_map=m._cin_perm.get(scope))
+        else:
+            ops_bwd.conv3x3_wgrad(x, dy, self.grads[scope + "/kernel"], self.grads[scope + "/bias"], stride=stride,
+                                  dilation=dilation, cin_map=m._cin_perm.get(scope))
         if gx is None:
             return
         k = m._k[scope]

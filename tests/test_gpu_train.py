@@ -67,6 +67,35 @@ def test_conv_dgrad_wgrad_match_autograd(P, case):
     _close(db, b.grad, name="db")
 
 
+WGRAD_TC_CASES = [  # B, H, W, Cin, Cout, stride, dilation
+    (2, 9, 13, 32, 64, 1, 1), (1, 11, 18, 36, 128, 1, 2), (1, 20, 40, 96, 64, 1, 8), (1, 7, 16, 128, 96, 1, 16),
+    (1, 10, 12, 148, 128, 1, 1), (1, 13, 17, 64, 96, 2, 1), (1, 3, 5, 192, 192, 1, 1), (2, 16, 70, 64, 32, 1, 1),
+    (1, 12, 300, 128, 128, 1, 1), (2, 14, 32, 276, 128, 1, 1), (1, 16, 24, 16, 32, 2, 1),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES)
+def test_conv_wgrad_tensor_core_matches_autograd(P, case):
+    """tsplit (transpose + fp16 split, bias gradient) + tcgen05 wgrad vs torch autograd of the oracle conv; fp32-class:
+    2e-5 relative to the largest gradient entry."""
+    from pwcnet_b200 import ops_bwd
+    B, H, W, Cin, Cout, s, d = case
+    x = torch.from_numpy(_rand((B, H, W, Cin), 1))
+    k = torch.from_numpy(_rand((3, 3, Cin, Cout), 2, 0.1)).requires_grad_(True)
+    b = torch.from_numpy(_rand((Cout,), 3, 0.1)).requires_grad_(True)
+    y = O.conv2d_same(x, k, b, s, d)
+    dy = torch.from_numpy(_rand(tuple(y.shape), 4, 1e-3))          # gradients are small: exercises fp16 subnormals of h
+    y.backward(dy)
+    xb = torch.zeros((B, H, W, Cin + 4), device="cuda"); xb[..., :Cin] = x.cuda()      # a slot view, like the concat buffers
+    db = torch.zeros((Cout,), device="cuda")
+    xT = ops_bwd.tsplit(xb[..., :Cin], conv_input=True, stride=s, dilation=d)
+    dyT = ops_bwd.tsplit(dy.cuda(), db=db)
+    dw = torch.zeros((3, 3, Cin, Cout), device="cuda")
+    ops_bwd.conv3x3_wgrad_tc(xT, dyT, dw, (B, H, W, Cin), Cout, stride=s, dilation=d)
+    _close(dw, k.grad, name="dw (tensor cores)")
+    _close(db, b.grad, name="db (tsplit)")
+
+
 def test_conv_dgrad_mask_accumulate_and_slots(P):
     """Leaky mask in the epilogue, accumulation, and reading/writing channel slots of wider buffers."""
     from pwcnet_b200 import ops_bwd
