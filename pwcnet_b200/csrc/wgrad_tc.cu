@@ -94,6 +94,8 @@ struct WtcParams {
     int B, OH, OW, stride, dil, pad_t, pad_l;
     int total_rows, rows_per_cta, xchunks;
     int b_bytes;       // n_tile * 64: one fp16 dy tile
+    int a_rows;        // rows of an x tile that are actually loaded (min(128, Cin rounded up to 8)); the rest of the
+                       // 128-row MMA operand is stale shared memory and only feeds accumulator rows that are never read
     int stage_bytes;
 };
 
@@ -145,7 +147,7 @@ wgrad_tc_kernel(const __grid_constant__ WtcMaps maps, const WtcParams p) {
         if (lane == 0 && n_chunks > 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[0]) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[1]) : "memory");
-            const uint32_t tx_bytes = ntaps * 2 * WT_A_TILE + 2 * p.b_bytes;
+            const uint32_t tx_bytes = ntaps * 2 * p.a_rows * 64 + 2 * p.b_bytes;
             int it = 0;
             for (int r = row_begin; r < row_end; ++r) {
                 const int b = r / p.OH, y = r - b * p.OH;
@@ -308,7 +310,8 @@ extern "C" int pwc_conv3x3_wgrad_tc(const void* xT, const void* dyT, float* dw, 
         const __half* xb = (const __half*)xT;
         const __half* yb = (const __half*)dyT;
         bool ok = true;
-        for (int i = 0; i < 6; ++i) ok = ok && wt_map(&maps.a[i], xb + (size_t)i * xplane, B, Cin, H, p.OW, OWp, 128);
+        p.a_rows = p.ci_tiles > 1 ? 128 : (Cin + 7) / 8 * 8;
+        for (int i = 0; i < 6; ++i) ok = ok && wt_map(&maps.a[i], xb + (size_t)i * xplane, B, Cin, H, p.OW, OWp, p.a_rows);
         for (int i = 0; i < 2; ++i) ok = ok && wt_map(&maps.b[i], yb + (size_t)i * yplane, B, Cout, p.OH, p.OW, OWp, p.n_tile);
         PWC_REQUIRE(ok, PWC_E_BADARG, "conv3x3_wgrad_tc: cuTensorMapEncodeTiled failed");
     }

@@ -70,7 +70,8 @@ def test_conv_dgrad_wgrad_match_autograd(P, case):
 WGRAD_TC_CASES = [  # B, H, W, Cin, Cout, stride, dilation
     (2, 9, 13, 32, 64, 1, 1), (1, 11, 18, 36, 128, 1, 2), (1, 20, 40, 96, 64, 1, 8), (1, 7, 16, 128, 96, 1, 16),
     (1, 10, 12, 148, 128, 1, 1), (1, 13, 17, 64, 96, 2, 1), (1, 3, 5, 192, 192, 1, 1), (2, 16, 70, 64, 32, 1, 1),
-    (1, 12, 300, 128, 128, 1, 1), (2, 14, 32, 276, 128, 1, 1), (1, 16, 24, 16, 32, 2, 1),
+    (1, 12, 300, 128, 128, 1, 1), (2, 14, 32, 276, 128, 1, 1), (1, 16, 24, 16, 32, 2, 1), (2, 20, 36, 16, 16, 1, 1),
+    (1, 9, 40, 20, 48, 1, 1),
 ]
 
 
