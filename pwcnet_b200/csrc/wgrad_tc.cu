@@ -120,11 +120,13 @@ wgrad_tc_kernel(const __grid_constant__ WtcMaps maps, const WtcParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[WT_STAGES]), bar_acc = smem_u32(&bars[2 * WT_STAGES]);
 
-    const int tg = blockIdx.z;                               // tap group: taps 2 tg, 2 tg + 1 (group 4: tap 8 only)
+    // blockIdx.x = tap group (fastest-varying: the five CTAs that read the same dy rows and x copies are scheduled
+    // together, so the re-reads hit L2), blockIdx.z = row range
+    const int tg = blockIdx.x;                               // taps 2 tg, 2 tg + 1 (group 4: tap 8 only)
     const int ntaps = tg == 4 ? 1 : 2;
     const int mt = blockIdx.y % p.ci_tiles, nt = blockIdx.y / p.ci_tiles;
     const int ci0 = mt * 128, co0 = nt * p.n_tile;
-    const int row_begin = blockIdx.x * p.rows_per_cta;
+    const int row_begin = blockIdx.z * p.rows_per_cta;
     const int row_end = min(row_begin + p.rows_per_cta, p.total_rows);
     const int n_chunks = (row_end - row_begin) * p.xchunks;
 
@@ -318,7 +320,8 @@ extern "C" int pwc_conv3x3_wgrad_tc(const void* xT, const void* dyT, float* dw, 
     const size_t smem = (size_t)WT_STAGES * p.stage_bytes + 1024;
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_wgrad_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    dim3 grid(R, tiles, 5);
+    PWC_REQUIRE(R <= 65535, PWC_E_BADARG, "conv3x3_wgrad_tc: too many row ranges");
+    dim3 grid(5, tiles, R);
     wgrad_tc_kernel<<<grid, WT_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
     PWC_CHECK_LAUNCH("wgrad_tc_kernel");
     return 0;
