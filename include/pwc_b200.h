@@ -80,6 +80,12 @@ int pwc_conv3x3_pack_weights(const float* w_hwio, float* w_packed, int Cin, int 
 int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_packed, const float* bias,
                            float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int stride, int dilation,
                            float alpha, void* stream);
+/* Flow heads on the tensor cores (modules.py:274-277, 325-326): the same conv with the MMA N padded to Cout_pad
+ * (multiple of 16; w_packed = pack of the kernel zero-padded to Cout_pad output channels, bias_pad zero-padded), only
+ * the first Cout channels are stored, `residual` (may be NULL) is added after the activation.  stride 1. */
+int pwc_conv3x3_tc_f16_head(const float* x, int x_cs, const void* w_packed, const float* bias_pad,
+                            const float* residual, int res_cs, float* y, int y_cs, int B, int H, int W, int Cin,
+                            int Cout, int Cout_pad, int dilation, float alpha, void* stream);
 long long pwc_conv3x3_packed_bytes_f16(int Cin, int Cout);
 int pwc_conv3x3_pack_weights_f16(const float* w_hwio, void* w_packed, int Cin, int Cout, void* stream);
 

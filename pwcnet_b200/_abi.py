@@ -27,6 +27,7 @@ SIGNATURES = {
     "pwc_conv3x3_fwd": (_i, [_f32p, _i, _f32p, _f32p, _f32p, _i, _f32p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "pwc_conv3x3_tc_fwd": (_i, [_f32p, _i, _f32p, _f32p, _f32p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "pwc_conv3x3_tc_f16_fwd": (_i, [_f32p, _i, _f32p, _f32p, _f32p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "pwc_conv3x3_tc_f16_head": (_i, [_f32p, _i, _f32p, _f32p, _f32p, _i, _f32p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "pwc_conv3x3_packed_bytes_f16": (C.c_longlong, [_i, _i]),
     "pwc_conv3x3_pack_weights_f16": (_i, [_f32p, _f32p, _i, _i, _vp]),
     "pwc_conv3x3_packed_bytes": (C.c_longlong, [_i, _i]),

@@ -43,6 +43,7 @@ struct F16Params {
     // (Cout is the MMA N, padded to a multiple of 16), the result is multiplied by leaky'(mask) and optionally
     // accumulated into y
     const float* mask; int mask_cs; float mask_alpha; int accumulate; int cout_valid;
+    const float* res; int res_cs;   // residual added after the activation (flow heads, modules.py:275-277, 326)
 };
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -215,7 +216,8 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
             const bool valid = oy < p.OH && ox < p.OW;
             float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs;
             const float* mrow = p.mask ? p.mask + (((size_t)b * p.OH + oy) * p.OW + ox) * p.mask_cs : nullptr;
-            const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y) && ((p.cout_valid & 3) == 0) &&
+            const float* rrow = p.res ? p.res + (((size_t)b * p.OH + oy) * p.OW + ox) * p.res_cs : nullptr;
+            const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y) && ((p.cout_valid & 3) == 0) && !p.res &&
                              (!p.mask || (((p.mask_cs & 3) == 0) && aligned16(p.mask)));
             for (int n0 = 0; n0 < p.Cout; n0 += 16) {
                 const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + n0;
@@ -259,6 +261,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                             if (n0 + j >= p.cout_valid) break;
                             float v = acc[j];
                             if (mrow) v *= __ldg(mrow + n0 + j) > 0.f ? 1.f : p.mask_alpha;
+                            if (rrow) v += __ldg(rrow + n0 + j);
                             if (p.accumulate) v += yrow[n0 + j];
                             yrow[n0 + j] = v;
                         }
@@ -320,11 +323,11 @@ extern "C" int pwc_conv3x3_pack_weights_f16(const float* w_hwio, void* w_packed,
 }
 
 namespace pwc {
-struct F16Extra { const float* mask; int mask_cs; float mask_alpha; int accumulate; int cout_valid; };
+struct F16Extra { const float* mask; int mask_cs; float mask_alpha; int accumulate; int cout_valid; const float* res; int res_cs; };
 // conv_tc_halo.cu: halo-resident variant for stride 1, dilation 1, wide rows, Cout <= 128
 int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
                      int B, int H, int W, int Cin, int Cout, int dilation, float alpha, const float* mask, int mask_cs,
-                     float mask_alpha, int accumulate, int cout_valid, cudaStream_t st);
+                     float mask_alpha, int accumulate, int cout_valid, const float* res, int res_cs, cudaStream_t st);
 }
 
 static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const float* bias,
@@ -349,7 +352,7 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
         const int halo_on = he ? atoi(he) : 1;
         if (halo_on && stride == 1 && dilation <= 16 && W >= 96 && Cout <= 128) {
             const int rc = launch_conv_halo(x, x_cs, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, dilation, alpha, ex.mask, ex.mask_cs,
-                                            ex.mask_alpha, ex.accumulate, ex.cout_valid, (cudaStream_t)stream);
+                                            ex.mask_alpha, ex.accumulate, ex.cout_valid, ex.res, ex.res_cs, (cudaStream_t)stream);
             if (rc != -1000) return rc;
         }
     }
@@ -379,6 +382,7 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     p.kchunks = cpad / F16_BK;
     p.alpha = alpha;
     p.mask = ex.mask; p.mask_cs = ex.mask_cs; p.mask_alpha = ex.mask_alpha; p.accumulate = ex.accumulate; p.cout_valid = ex.cout_valid;
+    p.res = ex.res; p.res_cs = ex.res_cs;
     p.b_bytes = Cout * 64;
     p.stage_bytes = (int)(F16_A_RAW + 2 * F16_A_HALF) + 1024 + 2 * p.b_bytes;
     p.shift = 0;
@@ -393,6 +397,9 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     p.stages = ((kt <= 18 ? 72 : 110) * 1024) / p.stage_bytes;
     if (p.stages < 2) p.stages = 2;
     if (p.stages > 4) p.stages = 4;
+    // small problems (coarse pyramid levels: fewer tiles than SMs) cannot use a second CTA per SM anyway and are bound by
+    // the serial K loop: give the one CTA a deeper ring so the TMA latency is hidden
+    if (tiles <= 148 && !getenv("PWC_TC_NO_DEEP")) { int deep = (200 * 1024) / p.stage_bytes; if (deep > 6) deep = 6; if (deep > p.stages) p.stages = deep; }
     if (const char* e = getenv("PWC_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 8 && v * p.stage_bytes <= budget) p.stages = v; }
     PWC_REQUIRE(p.stages >= 2, PWC_E_BADARG, "conv3x3_tc_f16: tile does not fit in shared memory");
     p.prefetch = 0;   // L2 prefetch of upcoming activation boxes: measured no gain (profiles/r01_f16_prefetch.log)
@@ -441,8 +448,20 @@ extern "C" int pwc_conv3x3_tc_f16_fwd(const float* x, int x_cs, const void* w_pa
                                       float* y, int y_cs, int B, int H, int W, int Cin, int Cout, int stride, int dilation,
                                       float alpha, void* stream) {
     PWC_REQUIRE(bias, PWC_E_BADARG, "conv3x3_tc_f16: null pointer");
-    const pwc::F16Extra ex{nullptr, 0, 1.f, 0, Cout};
+    const pwc::F16Extra ex{nullptr, 0, 1.f, 0, Cout, nullptr, 0};
     return launch_conv_f16(x, x_cs, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, stride, dilation, alpha, ex, stream);
+}
+
+// Same conv with the MMA N padded to Cout_pad (a multiple of 16; the packed kernel and the bias are zero-padded to it),
+// only the first Cout channels stored, and an optional residual added after the activation: the 2-channel flow heads
+// (modules.py:274-277, 325-326) on the tensor cores.
+extern "C" int pwc_conv3x3_tc_f16_head(const float* x, int x_cs, const void* w_packed, const float* bias_pad,
+                                       const float* residual, int res_cs, float* y, int y_cs, int B, int H, int W, int Cin,
+                                       int Cout, int Cout_pad, int dilation, float alpha, void* stream) {
+    PWC_REQUIRE(bias_pad, PWC_E_BADARG, "conv3x3_tc_f16_head: null pointer");
+    PWC_REQUIRE(Cout > 0 && Cout <= Cout_pad && (!residual || res_cs >= Cout), PWC_E_BADARG, "conv3x3_tc_f16_head: bad channel counts");
+    const pwc::F16Extra ex{nullptr, 0, 1.f, 0, Cout, residual, res_cs};
+    return launch_conv_f16(x, x_cs, w_packed, bias_pad, y, y_cs, B, H, W, Cin, Cout_pad, 1, dilation, alpha, ex, stream);
 }
 
 // Conv2DBackpropInput of a STRIDE-1 conv on the tensor cores: a SAME conv of dy with the 180-degree-rotated,
@@ -452,6 +471,6 @@ extern "C" int pwc_conv3x3_tc_f16_dgrad(const float* dy, int dy_cs, const void* 
                                         const float* mask, int mask_cs, float mask_alpha, int accumulate,
                                         int B, int H, int W, int Cdy, int Cdx, int Cdx_pad, int dilation, void* stream) {
     PWC_REQUIRE(!mask || mask_cs >= Cdx, PWC_E_BADARG, "conv3x3_tc_f16_dgrad: mask channel stride smaller than Cdx");
-    const pwc::F16Extra ex{mask, mask_cs, mask_alpha, accumulate, Cdx};
+    const pwc::F16Extra ex{mask, mask_cs, mask_alpha, accumulate, Cdx, nullptr, 0};
     return launch_conv_f16(dy, dy_cs, w_rot_packed, nullptr, dx, dx_cs, B, H, W, Cdy, Cdx_pad, 1, dilation, 1.f, ex, stream);
 }

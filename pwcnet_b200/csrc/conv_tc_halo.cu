@@ -33,7 +33,8 @@ constexpr float HL_SCALE = 2048.f, HL_INV_SCALE = 1.f / 2048.f;
 
 struct HaloParams {
     const float* bias; float* y; const uint8_t* w;
-    const float* mask;
+    const float* mask; const float* res;
+    int res_cs;
     int y_cs, mask_cs, B, H, W, Cin, Cout, cout_valid;
     int tiles_x, total_tiles, kchunks;
     int b_bytes;          // Cout * 64: one fp16 weight tile (h or l) of a (tap, slice)
@@ -208,7 +209,8 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
             const size_t pix = ((size_t)b * p.H + y) * p.W + x;
             float* yrow = p.y + pix * p.y_cs;
             const float* mrow = p.mask ? p.mask + pix * p.mask_cs : nullptr;
-            const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y) && ((p.cout_valid & 3) == 0) &&
+            const float* rrow = p.res ? p.res + pix * p.res_cs : nullptr;
+            const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y) && ((p.cout_valid & 3) == 0) && !p.res &&
                              (!p.mask || (((p.mask_cs & 3) == 0) && aligned16(p.mask)));
             const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + a * 256;
             for (int n0 = 0; n0 < p.Cout; n0 += 16) {
@@ -246,6 +248,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                             if (n0 + j >= p.cout_valid) break;
                             float v = acc[j];
                             if (mrow) v *= __ldg(mrow + n0 + j) > 0.f ? 1.f : p.mask_alpha;
+                            if (rrow) v += __ldg(rrow + n0 + j);
                             if (p.accumulate) v += yrow[n0 + j];
                             yrow[n0 + j] = v;
                         }
@@ -313,7 +316,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
 // Returns CONV_HALO_UNSUPPORTED when the arguments need the streaming kernel of conv_tc_f16.cu.
 int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
                      int B, int H, int W, int Cin, int Cout, int dilation, float alpha, const float* mask, int mask_cs,
-                     float mask_alpha, int accumulate, int cout_valid, cudaStream_t st) {
+                     float mask_alpha, int accumulate, int cout_valid, const float* res, int res_cs, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
     if (!enc || Cout > 128 || (Cout & 7) || dilation < 1 || dilation > 16) return -1000;   // two accumulator sets of 2*Cout columns must fit 512
     CUtensorMap tmX;
@@ -332,7 +335,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return PWC_E_BADARG; }
     }
     HaloParams p{};
-    p.bias = bias; p.y = y; p.w = (const uint8_t*)w_packed; p.mask = mask;
+    p.bias = bias; p.y = y; p.w = (const uint8_t*)w_packed; p.mask = mask; p.res = res; p.res_cs = res_cs;
     p.y_cs = y_cs; p.mask_cs = mask_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.cout_valid = cout_valid;
     p.tiles_x = (W + HL_M - 1) / HL_M;
     const long long tiles = (long long)p.tiles_x * H * B;

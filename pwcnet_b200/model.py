@@ -207,6 +207,8 @@ class PWCDCNet(object):
         if not hasattr(self, "_k"):
             self._k: Dict[str, torch.Tensor] = {}
             self._packed: Dict[str, torch.Tensor] = {}
+            self._head_k: Dict[str, torch.Tensor] = {}
+            self._head_b: Dict[str, torch.Tensor] = {}
             self._cin_perm: Dict[str, torch.Tensor] = {}     # scope -> CUDA int32 internal->reference channel map
             for scope, cin, cout in self._table:
                 self._k[scope] = self.params[scope + "/kernel"]
@@ -231,12 +233,21 @@ class PWCDCNet(object):
             scope = key.split("#")[0]
             if key.endswith("#rot"):
                 continue   # owned by the trainer
+            if key.endswith("#head"):
+                self._refresh_head(scope)
+                ops_tc.pack_weights_f16(self._head_k[scope], out=packed)
+                continue
             if packed.dtype == torch.float16:
                 ops_tc.pack_weights_f16(self._k[scope], out=packed)
             else:
                 ops_tc.pack_weights(self._k[scope], out=packed)
 
     refresh_derived = _prepare
+
+    def _refresh_head(self, scope) -> None:
+        """Zero-padded (16 output channels) copies of a 2-channel head's kernel and bias."""
+        self._head_k[scope][..., :2].copy_(self._k[scope])
+        self._head_b[scope][:2].copy_(self.params[scope + "/bias"])
 
     # ------------------------------------------------------------------ conv dispatch
     def _conv(self, x, scope, out, stride=1, dilation=1, alpha=0.1, residual=None):
@@ -245,6 +256,18 @@ class PWCDCNet(object):
         cin, cout = k.shape[2], k.shape[3]
         if self.precision == "cudnn":
             return self._conv_cudnn(x, k, b, out, stride, dilation, alpha, residual)
+        if self.precision == "3xf16" and cout == 2 and stride == 1 and cin >= 16 and cin % 4 == 0 \
+                and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
+            # 2-channel flow heads: tensor cores with the kernel zero-padded to 16 output channels (79 -> ~25 us at level 4)
+            from . import ops_tc
+            key = scope + "#head"
+            if key not in self._packed:
+                self._head_k[scope] = torch.zeros((3, 3, cin, 16), dtype=torch.float32, device=self.device)
+                self._head_b[scope] = torch.zeros((16,), dtype=torch.float32, device=self.device)
+                self._refresh_head(scope)
+                self._packed[key] = ops_tc.pack_weights_f16(self._head_k[scope])
+            return ops_tc.conv3x3_tc_f16_head(x, self._packed[key], self._head_b[scope], cin, 2, 16, dilation=dilation,
+                                              alpha=alpha, residual=residual, out=out)
         if self.precision == "3xf16" and cin == 16 and stride in (1, 2) and residual is None and cout % 16 == 0 \
                 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0 and not (stride == 1 and dilation == 1 and x.shape[2] >= 96):
             # 16-channel inputs (pyramid level 1): the tf32 kernel has a native 16-channel K slice (the streaming fp16

@@ -80,3 +80,29 @@ def conv3x3_tc_f16(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, al
                                        B, H, W, cin, cout, stride, dilation, float(alpha), _stream()),
           "pwc_conv3x3_tc_f16_fwd")
     return out
+
+
+def conv3x3_tc_f16_head(x, w_packed_pad, bias_pad, cin: int, cout: int, cout_pad: int, dilation: int = 1, alpha: float = 1.0,
+                        residual=None, out=None):
+    """Narrow-output conv (the 2-channel flow heads, modules.py:274-277, 325-326) on tcgen05: kernel and bias are
+    zero-padded to `cout_pad` (multiple of 16) output channels, only `cout` are stored; `residual` is added after the
+    activation."""
+    B, H, W, C, x_cs = _nhwc(x, "x")
+    if C != cin or cout_pad % 16 or cout > cout_pad:
+        raise ValueError("conv3x3_tc_f16_head: channel mismatch")
+    if bias_pad.shape != (cout_pad,) or w_packed_pad.numel() * 2 != lib().pwc_conv3x3_packed_bytes_f16(cin, cout_pad):
+        raise ValueError("conv3x3_tc_f16_head: bias / packed kernel must be padded to cout_pad")
+    if out is None:
+        out = new_nhwc(B, H, W, cout, x.device)
+    Bo, Ho, Wo, Co, y_cs = _nhwc(out, "out")
+    if (Bo, Ho, Wo, Co) != (B, H, W, cout):
+        raise ValueError("conv3x3_tc_f16_head: out shape mismatch")
+    rp, r_cs = None, 0
+    if residual is not None:
+        Br, Hr, Wr, Cr, r_cs = _nhwc(residual, "residual")
+        if (Br, Hr, Wr, Cr) != (B, H, W, cout):
+            raise ValueError("conv3x3_tc_f16_head: residual shape mismatch")
+        rp = residual.data_ptr()
+    check(lib().pwc_conv3x3_tc_f16_head(x.data_ptr(), x_cs, w_packed_pad.data_ptr(), bias_pad.data_ptr(), rp, r_cs, out.data_ptr(),
+                                        y_cs, B, H, W, cin, cout, cout_pad, dilation, float(alpha), _stream()), "pwc_conv3x3_tc_f16_head")
+    return out

@@ -362,6 +362,24 @@ def test_conv3x3_halo_resident_kernel_matches_oracle_and_streaming_kernel(P, cas
     np.testing.assert_allclose(out[..., 4:4 + Cout].cpu().numpy(), stream.cpu().numpy(), atol=2e-5, rtol=0)
 
 
+@pytest.mark.parametrize("shape", [(2, 7, 16, 32, 32), (1, 28, 64, 32, 36), (1, 20, 256, 32, 36), (1, 5, 130, 64, 64)])
+def test_flow_head_on_tensor_cores_matches_oracle(P, shape):
+    """2-channel flow heads (modules.py:274-277, 325-326): kernel zero-padded to 16 output channels, only 2 stored,
+    residual added after the (absent) activation, written into a 2-channel slot of a wider buffer."""
+    from pwcnet_b200 import ops_tc
+    B, H, W, Cin, cs = shape
+    buf = _rand((B, H, W, cs), 1); x = buf[..., :Cin]
+    k = _rand((3, 3, Cin, 2), 2, 1.0 / np.sqrt(9 * Cin)); b = _rand((2,), 3, 0.1); res = _rand((B, H, W, 2), 4)
+    ref = (O.conv2d_same(torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(k), torch.from_numpy(b)) + torch.from_numpy(res)).numpy()
+    kp = torch.zeros((3, 3, Cin, 16), device="cuda"); kp[..., :2] = _cuda(k)
+    bp = torch.zeros(16, device="cuda"); bp[:2] = _cuda(b)
+    out = torch.full((B, H, W, 6), 9.0, device="cuda")
+    ops_tc.conv3x3_tc_f16_head(_cuda(buf)[..., :Cin], ops_tc.pack_weights_f16(kp), bp, Cin, 2, 16, alpha=1.0,
+                               residual=_cuda(res), out=out[..., 2:4])
+    np.testing.assert_allclose(out[..., 2:4].cpu().numpy(), ref, atol=2e-5, rtol=0)
+    assert (out[..., :2] == 9.0).all() and (out[..., 4:] == 9.0).all()
+
+
 def test_conv3x3_f16x3_small_and_large_magnitudes(P):
     """The scaled residual keeps accuracy relative to the data scale from 1e-3 to 1e2."""
     from pwcnet_b200 import ops_tc
