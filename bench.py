@@ -239,6 +239,7 @@ def run_train(args):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    launches_per_step = trainer.launches_per_step()      # counted (after the timed regions: it re-runs a backward)
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -262,7 +263,7 @@ def run_train(args):
                 "e2e": {"value": total_pairs / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": int(host0.numel() + host1.numel() + hostg.numel()) * 4, "d2h_bytes_per_step": 12,
                         "what": "Trainer.step on pinned host images + GT flow; loss, multiscale loss and EPE copied back"},
-                "gpu_launches": args.steps * trainer.launches_per_step(), "clocks": clocks,
+                "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
                 "loss": float(out[0].item()), "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -82,7 +82,12 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0   # C-ABI compute calls that returned success (each enqueues one kernel; bench.py's gpu_launches)
+
+
 def check(rc: int, what: str) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = lib().pwc_last_error().decode(errors="replace")
         raise PwcError(f"{what} failed with code {rc}: {msg}")

@@ -347,16 +347,16 @@ class Trainer(object):
         np.savez(path, **self.state_dict())
 
     def launches_per_step(self) -> int:
-        """Kernel launches of ours in one training step (forward + losses + backward + update)."""
-        m = self.model
-        L = m.output_level
-        n_conv = len(m._table)
-        fwd = m.launches_per_forward()
-        losses = (L + 1) + 2
-        bwd = (L + 1)                                   # loss gradients
-        bwd += 2 * n_conv - 1                           # wgrad per layer, dgrad per layer but the first
-        bwd += 1 + (L + 1) + L                          # residual adds
-        bwd += (L + 1) + m.num_levels                   # stand-alone leaky'
-        bwd += (L + 1) + 3 * L                          # cost volume, warp, 2 x resize
-        upd = 1 + len(m._cin_perm) + len(m._packed)
-        return fwd + losses + bwd + upd
+        """Kernel launches of ours in one training step, counted: C-ABI calls issued by one step (losses, backward,
+        optimizer, derived-weight refresh) plus the forward's launches (replayed from its CUDA graph)."""
+        from . import _abi
+        if not self._gbufs:
+            raise RuntimeError("launches_per_step() needs one step to have run")
+        p = next(iter(self.model._plans.values()))
+        gt = torch.zeros((p.B, p.H, p.W, 2), dtype=torch.float32, device=self.model.device)
+        n0 = _abi.LAUNCHES
+        self._losses(p, gt)
+        self.backward(p, gt)
+        n1 = _abi.LAUNCHES
+        upd = 1 + len(self.model._cin_perm) + len(self.model._packed)
+        return self.model.launches_per_forward() + (n1 - n0) + upd
