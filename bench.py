@@ -253,12 +253,14 @@ def run_train(args):
                             "sample": "3 training steps on one 384x1024 pair; restated reference + torch autograd on CPU"}
         line = {"metric": TRAIN_METRIC, "value": total_pairs / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else precision + " forward, f32 backward",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else precision,
                 "data": "synthetic",
                 "config": {"workload": "PWCDCNet(use_dc=False) training step (forward, multiscale L2 loss + 4e-4 l2 regulariser, "
                                        "backward, gradient all-reduce, TF-Adam), batch=%d synthetic 384x1024 pairs + random GT "
                                        "flow per GPU (BASELINE config 5; 436x1024 is not divisible by 64)" % B,
                            "global_batch": B * world, "parallelism": f"dp{world} (one NCCL all-reduce of the 20.1 MB flat gradient per step)",
+                           "conv_path": precision + ": tcgen05 forward, dgrad and wgrad (3 x fp16 split, fp32 accumulation); "
+                                        "small-channel / stride-2 backward layers on CUDA cores in fp32",
                            "l2": "256 MiB write between timed iterations"},
                 "e2e": {"value": total_pairs / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": int(host0.numel() + host1.numel() + hostg.numel()) * 4, "d2h_bytes_per_step": 12,

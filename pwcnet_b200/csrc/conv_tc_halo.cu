@@ -26,7 +26,7 @@ namespace pwc {
 constexpr int HL_M = 128;                          // output pixels per tile (one row segment)
 constexpr int HL_BH = 3;                           // halo box: 3 rows (y-d, y, y+d) x (128 + 2d) pixels
 constexpr int HL_BK = 32;
-constexpr int HL_ACT_STAGES = 2, HL_W_STAGES = 4;
+constexpr int HL_MAX_ACT_STAGES = 3, HL_W_STAGES = 4;   // activation stages: 2 (3 selectable with PWC_HALO_STAGES=3)
 constexpr int HL_CONV_THREADS = 256;
 constexpr int HL_THREADS = 64 + 128 + HL_CONV_THREADS + 32;   // act TMA, MMA, 4 epilogue, 8 converter, weight producer
 constexpr float HL_SCALE = 2048.f, HL_INV_SCALE = 1.f / 2048.f;
@@ -43,6 +43,7 @@ struct HaloParams {
     int dil, bw;          // dilation d; box width 128 + 2d (pixel rows of one box row)
     int row_loads;        // 1: one box with row traversal stride d (d <= 8); 3: one single-row box per row (d > 8)
     int act_stage;        // bytes per activation stage (3 * bw * 128 rounded up to 1024)
+    int act_stages;       // 2 or 3
     float alpha, mask_alpha;
 };
 
@@ -61,18 +62,19 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     // barriers: act_full[2], act_conv[2], act_empty[2], w_full[4], w_empty[4], acc_full[2], acc_empty[2]
-    __shared__ __align__(8) uint64_t bars[3 * HL_ACT_STAGES + 2 * HL_W_STAGES + 4];
+    __shared__ __align__(8) uint64_t bars[3 * HL_MAX_ACT_STAGES + 2 * HL_W_STAGES + 4];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aconv = smem_u32(&bars[2]), bar_aempty = smem_u32(&bars[4]);
-    const uint32_t bar_wfull = smem_u32(&bars[6]), bar_wempty = smem_u32(&bars[10]);
-    const uint32_t bar_accf = smem_u32(&bars[14]), bar_acce = smem_u32(&bars[16]);
-    const uint32_t w_base = base + HL_ACT_STAGES * p.act_stage;
+    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aconv = smem_u32(&bars[3]), bar_aempty = smem_u32(&bars[6]);
+    const uint32_t bar_wfull = smem_u32(&bars[9]), bar_wempty = smem_u32(&bars[13]);
+    const uint32_t bar_accf = smem_u32(&bars[17]), bar_acce = smem_u32(&bars[19]);
+    const int AS = p.act_stages;
+    const uint32_t w_base = base + p.act_stages * p.act_stage;
     const int n_rows = HL_BH * p.bw;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < HL_ACT_STAGES; ++s) {
+        for (int s = 0; s < HL_MAX_ACT_STAGES; ++s) {
             mbar_init(bar_afull + 8 * s, 1);
             mbar_init(bar_aconv + 8 * s, HL_CONV_THREADS);
             mbar_init(bar_aempty + 8 * s, 1);
@@ -107,8 +109,8 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                 const int b = t / tiles_per_img, r = t - b * tiles_per_img;
                 const int y = r / p.tiles_x, x0 = (r - y * p.tiles_x) * HL_M;
                 for (int c = 0; c < KC; ++c, ++it) {
-                    const int s = it & 1;
-                    mbar_wait(bar_aempty + 8 * s, ((it >> 1) & 1) ^ 1);
+                    const int s = it % AS;
+                    mbar_wait(bar_aempty + 8 * s, ((it / AS) & 1) ^ 1);
                     mbar_expect_tx(bar_afull + 8 * s, (uint32_t)n_rows * 128);
                     if (p.row_loads == 1) {
                         tma_load_4d(base + s * p.act_stage, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - p.dil, y - p.dil, b);
@@ -156,8 +158,8 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                 }
                 const uint32_t d_main = tmem_acc + a * 256, d_corr = d_main + p.Cout;
                 for (int c = 0; c < KC; ++c, ++it) {
-                    const int s = it & 1;
-                    mbar_wait(bar_aconv + 8 * s, (it >> 1) & 1);
+                    const int s = it % AS;
+                    mbar_wait(bar_aconv + 8 * s, (it / AS) & 1);
                     tc_fence_after();
                     const uint32_t ast = base + s * p.act_stage;
                     for (int tap = 0; tap < 9; ++tap, ++wt) {
@@ -265,8 +267,8 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
         int it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             for (int c = 0; c < KC; ++c, ++it) {
-                const int s = it & 1;
-                mbar_wait(bar_afull + 8 * s, (it >> 1) & 1);
+                const int s = it % AS;
+                mbar_wait(bar_afull + 8 * s, (it / AS) & 1);
                 uint8_t* stp = base_ptr + (size_t)s * p.act_stage;
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
@@ -349,7 +351,10 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.act_stage = (HL_BH * p.bw * 128 + 1023) / 1024 * 1024;
     p.desc_mode = 0;
     if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
-    const size_t smem = (size_t)HL_ACT_STAGES * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024;
+    p.act_stages = 2;   // measured: a third activation stage does not help (174.6 vs 171.5 us at 128->128), the limit is operand bandwidth
+    if (const char* e = getenv("PWC_HALO_STAGES")) p.act_stages = atoi(e) == 3 ? 3 : 2;
+    size_t smem = (size_t)p.act_stages * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024;
+    if (smem > 227 * 1024) { p.act_stages = 2; smem = (size_t)2 * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024; }
     if (smem > 227 * 1024) return -1000;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc_halo: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
