@@ -44,8 +44,14 @@ struct HaloParams {
     int row_loads;        // 1: one box with row traversal stride d (d <= 8); 3: one single-row box per row (d > 8)
     int act_stage;        // bytes per activation stage (3 * bw * 128 rounded up to 1024)
     int act_stages;       // 2 or 3
+    int n_sets;           // independent (main | corr) accumulator sets per tile that the taps rotate over: consecutive MMAs
+                          // into ONE accumulator serialise on its latency (~125 clk measured), which dominates narrow layers
+    int w_resident;       // all 9 * kchunks weight images stay in shared memory (small layers): loaded once per CTA
     float alpha, mask_alpha;
+    unsigned long long* dbg;   // optional timeline (clock64): 8 events x 8 tiles per CTA; nullptr in production
 };
+
+#define HL_DBG(ev, tile) do { if (dbg && (tile) < 8) dbg[(ev) * 8 + (tile)] = clock64(); } while (0)
 
 __device__ __forceinline__ void hl_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -99,6 +105,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
     const uint32_t tmem_acc = tmem_base_slot;
     const int KC = p.kchunks;
     const int tiles_per_img = p.tiles_x * p.H;
+    unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
 
     if (warp == 0) {
         // ===================== activation producer =====================
@@ -111,6 +118,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                 for (int c = 0; c < KC; ++c, ++it) {
                     const int s = it % AS;
                     mbar_wait(bar_aempty + 8 * s, ((it / AS) & 1) ^ 1);
+                    HL_DBG(0, it);
                     mbar_expect_tx(bar_afull + 8 * s, (uint32_t)n_rows * 128);
                     if (p.row_loads == 1) {
                         tma_load_4d(base + s * p.act_stage, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - p.dil, y - p.dil, b);
@@ -128,6 +136,14 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
         if (lane == 0) {
             int wt = 0;
             const uint32_t bytes = 2 * p.b_bytes;
+            if (p.w_resident) {
+                // small layers: the weight stream would be latency-bound (a tap's MMAs are shorter than an L2 round trip),
+                // so every (slice, tap) image is loaded ONCE per persistent CTA
+                mbar_expect_tx(bar_wfull, (uint32_t)(9 * KC) * bytes);
+                for (int c = 0; c < KC; ++c)
+                    for (int tap = 0; tap < 9; ++tap)
+                        bulk_load_1d(w_base + (c * 9 + tap) * p.w_stage_bytes, p.w + (size_t)(tap * KC + c) * bytes, bytes, bar_wfull);
+            } else {
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 for (int c = 0; c < KC; ++c) {
                     for (int tap = 0; tap < 9; ++tap, ++wt) {
@@ -138,60 +154,66 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                     }
                 }
             }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const bool wide = p.Cout <= 128;   // [W_h | W_l] as one N = 2*Cout operand
             const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
             const uint32_t idesc_w = (1u << 4) | ((uint32_t)((2 * p.Cout) >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
             // A: K-major rows of 128 bytes ([h | l]), 128B swizzle, 8-row groups 1024 bytes apart
             const uint64_t adesc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             // B: K-major rows of 64 bytes, 64B swizzle, 8-row groups 512 bytes apart
             const uint64_t bdesc_hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+            // Everything that does not change is hoisted out of the issue loop (the nine tap offsets of the A descriptor,
+            // the accumulator-set stride, the weight-image stride).  Measured on narrow layers (16->16: 18 MMAs, 3.6 k clk
+            // per tile whatever the loop looks like): an M128 MMA costs >= ~130-200 clk for streaming its 128-row A operand
+            // from shared memory, independent of N, so layers with Cout <= 32 are bound by that, not by N * K.
+            uint32_t tapoff[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((tap / 3) * p.bw + (tap % 3) * p.dil) * 8;   // 128-byte rows, >> 4
+            const uint32_t setmask = (uint32_t)p.n_sets - 1, cout2 = 2 * p.Cout, n_sets = p.n_sets;
+            const uint32_t wsb16 = (uint32_t)p.w_stage_bytes >> 4;
+            const bool resident = p.w_resident != 0;
             int it = 0, wt = 0, tcount = 0;
+            if (resident) { mbar_wait(bar_wfull, 0); tc_fence_after(); }
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
                 const int a = tcount & 1, u = tcount >> 1;
                 if (u > 0) {                       // the epilogue has drained this accumulator set
                     mbar_wait(bar_acce + 8 * a, (u - 1) & 1);
                     tc_fence_after();
                 }
-                const uint32_t d_main = tmem_acc + a * 256, d_corr = d_main + p.Cout;
+                const uint32_t d_tile = tmem_acc + a * 256;
                 for (int c = 0; c < KC; ++c, ++it) {
                     const int s = it % AS;
                     mbar_wait(bar_aconv + 8 * s, (it / AS) & 1);
+                    HL_DBG(3, it);
                     tc_fence_after();
                     const uint32_t ast = base + s * p.act_stage;
-                    for (int tap = 0; tap < 9; ++tap, ++wt) {
-                        const int ws = wt & (HL_W_STAGES - 1);
-                        mbar_wait(bar_wfull + 8 * ws, (wt / HL_W_STAGES) & 1);
-                        tc_fence_after();
-                        const int ky = tap / 3, kx = tap - ky * 3;
-                        const uint32_t aaddr = ast + (uint32_t)(ky * p.bw + kx * p.dil) * 128;
-                        uint64_t ad = adesc_hi | (uint64_t)(((aaddr >> 4) & 0x3FFF) | (1u << 16));
-                        if (p.desc_mode == 1) ad |= (uint64_t)((aaddr >> 7) & 7) << 49;   // matrix base offset
-                        const uint32_t wst = w_base + ws * p.w_stage_bytes;
-                        const uint64_t bh = bdesc_hi | (uint64_t)(((wst >> 4) & 0x3FFF) | (1u << 16));
-                        const uint64_t bl = bdesc_hi | (uint64_t)((((wst + p.b_bytes) >> 4) & 0x3FFF) | (1u << 16));
-                        const uint32_t first = (c | tap) == 0 ? 0u : 1u;
-                        if (wide) {
+                    const bool ks2 = p.Cin - c * HL_BK > 16;             // channels 16..31 of the slice are zero padding otherwise
+                    const uint64_t ad0 = adesc_hi | (uint64_t)(((ast >> 4) & 0x3FFF) | (1u << 16));
+                    uint64_t bd = bdesc_hi | (uint64_t)((((w_base + (resident ? c * 9 * p.w_stage_bytes : 0)) >> 4) & 0x3FFF) | (1u << 16));
+                    const uint32_t use0 = (uint32_t)c * 9;
 #pragma unroll
-                            for (int k = 0; k < 2; ++k)   // A_h x [W_h | W_l] -> main | corr
-                                hl_mma(d_main, ad + 2 * k, bh + 2 * k, idesc_w, (first | k) ? 1u : 0u);
-#pragma unroll
-                            for (int k = 0; k < 2; ++k)   // A_l x W_h -> corr
-                                hl_mma(d_corr, ad + 4 + 2 * k, bh + 2 * k, idesc_n, 1u);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) hl_mma(d_main, ad + 2 * k, bh + 2 * k, idesc_n, (first | k) ? 1u : 0u);
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) hl_mma(d_corr, ad + 4 + 2 * k, bh + 2 * k, idesc_n, (first | k) ? 1u : 0u);
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) hl_mma(d_corr, ad + 2 * k, bl + 2 * k, idesc_n, 1u);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!resident) {
+                            const int ws = wt & (HL_W_STAGES - 1);
+                            mbar_wait(bar_wfull + 8 * ws, (wt / HL_W_STAGES) & 1);
+                            tc_fence_after();
+                            bd = bdesc_hi | (uint64_t)((((w_base + ws * p.w_stage_bytes) >> 4) & 0x3FFF) | (1u << 16));
                         }
-                        tc_commit(bar_wempty + 8 * ws);
+                        const uint64_t ad = ad0 + tapoff[tap];
+                        const uint32_t use = use0 + tap;
+                        const uint32_t d_main = d_tile + (use & setmask) * cout2, d_corr = d_main + p.Cout;
+                        hl_mma(d_main, ad, bd, idesc_w, use < n_sets ? 0u : 1u);          // A_h x [W_h | W_l] -> main | corr
+                        if (ks2) hl_mma(d_main, ad + 2, bd + 2, idesc_w, 1u);
+                        hl_mma(d_corr, ad + 4, bd, idesc_n, 1u);                            // A_l x W_h -> corr
+                        if (ks2) hl_mma(d_corr, ad + 6, bd + 2, idesc_n, 1u);
+                        if (resident) bd += wsb16;
+                        else { tc_commit(bar_wempty + 8 * (wt & (HL_W_STAGES - 1))); ++wt; }
                     }
                     tc_commit(bar_aempty + 8 * s);
+                    HL_DBG(4, it);
                 }
                 tc_commit(bar_accf + 8 * a);
             }
@@ -206,6 +228,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
             const int y = r / p.tiles_x, x = (r - y * p.tiles_x) * HL_M + m;
             const int a = tcount & 1, u = tcount >> 1;
             mbar_wait(bar_accf + 8 * a, u & 1);
+            if (threadIdx.x == 64) HL_DBG(5, tcount);
             tc_fence_after();
             const bool valid = x < p.W;
             const size_t pix = ((size_t)b * p.H + y) * p.W + x;
@@ -217,12 +240,18 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
             const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + a * 256;
             for (int n0 = 0; n0 < p.Cout; n0 += 16) {
                 uint32_t rm[16], rc[16];
-                tmem_ld16(tbase + p.Cout + n0, rc);
-                tmem_ld16(tbase + n0, rm);
-                tmem_ld_wait();
-                float acc[16];
+                float acc[16], accc[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rc[j]) * HL_INV_SCALE + __uint_as_float(rm[j]);
+                for (int j = 0; j < 16; ++j) { acc[j] = 0.f; accc[j] = 0.f; }
+                for (int st = 0; st < p.n_sets; ++st) {
+                    tmem_ld16(tbase + st * 2 * p.Cout + p.Cout + n0, rc);
+                    tmem_ld16(tbase + st * 2 * p.Cout + n0, rm);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { acc[j] += __uint_as_float(rm[j]); accc[j] += __uint_as_float(rc[j]); }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += accc[j] * HL_INV_SCALE;
                 if (valid) {
                     if (p.bias) {
 #pragma unroll
@@ -260,6 +289,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acce + 8 * a);
+            if (threadIdx.x == 64) HL_DBG(6, tcount);
         }
     } else {
         // ===================== converters (warps 6..13): fp32 pixel row -> [h | l * 2^11] fp16, in place =====================
@@ -269,6 +299,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
             for (int c = 0; c < KC; ++c, ++it) {
                 const int s = it % AS;
                 mbar_wait(bar_afull + 8 * s, (it / AS) & 1);
+                if (ct == 0) HL_DBG(1, it);
                 uint8_t* stp = base_ptr + (size_t)s * p.act_stage;
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
@@ -303,6 +334,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (ct == 0) HL_DBG(2, it);
                 mbar_arrive(bar_aconv + 8 * s);
             }
         }
@@ -351,16 +383,43 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.act_stage = (HL_BH * p.bw * 128 + 1023) / 1024 * 1024;
     p.desc_mode = 0;
     if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
+    p.n_sets = 1;                                  // power of two, <= 8, n_sets * 2 * Cout <= 256 columns per tile
+    while (p.n_sets < 8 && 2 * p.n_sets * 2 * Cout <= 256) p.n_sets *= 2;
+    if (const char* e = getenv("PWC_HALO_SETS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) { if (v <= p.n_sets) p.n_sets = v; } }
     p.act_stages = 2;   // measured: a third activation stage does not help (174.6 vs 171.5 us at 128->128), the limit is operand bandwidth
     if (const char* e = getenv("PWC_HALO_STAGES")) p.act_stages = atoi(e) == 3 ? 3 : 2;
-    size_t smem = (size_t)p.act_stages * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024;
+    const size_t w_all = (size_t)9 * p.kchunks * p.w_stage_bytes;
+    p.w_resident = (2 * (size_t)p.act_stage + w_all + 1024 <= 227 * 1024) && !getenv("PWC_HALO_NO_RESIDENT");
+    if (p.w_resident) p.act_stages = 2;
+    size_t smem = (size_t)p.act_stages * p.act_stage + (p.w_resident ? w_all : (size_t)HL_W_STAGES * p.w_stage_bytes) + 1024;
     if (smem > 227 * 1024) { p.act_stages = 2; smem = (size_t)2 * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024; }
     if (smem > 227 * 1024) return -1000;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc_halo: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
+    static unsigned long long* dbg_buf = nullptr;
+    if (getenv("PWC_HALO_DEBUG")) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 148 * 64 * 8);
+        cudaMemsetAsync(dbg_buf, 0, 148 * 64 * 8, st);
+        p.dbg = dbg_buf;
+    }
     conv3x3_tc_halo_kernel<<<grid, HL_THREADS, smem, st>>>(tmX, p);
     PWC_CHECK_LAUNCH("conv3x3_tc_halo_kernel");
+    if (p.dbg) {   // debugging aid only (synchronises): timeline of the first chunks / tiles of one CTA
+        cudaStreamSynchronize(st);
+        static int printed = 0;
+        if (printed++ < 1) {
+            unsigned long long h[64];
+            const char* names[8] = {"act_tma", "full_seen", "conv_done", "mma_start", "mma_issued", "acc_seen", "epi_done", "-"};
+            cudaMemcpy(h, p.dbg + 64 * (grid / 2), 64 * 8, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[halo dbg] cta %d Cin %d Cout %d kchunks %d resident %d (clk from first TMA issue; columns = chunks / tiles 0..7)\n", grid / 2, Cin, Cout, p.kchunks, p.w_resident);
+            for (int e = 0; e < 7; ++e) {
+                fprintf(stderr, "   %-10s", names[e]);
+                for (int t = 0; t < 8; ++t) fprintf(stderr, " %7lld", (long long)(h[e * 8 + t] - h[0]));
+                fprintf(stderr, "\n");
+            }
+        }
+    }
     return 0;
 }
 
