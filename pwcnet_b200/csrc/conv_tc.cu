@@ -104,7 +104,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
             const uint32_t tx_bytes = MT * A_BYTES + (NSPLIT == 3 ? 2 : 1) * p.b_bytes;
@@ -149,7 +149,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             // upper descriptor word: stride byte offset (next 8-row atom), version 1, swizzle mode

@@ -103,7 +103,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
             const uint32_t tx_bytes = F16_A_RAW + 2 * p.b_bytes;
             const int PF = p.prefetch;   // stages of L2 prefetch distance for the activation boxes
@@ -134,7 +134,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             // kind::f16: D = f32 (bit 4), A = B = F16 (format 0), K-major, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(F16_BM >> 4) << 24);
             // 64-byte-row K-major tiles: 8-row atoms 512 bytes apart, SWIZZLE_64B (layout type 4)

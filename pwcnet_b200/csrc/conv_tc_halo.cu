@@ -109,7 +109,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
 
     if (warp == 0) {
         // ===================== activation producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
             int it = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -133,7 +133,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
         }
     } else if (warp == 14) {
         // ===================== weight producer: [W_h | W_l] image of every (slice, tap), one bulk copy each =====================
-        if (lane == 0) {
+        if (elect_one()) {
             int wt = 0;
             const uint32_t bytes = 2 * p.b_bytes;
             if (p.w_resident) {
@@ -158,7 +158,9 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
+            const bool leader = true;
+            const uint32_t tmem_u = tmem_acc, base_u = base, w_base_u = w_base;
             const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
             const uint32_t idesc_w = (1u << 4) | ((uint32_t)((2 * p.Cout) >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
             // A: K-major rows of 128 bytes ([h | l]), 128B swizzle, 8-row groups 1024 bytes apart
@@ -166,9 +168,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
             // B: K-major rows of 64 bytes, 64B swizzle, 8-row groups 512 bytes apart
             const uint64_t bdesc_hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
             // Everything that does not change is hoisted out of the issue loop (the nine tap offsets of the A descriptor,
-            // the accumulator-set stride, the weight-image stride).  Measured on narrow layers (16->16: 18 MMAs, 3.6 k clk
-            // per tile whatever the loop looks like): an M128 MMA costs >= ~130-200 clk for streaming its 128-row A operand
-            // from shared memory, independent of N, so layers with Cout <= 32 are bound by that, not by N * K.
+            // the accumulator-set stride, the weight-image stride): on narrow layers the issuing thread is the critical path.
             uint32_t tapoff[9];
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((tap / 3) * p.bw + (tap % 3) * p.dil) * 8;   // 128-byte rows, >> 4
@@ -183,16 +183,16 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                     mbar_wait(bar_acce + 8 * a, (u - 1) & 1);
                     tc_fence_after();
                 }
-                const uint32_t d_tile = tmem_acc + a * 256;
+                const uint32_t d_tile = tmem_u + a * 256;
                 for (int c = 0; c < KC; ++c, ++it) {
                     const int s = it % AS;
                     mbar_wait(bar_aconv + 8 * s, (it / AS) & 1);
-                    HL_DBG(3, it);
+                    if (leader) HL_DBG(3, it);
                     tc_fence_after();
-                    const uint32_t ast = base + s * p.act_stage;
+                    const uint32_t ast = base_u + s * p.act_stage;
                     const bool ks2 = p.Cin - c * HL_BK > 16;             // channels 16..31 of the slice are zero padding otherwise
                     const uint64_t ad0 = adesc_hi | (uint64_t)(((ast >> 4) & 0x3FFF) | (1u << 16));
-                    uint64_t bd = bdesc_hi | (uint64_t)((((w_base + (resident ? c * 9 * p.w_stage_bytes : 0)) >> 4) & 0x3FFF) | (1u << 16));
+                    uint64_t bd = bdesc_hi | (uint64_t)((((w_base_u + (resident ? c * 9 * p.w_stage_bytes : 0)) >> 4) & 0x3FFF) | (1u << 16));
                     const uint32_t use0 = (uint32_t)c * 9;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
@@ -200,22 +200,22 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                             const int ws = wt & (HL_W_STAGES - 1);
                             mbar_wait(bar_wfull + 8 * ws, (wt / HL_W_STAGES) & 1);
                             tc_fence_after();
-                            bd = bdesc_hi | (uint64_t)((((w_base + ws * p.w_stage_bytes) >> 4) & 0x3FFF) | (1u << 16));
+                            bd = bdesc_hi | (uint64_t)((((w_base_u + ws * p.w_stage_bytes) >> 4) & 0x3FFF) | (1u << 16));
                         }
                         const uint64_t ad = ad0 + tapoff[tap];
                         const uint32_t use = use0 + tap;
                         const uint32_t d_main = d_tile + (use & setmask) * cout2, d_corr = d_main + p.Cout;
-                        hl_mma(d_main, ad, bd, idesc_w, use < n_sets ? 0u : 1u);          // A_h x [W_h | W_l] -> main | corr
-                        if (ks2) hl_mma(d_main, ad + 2, bd + 2, idesc_w, 1u);
-                        hl_mma(d_corr, ad + 4, bd, idesc_n, 1u);                            // A_l x W_h -> corr
-                        if (ks2) hl_mma(d_corr, ad + 6, bd + 2, idesc_n, 1u);
+                        if (leader) hl_mma(d_main, ad, bd, idesc_w, use < n_sets ? 0u : 1u);          // A_h x [W_h | W_l] -> main | corr
+                        if (ks2 && leader) hl_mma(d_main, ad + 2, bd + 2, idesc_w, 1u);
+                        if (leader) hl_mma(d_corr, ad + 4, bd, idesc_n, 1u);                            // A_l x W_h -> corr
+                        if (ks2 && leader) hl_mma(d_corr, ad + 6, bd + 2, idesc_n, 1u);
                         if (resident) bd += wsb16;
-                        else { tc_commit(bar_wempty + 8 * (wt & (HL_W_STAGES - 1))); ++wt; }
+                        else { if (leader) tc_commit(bar_wempty + 8 * (wt & (HL_W_STAGES - 1))); ++wt; }
                     }
-                    tc_commit(bar_aempty + 8 * s);
-                    HL_DBG(4, it);
+                    if (leader) tc_commit(bar_aempty + 8 * s);
+                    if (leader) HL_DBG(4, it);
                 }
-                tc_commit(bar_accf + 8 * a);
+                if (leader) tc_commit(bar_accf + 8 * a);
             }
         }
     } else if (warp < 6) {

@@ -143,7 +143,7 @@ cost_volume_tc_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_co
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f0) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f1) : "memory");
             int it = 0;
@@ -164,7 +164,7 @@ cost_volume_tc_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_co
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             // kind::f16: D = f32 (bit 4), A = B = F16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(X_NH >> 3) << 17) | ((uint32_t)(X_M >> 4) << 24);
             // K-major rows of 128 bytes (64 fp16: h | l), 128B swizzle, 8-row atoms 1024 bytes apart

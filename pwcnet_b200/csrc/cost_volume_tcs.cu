@@ -123,7 +123,7 @@ cost_volume_split_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f0) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f1) : "memory");
             int it = 0;
@@ -143,7 +143,7 @@ cost_volume_split_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(S_NH >> 3) << 17) | ((uint32_t)(S_M >> 4) << 24);
             const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             int it = 0, tcount = 0;

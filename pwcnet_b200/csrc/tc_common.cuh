@@ -66,6 +66,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+// One lane of a CONVERGED warp.  Guarding the single-thread roles (TMA producer, MMA issuer) with elect.sync instead of
+// `lane == 0` matters: ptxas recognises it and emits plain UTCHMMA / UTMALDG with uniform registers, while a lane test
+// makes it wrap every such instruction in an ELECT / BRA.U.ANY loop plus R2UR moves (measured: 54 clk minimum per MMA
+// from the wrapper alone, ~100-200 clk with descriptor arithmetic; profiles/r01_umma_issue_microbench.log).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {

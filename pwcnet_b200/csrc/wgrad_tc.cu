@@ -146,7 +146,7 @@ wgrad_tc_kernel(const __grid_constant__ WtcMaps maps, const WtcParams p) {
     const uint32_t off_b = 4 * WT_A_TILE;                   // [A_h0 | A_l0 | A_h1 | A_l1 | B_h | B_l]
 
     if (warp == 0) {
-        if (lane == 0 && n_chunks > 0) {
+        if (n_chunks > 0 && elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[0]) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[1]) : "memory");
             const uint32_t tx_bytes = ntaps * 2 * p.a_rows * 64 + 2 * p.b_bytes;
@@ -170,7 +170,7 @@ wgrad_tc_kernel(const __grid_constant__ WtcMaps maps, const WtcParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && n_chunks > 0) {
+        if (n_chunks > 0 && elect_one()) {
             const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_w = (1u << 4) | ((uint32_t)((2 * p.n_tile) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             // K-major rows of 64 bytes (32 positions of fp16), 64B swizzle, 8-row groups 512 bytes apart

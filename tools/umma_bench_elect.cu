@@ -28,7 +28,9 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int layout, int nacc, int
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = slot;
-    if (threadIdx.x == 0) {
+    uint32_t is_leader = 0;
+    if (threadIdx.x < 32) asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(is_leader));
+    if (is_leader) {
         const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         // layout 0: rows of 128 B, 128B swizzle (SBO 1024); layout 1: rows of 64 B, 64B swizzle (SBO 512)
         const uint64_t hi = layout != 1 ? (((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61))
