@@ -347,10 +347,11 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     PWC_REQUIRE(enc != nullptr, PWC_E_NOTBUILT, "conv3x3_tc_f16: cuTensorMapEncodeTiled not available from the driver");
     {
         // halo-resident kernel (conv_tc_halo.cu): one 3 x (128+2d) pixel box per 32-channel slice instead of nine shifted
-        // tiles; rows of at least 96 pixels keep its 128-pixel row tiles mostly full.  PWC_CONV_HALO=0 disables it.
+        // tiles; rows narrower than 128 pixels are packed several to a tile (flat mode).  PWC_CONV_HALO=0 disables it.
         const char* he = getenv("PWC_CONV_HALO");
         const int halo_on = he ? atoi(he) : 1;
-        if (halo_on && stride == 1 && dilation <= 16 && W >= 96 && Cout <= 128) {
+        static const int halo_min_w = []() { const char* e = getenv("PWC_HALO_MINW"); return e ? atoi(e) : 8; }();
+        if (halo_on && stride == 1 && dilation <= 16 && W >= halo_min_w && Cout <= 128) {
             const int rc = launch_conv_halo(x, x_cs, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, dilation, alpha, ex.mask, ex.mask_cs,
                                             ex.mask_alpha, ex.accumulate, ex.cout_valid, ex.res, ex.res_cs, (cudaStream_t)stream);
             if (rc != -1000) return rc;

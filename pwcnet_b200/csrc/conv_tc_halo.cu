@@ -40,7 +40,10 @@ struct HaloParams {
     int b_bytes;          // Cout * 64: one fp16 weight tile (h or l) of a (tap, slice)
     int w_stage_bytes;    // 2 * b_bytes rounded up to 1024
     int accumulate, desc_mode;
-    int dil, bw;          // dilation d; box width 128 + 2d (pixel rows of one box row)
+    int dil, bw;          // dilation d; box width in pixels (128 + 2d, or W + 2 in flat mode)
+    int flat, nr;         // flat mode (W < 128, d = 1): a tile is 128 consecutive SLOTS of the padded row-major space
+                          // (rows of bw = W + 2 slots); nr = box rows.  Tap (ky,kx) is still one uniform shift ky*bw + kx.
+    int tiles_img;        // tiles per image
     int row_loads;        // 1: one box with row traversal stride d (d <= 8); 3: one single-row box per row (d > 8)
     int act_stage;        // bytes per activation stage (3 * bw * 128 rounded up to 1024)
     int act_stages;       // 2 or 3
@@ -77,7 +80,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
     const uint32_t bar_accf = smem_u32(&bars[17]), bar_acce = smem_u32(&bars[19]);
     const int AS = p.act_stages;
     const uint32_t w_base = base + p.act_stages * p.act_stage;
-    const int n_rows = HL_BH * p.bw;
+    const int n_rows = (p.flat ? p.nr : HL_BH) * p.bw;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < HL_MAX_ACT_STAGES; ++s) {
@@ -104,7 +107,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base_slot;
     const int KC = p.kchunks;
-    const int tiles_per_img = p.tiles_x * p.H;
+    const int tiles_per_img = p.tiles_img;
     unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
 
     if (warp == 0) {
@@ -114,7 +117,9 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
             int it = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const int b = t / tiles_per_img, r = t - b * tiles_per_img;
-                const int y = r / p.tiles_x, x0 = (r - y * p.tiles_x) * HL_M;
+                int y, x0;
+                if (p.flat) { y = (r * HL_M) / p.bw; x0 = 0; }           // first row touched by the tile's slots
+                else { y = r / p.tiles_x; x0 = (r - y * p.tiles_x) * HL_M; }
                 for (int c = 0; c < KC; ++c, ++it) {
                     const int s = it % AS;
                     mbar_wait(bar_aempty + 8 * s, ((it / AS) & 1) ^ 1);
@@ -124,9 +129,9 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                         tma_load_4d(base + s * p.act_stage, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - p.dil, y - p.dil, b);
                     } else {
 #pragma unroll
-                        for (int r = 0; r < HL_BH; ++r)
-                            tma_load_4d(base + s * p.act_stage + r * p.bw * 128, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - p.dil,
-                                        y + (r - 1) * p.dil, b);
+                        for (int r2 = 0; r2 < HL_BH; ++r2)
+                            tma_load_4d(base + s * p.act_stage + r2 * p.bw * 128, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - p.dil,
+                                        y + (r2 - 1) * p.dil, b);
                     }
                 }
             }
@@ -184,6 +189,8 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                     tc_fence_after();
                 }
                 const uint32_t d_tile = tmem_u + a * 256;
+                uint32_t c0off = 0;                                   // flat mode: the tile starts c0 slots into its first row
+                if (p.flat) { const int r = t % tiles_per_img; c0off = (uint32_t)((r * HL_M) % p.bw) * 8; }
                 for (int c = 0; c < KC; ++c, ++it) {
                     const int s = it % AS;
                     mbar_wait(bar_aconv + 8 * s, (it / AS) & 1);
@@ -191,7 +198,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                     tc_fence_after();
                     const uint32_t ast = base_u + s * p.act_stage;
                     const bool ks2 = p.Cin - c * HL_BK > 16;             // channels 16..31 of the slice are zero padding otherwise
-                    const uint64_t ad0 = adesc_hi | (uint64_t)(((ast >> 4) & 0x3FFF) | (1u << 16));
+                    const uint64_t ad0 = (adesc_hi | (uint64_t)(((ast >> 4) & 0x3FFF) | (1u << 16))) + c0off;
                     uint64_t bd = bdesc_hi | (uint64_t)((((w_base_u + (resident ? c * 9 * p.w_stage_bytes : 0)) >> 4) & 0x3FFF) | (1u << 16));
                     const uint32_t use0 = (uint32_t)c * 9;
 #pragma unroll
@@ -225,12 +232,14 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
         int tcount = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
             const int b = t / tiles_per_img, r = t - b * tiles_per_img;
-            const int y = r / p.tiles_x, x = (r - y * p.tiles_x) * HL_M + m;
+            int y, x;
+            if (p.flat) { const int slot = r * HL_M + m; y = slot / p.bw; x = slot - y * p.bw; }
+            else { y = r / p.tiles_x; x = (r - y * p.tiles_x) * HL_M + m; }
             const int a = tcount & 1, u = tcount >> 1;
             mbar_wait(bar_accf + 8 * a, u & 1);
             if (threadIdx.x == 64) HL_DBG(5, tcount);
             tc_fence_after();
-            const bool valid = x < p.W;
+            const bool valid = x < p.W && y < p.H;
             const size_t pix = ((size_t)b * p.H + y) * p.W + x;
             float* yrow = p.y + pix * p.y_cs;
             const float* mrow = p.mask ? p.mask + pix * p.mask_cs : nullptr;
@@ -353,6 +362,9 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
                      float mask_alpha, int accumulate, int cout_valid, const float* res, int res_cs, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
     if (!enc || Cout > 128 || (Cout & 7) || dilation < 1 || dilation > 16) return -1000;   // two accumulator sets of 2*Cout columns must fit 512
+    // rows narrower than a tile: flat mode (d = 1 only) packs several rows into the 128 MMA rows
+    const int flat = (W < HL_M && dilation == 1 && !getenv("PWC_HALO_NO_FLAT")) ? 1 : 0;
+    const int nr = flat ? (HL_M - 1 + (W + 2) - 1) / (W + 2) + 3 : 0;
     CUtensorMap tmX;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -363,6 +375,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         if (!strided && (((HL_M + 2 * dilation) * 128) & 1023)) return -1000;
         cuuint32_t box[4] = {HL_BK, (cuuint32_t)(HL_M + 2 * dilation), (cuuint32_t)(strided ? HL_BH * dilation : 1), 1};
         cuuint32_t es[4] = {1, 1, (cuuint32_t)(strided ? dilation : 1), 1};
+        if (flat) { box[1] = (cuuint32_t)(W + 2); box[2] = (cuuint32_t)nr; es[2] = 1; }
         CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -372,15 +385,17 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.bias = bias; p.y = y; p.w = (const uint8_t*)w_packed; p.mask = mask; p.res = res; p.res_cs = res_cs;
     p.y_cs = y_cs; p.mask_cs = mask_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.cout_valid = cout_valid;
     p.tiles_x = (W + HL_M - 1) / HL_M;
-    const long long tiles = (long long)p.tiles_x * H * B;
+    p.flat = flat; p.nr = nr;
+    p.tiles_img = flat ? (H * (W + 2) + HL_M - 1) / HL_M : p.tiles_x * H;
+    const long long tiles = (long long)p.tiles_img * B;
     if (tiles >= (1ll << 30)) return -1000;
     p.total_tiles = (int)tiles;
     p.kchunks = (Cin + HL_BK - 1) / HL_BK;
     p.b_bytes = Cout * 64;
     p.w_stage_bytes = (2 * p.b_bytes + 1023) / 1024 * 1024;
     p.accumulate = accumulate; p.alpha = alpha; p.mask_alpha = mask_alpha;
-    p.dil = dilation; p.bw = HL_M + 2 * dilation; p.row_loads = dilation <= 8 ? 1 : HL_BH;
-    p.act_stage = (HL_BH * p.bw * 128 + 1023) / 1024 * 1024;
+    p.dil = dilation; p.bw = flat ? W + 2 : HL_M + 2 * dilation; p.row_loads = dilation <= 8 ? 1 : HL_BH;
+    p.act_stage = ((flat ? nr : HL_BH) * p.bw * 128 + 1023) / 1024 * 1024;
     p.desc_mode = 0;
     if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
     p.n_sets = 1;                                  // power of two, <= 8, n_sets * 2 * Cout <= 256 columns per tile
