@@ -86,6 +86,8 @@ class Trainer(object):
         self.tc_dgrad = model.precision == "3xf16" if tc_dgrad is None else bool(tc_dgrad)
         self.tc_wgrad = model.precision == "3xf16" if tc_wgrad is None else bool(tc_wgrad)
         self._tscratch = None
+        import os
+        self.tc_wgrad_small = os.environ.get("PWC_WGRAD_TC_SMALL", "0") == "1"
 
     # ------------------------------------------------------------------ gradient workspace
     def _grad_buffers(self, p) -> _Grads:
@@ -127,7 +129,7 @@ class Trainer(object):
         m = self.model
         cin, cout = x.shape[3], dy.shape[3]
         # (layers with Cin, Cout <= 32 stay on the persistent CUDA-core kernel: measured equal, one launch instead of three)
-        if self.tc_wgrad and cout % 16 == 0 and cin % 4 == 0 and not (cin <= 32 and cout <= 32) and stride in (1, 2) \
+        if self.tc_wgrad and cout % 16 == 0 and cin % 4 == 0 and (self.tc_wgrad_small or not (cin <= 32 and cout <= 32)) and stride in (1, 2) \
                 and x.stride(2) % 4 == 0 and dy.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0:
             # tensor-core wgrad: transpose + split both operands into channel-major fp16 planes (the dy pass also
             # reduces the bias gradient), then one GEMM launch over (tap pairs, channel tiles, row ranges)
