@@ -40,6 +40,21 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _tensor_peak():
+    """Dense bf16/fp16 TFLOP/s from MEASURED_PEAKS.json: the burst figure (the conv kernel is timed alone, one launch
+    between L2 flushes), else the nominal number."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        for k in ("bf16_tflops", "bf16_tflops_sustained"):
+            if k in d:
+                return float(d[k]), f"measured (MEASURED_PEAKS.json {k})"
+        vals = [float(v) for k, v in d.items() if "bf16" in k.lower() and isinstance(v, (int, float))]
+        if vals:
+            return min(vals), "measured (MEASURED_PEAKS.json, lowest bf16 figure)"
+    return 2250.0, "nominal dense bf16 (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -434,6 +449,32 @@ def main():
         roofline = {"kernel": "cost_volume_tma_kernel<true> level-2 112x256x32 -> 81-ch slot of the 148-wide concat buffer, B=%d" % B, "bound": "hbm",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "us_per_launch": cv_us, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}
+        # ------------------------------------------------------------ the kernel that dominates the step by time (77 %):
+        # the halo-resident tcgen05 conv, measured on the level-4 estimator layer 128 -> 128 (tensor roofline)
+        from pwcnet_b200 import ops_tc
+        xc = torch.randn((B, h2, w2, 128), device=dev, generator=g)
+        kc = torch.randn((3, 3, 128, 128), device=dev, generator=g) / 34.0
+        bc = torch.zeros(128, device=dev)
+        yc = torch.empty((B, h2, w2, 128), device=dev)
+        wpk = ops_tc.pack_weights_f16(kc)
+        for _ in range(3):
+            ops_tc.conv3x3_tc_f16(xc, wpk, bc, 128, 128, alpha=0.1, out=yc)
+        cev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for s_, e_ in cev2:
+            flush.fill_(3)
+            s_.record()
+            ops_tc.conv3x3_tc_f16(xc, wpk, bc, 128, 128, alpha=0.1, out=yc)
+            e_.record()
+        torch.cuda.synchronize()
+        conv_us = 1e3 * float(np.mean([s_.elapsed_time(e_) for s_, e_ in cev2]))
+        conv_flops = 2.0 * 9 * 128 * 128 * B * h2 * w2
+        tpeak, tpeak_src = _tensor_peak()
+        conv_tflops = conv_flops / (conv_us * 1e-6) / 1e12
+        roofline_conv = {"kernel": "conv3x3_tc_halo_kernel, level-4 estimator conv 128->128 at 112x256, B=%d (3 x fp16 split: every "
+                                   "useful flop costs 3 fp16 MMA flops)" % B,
+                         "bound": "tensor", "achieved": conv_tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": conv_tflops / tpeak,
+                         "mma_issue_tflops": 3 * conv_tflops, "mma_issue_frac": 3 * conv_tflops / tpeak, "traffic": None,
+                         "us_per_launch": conv_us, "algorithmic_flops": conv_flops, "peak_source": tpeak_src}
         cpu_baseline = None
         if not args.no_cpu_baseline:
             pps, cores, _ = cpu_oracle_pairs_per_s(args.cpu_pairs)
@@ -456,7 +497,7 @@ def main():
                             "flows in pinned host memory, H2D/D2H of neighbouring requests overlapped with the forward; "
                             "sync_value = one PWCDCNet.__call__ at a time, no overlap"},
             "gpu_launches": args.steps * model.launches_per_forward(),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "roofline": roofline, "roofline_conv": roofline_conv, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

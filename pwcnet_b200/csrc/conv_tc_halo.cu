@@ -40,6 +40,7 @@ struct HaloParams {
     int b_bytes;          // Cout * 64: one fp16 weight tile (h or l) of a (tap, slice)
     int w_stage_bytes;    // 2 * b_bytes rounded up to 1024
     int accumulate, desc_mode;
+    int exp_skip_conv;    // experiment (PWC_HALO_EXP=1): converters do nothing -> wrong results, upper bound of a split-input variant
     int dil, bw;          // dilation d; box width in pixels (128 + 2d, or W + 2 in flat mode)
     int flat, nr;         // flat mode (W < 128, d = 1): a tile is 128 consecutive SLOTS of the padded row-major space
                           // (rows of bw = W + 2 slots); nr = box rows.  Tap (ky,kx) is still one uniform shift ky*bw + kx.
@@ -313,7 +314,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int R = ct + rr * HL_CONV_THREADS;
-                    if (R < n_rows) {
+                    if (R < n_rows && !p.exp_skip_conv) {
                         uint8_t* row = stp + (size_t)R * 128;
                         const int sw = R & 7;              // 128B swizzle: logical 16-byte chunk j sits at chunk j ^ (R & 7)
                         float4 v[8];
@@ -397,6 +398,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.dil = dilation; p.bw = flat ? W + 2 : HL_M + 2 * dilation; p.row_loads = dilation <= 8 ? 1 : HL_BH;
     p.act_stage = ((flat ? nr : HL_BH) * p.bw * 128 + 1023) / 1024 * 1024;
     p.desc_mode = 0;
+    p.exp_skip_conv = getenv("PWC_HALO_EXP") ? 1 : 0;
     if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
     p.n_sets = 1;                                  // power of two, <= 8, n_sets * 2 * Cout <= 256 columns per tile
     while (p.n_sets < 8 && 2 * p.n_sets * 2 * Cout <= 256) p.n_sets *= 2;
