@@ -130,6 +130,12 @@ int pwc_leaky_bwd(float* g, int g_cs, const float* y, int y_cs, long long n_pix,
 int pwc_add_strided(float* dst, int dst_cs, const float* src, int src_cs, long long n_pix, int C, float scale,
                     void* stream);
 
+/* Zero insertion for the stride-2 dgrad (gradient of conv2d(strides=2), modules.py:60): out (B,H,W,C) dense,
+ * out[b, 2y+oy, 2x+ox, :] = dy[b,y,x,:], zeros elsewhere; oy = 1 - pad_top, ox = 1 - pad_left of the SAME padding.
+ * The stride-1 dgrad of `out` (pwc_conv3x3_tc_f16_dgrad) then equals the stride-2 dgrad of dy. */
+int pwc_dilate2(const float* dy, int dy_cs, float* out, int B, int OH, int OW, int C, int H, int W, int oy, int ox,
+                void* stream);
+
 /* Gradient of pwc_cost_volume_fwd (modules.py:164-204).  g = gradient w.r.t. the cost volume OUTPUT, cv = that
  * output (for the leaky slope).  df0 += d/df0 (+ g_f0slot if not NULL: the gradient that arrived through the
  * f0 copy in the concat buffer); df1 = d/df1 (accumulate_f1 != 0: +=). */

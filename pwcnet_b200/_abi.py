@@ -39,6 +39,7 @@ SIGNATURES = {
     "pwc_conv3x3_wgrad": (_i, [_f32p, _i, _f32p, _i, _f32p, _f32p, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pwc_leaky_bwd": (_i, [_f32p, _i, _f32p, _i, _ll, _i, _f, _vp]),
     "pwc_add_strided": (_i, [_f32p, _i, _f32p, _i, _ll, _i, _f, _vp]),
+    "pwc_dilate2": (_i, [_f32p, _i, _f32p, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pwc_cost_volume_bwd": (_i, [_f32p, _i, _f32p, _i, _f32p, _i, _f32p, _i, _f32p, _i, _f32p, _i, _f32p, _i, _i,
                                  _i, _i, _i, _i, _i, _f, _vp]),
     "pwc_warp_bwd": (_i, [_f32p, _i, _f32p, _i, _f, _i, _f32p, _i, _f32p, _i, _f32p, _i, _i, _i, _i, _i, _vp]),

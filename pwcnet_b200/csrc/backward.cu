@@ -16,6 +16,8 @@
 // Gradient buffers mirror the activation buffers (same NHWC shapes and channel strides).  A buffer holds the
 // gradient w.r.t. the PRE-activation output of its layer by the time that layer's dgrad/wgrad run.
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace pwc {
 
@@ -286,110 +288,157 @@ __global__ void __launch_bounds__(WG_THREADS, 2) conv3x3_wgrad_kernel(const Wgra
 // heads).  These layers are memory/latency-bound, so one persistent CTA handles ALL nine taps of a 4 x 32 output tile
 // from one shared-memory patch of x and one tile of dy (each input byte is read once instead of nine times), keeps
 // its (tap, 4 ci, 4 co) register tiles across all of its tiles and issues its atomics once at the end.
-constexpr int WS_TW = 32, WS_TH = 4, WS_PIX = WS_TW * WS_TH, WS_ITEMS = 3;
-__global__ void __launch_bounds__(256) conv3x3_wgrad_small_kernel(const WgradParams p, int tiles_x, int tiles_y, int n_tiles) {
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool ok) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = ok ? 16 : 0;                          // src-size 0: nothing is read, the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool ok) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = ok ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int WS_TW = 32, WS_TH = 4, WS_PIX = WS_TW * WS_TH, WS_MAXT = 288;
+// Work items = (tap, TI input channels, TO output channels) register tiles; thread = (item, pixel group g of k), group g
+// takes the tile columns g, g+k, ...  8 x 8 tiles: four LDS.128 feed 64 FMAs (the first version, 4 x 4 tiles, was bound by
+// shared-memory wavefronts: 8 per 16 FMAs); the k groups keep all 288 threads busy although a 16->16 layer has only
+// 36 items.  The groups' partial sums meet in shared memory before the one global atomic per weight and CTA.
+template <int TI, int TO>
+__global__ void __launch_bounds__(WS_MAXT, 2) conv3x3_wgrad_small_kernel(const WgradParams p, int tiles_x, int tiles_y, int n_tiles,
+                                                                         int n_items, int k) {
     extern __shared__ __align__(16) float ws_smem[];
-    const int C4i = (p.Cin + 3) >> 2, C4o = (p.Cout + 3) >> 2, Cip = C4i * 4, Cop = C4o * 4;
+    const int Cgi = (p.Cin + TI - 1) / TI, Cgo = (p.Cout + TO - 1) / TO, Cip = Cgi * TI, Cop = Cgo * TO;
+    const int C4i = Cip >> 2, C4o = Cop >> 2;
     const int prow = (WS_TH - 1) * p.stride + 3, pcol = (WS_TW - 1) * p.stride + 3;
-    float* patch = ws_smem;                              // [prow][pcol][Cip]
-    float* dys = ws_smem + prow * pcol * Cip;            // [WS_PIX][Cop]
-    const int tid = threadIdx.x;
-    const int n_items = 9 * C4i * C4o;
-    int xoff[WS_ITEMS], doff[WS_ITEMS];                  // per item: patch offset of its tap / channel group, dy offset
-    bool live[WS_ITEMS];
-    float acc[WS_ITEMS][4][4];
+    const int tid = threadIdx.x, nthr = blockDim.x;       // smem: 2 x ([prow][pcol][Cip] patch + [WS_PIX][Cop] dy tile)
+    const int grp = tid / n_items, item = tid - grp * n_items;
+    const bool live = grp < k;
+    const int tap = item / (Cgi * Cgo), rem = item - tap * (Cgi * Cgo);
+    const int cig = rem / Cgo, cog = rem - cig * Cgo;
+    const int xoff = ((tap / 3) * pcol + (tap % 3)) * Cip + cig * TI, doff = cog * TO;
+    float acc[TI][TO];
 #pragma unroll
-    for (int j = 0; j < WS_ITEMS; ++j) {
-        const int item = tid + 256 * j;
-        live[j] = item < n_items;
-        const int it = live[j] ? item : 0;
-        const int tap = it / (C4i * C4o), rem = it - tap * (C4i * C4o);
-        const int ci4 = rem / C4o, co4 = rem - ci4 * C4o;
-        xoff[j] = ((tap / 3) * pcol + (tap % 3)) * Cip + ci4 * 4;
-        doff[j] = co4 * 4;
+    for (int a = 0; a < TI; ++a)
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[j][a][b] = 0.f;
-    }
+        for (int b = 0; b < TO; ++b) acc[a][b] = 0.f;
+    const int xstep = p.stride * Cip;
+    const int bc = tid % Cop, bg = tid / Cop, nbg = nthr / Cop;   // bias gradient: thread = (channel, pixel group)
     float bsum = 0.f;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    // Two tile buffers filled with cp.async (zero fill outside the image): the next tile streams in while this one is
+    // reduced -- with one buffer the kernel was bound by the load latency (0.5 TB/s on the level-1 layers).
+    const int stage_floats = prow * pcol * Cip + WS_PIX * Cop;
+    for (int e = tid; e < 2 * stage_floats; e += nthr) ws_smem[e] = 0.f;   // channel padding stays zero
+    __syncthreads();
+    const int s_c4 = tid % C4i, s_px = (tid / C4i) % pcol, s_py = tid / (C4i * pcol);
+    const int d_c4 = nthr % C4i, d_px = (nthr / C4i) % pcol, d_py = nthr / (C4i * pcol);
+    const int s_o4 = tid % C4o, s_pp = tid / C4o, d_o4 = nthr % C4o, d_pp = nthr / C4o;
+    auto load_tile = [&](int t, float* patch, float* dys) {
         const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
         const int oy0 = ty * WS_TH, ox0 = tx * WS_TW;
         const int iy0 = oy0 * p.stride - p.pad_t, ix0 = ox0 * p.stride - p.pad_l;
-        __syncthreads();                                 // previous tile fully consumed
         const float* xb = p.x + (size_t)b * p.H * p.W * p.x_cs;
-        for (int e = tid; e < prow * pcol * C4i; e += 256) {
-            const int c4 = e % C4i, px = (e / C4i) % pcol, py = e / (C4i * pcol);
+        // (c4, px, py) of element e = tid + i * nthr advance incrementally: no divisions in the copy loops
+        int c4 = s_c4, px = s_px, py = s_py;
+        for (int e = tid; e < prow * pcol * C4i; e += nthr) {
             const int iy = iy0 + py, ix = ix0 + px;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-                const float* xp = xb + ((size_t)iy * p.W + ix) * p.x_cs + 4 * c4;
-                if (p.vec_x && 4 * c4 + 3 < p.Cin) v = ldg4(xp);
-                else {
-                    if (4 * c4 + 0 < p.Cin) v.x = __ldg(xp + 0);
-                    if (4 * c4 + 1 < p.Cin) v.y = __ldg(xp + 1);
-                    if (4 * c4 + 2 < p.Cin) v.z = __ldg(xp + 2);
-                    if (4 * c4 + 3 < p.Cin) v.w = __ldg(xp + 3);
-                }
+            const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            const float* xp = ok ? xb + ((size_t)iy * p.W + ix) * p.x_cs + 4 * c4 : p.x;
+            float* dst = patch + 4 * e;
+            if (p.vec_x && 4 * c4 + 3 < p.Cin) cp_async16(dst, xp, ok);
+            else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (4 * c4 + q < p.Cin) cp_async4(dst + q, ok ? xp + q : p.x, ok);
             }
-            *reinterpret_cast<float4*>(patch + (py * pcol + px) * Cip + 4 * c4) = v;
+            c4 += d_c4; px += d_px; py += d_py;
+            if (c4 >= C4i) { c4 -= C4i; ++px; }
+            if (px >= pcol) { px -= pcol; ++py; }
         }
-        for (int e = tid; e < WS_PIX * C4o; e += 256) {
-            const int c4 = e % C4o, pp = e / C4o;
+        int o4 = s_o4, pp = s_pp;
+        for (int e = tid; e < WS_PIX * C4o; e += nthr) {
             const int oy = oy0 + (pp >> 5), ox = ox0 + (pp & 31);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (oy < p.OH && ox < p.OW) {
-                const float* dp = p.dy + (((size_t)b * p.OH + oy) * p.OW + ox) * p.dy_cs + 4 * c4;
-                if (p.vec_dy && 4 * c4 + 3 < p.Cout) v = ldg4(dp);
-                else {
-                    if (4 * c4 + 0 < p.Cout) v.x = __ldg(dp + 0);
-                    if (4 * c4 + 1 < p.Cout) v.y = __ldg(dp + 1);
-                    if (4 * c4 + 2 < p.Cout) v.z = __ldg(dp + 2);
-                    if (4 * c4 + 3 < p.Cout) v.w = __ldg(dp + 3);
-                }
+            const bool ok = oy < p.OH && ox < p.OW;
+            const float* dp = ok ? p.dy + (((size_t)b * p.OH + oy) * p.OW + ox) * p.dy_cs + 4 * o4 : p.dy;
+            float* dst = dys + 4 * e;
+            if (p.vec_dy && 4 * o4 + 3 < p.Cout) cp_async16(dst, dp, ok);
+            else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (4 * o4 + q < p.Cout) cp_async4(dst + q, ok ? dp + q : p.dy, ok);
             }
-            *reinterpret_cast<float4*>(dys + pp * Cop + 4 * c4) = v;
+            o4 += d_o4; pp += d_pp;
+            if (o4 >= C4o) { o4 -= C4o; ++pp; }
+        }
+        cp_async_commit();
+    };
+    int buf = 0;
+    if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x, ws_smem, ws_smem + prow * pcol * Cip);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= 1) {
+        const float* patch = ws_smem + buf * stage_floats;
+        const float* dys = patch + prow * pcol * Cip;
+        const int tn = t + gridDim.x;
+        if (tn < n_tiles) {
+            float* np = ws_smem + (buf ^ 1) * stage_floats;
+            load_tile(tn, np, np + prow * pcol * Cip);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        if (live) {
 #pragma unroll
-        for (int j = 0; j < WS_ITEMS; ++j) {
-            if (!live[j]) continue;
-            const float* xq = patch + xoff[j];
-            const float* dq = dys + doff[j];
-#pragma unroll 4
-            for (int pp = 0; pp < WS_PIX; ++pp) {
-                const float4 xv = *reinterpret_cast<const float4*>(xq + (((pp >> 5) * p.stride) * pcol + (pp & 31) * p.stride) * Cip);
-                const float4 dv = *reinterpret_cast<const float4*>(dq + pp * Cop);
-                const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+            for (int r = 0; r < WS_TH; ++r) {
+                const float* xr = patch + xoff + (r * p.stride * pcol) * Cip;
+                const float* dr = dys + doff + (r * WS_TW) * Cop;
+#pragma unroll 1
+                for (int c = grp; c < WS_TW; c += k) {
+                    float xa[TI], da[TO];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                    for (int q = 0; q < TI / 4; ++q) {
+                        const float4 v = *reinterpret_cast<const float4*>(xr + c * xstep + 4 * q);
+                        xa[4 * q] = v.x; xa[4 * q + 1] = v.y; xa[4 * q + 2] = v.z; xa[4 * q + 3] = v.w;
+                    }
 #pragma unroll
-                    for (int b2 = 0; b2 < 4; ++b2) acc[j][a][b2] = fmaf(xa[a], da[b2], acc[j][a][b2]);
+                    for (int q = 0; q < TO / 4; ++q) {
+                        const float4 v = *reinterpret_cast<const float4*>(dr + c * Cop + 4 * q);
+                        da[4 * q] = v.x; da[4 * q + 1] = v.y; da[4 * q + 2] = v.z; da[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int a = 0; a < TI; ++a)
+#pragma unroll
+                        for (int b2 = 0; b2 < TO; ++b2) acc[a][b2] = fmaf(xa[a], da[b2], acc[a][b2]);
+                }
             }
         }
-        if (p.db && tid < p.Cout) {
-            for (int pp = 0; pp < WS_PIX; ++pp) bsum += dys[pp * Cop + tid];
+        if (p.db && bg < nbg) {
+            for (int pp = bg; pp < WS_PIX; pp += nbg) bsum += dys[pp * Cop + bc];
         }
+        __syncthreads();                                 // this buffer is refilled by the next iteration's prefetch
     }
+    // reduce the k pixel groups (and the bias groups) in shared memory, then one global atomic per weight
+    __syncthreads();
+    float* red = ws_smem;                                // [TI*TO][n_items] + [Cop]
+    for (int e = tid; e < n_items * TI * TO + Cop; e += nthr) red[e] = 0.f;
+    __syncthreads();
+    if (live) {
 #pragma unroll
-    for (int j = 0; j < WS_ITEMS; ++j) {
-        if (!live[j]) continue;
-        const int item = tid + 256 * j;
-        const int tap = item / (C4i * C4o), rem = item - tap * (C4i * C4o);
-        const int ci4 = rem / C4o, co4 = rem - ci4 * C4o;
+        for (int a = 0; a < TI; ++a)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int ci = ci4 * 4 + a;
-            if (ci >= p.Cin) continue;
-#pragma unroll
-            for (int b2 = 0; b2 < 4; ++b2) {
-                const int co = co4 * 4 + b2;
-                if (co < p.Cout) atomicAdd(p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + co, acc[j][a][b2]);
-            }
-        }
+            for (int b2 = 0; b2 < TO; ++b2) atomicAdd(red + (a * TO + b2) * n_items + item, acc[a][b2]);   // item fastest: conflict-free
     }
-    if (p.db && tid < p.Cout) atomicAdd(p.db + tid, bsum);
+    if (p.db && bg < nbg) atomicAdd(red + n_items * TI * TO + bc, bsum);
+    __syncthreads();
+    for (int e = tid; e < n_items * TI * TO; e += nthr) {
+        const int ab = e / n_items, it = e - ab * n_items, a = ab / TO, b2 = ab - a * TO;
+        const int tp = it / (Cgi * Cgo), rm = it - tp * (Cgi * Cgo);
+        const int ci = (rm / Cgo) * TI + a, co = (rm % Cgo) * TO + b2;
+        if (ci < p.Cin && co < p.Cout) atomicAdd(p.dw + ((size_t)tp * p.Cin + ci) * p.Cout + co, red[e]);
+    }
+    if (p.db && tid < p.Cout) atomicAdd(p.db + tid, red[n_items * TI * TO + tid]);
 }
 
 // ------------------------------------------------------------------------------------- element-wise helpers
@@ -467,6 +516,176 @@ __global__ void cost_volume_bwd_kernel(const CvBwdParams p) {
         float4 o1 = make_float4(a1.x * p.inv_c, a1.y * p.inv_c, a1.z * p.inv_c, a1.w * p.inv_c);
         if (p.acc_f1) { const float4 t = *d1; o1.x += t.x; o1.y += t.y; o1.z += t.z; o1.w += t.w; }
         *d1 = o1;
+    }
+}
+
+// Tiled variant (search range 4).  The gather kernel above re-reads g, cv and the features through L1 for every (pixel,
+// 4-channel group): 468 us at level 2 for 1 GFMA and 0.28 GB of algorithmic traffic.  Here one CTA owns an 8 x 16 pixel
+// tile and a 32-channel slice, in one of two directions that share the arithmetic
+//     out[p, c] = sum_d G[d][p] * F[p +- d][c]
+//   DIR 0 (df0): G[d][p] = g'(p, d),      F = f1, offset +d
+//   DIR 1 (df1): G[d][q] = g'(q - d, d),  F = f0, offset -d     (g' = g * leaky'(cv) / C, zero outside the image)
+// G (81 x 128, pixel-fastest, the shift of DIR 1 applied while loading) and the 16 x 24 halo tile of F live in shared
+// memory; a thread keeps a 4-pixel x 4-channel register tile and, per displacement row, a 12-pixel window of F, so 21
+// LDS.128 feed 144 FMAs.
+constexpr int CB_TH = 8, CB_TW = 16, CB_PIX = CB_TH * CB_TW, CB_CS = 32, CB_FS = CB_CS + 4, CB_FH = CB_TH + 8, CB_FW = CB_TW + 8,
+              CB_GS = CB_PIX + 4, CB_THREADS = 256;
+constexpr size_t CB_SMEM = ((size_t)81 * CB_GS + (size_t)CB_FH * CB_FW * CB_FS) * sizeof(float);
+
+template <int DIR>
+__device__ __forceinline__ void cv_bwd_tile(const CvBwdParams& p, float* __restrict__ Gs, float* __restrict__ Fs, int b, int y0, int x0,
+                                            int c0) {
+    const int tid = threadIdx.x;
+    const size_t img = (size_t)b * p.H * p.W;
+    // All three copy loops issue a batch of independent loads before the first shared-memory store (one load pair in
+    // flight per thread made the first version latency-bound: 390 us at level 2).
+    constexpr int GU = 8;
+    if (DIR == 0) {
+        for (int e0 = tid; e0 < CB_PIX * 81; e0 += CB_THREADS * GU) {
+            float gv[GU], cvv[GU];
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                const int e = e0 + u * CB_THREADS;
+                const int px = e / 81, d = e - px * 81;
+                const int y = y0 + (px >> 4), x = x0 + (px & 15);
+                gv[u] = 0.f; cvv[u] = 1.f;
+                if (e < CB_PIX * 81 && y < p.H && x < p.W) {
+                    const size_t pix = img + (size_t)y * p.W + x;
+                    gv[u] = __ldg(p.g + pix * p.g_cs + d);
+                    cvv[u] = __ldg(p.cv + pix * p.cv_cs + d);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                const int e = e0 + u * CB_THREADS;
+                const int px = e / 81, d = e - px * 81;
+                if (e < CB_PIX * 81) Gs[d * CB_GS + px] = gv[u] * (cvv[u] > 0.f ? p.inv_c : p.inv_c * p.alpha);
+            }
+        }
+    } else {
+        constexpr int N1 = 9 * CB_TH * CB_FW * 9;
+        for (int e0 = tid; e0 < N1; e0 += CB_THREADS * GU) {
+            float gv[GU], cvv[GU];
+            int dst[GU];
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                const int e = e0 + u * CB_THREADS;
+                const int h = e % 9; int t = e / 9;
+                const int c = t % CB_FW; t /= CB_FW;
+                const int r = t & (CB_TH - 1), v = t >> 3;
+                const int x = c - 4 + (h - 4);           // output column that sees source column c through displacement h
+                const int sy = y0 + r - (v - 4), sx = x0 - 4 + c, d = v * 9 + h;
+                gv[u] = 0.f; cvv[u] = 1.f;
+                dst[u] = (e < N1 && x >= 0 && x < CB_TW) ? d * CB_GS + r * CB_TW + x : -1;
+                if (dst[u] >= 0 && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) {
+                    const size_t pix = img + (size_t)sy * p.W + sx;
+                    gv[u] = __ldg(p.g + pix * p.g_cs + d);
+                    cvv[u] = __ldg(p.cv + pix * p.cv_cs + d);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GU; ++u)
+                if (dst[u] >= 0) Gs[dst[u]] = gv[u] * (cvv[u] > 0.f ? p.inv_c : p.inv_c * p.alpha);
+        }
+    }
+    const float* F = DIR ? p.f0 : p.f1;
+    const int f_cs = DIR ? p.f0_cs : p.f1_cs;
+    constexpr int FU = 6, NF = CB_FH * CB_FW * (CB_CS / 4);
+    static_assert(NF % (CB_THREADS * FU) == 0, "F tile copy: whole batches");
+    for (int e0 = tid; e0 < NF; e0 += CB_THREADS * FU) {
+        float4 fv[FU];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            const int e = e0 + u * CB_THREADS;
+            const int c4 = e & 7, pxl = e >> 3, fr = pxl / CB_FW, fc = pxl - fr * CB_FW;
+            const int y = y0 - 4 + fr, x = x0 - 4 + fc, ch = c0 + 4 * c4;
+            fv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < p.H && x >= 0 && x < p.W && ch < p.C) fv[u] = ldg4(F + (img + (size_t)y * p.W + x) * f_cs + ch);
+        }
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+            const int e = e0 + u * CB_THREADS;
+            *reinterpret_cast<float4*>(Fs + (e >> 3) * CB_FS + 4 * (e & 7)) = fv[u];
+        }
+    }
+    __syncthreads();
+
+    const int cg = tid & 7, quad = tid >> 3, r = quad >> 2, xq = (quad & 3) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+    for (int v = 0; v < 9; ++v) {
+        const int frow = r + 4 + (DIR ? 4 - v : v - 4);
+        const float* frp = Fs + (frow * CB_FW + xq) * CB_FS + cg * 4;
+        float4 win[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) win[j] = *reinterpret_cast<const float4*>(frp + j * CB_FS);
+        const float* gp = Gs + (v * 9) * CB_GS + r * CB_TW + xq;
+#pragma unroll
+        for (int h = 0; h < 9; ++h) {
+            const float4 gq = *reinterpret_cast<const float4*>(gp + h * CB_GS);
+            const float ga[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 f = win[i + 4 + (DIR ? 4 - h : h - 4)];
+                acc[i][0] = fmaf(ga[i], f.x, acc[i][0]); acc[i][1] = fmaf(ga[i], f.y, acc[i][1]);
+                acc[i][2] = fmaf(ga[i], f.z, acc[i][2]); acc[i][3] = fmaf(ga[i], f.w, acc[i][3]);
+            }
+        }
+    }
+    const int y = y0 + r, ch = c0 + 4 * cg;
+    if (y >= p.H || ch >= p.C) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x0 + xq + i;
+        if (x >= p.W) continue;
+        const size_t pix = img + (size_t)y * p.W + x;
+        float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (DIR == 0) {
+            float4* d0 = reinterpret_cast<float4*>(p.df0 + pix * p.df0_cs + ch);
+            const float4 t = *d0;
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            if (p.g_f0slot) {
+                const float4 sl = ldg4(p.g_f0slot + pix * p.gs_cs + ch);
+                o.x += sl.x; o.y += sl.y; o.z += sl.z; o.w += sl.w;
+            }
+            *d0 = o;
+        } else {
+            float4* d1 = reinterpret_cast<float4*>(p.df1 + pix * p.df1_cs + ch);
+            if (p.acc_f1) { const float4 t = *d1; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            *d1 = o;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CB_THREADS, 2) cost_volume_bwd_tiled_kernel(const CvBwdParams p, int tiles_x, int tiles_y) {
+    extern __shared__ __align__(16) float cb_smem[];
+    float* Gs = cb_smem;
+    float* Fs = cb_smem + 81 * CB_GS;
+    const int t = blockIdx.x, tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+    if (blockIdx.z) cv_bwd_tile<1>(p, Gs, Fs, b, ty * CB_TH, tx * CB_TW, blockIdx.y * CB_CS);
+    else cv_bwd_tile<0>(p, Gs, Fs, b, ty * CB_TH, tx * CB_TW, blockIdx.y * CB_CS);
+}
+
+// ------------------------------------------------------------------------------------------------ zero insertion
+// out (B,H,W,C) dense: out[b, 2y+oy, 2x+ox, :] = dy[b,y,x,:], zeros elsewhere.  With oy = 1 - pad_top (same for x) the
+// stride-2 dgrad becomes the stride-1 dgrad of `out`, which runs on the tcgen05 conv kernel (3/4 of its MMAs multiply
+// zeros, still several times faster than the CUDA-core parity-class kernel).
+__global__ void dilate2_kernel(const float* __restrict__ dy, int dy_cs, float* __restrict__ out, int B, int OH, int OW,
+                               int C4, int H, int W, int oy, int ox) {
+    const size_t total = (size_t)B * H * W * C4;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int k = idx % C4; const size_t pix = idx / C4;
+        const int x = pix % W; const size_t row = pix / W;
+        const int y = row % H; const size_t b = row / H;
+        const int sy = y - oy, sx = x - ox;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sy >= 0 && sx >= 0 && !(sy & 1) && !(sx & 1) && (sy >> 1) < OH && (sx >> 1) < OW)
+            v = ldg4(dy + ((b * OH + (sy >> 1)) * OW + (sx >> 1)) * dy_cs + 4 * k);
+        reinterpret_cast<float4*>(out)[idx] = v;
     }
 }
 
@@ -688,13 +907,26 @@ extern "C" int pwc_conv3x3_wgrad(const float* x, int x_cs, const float* dy, int 
         const int tiles_x = (p.OW + WS_TW - 1) / WS_TW, tiles_y = (p.OH + WS_TH - 1) / WS_TH;
         const long long n_tiles = (long long)tiles_x * tiles_y * B;
         if (n_tiles < (1ll << 30)) {
-            const int Cip = (Cin + 3) / 4 * 4, Cop = (Cout + 3) / 4 * 4;
+            const int TI = Cin <= 4 ? 4 : 8, TO = Cout <= 4 ? 4 : 8;
+            const int Cip = (Cin + TI - 1) / TI * TI, Cop = (Cout + TO - 1) / TO * TO;
             const int prow = (WS_TH - 1) * stride + 3, pcol = (WS_TW - 1) * stride + 3;
-            const size_t smem = ((size_t)prow * pcol * Cip + (size_t)WS_PIX * Cop) * 4;
-            cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { set_error("conv3x3_wgrad_small: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+            const int n_items = 9 * (Cip / TI) * (Cop / TO);                 // <= 144
+            size_t smem = 2 * ((size_t)prow * pcol * Cip + (size_t)WS_PIX * Cop) * 4;   // two tile buffers
+            const size_t red = ((size_t)n_items * TI * TO + Cop) * 4;       // final reduction reuses the tile buffers
+            if (smem < red) smem = red;
+            int k = WS_MAXT / n_items;                                       // pixel groups
+            if (k > WS_TW) k = WS_TW;
+            const int threads = (n_items * k + 31) / 32 * 32;
             const int grid = (int)(n_tiles < 148 * 2 ? n_tiles : 148 * 2);
-            conv3x3_wgrad_small_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, tiles_x, tiles_y, (int)n_tiles);
+            auto launch = [&](auto kern) -> cudaError_t {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                kern<<<grid, threads, smem, (cudaStream_t)stream>>>(p, tiles_x, tiles_y, (int)n_tiles, n_items, k);
+                return cudaSuccess;
+            };
+            cudaError_t e = TI == 4 ? (TO == 4 ? launch(conv3x3_wgrad_small_kernel<4, 4>) : launch(conv3x3_wgrad_small_kernel<4, 8>))
+                                    : (TO == 4 ? launch(conv3x3_wgrad_small_kernel<8, 4>) : launch(conv3x3_wgrad_small_kernel<8, 8>));
+            if (e != cudaSuccess) { set_error("conv3x3_wgrad_small: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             PWC_CHECK_LAUNCH("conv3x3_wgrad_small_kernel");
             return 0;
         }
@@ -740,6 +972,18 @@ extern "C" int pwc_add_strided(float* dst, int dst_cs, const float* src, int src
     return 0;
 }
 
+extern "C" int pwc_dilate2(const float* dy, int dy_cs, float* out, int B, int OH, int OW, int C, int H, int W, int oy, int ox,
+                           void* stream) {
+    PWC_REQUIRE(dy && out, PWC_E_BADARG, "dilate2: null pointer");
+    PWC_REQUIRE(B > 0 && OH > 0 && OW > 0 && C > 0 && H > 0 && W > 0 && dy_cs >= C, PWC_E_BADARG, "dilate2: bad dims");
+    PWC_REQUIRE((C & 3) == 0 && (dy_cs & 3) == 0 && aligned16(dy) && aligned16(out), PWC_E_ALIGN,
+                "dilate2: C and the channel stride must be multiples of 4, pointers 16-byte aligned");
+    dilate2_kernel<<<grid_for((size_t)B * H * W * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(dy, dy_cs, out, B, OH, OW, C >> 2,
+                                                                                                 H, W, oy, ox);
+    PWC_CHECK_LAUNCH("dilate2_kernel");
+    return 0;
+}
+
 extern "C" int pwc_cost_volume_bwd(const float* g, int g_cs, const float* cv, int cv_cs, const float* f0, int f0_cs,
                                    const float* f1, int f1_cs, const float* g_f0slot, int gs_cs,
                                    float* df0, int df0_cs, float* df1, int df1_cs, int accumulate_f1,
@@ -757,6 +1001,16 @@ extern "C" int pwc_cost_volume_bwd(const float* g, int g_cs, const float* cv, in
     p.g_cs = g_cs; p.cv_cs = cv_cs; p.f0_cs = f0_cs; p.f1_cs = f1_cs; p.gs_cs = gs_cs; p.df0_cs = df0_cs; p.df1_cs = df1_cs;
     p.B = B; p.H = H; p.W = W; p.C = C; p.r = search_range; p.alpha = alpha; p.inv_c = 1.f / (float)C;
     p.acc_f1 = accumulate_f1;
+    static const bool gather = [] { const char* e = getenv("PWC_CV_BWD"); return e && !strcmp(e, "gather"); }();
+    const long long tiles_x = (W + CB_TW - 1) / CB_TW, tiles_y = (H + CB_TH - 1) / CB_TH;
+    if (search_range == 4 && !gather && tiles_x * tiles_y * B < (1ll << 31) && (C + CB_CS - 1) / CB_CS <= 65535) {
+        cudaError_t e = cudaFuncSetAttribute(cost_volume_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CB_SMEM);
+        if (e != cudaSuccess) { set_error("cost_volume_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        dim3 grid((unsigned)(tiles_x * tiles_y * B), (C + CB_CS - 1) / CB_CS, 2);
+        cost_volume_bwd_tiled_kernel<<<grid, CB_THREADS, CB_SMEM, (cudaStream_t)stream>>>(p, (int)tiles_x, (int)tiles_y);
+        PWC_CHECK_LAUNCH("cost_volume_bwd_tiled_kernel");
+        return 0;
+    }
     const size_t total = (size_t)B * H * W * (C / 4);
     cost_volume_bwd_kernel<<<grid_for(total, 128, 148 * 32), 128, 0, (cudaStream_t)stream>>>(p);
     PWC_CHECK_LAUNCH("cost_volume_bwd_kernel");

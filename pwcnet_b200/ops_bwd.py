@@ -75,6 +75,16 @@ def add_(dst, src, scale: float = 1.0):
     return dst
 
 
+def dilate2(dy, out, oy: int, ox: int):
+    """Zero insertion: out[b, 2y+oy, 2x+ox] = dy[b, y, x], zeros elsewhere (out dense NHWC with dy's channel count)."""
+    B, OH, OW, C, dy_cs = _nhwc(dy, "dy")
+    Bo, H, W, Co, o_cs = _nhwc(out, "out")
+    if Bo != B or Co != C or o_cs != C:
+        raise ValueError("dilate2: out must be dense NHWC with dy's batch and channels")
+    check(lib().pwc_dilate2(dy.data_ptr(), dy_cs, out.data_ptr(), B, OH, OW, C, H, W, int(oy), int(ox), _stream()), "pwc_dilate2")
+    return out
+
+
 def cost_volume_bwd(g, cv, f0, f1, df0, df1, g_f0slot=None, accumulate_f1: bool = False, search_range: int = 4,
                     alpha: float = 0.1):
     """df0 += dCV/df0 (+ g_f0slot), df1 (=|+=) dCV/df1 for cv = cost_volume(f0, f1)."""

@@ -86,7 +86,9 @@ class Trainer(object):
         self.tc_dgrad = model.precision == "3xf16" if tc_dgrad is None else bool(tc_dgrad)
         self.tc_wgrad = model.precision == "3xf16" if tc_wgrad is None else bool(tc_wgrad)
         self._tscratch = None
+        self._dil = None
         import os
+        self.tc_dgrad_s2 = os.environ.get("PWC_DGRAD_S2_TC", "1") != "0"
         self.tc_wgrad_small = os.environ.get("PWC_WGRAD_TC_SMALL", "0") == "1"
 
     # ------------------------------------------------------------------ gradient workspace
@@ -147,6 +149,18 @@ class Trainer(object):
         if gx is None:
             return
         k = m._k[scope]
+        if self.tc_dgrad and self.tc_dgrad_s2 and stride == 2 and dilation == 1 and cout >= 16 and cout % 4 == 0 \
+                and dy.stride(2) % 4 == 0 and dy.data_ptr() % 16 == 0:
+            # stride-2 dgrad == stride-1 dgrad of the zero-inserted dy (odd/even positions chosen by the SAME padding):
+            # one streaming pass + the tcgen05 kernel instead of the CUDA-core parity-class kernel (conv2a: 681 -> ~200 us)
+            B, H, W = gx.shape[0], gx.shape[1], gx.shape[2]
+            OH, OW = dy.shape[1], dy.shape[2]
+            pad_t, pad_l = max((OH - 1) * 2 + 3 - H, 0) // 2, max((OW - 1) * 2 + 3 - W, 0) // 2
+            n = B * H * W * cout
+            if self._dil is None or self._dil.numel() < n:
+                self._dil = torch.empty(n, dtype=torch.float32, device=dy.device)
+            dy = ops_bwd.dilate2(dy, self._dil[:n].view(B, H, W, cout), 1 - pad_t, 1 - pad_l)
+            stride = 1
         if self.tc_dgrad and stride == 1 and k.shape[3] >= 16 and dy.stride(2) % 4 == 0 and dy.data_ptr() % 16 == 0:
             # stride-1 dgrad == SAME conv of dy with the rotated kernel: runs on the tcgen05 forward kernel
             # (3 x fp16 split, fp32-class).  dx channel ranges wider than 256 / not a multiple of 16 are split / padded.

@@ -43,7 +43,7 @@ def _close(got, ref, rel=2e-5, name=""):
 CONV_CASES = [  # B, H, W, Cin, Cout, stride, dilation
     (2, 12, 20, 3, 16, 2, 1), (1, 16, 24, 16, 32, 2, 1), (2, 9, 13, 32, 32, 1, 1), (1, 11, 18, 34, 128, 1, 2),
     (1, 20, 40, 96, 64, 1, 8), (1, 7, 16, 128, 96, 1, 16), (2, 8, 16, 32, 2, 1, 1), (1, 10, 12, 147, 128, 1, 1),
-    (1, 13, 17, 64, 70, 2, 1), (1, 1, 2, 192, 192, 1, 1),
+    (1, 13, 17, 64, 70, 2, 1), (1, 1, 2, 192, 192, 1, 1), (1, 17, 45, 16, 16, 1, 1), (1, 8, 70, 20, 12, 1, 1), (2, 9, 33, 4, 2, 2, 1),
 ]
 
 
@@ -183,6 +183,28 @@ def test_tc_dgrad_matches_cuda_core_dgrad(P, case):
                                      accumulate=True)
     _close(got, ref, rel=2e-5, name="tc dgrad")
     assert float(buf[..., :4].abs().max()) == 0 and float(buf[..., 4 + Cdx:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("case", [(2, 12, 16, 16, 32), (1, 11, 13, 32, 64), (1, 24, 32, 128, 196), (1, 7, 10, 64, 96)])
+def test_stride2_dgrad_through_zero_insertion_matches_cuda_core_dgrad(P, case):
+    """Stride-2 dgrad = stride-1 tcgen05 dgrad of the zero-inserted dy (even and odd H/W: pad_top 0 / 1), vs the exact
+    fp32 parity-class kernel, accumulating into an existing gradient."""
+    from pwcnet_b200 import ops_bwd, ops_tc
+    B, H, W, Cdx, Cdy = case
+    OH, OW = (H + 1) // 2, (W + 1) // 2
+    k = _cuda(_rand((3, 3, Cdx, Cdy), 2, 0.1))
+    dy = _cuda(_rand((B, OH, OW, Cdy), 4))
+    prev = _rand((B, H, W, Cdx), 6)
+    ref = _cuda(prev)
+    ops_bwd.conv3x3_dgrad(dy, k, ref, stride=2, accumulate=True)
+    pad_t, pad_l = max((OH - 1) * 2 + 3 - H, 0) // 2, max((OW - 1) * 2 + 3 - W, 0) // 2
+    dil = ops_bwd.dilate2(dy, torch.full((B, H, W, Cdy), 7.0, device="cuda"), 1 - pad_t, 1 - pad_l)
+    assert int((dil != 0).sum()) == int((dy != 0).sum()) and float(dil.sum()) == pytest.approx(float(dy.sum()), rel=1e-4, abs=1e-2)
+    got = _cuda(prev)
+    pad = (Cdx + 15) // 16 * 16
+    packed = ops_tc.pack_weights_f16(ops_bwd.rot_weights(k, ci_pad=pad))
+    ops_bwd.conv3x3_tc_f16_dgrad(dil, packed, got, pad, accumulate=True)
+    _close(got, ref, rel=2e-5, name="stride-2 tc dgrad")
 
 
 @pytest.mark.parametrize("shape", [(2, 7, 16, 192), (1, 14, 32, 128), (1, 28, 64, 32), (2, 5, 9, 16), (1, 1, 2, 32), (1, 13, 21, 36)])
