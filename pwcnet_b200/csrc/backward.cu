@@ -537,76 +537,89 @@ __device__ __forceinline__ void cv_bwd_tile(const CvBwdParams& p, float* __restr
                                             int c0) {
     const int tid = threadIdx.x;
     const size_t img = (size_t)b * p.H * p.W;
-    // All three copy loops issue a batch of independent loads before the first shared-memory store (one load pair in
-    // flight per thread made the first version latency-bound: 390 us at level 2).
-    constexpr int GU = 8;
+    // Copy loops: warp w owns tile row w; every lane issues a batch of independent loads (12-21 per array) before the
+    // first shared-memory store, with no divisions by run-time values (the first versions were bound by load latency
+    // and index arithmetic: 390 / 334 us at level 2).
+    const int wid = tid >> 5, lane = tid & 31;
+    const float inv_c = p.inv_c, inv_ca = p.inv_c * p.alpha;
     if (DIR == 0) {
-        for (int e0 = tid; e0 < CB_PIX * 81; e0 += CB_THREADS * GU) {
-            float gv[GU], cvv[GU];
+        const int y = y0 + wid;
+        const size_t rowpix = img + (size_t)y * p.W + x0;
+#pragma unroll 1
+        for (int p0 = 0; p0 < CB_TW; p0 += 4) {
+            float gv[4][3], cvv[4][3];
 #pragma unroll
-            for (int u = 0; u < GU; ++u) {
-                const int e = e0 + u * CB_THREADS;
-                const int px = e / 81, d = e - px * 81;
-                const int y = y0 + (px >> 4), x = x0 + (px & 15);
-                gv[u] = 0.f; cvv[u] = 1.f;
-                if (e < CB_PIX * 81 && y < p.H && x < p.W) {
-                    const size_t pix = img + (size_t)y * p.W + x;
-                    gv[u] = __ldg(p.g + pix * p.g_cs + d);
-                    cvv[u] = __ldg(p.cv + pix * p.cv_cs + d);
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = y < p.H && x0 + p0 + i < p.W;
+                const float* gp = p.g + (rowpix + p0 + i) * p.g_cs;
+                const float* cp = p.cv + (rowpix + p0 + i) * p.cv_cs;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int d = lane + 32 * j;
+                    gv[i][j] = 0.f; cvv[i][j] = 1.f;
+                    if (ok && d < 81) { gv[i][j] = __ldg(gp + d); cvv[i][j] = __ldg(cp + d); }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < GU; ++u) {
-                const int e = e0 + u * CB_THREADS;
-                const int px = e / 81, d = e - px * 81;
-                if (e < CB_PIX * 81) Gs[d * CB_GS + px] = gv[u] * (cvv[u] > 0.f ? p.inv_c : p.inv_c * p.alpha);
-            }
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int d = lane + 32 * j;
+                    if (d < 81) Gs[d * CB_GS + wid * CB_TW + p0 + i] = gv[i][j] * (cvv[i][j] > 0.f ? inv_c : inv_ca);
+                }
         }
     } else {
-        constexpr int N1 = 9 * CB_TH * CB_FW * 9;
-        for (int e0 = tid; e0 < N1; e0 += CB_THREADS * GU) {
-            float gv[GU], cvv[GU];
-            int dst[GU];
+        // output row r = wid; for displacement row v the sources are row y0 + r - (v - 4), columns x0 - 4 .. x0 + 19,
+        // group v of their 81 values (9 contiguous floats per pixel): element idx = c * 9 + h, 216 per (r, v)
+#pragma unroll 1
+        for (int v0 = 0; v0 < 9; v0 += 3) {
+            float gv[3][7], cvv[3][7];
 #pragma unroll
-            for (int u = 0; u < GU; ++u) {
-                const int e = e0 + u * CB_THREADS;
-                const int h = e % 9; int t = e / 9;
-                const int c = t % CB_FW; t /= CB_FW;
-                const int r = t & (CB_TH - 1), v = t >> 3;
-                const int x = c - 4 + (h - 4);           // output column that sees source column c through displacement h
-                const int sy = y0 + r - (v - 4), sx = x0 - 4 + c, d = v * 9 + h;
-                gv[u] = 0.f; cvv[u] = 1.f;
-                dst[u] = (e < N1 && x >= 0 && x < CB_TW) ? d * CB_GS + r * CB_TW + x : -1;
-                if (dst[u] >= 0 && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W) {
-                    const size_t pix = img + (size_t)sy * p.W + sx;
-                    gv[u] = __ldg(p.g + pix * p.g_cs + d);
-                    cvv[u] = __ldg(p.cv + pix * p.cv_cs + d);
+            for (int i = 0; i < 3; ++i) {
+                const int v = v0 + i, sy = y0 + wid - (v - 4);
+                const bool yok = sy >= 0 && sy < p.H;
+                const size_t rowpix = img + (size_t)sy * p.W + (x0 - 4);
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const int idx = lane + 32 * j, c = idx / 9, h = idx - c * 9, x = c - 8 + h, sx = x0 - 4 + c;
+                    gv[i][j] = 0.f; cvv[i][j] = 1.f;
+                    if (yok && idx < 216 && x >= 0 && x < CB_TW && sx >= 0 && sx < p.W) {
+                        gv[i][j] = __ldg(p.g + (rowpix + c) * p.g_cs + v * 9 + h);
+                        cvv[i][j] = __ldg(p.cv + (rowpix + c) * p.cv_cs + v * 9 + h);
+                    }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < GU; ++u)
-                if (dst[u] >= 0) Gs[dst[u]] = gv[u] * (cvv[u] > 0.f ? p.inv_c : p.inv_c * p.alpha);
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const int idx = lane + 32 * j, c = idx / 9, h = idx - c * 9, x = c - 8 + h;
+                    if (idx < 216 && x >= 0 && x < CB_TW)
+                        Gs[((v0 + i) * 9 + h) * CB_GS + wid * CB_TW + x] = gv[i][j] * (cvv[i][j] > 0.f ? inv_c : inv_ca);
+                }
         }
     }
-    const float* F = DIR ? p.f0 : p.f1;
-    const int f_cs = DIR ? p.f0_cs : p.f1_cs;
-    constexpr int FU = 6, NF = CB_FH * CB_FW * (CB_CS / 4);
-    static_assert(NF % (CB_THREADS * FU) == 0, "F tile copy: whole batches");
-    for (int e0 = tid; e0 < NF; e0 += CB_THREADS * FU) {
-        float4 fv[FU];
+    {   // F halo tile: warp w copies rows 2w, 2w+1 (24 pixels x 8 float4 each)
+        const float* F = DIR ? p.f0 : p.f1;
+        const int f_cs = DIR ? p.f0_cs : p.f1_cs;
+        const int c4 = lane & 7, ch = c0 + 4 * c4;
+        float4 fv[2][6];
 #pragma unroll
-        for (int u = 0; u < FU; ++u) {
-            const int e = e0 + u * CB_THREADS;
-            const int c4 = e & 7, pxl = e >> 3, fr = pxl / CB_FW, fc = pxl - fr * CB_FW;
-            const int y = y0 - 4 + fr, x = x0 - 4 + fc, ch = c0 + 4 * c4;
-            fv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y >= 0 && y < p.H && x >= 0 && x < p.W && ch < p.C) fv[u] = ldg4(F + (img + (size_t)y * p.W + x) * f_cs + ch);
+        for (int i = 0; i < 2; ++i) {
+            const int fr = 2 * wid + i, y = y0 - 4 + fr;
+            const bool yok = y >= 0 && y < p.H && ch < p.C;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int fc = (lane >> 3) + 4 * j, x = x0 - 4 + fc;
+                fv[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (yok && x >= 0 && x < p.W) fv[i][j] = ldg4(F + (img + (size_t)y * p.W + x) * f_cs + ch);
+            }
         }
 #pragma unroll
-        for (int u = 0; u < FU; ++u) {
-            const int e = e0 + u * CB_THREADS;
-            *reinterpret_cast<float4*>(Fs + (e >> 3) * CB_FS + 4 * (e & 7)) = fv[u];
-        }
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                *reinterpret_cast<float4*>(Fs + ((2 * wid + i) * CB_FW + (lane >> 3) + 4 * j) * CB_FS + 4 * c4) = fv[i][j];
     }
     __syncthreads();
 
