@@ -26,7 +26,7 @@ namespace pwc {
 constexpr int HL_M = 128;                          // output pixels per tile (one row segment)
 constexpr int HL_BH = 3;                           // halo box: 3 rows (y-d, y, y+d) x (128 + 2d) pixels
 constexpr int HL_BK = 32;
-constexpr int HL_MAX_ACT_STAGES = 3, HL_W_STAGES = 4;   // activation stages: 2 (3 selectable with PWC_HALO_STAGES=3)
+constexpr int HL_MAX_ACT_STAGES = 4, HL_W_STAGES = 4;   // activation stages: 2, up to 4 for layers with resident weights
 constexpr int HL_CONV_THREADS = 256;
 constexpr int HL_THREADS = 64 + 128 + HL_CONV_THREADS + 32;   // act TMA, MMA, 4 epilogue, 8 converter, weight producer
 constexpr float HL_SCALE = 2048.f, HL_INV_SCALE = 1.f / 2048.f;
@@ -47,7 +47,7 @@ struct HaloParams {
     int tiles_img;        // tiles per image
     int row_loads;        // 1: one box with row traversal stride d (d <= 8); 3: one single-row box per row (d > 8)
     int act_stage;        // bytes per activation stage (3 * bw * 128 rounded up to 1024)
-    int act_stages;       // 2 or 3
+    int act_stages;       // 2..4
     int n_sets;           // independent (main | corr) accumulator sets per tile that the taps rotate over: consecutive MMAs
                           // into ONE accumulator serialise on its latency (~125 clk measured), which dominates narrow layers
     int w_resident;       // all 9 * kchunks weight images stay in shared memory (small layers): loaded once per CTA
@@ -76,9 +76,10 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aconv = smem_u32(&bars[3]), bar_aempty = smem_u32(&bars[6]);
-    const uint32_t bar_wfull = smem_u32(&bars[9]), bar_wempty = smem_u32(&bars[13]);
-    const uint32_t bar_accf = smem_u32(&bars[17]), bar_acce = smem_u32(&bars[19]);
+    constexpr int MS = HL_MAX_ACT_STAGES;
+    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aconv = smem_u32(&bars[MS]), bar_aempty = smem_u32(&bars[2 * MS]);
+    const uint32_t bar_wfull = smem_u32(&bars[3 * MS]), bar_wempty = smem_u32(&bars[3 * MS + HL_W_STAGES]);
+    const uint32_t bar_accf = smem_u32(&bars[3 * MS + 2 * HL_W_STAGES]), bar_acce = smem_u32(&bars[3 * MS + 2 * HL_W_STAGES + 2]);
     const int AS = p.act_stages;
     const uint32_t w_base = base + p.act_stages * p.act_stage;
     const int n_rows = (p.flat ? p.nr : HL_BH) * p.bw;
@@ -400,14 +401,27 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.desc_mode = 0;
     p.exp_skip_conv = getenv("PWC_HALO_EXP") ? 1 : 0;
     if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
-    p.n_sets = 1;                                  // power of two, <= 8, n_sets * 2 * Cout <= 256 columns per tile
-    while (p.n_sets < 8 && 2 * p.n_sets * 2 * Cout <= 256) p.n_sets *= 2;
-    if (const char* e = getenv("PWC_HALO_SETS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) { if (v <= p.n_sets) p.n_sets = v; } }
+    // Rotating accumulator sets (power of two, <= 8, n_sets * 2 * Cout <= 256 columns per tile) paid off while the MMA
+    // issue was slowed by the lane-0 wrapper; with elect.sync one set is fastest (the epilogue reads every set back:
+    // 2.4k clk per 16-channel tile with 8 sets), so 1 is the default and PWC_HALO_SETS selects more.
+    int max_sets = 1;
+    while (max_sets < 8 && 2 * max_sets * 2 * Cout <= 256) max_sets *= 2;
+    p.n_sets = 1;
+    if (const char* e = getenv("PWC_HALO_SETS")) { int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v <= max_sets) p.n_sets = v; }
     p.act_stages = 2;   // measured: a third activation stage does not help (174.6 vs 171.5 us at 128->128), the limit is operand bandwidth
-    if (const char* e = getenv("PWC_HALO_STAGES")) p.act_stages = atoi(e) == 3 ? 3 : 2;
+    int want_stages = 0;
+    if (const char* e = getenv("PWC_HALO_STAGES")) want_stages = atoi(e);
+    if (want_stages == 3) p.act_stages = 3;
     const size_t w_all = (size_t)9 * p.kchunks * p.w_stage_bytes;
     p.w_resident = (2 * (size_t)p.act_stage + w_all + 1024 <= 227 * 1024) && !getenv("PWC_HALO_NO_RESIDENT");
-    if (p.w_resident) p.act_stages = 2;
+    if (p.w_resident) {
+        // small layers (resident weights): a stage is held from the TMA issue to the last MMA that reads it (~5k clk
+        // at 16->16: 1.9k TMA latency + 1.4k conversion + 1.7k MMAs), so two stages cap the tile period at ~2.5k clk
+        p.act_stages = 2;
+        const int fit = (int)((227 * 1024 - 1024 - w_all) / p.act_stage);
+        const int lim = want_stages >= 2 && want_stages <= HL_MAX_ACT_STAGES ? want_stages : HL_MAX_ACT_STAGES;
+        if (fit > 2) p.act_stages = fit < lim ? fit : lim;
+    }
     size_t smem = (size_t)p.act_stages * p.act_stage + (p.w_resident ? w_all : (size_t)HL_W_STAGES * p.w_stage_bytes) + 1024;
     if (smem > 227 * 1024) { p.act_stages = 2; smem = (size_t)2 * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024; }
     if (smem > 227 * 1024) return -1000;
