@@ -237,19 +237,38 @@ def run_train(args):
         e.record()
     barrier()
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
-    # e2e: pinned host batch in, loss/EPE scalars back on the host, every step
+    # e2e: pinned host batch in, loss/EPE scalars back on the host, every step.  TrainStream stages batch i+1 (H2D on a
+    # copy stream) while step i computes; sync_value is the un-pipelined Trainer.step(host batch).
     res_host = torch.empty(3, dtype=torch.float32).pin_memory()
-    def e2e_step():
+    def sync_step():
         loss, lms, epe = trainer.step(host0, host1, hostg)
         res_host.copy_(torch.stack([loss, lms, epe]), non_blocking=True)
         torch.cuda.current_stream().synchronize()
     for _ in range(2):
-        e2e_step()
+        sync_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_sync = max(3, args.steps // 4)
+    e0.record()
+    for _ in range(n_sync):
+        sync_step()
+    e1.record()
+    barrier()
+    sync_ms = e0.elapsed_time(e1) / n_sync
+    ts = P.TrainStream(trainer, depth=2)
+    def piped(n):
+        ts.submit(host0, host1, hostg)                     # the first copy is exposed, the others overlap a step
+        for k in range(n):
+            if k + 1 < n:
+                ts.submit(host0, host1, hostg)
+            loss, lms, epe = ts.step()
+            res_host.copy_(torch.stack([loss, lms, epe]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()     # the caller reads the loss of every step
+    piped(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    piped(args.steps)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -279,7 +298,10 @@ def run_train(args):
                            "l2": "256 MiB write between timed iterations"},
                 "e2e": {"value": total_pairs / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": int(host0.numel() + host1.numel() + hostg.numel()) * 4, "d2h_bytes_per_step": 12,
-                        "what": "Trainer.step on pinned host images + GT flow; loss, multiscale loss and EPE copied back"},
+                        "sync_value": B * world / (sync_ms * 1e-3),
+                        "what": "TrainStream(trainer, depth=2).submit/step: pinned host images + GT flow -> device staging on a copy "
+                                "stream (batch i+1 overlaps step i), loss, multiscale loss and EPE copied back and read every step; "
+                                "sync_value = Trainer.step(host batch), no overlap"},
                 "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
                 "loss": float(out[0].item()), "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)

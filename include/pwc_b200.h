@@ -89,6 +89,13 @@ int pwc_conv3x3_tc_f16_head(const float* x, int x_cs, const void* w_packed, cons
 long long pwc_conv3x3_packed_bytes_f16(int Cin, int Cout);
 int pwc_conv3x3_pack_weights_f16(const float* w_hwio, void* w_packed, int Cin, int Cout, void* stream);
 
+/* Batched pack: `jobs` is a DEVICE array of n_jobs x 8 int64 {w, out, K, N, mode, a, b, c}; one launch for all layers.
+ * mode 0: out = pack_weights_f16 of the (3,3,K,a) HWIO kernel w, output channels zero-padded to N (a <= N);
+ * mode 1: out = pack_weights_f16(rot_weights(w, ci_begin=b, ci_count=c, ci_pad=N)) for the (3,3,a,K) HWIO kernel w,
+ *         i.e. the stride-1 dgrad kernel (Conv2DBackpropInput, train.py:89) of input channels [b, b+c).
+ * `out` sizes as pwc_conv3x3_packed_bytes_f16(K, N). */
+int pwc_conv3x3_pack_weights_f16_batched(const long long* jobs, int n_jobs, void* stream);
+
 /* tf.image.resize_bilinear(x,(OH,OW)) with align_corners=False as in TF 1.8 (no half-pixel
  * offset; modules.py:283-284, model.py:127), result multiplied by `mul` (model.py:127 "*20."). */
 int pwc_resize_bilinear_fwd(const float* x, int x_cs, float* y, int y_cs, int B, int H, int W, int C,

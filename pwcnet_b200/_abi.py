@@ -31,6 +31,7 @@ SIGNATURES = {
     "pwc_conv3x3_packed_bytes_f16": (C.c_longlong, [_i, _i]),
     "pwc_conv3x3_pack_weights_f16": (_i, [_f32p, _f32p, _i, _i, _vp]),
     "pwc_conv3x3_packed_bytes": (C.c_longlong, [_i, _i]),
+    "pwc_conv3x3_pack_weights_f16_batched": (_i, [_vp, _i, _vp]),
     "pwc_conv3x3_pack_weights": (_i, [_f32p, _f32p, _i, _i, _vp]),
     "pwc_resize_bilinear_fwd": (_i, [_f32p, _i, _f32p, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "pwc_lploss_level_fwd": (_i, [_f32p, _i, _i, _f32p, _i, _i, _i, _i, _f, _f, _i, _f32p, _vp]),

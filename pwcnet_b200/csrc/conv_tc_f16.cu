@@ -306,7 +306,47 @@ __global__ void pack_weights_f16_kernel(const float* __restrict__ w, __half* __r
 
 static inline int f16_cin_pad(int Cin) { return (Cin + F16_BK - 1) / F16_BK * F16_BK; }
 
+// Batched form: one launch packs every layer of the model (a training step re-packs ~115 weight tensors: the forward
+// kernels after the Adam update, the rotated dgrad kernels before the backward pass; as single launches that was
+// 0.7 ms of 16 ms).  Job = 8 x int64 {w, out, K channels, N channels, mode, a, b, c}:
+//   mode 0: forward kernel, w = (3,3,K,a) HWIO with a <= N output channels (zero-padded to N: the 2-channel heads);
+//   mode 1: stride-1 dgrad kernel of w = (3,3,a,K) HWIO for the input-channel range [b, b+c) zero-padded to N:
+//           out(tap, k, n) = w(8 - tap, b + n, k)   (what pwc_conv3x3_rot_weights + pack produce).
+__global__ void pack_weights_f16_batched_kernel(const long long* __restrict__ jobs) {
+    const long long* j = jobs + 8 * (size_t)blockIdx.y;
+    const float* __restrict__ w = reinterpret_cast<const float*>(j[0]);
+    __half* __restrict__ out = reinterpret_cast<__half*>(j[1]);
+    const int K = (int)j[2], N = (int)j[3], mode = (int)j[4], a = (int)j[5], b = (int)j[6], c = (int)j[7];
+    const int Kp = (K + F16_BK - 1) / F16_BK * F16_BK, kchunks = Kp / F16_BK;
+    const size_t total = (size_t)9 * N * Kp;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int k = idx % Kp; size_t r = idx / Kp;
+        const int n = r % N; const int tap = r / N;
+        float v = 0.f;
+        if (k < K) {
+            if (mode == 0) { if (n < a) v = w[((size_t)tap * K + k) * a + n]; }
+            else if (n < c) v = w[((size_t)(8 - tap) * a + b + n) * K + k];
+        }
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn((v - __half2float(h)) * F16_SCALE);
+        const int kc = k / F16_BK, cc = k % F16_BK;
+        const size_t tile = ((size_t)(tap * kchunks + kc) * 2) * N * F16_BK;          // halfs
+        const size_t off = (size_t)n * F16_BK + ((((cc >> 3) ^ ((n >> 1) & 3))) << 3) + (cc & 7);
+        out[tile + off] = h;
+        out[tile + (size_t)N * F16_BK + off] = l;
+    }
+}
+
 }  // namespace pwc
+
+extern "C" int pwc_conv3x3_pack_weights_f16_batched(const long long* jobs, int n_jobs, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(jobs, PWC_E_BADARG, "pack_weights_f16_batched: null pointer");
+    PWC_REQUIRE(n_jobs > 0 && n_jobs <= 65535, PWC_E_BADARG, "pack_weights_f16_batched: 1..65535 jobs");
+    pack_weights_f16_batched_kernel<<<dim3(16, n_jobs), 256, 0, (cudaStream_t)stream>>>(jobs);
+    PWC_CHECK_LAUNCH("pack_weights_f16_batched_kernel");
+    return 0;
+}
 
 extern "C" long long pwc_conv3x3_packed_bytes_f16(int Cin, int Cout) {
     if (Cin <= 0 || Cout <= 0) return 0;

@@ -229,17 +229,24 @@ class PWCDCNet(object):
         for scope, perm in self._cin_perm.items():
             ops_bwd.permute_cin(self.params[scope + "/kernel"], self._k[scope], perm)
         from . import ops_tc
+        # every fp16-packed kernel in ONE launch (job table rebuilt when the first forward has created more packs)
+        keys = [key for key, packed in self._packed.items() if packed.dtype == torch.float16 and not key.endswith("#rot")]
+        if keys and getattr(self, "_pack_keys", None) != keys:
+            self._pack_jobs = ops_tc.PackJobs(self.device)
+            for key in keys:
+                scope = key.split("#")[0]
+                if key.endswith("#head"):     # 2-channel head: zero-padded to 16 output channels by the pack itself
+                    self._pack_jobs.add_forward(self._k[scope], self._packed[key], cout_pad=16)
+                else:
+                    self._pack_jobs.add_forward(self._k[scope], self._packed[key])
+            self._pack_keys = keys
+        if keys:
+            self._pack_jobs.run()
         for key, packed in self._packed.items():
             scope = key.split("#")[0]
-            if key.endswith("#rot"):
-                continue   # owned by the trainer
             if key.endswith("#head"):
                 self._refresh_head(scope)
-                ops_tc.pack_weights_f16(self._head_k[scope], out=packed)
-                continue
-            if packed.dtype == torch.float16:
-                ops_tc.pack_weights_f16(self._k[scope], out=packed)
-            else:
+            elif packed.dtype != torch.float16:
                 ops_tc.pack_weights(self._k[scope], out=packed)
 
     refresh_derived = _prepare

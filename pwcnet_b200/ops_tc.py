@@ -60,6 +60,51 @@ def pack_weights_f16(kernel_hwio: torch.Tensor, out=None) -> torch.Tensor:
     return out
 
 
+class PackJobs:
+    """Device job table for `pack_weights_f16_batched`: every job packs one weight tensor, all of them in one launch.
+    The tensors are referenced by address: they must stay allocated (the model refreshes them in place)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._rows = []
+        self._keep = []
+        self._table = None
+
+    def __len__(self):
+        return len(self._rows)
+
+    def _check(self, w, out, K, N):
+        if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 4 and tuple(w.shape[:2]) == (3, 3)):
+            raise ValueError("PackJobs: kernel must be a contiguous CUDA float32 HWIO (3,3,Cin,Cout) tensor")
+        if out.dtype != torch.float16 or not out.is_contiguous() or out.numel() * 2 != lib().pwc_conv3x3_packed_bytes_f16(K, N):
+            raise ValueError("PackJobs: out has the wrong dtype/size")
+
+    def add_forward(self, kernel_hwio, out, cout_pad=None):
+        """out = pack_weights_f16(kernel zero-padded to cout_pad output channels)."""
+        K, a = kernel_hwio.shape[2], kernel_hwio.shape[3]
+        N = a if cout_pad is None else cout_pad
+        self._check(kernel_hwio, out, K, N)
+        self._rows.append([kernel_hwio.data_ptr(), out.data_ptr(), K, N, 0, a, 0, 0])
+        self._keep.append((kernel_hwio, out)); self._table = None
+
+    def add_dgrad(self, kernel_hwio, out, ci_begin, ci_count, ci_pad):
+        """out = pack_weights_f16(rot_weights(kernel, ci_begin, ci_count, ci_pad)): the stride-1 dgrad kernel."""
+        a, K = kernel_hwio.shape[2], kernel_hwio.shape[3]
+        if not (0 <= ci_begin and ci_count > 0 and ci_begin + ci_count <= a and ci_count <= ci_pad):
+            raise ValueError("PackJobs: bad input-channel range")
+        self._check(kernel_hwio, out, K, ci_pad)
+        self._rows.append([kernel_hwio.data_ptr(), out.data_ptr(), K, ci_pad, 1, a, ci_begin, ci_count])
+        self._keep.append((kernel_hwio, out)); self._table = None
+
+    def run(self):
+        if not self._rows:
+            return
+        if self._table is None:
+            self._table = torch.tensor(self._rows, dtype=torch.int64, device=self.device)
+        check(lib().pwc_conv3x3_pack_weights_f16_batched(self._table.data_ptr(), len(self._rows), _stream()),
+              "pwc_conv3x3_pack_weights_f16_batched")
+
+
 def conv3x3_tc_f16(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, alpha: float = 1.0, out=None,
                    stride: int = 1):
     """3x3 SAME conv (stride 1 or 2) + bias + leaky on tcgen05 kind::f16 with the 3 x fp16 scaled-residual split."""

@@ -103,3 +103,75 @@ class InferenceStream:
     def drain(self):
         for t in list(self._pending):
             self.collect(t)
+
+
+class TrainStream:
+    """Input side of the training loop (the reference feeds its step from a prefetching tf.data pipeline,
+    train.py:33-47): `submit()` starts the H2D copy of a (pinned) host batch into one of `depth` device staging sets on
+    a copy stream, `step()` runs `Trainer.step` on the oldest staged batch.  With depth >= 2 the copy of batch i+1
+    overlaps the step of batch i; the bytes moved per step are those of the synchronous `Trainer.step(host...)`.
+
+        ts = TrainStream(trainer)
+        ts.submit(im0, im1, gt)
+        for batch in batches:            # steady state: one submit, one step
+            ts.submit(*batch)
+            loss, multiscale_loss, epe = ts.step()
+    """
+
+    def __init__(self, trainer, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.trainer = trainer
+        self.depth = depth
+        self.dev = trainer.model.device
+        self.s_in = torch.cuda.Stream(device=self.dev)
+        self._slots = None
+        self._shape = None
+        self._head = 0          # next slot to fill
+        self._tail = 0          # next slot to train on
+
+    def _alloc(self, B, H, W):
+        self._slots = [dict(im0=torch.empty((B, H, W, 3), dtype=torch.float32, device=self.dev),
+                            im1=torch.empty((B, H, W, 3), dtype=torch.float32, device=self.dev),
+                            gt=torch.empty((B, H, W, 2), dtype=torch.float32, device=self.dev),
+                            ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), used=False)
+                       for _ in range(self.depth)]
+        self._shape = (B, H, W)
+        self._head = self._tail = 0
+
+    def pending(self) -> int:
+        return self._head - self._tail
+
+    def submit(self, images_0, images_1, flows_gt) -> None:
+        i0, i1 = InferenceStream._host(images_0, "images_0"), InferenceStream._host(images_1, "images_1")
+        gt = flows_gt if isinstance(flows_gt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(flows_gt))
+        B, H, W, _ = i0.shape
+        if i1.shape != i0.shape or gt.is_cuda or gt.dtype != torch.float32 or tuple(gt.shape) != (B, H, W, 2):
+            raise ValueError("submit: images_0/images_1 (B,H,W,3) and flows_gt (B,H,W,2) must be float32 host arrays of one batch")
+        if self._shape != (B, H, W):
+            if self.pending():
+                raise RuntimeError("submit: batch shape changed while staged batches are pending; step() them first")
+            self._alloc(B, H, W)
+        if self.pending() >= self.depth:
+            raise RuntimeError(f"submit: all {self.depth} staging sets hold batches that were not trained on yet")
+        sl = self._slots[self._head % self.depth]
+        with torch.cuda.stream(self.s_in):
+            if sl["used"]:
+                self.s_in.wait_event(sl["ev_done"])      # the step that read this staging set has finished
+            sl["im0"].copy_(i0, non_blocking=True)
+            sl["im1"].copy_(i1, non_blocking=True)
+            sl["gt"].copy_(gt, non_blocking=True)
+            sl["ev_in"].record(self.s_in)
+        sl["used"] = True
+        self._head += 1
+
+    def step(self):
+        if not self.pending():
+            raise RuntimeError("step: no staged batch; submit() one first")
+        sl = self._slots[self._tail % self.depth]
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(sl["ev_in"])
+        out = self.trainer.step(sl["im0"], sl["im1"], sl["gt"])
+        sl["ev_done"].record(cur)
+        self._tail += 1
+        return out

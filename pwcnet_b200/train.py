@@ -87,6 +87,7 @@ class Trainer(object):
         self.tc_wgrad = model.precision == "3xf16" if tc_wgrad is None else bool(tc_wgrad)
         self._tscratch = None
         self._dil = None
+        self._dgrad_jobs, self._dgrad_jobs_n, self._dgrad_batched = None, -1, set()
         import os
         self.tc_dgrad_s2 = os.environ.get("PWC_DGRAD_S2_TC", "1") != "0"
         self.tc_wgrad_small = os.environ.get("PWC_WGRAD_TC_SMALL", "0") == "1"
@@ -165,9 +166,11 @@ class Trainer(object):
             # stride-1 dgrad == SAME conv of dy with the rotated kernel: runs on the tcgen05 forward kernel
             # (3 x fp16 split, fp32-class).  dx channel ranges wider than 256 / not a multiple of 16 are split / padded.
             from . import ops_tc
+            batched = scope in self._dgrad_batched      # packed by the one launch at the start of backward()
             for c0, cnt, pad, rot, packed in self._dgrad_parts(scope):
-                ops_bwd.rot_weights(k, out=rot, ci_begin=c0, ci_count=cnt, ci_pad=pad)
-                ops_tc.pack_weights_f16(rot, out=packed)
+                if not batched:
+                    ops_bwd.rot_weights(k, out=rot, ci_begin=c0, ci_count=cnt, ci_pad=pad)
+                    ops_tc.pack_weights_f16(rot, out=packed)
                 ops_bwd.conv3x3_tc_f16_dgrad(dy, packed, gx[..., c0:c0 + cnt], pad, dilation=dilation,
                                              mask=None if mask is None else mask[..., c0:c0 + cnt], mask_alpha=0.1,
                                              accumulate=accumulate)
@@ -204,6 +207,17 @@ class Trainer(object):
         g = self._grad_buffers(p)
         g.flat.zero_()
         self.grad_flat.zero_()
+        # rotated + packed dgrad kernels of every layer seen by an earlier backward pass: one launch (the first pass
+        # packs layer by layer and records the parts)
+        if self._dgrad_jobs is None or self._dgrad_jobs_n != len(self._parts):
+            from . import ops_tc
+            self._dgrad_jobs = ops_tc.PackJobs(m.device)
+            for scope, parts in self._parts.items():
+                for c0, cnt, pad, rot, packed in parts:
+                    self._dgrad_jobs.add_dgrad(m._k[scope], packed, c0, cnt, pad)
+            self._dgrad_jobs_n = len(self._parts)
+            self._dgrad_batched = set(self._parts)
+        self._dgrad_jobs.run()
         for l in range(L + 1):
             ops_bwd.lploss_level_bwd(flows_gt, p.flows[l], self.loss_weights[l], g.flows[l], gt_div=20.0, ord=2)
 

@@ -378,6 +378,68 @@ def test_three_training_steps_match_oracle(P):
     assert torch.equal(ff, ff2)
 
 
+def test_train_stream_matches_synchronous_steps(P):
+    """TrainStream (staged H2D on a copy stream, batch i+1 in flight during step i) trains exactly like
+    Trainer.step on the same host batches, including when a staging set is reused."""
+    from pwcnet_b200.train import Trainer
+    W = O.glorot_weights(5, gain=1.2, bias_scale=0.02)
+    rng = np.random.default_rng(9)
+    batches = []
+    for i in range(4):
+        im0, im1 = O.synthetic_pair(2, 64, 64, 20 + i, shift=(1, -1))
+        batches.append((torch.from_numpy(im0).pin_memory(), torch.from_numpy(im1).pin_memory(),
+                        torch.from_numpy(rng.normal(0, 3, (2, 64, 64, 2)).astype(np.float32)).pin_memory()))
+    ref_tr = Trainer(P.PWCDCNet(weights=W))
+    ref = [[float(v) for v in ref_tr.step(*b)] for b in batches]
+    tr = Trainer(P.PWCDCNet(weights=W))
+    ts = P.TrainStream(tr, depth=2)
+    with pytest.raises(RuntimeError):
+        ts.step()
+    got = []
+    ts.submit(*batches[0])
+    for i in range(4):
+        if i + 1 < 4:
+            ts.submit(*batches[i + 1])
+        got.append([float(v) for v in ts.step()])
+    assert ts.pending() == 0 and tr.global_step == 4
+    np.testing.assert_allclose(got, ref, rtol=1e-4)          # fp32 atomics in the wgrad kernels: not bit-reproducible
+    assert float((tr.model.flat - ref_tr.model.flat).abs().max()) < 1e-4
+    ts.submit(*batches[0]); ts.submit(*batches[1])
+    with pytest.raises(RuntimeError):
+        ts.submit(*batches[2])
+
+
+def test_batched_weight_packs_equal_per_layer_packs(P):
+    """The one-launch packs (dgrad kernels before a backward pass, forward kernels after the Adam update) write exactly
+    the bytes of the per-layer rot_weights + pack_weights_f16 calls, and the gradient does not depend on which ran."""
+    from pwcnet_b200 import ops_bwd, ops_tc
+    from pwcnet_b200.train import Trainer
+    W = O.glorot_weights(6, gain=1.2, bias_scale=0.02)
+    im0, im1 = O.synthetic_pair(2, 64, 128, 31, shift=(2, -1))
+    gt = np.random.default_rng(3).normal(0, 3, (2, 64, 128, 2)).astype(np.float32)
+    tr = Trainer(P.PWCDCNet(weights=W))
+    m = tr.model
+    tr.forward_backward(im0, im1, gt)          # first pass: layer-by-layer packs, records the parts
+    g1 = tr.grad_flat.clone()
+    tr.forward_backward(im0, im1, gt)          # second pass: one batched launch
+    g2 = tr.grad_flat.clone()
+    assert len(tr._dgrad_jobs) > 30 and tr._dgrad_batched == set(tr._parts)
+    assert float((g1 - g2).abs().max()) < 1e-5 * float(g1.abs().max())
+    for scope, parts in tr._parts.items():
+        for c0, cnt, pad, rot, packed in parts:
+            ref = ops_tc.pack_weights_f16(ops_bwd.rot_weights(m._k[scope], ci_begin=c0, ci_count=cnt, ci_pad=pad))
+            assert torch.equal(ref, packed), scope
+    tr.step(im0, im1, gt)                      # Adam update -> refresh_derived -> batched forward packs
+    assert len(m._pack_keys) > 40
+    for key in m._pack_keys:
+        scope = key.split("#")[0]
+        src = m._head_k[scope] if key.endswith("#head") else m._k[scope]
+        assert torch.equal(ops_tc.pack_weights_f16(src), m._packed[key]), key
+    ff, _ = m(im0, im1)
+    ff2, _ = P.PWCDCNet(weights=m.state_dict())(im0, im1)
+    assert torch.equal(ff, ff2)
+
+
 def test_trainer_rejects_unsupported_models(P):
     from pwcnet_b200.train import Trainer
     with pytest.raises(NotImplementedError):
