@@ -27,6 +27,7 @@
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <cstring>
 
 namespace pwc {
 
@@ -258,6 +259,209 @@ cost_volume_split_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (opt-in PWC_CV_SPLIT=row32; written at the end of round 1 without GPU time left: compiles, NOT yet run).
+// Same band GEMM, re-tiled so that the band extraction is cheap (DESIGN.md 3.1, round-2 plan):
+//   tile = 4 image rows x 32 pixels (M = 128: TMEM lane quadrant q = tile row, lane = pixel column), f1 patch 12 rows x
+//   40 columns = 480 accumulator columns in two halves of 240 (candidate rows 0-5 | 6-11), two N = 240 MMAs per K step.
+//   One epilogue warp per quadrant.  The window of displacement row dv is candidate row q + dv -- warp-uniform -- i.e.
+//   40 contiguous accumulator columns: tcgen05.ld x16 + x16 + x8, copied unconditionally to a per-warp row buffer
+//   (10 st.shared.v4), then every lane picks its nine values at columns lane + 0..8 (9 ld.shared, conflict-free pitch)
+//   and appends them to its 81-float output row; rows leave as coalesced 324-byte runs as in the kernel above.
+//   ~40 issue slots per displacement row and lane instead of ~80 (bit test + predicated store per accumulator element).
+constexpr int R_TW = 32, R_TH = 4, R_FW = R_TW + 8, R_FH = R_TH + 8;
+constexpr int R_M = R_TW * R_TH;                   // 128
+constexpr int R_NH = R_FW * (R_FH / 2);            // 240 columns per accumulator half
+constexpr uint32_t R_F0_BYTES = R_M * 128;         // 16 KB
+constexpr uint32_t R_F1_BYTES = 2 * R_NH * 128;    // 60 KB
+constexpr uint32_t R_STAGE_BYTES = R_F0_BYTES + R_F1_BYTES;   // 76 KB (multiple of 1024)
+constexpr int R_STAGES = 2;
+constexpr int R_THREADS = 64 + 4 * 32;             // TMA, MMA, 4 epilogue warps
+constexpr int R_IN_PITCH = 44, R_OUT_PITCH = 84;
+constexpr uint32_t R_WARP_SLAB = 32 * (R_IN_PITCH + R_OUT_PITCH) * 4;   // 16 KB per epilogue warp
+constexpr uint32_t R_SMEM_BYTES = R_STAGES * R_STAGE_BYTES + 4 * R_WARP_SLAB + 1024;
+static_assert(R_STAGE_BYTES % 1024 == 0 && (R_NH * 128) % 1024 == 0, "operand halves must start on swizzle atoms");
+static_assert(R_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(R_THREADS, 1)
+cost_volume_split_row32_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1, const CvSplitParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    __shared__ __align__(8) uint64_t bars[2 * R_STAGES + 4];   // full[2], empty[2], acc_full[2], acc_empty[2]
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[R_STAGES]);
+    const uint32_t bar_accf = smem_u32(&bars[2 * R_STAGES]), bar_acce = smem_u32(&bars[2 * R_STAGES + 2]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < R_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(bar_accf + 8 * h, 1);
+            mbar_init(bar_acce + 8 * h, 4);           // one arrival per quadrant warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+    const int KC = p.kchunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f0) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f1) : "memory");
+            int it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * R_TW, y0 = ty * R_TH;
+                for (int c = 0; c < KC; ++c, ++it) {
+                    const int s = it % R_STAGES;
+                    mbar_wait(bar_empty + 8 * s, ((it / R_STAGES) & 1) ^ 1);
+                    const uint32_t st = base + s * R_STAGE_BYTES;
+                    mbar_expect_tx(bar_full + 8 * s, R_STAGE_BYTES);
+                    tma_load_4d(st, &tm_f0, bar_full + 8 * s, c * 64, x0, y0, b);
+                    tma_load_4d(st + R_F0_BYTES, &tm_f1, bar_full + 8 * s, c * 64, x0 - 4, y0 - 4, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(R_NH >> 3) << 17) | ((uint32_t)(R_M >> 4) << 24);
+            const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            int it = 0, tcount = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+                for (int c = 0; c < KC; ++c, ++it) {
+                    const int s = it % R_STAGES;
+                    mbar_wait(bar_full + 8 * s, (it / R_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t st = base + s * R_STAGE_BYTES;
+                    const uint32_t a0 = ((st >> 4) & 0x3FFF) | (1u << 16);
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {
+                        if (c == 0 && tcount > 0) {   // the four quadrant warps have read this half of the previous tile
+                            mbar_wait(bar_acce + 8 * hb, (tcount - 1) & 1);
+                            tc_fence_after();
+                        }
+                        const uint32_t b0 = (((st + R_F0_BYTES + hb * R_NH * 128) >> 4) & 0x3FFF) | (1u << 16);
+                        const uint32_t d = tmem_acc + hb * R_NH;
+                        // k-steps of 32 bytes inside the 128-byte row: 0,1 = h (channels 0-15, 16-31), 2,3 = l
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) s_mma(d, desc_hi | (a0 + 2 * k), desc_hi | (b0 + 2 * k), idesc, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) s_mma(d, desc_hi | (a0 + 4 + 2 * k), desc_hi | (b0 + 2 * k), idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) s_mma(d, desc_hi | (a0 + 2 * k), desc_hi | (b0 + 4 + 2 * k), idesc, 1u);
+                        if (c == KC - 1) tc_commit(bar_accf + 8 * hb);
+                    }
+                    tc_commit(bar_empty + 8 * s);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: warp -> TMEM lane quadrant q = tile row =====================
+        const int q = warp & 3;
+        float* in_slab = reinterpret_cast<float*>(base_ptr + R_STAGES * R_STAGE_BYTES + (warp - 2) * R_WARP_SLAB);
+        float* out_slab = in_slab + 32 * R_IN_PITCH;
+        float* in_lane = in_slab + lane * R_IN_PITCH;
+        float* out_lane = out_slab + lane * R_OUT_PITCH;
+        const uint32_t tq = tmem_acc + ((uint32_t)(q * 32) << 16);
+        const int cs = p.out_cs;
+        const float scale = p.scale, alpha = p.alpha;
+        int tcount = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+            const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+            const int x0 = tx * R_TW, yy = ty * R_TH + q;
+#pragma unroll 1
+            for (int dv = 0; dv < 9; ++dv) {
+                const int r = q + dv, hb = r >= R_FH / 2 ? 1 : 0;                 // candidate row, accumulator half
+                if (r == q || r == R_FH / 2) {                                    // first row this warp reads of a half
+                    mbar_wait(bar_accf + 8 * hb, tcount & 1);
+                    tc_fence_after();
+                }
+                const uint32_t ta = tq + hb * R_NH + (r - hb * (R_FH / 2)) * R_FW;
+                uint32_t v[40];
+                tmem_ld16(ta, v); tmem_ld16(ta + 16, v + 16); tmem_ld8(ta + 32, v + 32);
+                tmem_ld_wait();
+                if (r == R_FH / 2 - 1 || dv == 8) {                               // last row of a half: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acce + 8 * hb);
+                }
+#pragma unroll
+                for (int j = 0; j < 10; ++j)
+                    *reinterpret_cast<uint4*>(in_lane + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                // D[m = lane][candidate column lane + dh] = f0(x0 + lane) . f1(x0 - 4 + lane + dh): displacement h = dh - 4
+#pragma unroll
+                for (int dh = 0; dh < 9; ++dh) out_lane[dv * 9 + dh] = in_lane[lane + dh];
+                __syncwarp();
+            }
+            // ---- 32 pixels x 81 floats -> HBM as 324-byte runs; scale and leaky applied here
+            if (yy < p.H) {
+                float* orow = p.out + (((size_t)b * p.H + yy) * p.W + x0) * cs;
+                const int npx = min(32, p.W - x0);
+                if (p.vec) {
+                    int pix = lane / 21, k = lane - pix * 21;                   // unit u = lane + 32 m: pixel u / 21, float4 (or tail scalar) u % 21
+#pragma unroll 3
+                    for (int m = 0; m < 21; ++m) {
+                        if (pix < npx) {
+                            const float* src = out_slab + pix * R_OUT_PITCH + 4 * k;
+                            float* dst = orow + (size_t)pix * cs + 4 * k;
+                            if (k < 20) {
+                                float4 w = *reinterpret_cast<const float4*>(src);
+                                w.x *= scale; w.y *= scale; w.z *= scale; w.w *= scale;
+                                w.x = fmaxf(w.x, alpha * w.x); w.y = fmaxf(w.y, alpha * w.y);
+                                w.z = fmaxf(w.z, alpha * w.z); w.w = fmaxf(w.w, alpha * w.w);
+                                *reinterpret_cast<float4*>(dst) = w;
+                            } else {
+                                const float w = *src * scale;
+                                *dst = fmaxf(w, alpha * w);
+                            }
+                        }
+                        k += 11; pix += 1;                  // u += 32 = 21 + 11
+                        if (k >= 21) { k -= 21; pix += 1; }
+                    }
+                } else {
+                    int pix = 0, k = lane;                  // 32 pixels x 81 scalars
+#pragma unroll 3
+                    for (int m = 0; m < 81; ++m) {
+                        if (pix < npx) {
+                            const float w = out_slab[pix * R_OUT_PITCH + k] * scale;
+                            orow[(size_t)pix * cs + k] = fmaxf(w, alpha * w);
+                        }
+                        k += 32;
+                        if (k >= 81) { k -= 81; pix += 1; }
+                    }
+                }
+            }
+            __syncwarp();                                   // the slabs are rewritten by the next tile
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512));
+    }
+}
+
 // fp32 NHWC -> split rows: per pixel and 32-channel slice [h: 32 x fp16 | l: 32 x fp16], h = fp16(x), l = fp16(x - h);
 // optionally also copies x to a second fp32 destination (the estimator's concat slot, modules.py:262).
 __global__ void split_f16_kernel(const float* __restrict__ x, int x_cs, __half* __restrict__ out, float* __restrict__ copy,
@@ -389,6 +593,27 @@ extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float
     PWC_REQUIRE((C % 32) == 0 && aligned16(f0s) && aligned16(f1s), PWC_E_ALIGN,
                 "cost_volume_split: C must be a multiple of 32 and the operands 16-byte aligned");
     CUtensorMap tm0, tm1;
+    {   // experimental 4 x 32 tiling (not validated on hardware yet: opt-in only)
+        const char* ev = getenv("PWC_CV_SPLIT");
+        if (ev && !strcmp(ev, "row32")) {
+            PWC_REQUIRE(make_map_split(&tm0, f0s, B, H, W, C, R_TW, R_TH) && make_map_split(&tm1, f1s, B, H, W, C, R_FW, R_FH),
+                        PWC_E_BADARG, "cost_volume_split: cuTensorMapEncodeTiled failed");
+            CvSplitParams p{};
+            p.out = out; p.out_cs = out_cs; p.B = B; p.H = H; p.W = W; p.kchunks = C / 32;
+            p.tiles_x = (W + R_TW - 1) / R_TW; p.tiles_y = (H + R_TH - 1) / R_TH;
+            const long long tiles = (long long)p.tiles_x * p.tiles_y * B;
+            PWC_REQUIRE(tiles < (1ll << 30), PWC_E_BADARG, "cost_volume_split: too many tiles");
+            p.total_tiles = (int)tiles;
+            p.alpha = alpha; p.scale = scale;
+            p.vec = aligned16(out) && (out_cs & 3) == 0;
+            cudaError_t e = cudaFuncSetAttribute(cost_volume_split_row32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_BYTES);
+            if (e != cudaSuccess) { set_error("cost_volume_split(row32): smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+            const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
+            cost_volume_split_row32_kernel<<<grid, R_THREADS, R_SMEM_BYTES, (cudaStream_t)stream>>>(tm0, tm1, p);
+            PWC_CHECK_LAUNCH("cost_volume_split_row32_kernel");
+            return 0;
+        }
+    }
     PWC_REQUIRE(make_map_split(&tm0, f0s, B, H, W, C, S_TW, S_TH) && make_map_split(&tm1, f1s, B, H, W, C, S_FW, S_FH),
                 PWC_E_BADARG, "cost_volume_split: cuTensorMapEncodeTiled failed");
     CvSplitParams p{};
