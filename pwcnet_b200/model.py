@@ -84,7 +84,7 @@ class _Plan:
 class PWCDCNet(object):
     def __init__(self, num_levels=6, search_range=4, warp_type='bilinear', use_dc=False,
                  output_level=4, name='pwcdcnet', *, device=None, weights=None, seed=0,
-                 precision=None, use_cuda_graph=True, fuse_warp=False):
+                 precision=None, use_cuda_graph=True, fuse_warp=False, cv_pipeline=None):
         self.num_levels = num_levels
         self.s_range = search_range
         self.warp_type = warp_type
@@ -103,6 +103,13 @@ class PWCDCNet(object):
         # PWC_NO_GRAPH=1: eager launches (ncu cannot profile the tf32 16-channel kernel as a graph node: LaunchFailed)
         self.use_cuda_graph = use_cuda_graph and not os.environ.get("PWC_NO_GRAPH")
         self.fuse_warp = fuse_warp
+        # cv_pipeline="split" (or PWC_CV_PIPELINE=split): inference-only experiment -- the levels with C % 32 == 0 run
+        # split_f16 / warp_split producers + the tcgen05 band-GEMM cost volume instead of warp + the CUDA-core kernel
+        # (slower with the round-1 split kernel, kept for the 4 x 32 re-tiling, PWC_CV_SPLIT=row32)
+        cv_pipeline = os.environ.get("PWC_CV_PIPELINE") if cv_pipeline is None else cv_pipeline
+        if cv_pipeline not in (None, "", "default", "split"):
+            raise ValueError("cv_pipeline must be None, 'default' or 'split'")
+        self.cv_split = cv_pipeline == "split" and search_range == 4 and not fuse_warp
         if not torch.cuda.is_available():
             raise PwcError("PWCDCNet needs a CUDA device: the compute path is sm_100a CUDA only (no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -337,6 +344,7 @@ class PWCDCNet(object):
             p.pyr.append([torch.empty((2 * B, h, w, C), dtype=torch.float32, device=dev) for _ in range(3)])
         pre_total = sum(ESTIMATOR_FILTERS) if self.use_dc else 0
         p.S, p.tmp, p.flows, p.f1w = [], [], [], []
+        p.f0s, p.f1s = [], []
         for l, lv in enumerate(self._lv):
             ph, pw = p.pyr[self.num_levels - 1 - l][2].shape[1:3]
             is_out = l == self.output_level
@@ -351,7 +359,11 @@ class PWCDCNet(object):
                 last = torch.zeros((B, ph, pw, ESTIMATOR_FILTERS[-1] + (4 if is_out else 0)), dtype=torch.float32, device=dev)
                 p.tmp.append(tmps + [last])
             p.flows.append(torch.empty((B, ph, pw, 2), dtype=torch.float32, device=dev))
-            p.f1w.append(torch.empty((B, ph, pw, lv["C"]), dtype=torch.float32, device=dev) if l and not self.fuse_warp else None)
+            split = self.cv_split and lv["C"] % 32 == 0
+            p.f1w.append(torch.empty((B, ph, pw, lv["C"]), dtype=torch.float32, device=dev)
+                         if l and not self.fuse_warp and not split else None)
+            p.f0s.append(torch.empty((B, ph, pw, 2 * lv["C"]), dtype=torch.float16, device=dev) if split else None)
+            p.f1s.append(torch.empty((B, ph, pw, 2 * lv["C"]), dtype=torch.float16, device=dev) if split else None)
         ph, pw = p.flows[-1].shape[1:3]
         p.ctx = [torch.empty((B, ph, pw, f), dtype=torch.float32, device=dev) for f in CONTEXT_FILTERS[:-1]]
         up = 2 ** (self.num_levels - self.output_level)
@@ -378,7 +390,14 @@ class PWCDCNet(object):
             cv = X[..., 0:nd]
             f0slot = X[..., lv["off_f0"]:lv["off_f0"] + lv["C"]]
             flow_up = X[..., lv["off_flow"]:lv["off_flow"] + 2] if l else None
-            if l == 0:
+            if p.f0s[l] is not None:
+                # split pipeline: 1/C folded into the f0 producer (which also fills the f0 slot), f1 warped straight into
+                # [h|l] fp16 rows, band GEMM on tcgen05
+                f0s = ops.split_f16(f0, out=p.f0s[l], copy=f0slot, scale=1.0 / lv["C"])
+                f1s = ops.split_f16(f1, out=p.f1s[l]) if l == 0 else \
+                    ops.warp_split(f1, flow_up, self.scales[l], self.warp_type, out=p.f1s[l])
+                ops.cost_volume_split(f0s, f1s, 0.1, out=cv, prescaled=True)
+            elif l == 0:
                 ops.cost_volume(f0, f1, self.s_range, 0.1, out=cv, f0_copy=f0slot)
             elif self.fuse_warp:
                 ops.warp_cost_volume(f0, f1, flow_up, self.scales[l], self.warp_type, self.s_range, 0.1,
@@ -499,6 +518,8 @@ class PWCDCNet(object):
         n = 3 * self.num_levels                      # pyramid (both images batched)
         n += (self.output_level + 1) * (1 + len(ESTIMATOR_FILTERS) + 1)   # cv + estimator convs + head
         n += 0 if self.fuse_warp else self.output_level              # stand-alone warp kernels
+        if self.cv_split:                                             # split producers: +1 launch per split level (+2 at l = 0)
+            n += sum((2 if l == 0 else 1) for l, lv in enumerate(self._lv) if lv["C"] % 32 == 0)
         n += self.output_level * 2                    # up-sampling of flows and features
         n += len(CONTEXT_FILTERS) + 1                 # context + final x4 resize
         return n

@@ -55,8 +55,9 @@ class Trainer(object):
         if model.use_dc:
             raise NotImplementedError("Trainer: use_dc=True is inference-only in this build (no reference checkpoint "
                                       "or BASELINE config trains it)")
-        if model.fuse_warp:
-            raise PwcError("Trainer needs the warped features in memory: construct the model with fuse_warp=False")
+        if model.fuse_warp or getattr(model, "cv_split", False):
+            raise PwcError("Trainer needs the warped features in memory: construct the model with fuse_warp=False and "
+                           "the default cost-volume pipeline")
         if model.precision == "cudnn":
             raise PwcError("Trainer: the cuDNN baseline arm has no backward path")
         if len(weights) != model.output_level + 1:
