@@ -288,6 +288,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
 }
 
+template <bool PIPE>
 __global__ void __launch_bounds__(R_THREADS, 1)
 cost_volume_split_row32_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1, const CvSplitParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -388,22 +389,8 @@ cost_volume_split_row32_kernel(const __grid_constant__ CUtensorMap tm_f0, const 
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
             const int x0 = tx * R_TW, yy = ty * R_TH + q;
-#pragma unroll 1
-            for (int dv = 0; dv < 9; ++dv) {
-                const int r = q + dv, hb = r >= R_FH / 2 ? 1 : 0;                 // candidate row, accumulator half
-                if (r == q || r == R_FH / 2) {                                    // first row this warp reads of a half
-                    mbar_wait(bar_accf + 8 * hb, tcount & 1);
-                    tc_fence_after();
-                }
-                const uint32_t ta = tq + hb * R_NH + (r - hb * (R_FH / 2)) * R_FW;
-                uint32_t v[40];
-                tmem_ld16(ta, v); tmem_ld16(ta + 16, v + 16); tmem_ld8(ta + 32, v + 32);
-                tmem_ld_wait();
-                if (r == R_FH / 2 - 1 || dv == 8) {                               // last row of a half: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acce + 8 * hb);
-                }
+            // one displacement row: 40 accumulator words -> row buffer -> the lane's nine values -> its output row
+            auto process = [&](const uint32_t* v, int dv) {
 #pragma unroll
                 for (int j = 0; j < 10; ++j)
                     *reinterpret_cast<uint4*>(in_lane + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -412,6 +399,53 @@ cost_volume_split_row32_kernel(const __grid_constant__ CUtensorMap tm_f0, const 
 #pragma unroll
                 for (int dh = 0; dh < 9; ++dh) out_lane[dv * 9 + dh] = in_lane[lane + dh];
                 __syncwarp();
+            };
+            auto row_taddr = [&](int dv) {                                        // candidate row q + dv inside its half
+                const int r = q + dv, hb = r >= R_FH / 2 ? 1 : 0;
+                return tq + hb * R_NH + (r - hb * (R_FH / 2)) * R_FW;
+            };
+            auto acquire = [&](int dv) {                                          // first row this warp reads of a half
+                const int r = q + dv;
+                if (r == q || r == R_FH / 2) {
+                    mbar_wait(bar_accf + 8 * (r >= R_FH / 2 ? 1 : 0), tcount & 1);
+                    tc_fence_after();
+                }
+            };
+            auto release = [&](int dv) {                                          // last row of a half: hand it back to the MMA warp
+                const int r = q + dv;
+                if (r == R_FH / 2 - 1 || dv == 8) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acce + 8 * (r >= R_FH / 2 ? 1 : 0));
+                }
+            };
+            if (PIPE) {
+                // the tcgen05.ld of row dv + 1 is in flight while row dv goes through the row buffer
+                uint32_t v[2][40];
+                acquire(0);
+                { const uint32_t ta = row_taddr(0); tmem_ld16(ta, v[0]); tmem_ld16(ta + 16, v[0] + 16); tmem_ld8(ta + 32, v[0] + 32); }
+#pragma unroll
+                for (int dv = 0; dv < 9; ++dv) {
+                    tmem_ld_wait();                                               // row dv is in v[dv & 1]
+                    release(dv);
+                    if (dv < 8) {
+                        acquire(dv + 1);
+                        const uint32_t ta = row_taddr(dv + 1);
+                        tmem_ld16(ta, v[(dv + 1) & 1]); tmem_ld16(ta + 16, v[(dv + 1) & 1] + 16); tmem_ld8(ta + 32, v[(dv + 1) & 1] + 32);
+                    }
+                    process(v[dv & 1], dv);
+                }
+            } else {
+#pragma unroll 1
+                for (int dv = 0; dv < 9; ++dv) {
+                    acquire(dv);
+                    const uint32_t ta = row_taddr(dv);
+                    uint32_t v[40];
+                    tmem_ld16(ta, v); tmem_ld16(ta + 16, v + 16); tmem_ld8(ta + 32, v + 32);
+                    tmem_ld_wait();
+                    release(dv);
+                    process(v, dv);
+                }
             }
             // ---- 32 pixels x 81 floats -> HBM as 324-byte runs; scale and leaky applied here
             if (yy < p.H) {
@@ -595,7 +629,8 @@ extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float
     CUtensorMap tm0, tm1;
     {   // experimental 4 x 32 tiling (not validated on hardware yet: opt-in only)
         const char* ev = getenv("PWC_CV_SPLIT");
-        if (ev && !strcmp(ev, "row32")) {
+        if (ev && (!strcmp(ev, "row32") || !strcmp(ev, "row32p"))) {
+            const bool pipe = !strcmp(ev, "row32p");       // row32p: TMEM loads of the next row overlap the current row
             PWC_REQUIRE(make_map_split(&tm0, f0s, B, H, W, C, R_TW, R_TH) && make_map_split(&tm1, f1s, B, H, W, C, R_FW, R_FH),
                         PWC_E_BADARG, "cost_volume_split: cuTensorMapEncodeTiled failed");
             CvSplitParams p{};
@@ -606,10 +641,11 @@ extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float
             p.total_tiles = (int)tiles;
             p.alpha = alpha; p.scale = scale;
             p.vec = aligned16(out) && (out_cs & 3) == 0;
-            cudaError_t e = cudaFuncSetAttribute(cost_volume_split_row32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_BYTES);
+            auto kern = pipe ? cost_volume_split_row32_kernel<true> : cost_volume_split_row32_kernel<false>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_BYTES);
             if (e != cudaSuccess) { set_error("cost_volume_split(row32): smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
-            cost_volume_split_row32_kernel<<<grid, R_THREADS, R_SMEM_BYTES, (cudaStream_t)stream>>>(tm0, tm1, p);
+            kern<<<grid, R_THREADS, R_SMEM_BYTES, (cudaStream_t)stream>>>(tm0, tm1, p);
             PWC_CHECK_LAUNCH("cost_volume_split_row32_kernel");
             return 0;
         }

@@ -98,15 +98,16 @@ def test_cost_volume_split_pipeline_matches_oracle(P, shape):
 
 @pytest.mark.skipif(os.environ.get("PWC_TEST_EXPERIMENTAL") != "1", reason="experimental kernel, written without GPU time "
                     "left in round 1: run with PWC_TEST_EXPERIMENTAL=1 to validate it (DESIGN.md 3.1, round-2 plan)")
+@pytest.mark.parametrize("variant", ["row32", "row32p"])
 @pytest.mark.parametrize("shape", [(1, 8, 64, 32), (2, 13, 70, 32), (1, 28, 64, 64), (1, 5, 31, 96)])
-def test_cost_volume_split_row32_experimental(P, shape, monkeypatch):
+def test_cost_volume_split_row32_experimental(P, shape, variant, monkeypatch):
     """4 x 32-pixel tiling of the split band GEMM (PWC_CV_SPLIT=row32) vs the oracle and the default split kernel."""
     B, H, W, C = shape
     f0, f1 = _rand(shape, 1), _rand(shape, 2)
     ref = O.cost_volume(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy()
     f0s, f1s = P.ops.split_f16(_cuda(f0)), P.ops.split_f16(_cuda(f1))
     base = P.ops.cost_volume_split(f0s, f1s, 0.1)
-    monkeypatch.setenv("PWC_CV_SPLIT", "row32")
+    monkeypatch.setenv("PWC_CV_SPLIT", variant)     # row32p: TMEM loads of the next row in flight
     buf = torch.full((B, H, W, 88), 7.0, device="cuda")
     P.ops.cost_volume_split(f0s, f1s, 0.1, out=buf[..., :81])
     np.testing.assert_allclose(buf[..., :81].cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
