@@ -29,6 +29,11 @@ extern "C" {
 int pwc_version(void);
 const char* pwc_last_error(void);
 
+/* CRC-32C (Castagnoli) of n host bytes, continuing from `crc` (0 to start).  HOST code (slice-by-8): the checksum
+ * TensorFlow's checkpoint bundles carry per tensor and per table block (tf.train.Saver.save, train.py:95,166);
+ * used by pwcnet_b200/checkpoint.py:save_checkpoint. */
+unsigned int pwc_crc32c(const void* data, long long n, unsigned int crc);
+
 /* CostVolumeLayer.__call__ -> get_cost x (2r+1)^2  (modules.py:164-204).
  * out[b,y,x,(v+r)*(2r+1)+(h+r)] = leaky_alpha( (1/C) sum_c f0[b,y,x,c] * f1[b,y+v,x+h,c] ),
  * zero outside the image.  If f0_copy != NULL the f0 tile staged on chip is also written to

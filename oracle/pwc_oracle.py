@@ -447,3 +447,42 @@ def synthetic_pair(B: int, H: int, W: int, seed: int = 0, shift: Optional[Tuple[
         dx, dy = shift
         imgs[:, 1] = np.roll(imgs[:, 0], (dy, dx), axis=(1, 2))
     return imgs[:, 0].copy(), imgs[:, 1].copy()
+
+
+def synthetic_textured_pair(B: int, H: int, W: int, seed: int = 0, max_disp: float = 12.0):
+    """SURVEY 8(d) 'shifted-texture pair': image_0 = smooth multi-octave random texture in [0,1], image_1 = image_0
+    displaced by a smooth known field of up to +-max_disp pixels (bilinear resampling, numpy only).  Returns
+    (image_0, image_1, flow) with flow (B,H,W,2) = the displacement image_1 was built from (ch0 = x, ch1 = y):
+    image_1(y, x) = image_0(y - flow_y, x - flow_x), i.e. content moves by +flow from frame 0 to frame 1."""
+    rng = np.random.default_rng(seed)
+    tex = np.zeros((B, H, W, 3), np.float64)
+    amp = 0.0
+    for octave, cell in enumerate((64, 32, 16, 8, 4, 2)):
+        gh, gw = -(-H // cell) + 2, -(-W // cell) + 2
+        g = rng.random((B, gh, gw, 3))
+        yy = (np.arange(H) + 0.5) / cell
+        xx = (np.arange(W) + 0.5) / cell
+        y0, x0 = np.floor(yy).astype(int), np.floor(xx).astype(int)
+        fy, fx = (yy - y0)[None, :, None, None], (xx - x0)[None, None, :, None]
+        a = g[:, y0][:, :, x0] * (1 - fx) + g[:, y0][:, :, x0 + 1] * fx
+        b = g[:, y0 + 1][:, :, x0] * (1 - fx) + g[:, y0 + 1][:, :, x0 + 1] * fx
+        wgt = 0.5 ** octave if octave < 4 else 0.5 ** 3
+        tex += wgt * (a * (1 - fy) + b * fy)
+        amp += wgt
+    im0 = (tex / amp).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    flow = np.zeros((B, H, W, 2), np.float32)
+    im1 = np.empty_like(im0)
+    for b in range(B):
+        ph = rng.uniform(0, 2 * np.pi, 4)
+        fx_ = max_disp * np.sin(2 * np.pi * ys / H + ph[0]) * np.cos(2 * np.pi * xs / W + ph[1])
+        fy_ = 0.5 * max_disp * np.cos(2 * np.pi * ys / H + ph[2]) * np.sin(4 * np.pi * xs / W + ph[3])
+        flow[b, ..., 0], flow[b, ..., 1] = fx_, fy_
+        sy, sx = np.clip(ys - fy_, 0, H - 1), np.clip(xs - fx_, 0, W - 1)
+        y0, x0 = np.floor(sy).astype(int), np.floor(sx).astype(int)
+        y1, x1 = np.minimum(y0 + 1, H - 1), np.minimum(x0 + 1, W - 1)
+        wy, wx = (sy - y0)[..., None], (sx - x0)[..., None]
+        src = im0[b].astype(np.float64)
+        im1[b] = ((src[y0, x0] * (1 - wx) + src[y0, x1] * wx) * (1 - wy) +
+                  (src[y1, x0] * (1 - wx) + src[y1, x1] * wx) * wy).astype(np.float32)
+    return im0, im1, flow

@@ -20,6 +20,7 @@ _ll = C.c_longlong
 SIGNATURES = {
     "pwc_version": (_i, []),
     "pwc_last_error": (C.c_char_p, []),
+    "pwc_crc32c": (C.c_uint, [_vp, _ll, C.c_uint]),
     "pwc_cost_volume_fwd": (_i, [_f32p, _i, _f32p, _i, _f32p, _i, _f32p, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "pwc_warp_cost_volume_fwd": (_i, [_f32p, _i, _f32p, _i, _f32p, _i, _f, _i, _f32p, _i, _f32p, _i,
                                       _i, _i, _i, _i, _i, _f, _vp]),

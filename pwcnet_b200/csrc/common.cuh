@@ -8,6 +8,7 @@
 namespace pwc {
 
 void set_error(const char* fmt, ...);
+int sm_count();   // SMs of the current device (abi.cu)
 
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

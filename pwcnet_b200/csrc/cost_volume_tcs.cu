@@ -260,56 +260,117 @@ cost_volume_split_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (opt-in PWC_CV_SPLIT=row32; written at the end of round 1 without GPU time left: compiles, NOT yet run).
-// Same band GEMM, re-tiled so that the band extraction is cheap (DESIGN.md 3.1, round-2 plan):
-//   tile = 4 image rows x 32 pixels (M = 128: TMEM lane quadrant q = tile row, lane = pixel column), f1 patch 12 rows x
-//   40 columns = 480 accumulator columns in two halves of 240 (candidate rows 0-5 | 6-11), two N = 240 MMAs per K step.
-//   One epilogue warp per quadrant.  The window of displacement row dv is candidate row q + dv -- warp-uniform -- i.e.
-//   40 contiguous accumulator columns: tcgen05.ld x16 + x16 + x8, copied unconditionally to a per-warp row buffer
-//   (10 st.shared.v4), then every lane picks its nine values at columns lane + 0..8 (9 ld.shared, conflict-free pitch)
-//   and appends them to its 81-float output row; rows leave as coalesced 324-byte runs as in the kernel above.
-//   ~40 issue slots per displacement row and lane instead of ~80 (bit test + predicated store per accumulator element).
-constexpr int R_TW = 32, R_TH = 4, R_FW = R_TW + 8, R_FH = R_TH + 8;
-constexpr int R_M = R_TW * R_TH;                   // 128
-constexpr int R_NH = R_FW * (R_FH / 2);            // 240 columns per accumulator half
-constexpr uint32_t R_F0_BYTES = R_M * 128;         // 16 KB
-constexpr uint32_t R_F1_BYTES = 2 * R_NH * 128;    // 60 KB
-constexpr uint32_t R_STAGE_BYTES = R_F0_BYTES + R_F1_BYTES;   // 76 KB (multiple of 1024)
-constexpr int R_STAGES = 2;
-constexpr int R_THREADS = 64 + 4 * 32;             // TMA, MMA, 4 epilogue warps
-constexpr int R_IN_PITCH = 44, R_OUT_PITCH = 84;
-constexpr uint32_t R_WARP_SLAB = 32 * (R_IN_PITCH + R_OUT_PITCH) * 4;   // 16 KB per epilogue warp
-constexpr uint32_t R_SMEM_BYTES = R_STAGES * R_STAGE_BYTES + 4 * R_WARP_SLAB + 1024;
-static_assert(R_STAGE_BYTES % 1024 == 0 && (R_NH * 128) % 1024 == 0, "operand halves must start on swizzle atoms");
-static_assert(R_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+// Quadrant-block kernel (round 2; PWC_CV_SPLIT=quad).  Same band GEMM, re-tiled so that the band
+// extraction never touches shared memory:
+//   tile = 16 image rows x 8 pixels (M = 128, A row m = 8 y + x: ONE TMA box), f1 patch 24 rows x 16 columns = 384
+//   accumulator columns n = 16 fy + fx in two halves of 192 (one box, two N = 192 MMAs per K step).
+//   TMEM lane quadrant q = image rows 4q .. 4q+3 of the tile (a 4 x 8 pixel block, lane = 8 yy + xx): the block's
+//   windows span patch rows 4q .. 4q+11 x all 16 columns = 192 CONTIGUOUS accumulator columns [64 q, 64 q + 192).
+//   Two epilogue warps per quadrant: role 0 extracts displacement rows dv = 0..4 (patch rows 4q..4q+7, 128 columns),
+//   role 1 dv = 5..8 (patch rows 4q+5..4q+11, 112 columns), with tcgen05.ld x64/x32/x16 straight into registers;
+//   the accumulator is handed back to the MMA warp as soon as the loads have landed.  The lane-dependent window
+//   offset (yy in 0..3, xx in 0..7) is resolved by a 5-stage select network IN REGISTERS (shift by 4/2/1 columns, then
+//   2/1 rows; ~300 SEL per lane and role) instead of the predicated shared-memory scatter of the kernel above (which is
+//   shared-memory-port bound: TMA writes 64 KB + UMMA operand reads 120 KB + scatter per 128-pixel tile).  Only the
+//   81 useful values per pixel go through shared memory, once, to leave as coalesced 324-byte runs (two slab buffers:
+//   one named barrier per tile and quadrant).
+// Measured on B200 (profiles/r02_tmem_ld_bench.log): tcgen05.ld is latency- not bandwidth-bound (218 clk per isolated
+// x16 load, >450 B/clk/SM with 16 warps x 4 loads in flight), fma.rn.f32x2 issues at the FMA-pipe rate of scalar FFMA,
+// and 16-byte-per-lane stores of 324-byte runs are 2.2x slower than coalesced float4 units -- hence the slab.
+constexpr int Q_TW = 8, Q_TH = 16, Q_FW = Q_TW + 8, Q_FH = Q_TH + 8;
+constexpr int Q_M = Q_TW * Q_TH;                   // 128
+constexpr int Q_NH = Q_FW * (Q_FH / 2);            // 192 columns per accumulator half
+constexpr uint32_t Q_F0_BYTES = Q_M * 128;         // 16 KB
+constexpr uint32_t Q_F1_BYTES = 2 * Q_NH * 128;    // 48 KB
+constexpr uint32_t Q_STAGE_BYTES = Q_F0_BYTES + Q_F1_BYTES;
+constexpr int Q_STAGES = 2;
+constexpr int Q_EPI_WARPS = 8;
+constexpr int Q_THREADS = 64 + Q_EPI_WARPS * 32;   // 320
+constexpr int Q_PITCH = 84;                        // slab row pitch in words: STS.128 / LDS.128 conflict-free
+constexpr uint32_t Q_SLAB_BYTES = 4 * 32 * Q_PITCH * 4;   // one buffer: 4 quadrants x 32 pixels
+constexpr uint32_t Q_SMEM_BYTES = Q_STAGES * Q_STAGE_BYTES + 2 * Q_SLAB_BYTES + 1024;
+static_assert(Q_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+                 "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"
+                 "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+                   "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+                   "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+                   "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                 : "r"(taddr));
 }
 
-template <bool PIPE>
-__global__ void __launch_bounds__(R_THREADS, 1)
-cost_volume_split_row32_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1, const CvSplitParams p) {
+// Band extraction of one epilogue warp: ROLE r owns patch rows J = 6r .. 6r+5 of the quadrant's twelve (96 accumulator
+// columns, tcgen05.ld x64 + x32).  Row J holds displacement row dv = J - yy of the lane's pixel (if 0 <= dv <= 8): its 16
+// words are shifted left by xx in registers (three select stages, 31 SEL) and the nine window words are stored to the
+// lane's slab row at word 9 dv + i = (9 J + i) - 9 yy, i.e. a lane-constant base plus an immediate: the ROW shift costs
+// nothing, rows outside the lane's window are predicated off.  (bank of the store = 20 xx - 9 yy + const mod 32: the 32
+// lanes hit 32 different banks.)
+template <int ROLE>
+__device__ __forceinline__ void q_extract(uint32_t tq, int q, int lane, uint32_t* slab_lane, uint32_t bar_acce) {
+    uint32_t v[96];
+    const uint32_t t0 = tq + (uint32_t)((4 * q + 6 * ROLE) * Q_FW);
+    tmem_ld64(t0, v);
+    tmem_ld32(t0 + 64, v + 64);
+    tmem_ld_wait();
+    // the accumulator words are in registers: hand this warp's share of the accumulator back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_acce);
+    const bool c4 = (lane & 4) != 0, c2 = (lane & 2) != 0, c1 = (lane & 1) != 0;      // xx = lane & 7
+    const int yy = lane >> 3;
+    uint32_t* dst = slab_lane - 9 * yy;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        constexpr int dummy = 0; (void)dummy;
+        const int J = 6 * ROLE + j;
+        uint32_t a[12], b[10], w[9];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) a[i] = c4 ? v[16 * j + i + 4] : v[16 * j + i];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) b[i] = c2 ? a[i + 2] : a[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w[i] = c1 ? b[i + 1] : b[i];
+        if ((unsigned)(J - yy) <= 8u) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dst[9 * J + i] = w[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(Q_THREADS, 1)
+cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1, const CvSplitParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    __shared__ __align__(8) uint64_t bars[2 * R_STAGES + 4];   // full[2], empty[2], acc_full[2], acc_empty[2]
+    __shared__ __align__(8) uint64_t bars[2 * Q_STAGES + 2];   // full[2], empty[2], acc_full, acc_empty
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[R_STAGES]);
-    const uint32_t bar_accf = smem_u32(&bars[2 * R_STAGES]), bar_acce = smem_u32(&bars[2 * R_STAGES + 2]);
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[Q_STAGES]);
+    const uint32_t bar_accf = smem_u32(&bars[2 * Q_STAGES]), bar_acce = smem_u32(&bars[2 * Q_STAGES + 1]);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < R_STAGES; ++s) {
+        for (int s = 0; s < Q_STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        for (int h = 0; h < 2; ++h) {
-            mbar_init(bar_accf + 8 * h, 1);
-            mbar_init(bar_acce + 8 * h, 4);           // one arrival per quadrant warp
-        }
+        mbar_init(bar_accf, 1);
+        mbar_init(bar_acce, Q_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -321,6 +382,7 @@ cost_volume_split_row32_kernel(const __grid_constant__ CUtensorMap tm_f0, const 
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base_slot;
     const int KC = p.kchunks;
+    unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -330,38 +392,38 @@ cost_volume_split_row32_kernel(const __grid_constant__ CUtensorMap tm_f0, const 
             int it = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * R_TW, y0 = ty * R_TH;
+                const int x0 = tx * Q_TW, y0 = ty * Q_TH;
                 for (int c = 0; c < KC; ++c, ++it) {
-                    const int s = it % R_STAGES;
-                    mbar_wait(bar_empty + 8 * s, ((it / R_STAGES) & 1) ^ 1);
-                    const uint32_t st = base + s * R_STAGE_BYTES;
-                    mbar_expect_tx(bar_full + 8 * s, R_STAGE_BYTES);
+                    const int s = it % Q_STAGES;
+                    mbar_wait(bar_empty + 8 * s, ((it / Q_STAGES) & 1) ^ 1);
+                    S_DBG(0, it);
+                    const uint32_t st = base + s * Q_STAGE_BYTES;
+                    mbar_expect_tx(bar_full + 8 * s, Q_STAGE_BYTES);
                     tma_load_4d(st, &tm_f0, bar_full + 8 * s, c * 64, x0, y0, b);
-                    tma_load_4d(st + R_F0_BYTES, &tm_f1, bar_full + 8 * s, c * 64, x0 - 4, y0 - 4, b);
+                    tma_load_4d(st + Q_F0_BYTES, &tm_f1, bar_full + 8 * s, c * 64, x0 - 4, y0 - 4, b);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(R_NH >> 3) << 17) | ((uint32_t)(R_M >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(Q_NH >> 3) << 17) | ((uint32_t)(Q_M >> 4) << 24);
             const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             int it = 0, tcount = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
                 for (int c = 0; c < KC; ++c, ++it) {
-                    const int s = it % R_STAGES;
-                    mbar_wait(bar_full + 8 * s, (it / R_STAGES) & 1);
+                    const int s = it % Q_STAGES;
+                    mbar_wait(bar_full + 8 * s, (it / Q_STAGES) & 1);
+                    S_DBG(1, it);
+                    if (c == 0 && tcount > 0) mbar_wait(bar_acce, (tcount - 1) & 1);   // all eight warps hold the previous tile in registers
+                    S_DBG(2, it);
                     tc_fence_after();
-                    const uint32_t st = base + s * R_STAGE_BYTES;
+                    const uint32_t st = base + s * Q_STAGE_BYTES;
                     const uint32_t a0 = ((st >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
                     for (int hb = 0; hb < 2; ++hb) {
-                        if (c == 0 && tcount > 0) {   // the four quadrant warps have read this half of the previous tile
-                            mbar_wait(bar_acce + 8 * hb, (tcount - 1) & 1);
-                            tc_fence_after();
-                        }
-                        const uint32_t b0 = (((st + R_F0_BYTES + hb * R_NH * 128) >> 4) & 0x3FFF) | (1u << 16);
-                        const uint32_t d = tmem_acc + hb * R_NH;
+                        const uint32_t b0 = (((st + Q_F0_BYTES + hb * Q_NH * 128) >> 4) & 0x3FFF) | (1u << 16);
+                        const uint32_t d = tmem_acc + hb * Q_NH;
                         // k-steps of 32 bytes inside the 128-byte row: 0,1 = h (channels 0-15, 16-31), 2,3 = l
 #pragma unroll
                         for (int k = 0; k < 2; ++k) s_mma(d, desc_hi | (a0 + 2 * k), desc_hi | (b0 + 2 * k), idesc, (c | k) != 0 ? 1u : 0u);
@@ -369,123 +431,86 @@ cost_volume_split_row32_kernel(const __grid_constant__ CUtensorMap tm_f0, const 
                         for (int k = 0; k < 2; ++k) s_mma(d, desc_hi | (a0 + 4 + 2 * k), desc_hi | (b0 + 2 * k), idesc, 1u);
 #pragma unroll
                         for (int k = 0; k < 2; ++k) s_mma(d, desc_hi | (a0 + 2 * k), desc_hi | (b0 + 4 + 2 * k), idesc, 1u);
-                        if (c == KC - 1) tc_commit(bar_accf + 8 * hb);
                     }
                     tc_commit(bar_empty + 8 * s);
+                    if (c == KC - 1) tc_commit(bar_accf);
                 }
             }
         }
     } else {
-        // ===================== epilogue: warp -> TMEM lane quadrant q = tile row =====================
-        const int q = warp & 3;
-        float* in_slab = reinterpret_cast<float*>(base_ptr + R_STAGES * R_STAGE_BYTES + (warp - 2) * R_WARP_SLAB);
-        float* out_slab = in_slab + 32 * R_IN_PITCH;
-        float* in_lane = in_slab + lane * R_IN_PITCH;
-        float* out_lane = out_slab + lane * R_OUT_PITCH;
+        // ===================== epilogue: warps 2..9, TMEM lane quadrant q = warp % 4, role = (warp - 2) / 4 ==========
+        const int q = warp & 3, role = (warp - 2) >> 2;
+        float* slabs = reinterpret_cast<float*>(base_ptr + Q_STAGES * Q_STAGE_BYTES);
         const uint32_t tq = tmem_acc + ((uint32_t)(q * 32) << 16);
         const int cs = p.out_cs;
         const float scale = p.scale, alpha = p.alpha;
         int tcount = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
-            const int x0 = tx * R_TW, yy = ty * R_TH + q;
-            // one displacement row: 40 accumulator words -> row buffer -> the lane's nine values -> its output row
-            auto process = [&](const uint32_t* v, int dv) {
+            const int x0 = tx * Q_TW, y0 = ty * Q_TH;
+            float* slab = slabs + (tcount & 1) * (Q_SLAB_BYTES / 4) + q * 32 * Q_PITCH;
+            mbar_wait(bar_accf, tcount & 1);
+            if (warp == 2 && lane == 0) S_DBG(3, tcount);
+            tc_fence_after();
+            if (role == 0) q_extract<0>(tq, q, lane, reinterpret_cast<uint32_t*>(slab) + lane * Q_PITCH, bar_acce);
+            else           q_extract<1>(tq, q, lane, reinterpret_cast<uint32_t*>(slab) + lane * Q_PITCH, bar_acce);
+            if (warp == 2 && lane == 0) S_DBG(4, tcount);
+            if (warp == 6 && lane == 0) S_DBG(5, tcount);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // both roles of the quadrant have filled the slab
+            if (warp == 2 && lane == 0) S_DBG(6, tcount);
+            // ---- slab -> HBM: this warp writes image rows y0 + 4q + 2 role + {0, 1}, 8 pixels each (slab rows 16 role ..
+            //      + 15), one pixel (324 contiguous bytes) per step: lanes 0..19 a float4 each, lane 20 the 81st word.
+            //      scale and the leaky slope are applied here.
+            const int ybase = y0 + 4 * q + 2 * role;
+            const int npx = min(Q_TW, p.W - x0);
+            const float* srow = slab + 16 * role * Q_PITCH;
+            float* grow = p.out + (((size_t)b * p.H + ybase) * p.W + x0) * cs;
+            const size_t gpitch = (size_t)p.W * cs;
+            if (p.vec) {
+                const float* sl = srow + 4 * lane;
+                float* gl = grow + 4 * lane;
+                if (lane < 20) {
 #pragma unroll
-                for (int j = 0; j < 10; ++j)
-                    *reinterpret_cast<uint4*>(in_lane + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __syncwarp();
-                // D[m = lane][candidate column lane + dh] = f0(x0 + lane) . f1(x0 - 4 + lane + dh): displacement h = dh - 4
+                    for (int half = 0; half < 2; ++half) {
+                        if (ybase + half < p.H) {
+                            float4 w[8];
 #pragma unroll
-                for (int dh = 0; dh < 9; ++dh) out_lane[dv * 9 + dh] = in_lane[lane + dh];
-                __syncwarp();
-            };
-            auto row_taddr = [&](int dv) {                                        // candidate row q + dv inside its half
-                const int r = q + dv, hb = r >= R_FH / 2 ? 1 : 0;
-                return tq + hb * R_NH + (r - hb * (R_FH / 2)) * R_FW;
-            };
-            auto acquire = [&](int dv) {                                          // first row this warp reads of a half
-                const int r = q + dv;
-                if (r == q || r == R_FH / 2) {
-                    mbar_wait(bar_accf + 8 * (r >= R_FH / 2 ? 1 : 0), tcount & 1);
-                    tc_fence_after();
-                }
-            };
-            auto release = [&](int dv) {                                          // last row of a half: hand it back to the MMA warp
-                const int r = q + dv;
-                if (r == R_FH / 2 - 1 || dv == 8) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acce + 8 * (r >= R_FH / 2 ? 1 : 0));
-                }
-            };
-            if (PIPE) {
-                // the tcgen05.ld of row dv + 1 is in flight while row dv goes through the row buffer
-                uint32_t v[2][40];
-                acquire(0);
-                { const uint32_t ta = row_taddr(0); tmem_ld16(ta, v[0]); tmem_ld16(ta + 16, v[0] + 16); tmem_ld8(ta + 32, v[0] + 32); }
+                            for (int x = 0; x < 8; ++x) w[x] = *reinterpret_cast<const float4*>(sl + (8 * half + x) * Q_PITCH);
 #pragma unroll
-                for (int dv = 0; dv < 9; ++dv) {
-                    tmem_ld_wait();                                               // row dv is in v[dv & 1]
-                    release(dv);
-                    if (dv < 8) {
-                        acquire(dv + 1);
-                        const uint32_t ta = row_taddr(dv + 1);
-                        tmem_ld16(ta, v[(dv + 1) & 1]); tmem_ld16(ta + 16, v[(dv + 1) & 1] + 16); tmem_ld8(ta + 32, v[(dv + 1) & 1] + 32);
+                            for (int x = 0; x < 8; ++x) {
+                                w[x].x *= scale; w[x].y *= scale; w[x].z *= scale; w[x].w *= scale;
+                                w[x].x = fmaxf(w[x].x, alpha * w[x].x); w[x].y = fmaxf(w[x].y, alpha * w[x].y);
+                                w[x].z = fmaxf(w[x].z, alpha * w[x].z); w[x].w = fmaxf(w[x].w, alpha * w[x].w);
+                                if (x < npx) *reinterpret_cast<float4*>(gl + half * gpitch + (size_t)x * cs) = w[x];
+                            }
+                        }
                     }
-                    process(v[dv & 1], dv);
+                } else if (lane == 20) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        if (ybase + half < p.H) {
+                            float w[8];
+#pragma unroll
+                            for (int x = 0; x < 8; ++x) w[x] = sl[(8 * half + x) * Q_PITCH] * scale;
+#pragma unroll
+                            for (int x = 0; x < 8; ++x)
+                                if (x < npx) gl[half * gpitch + (size_t)x * cs] = fmaxf(w[x], alpha * w[x]);
+                        }
+                    }
                 }
             } else {
 #pragma unroll 1
-                for (int dv = 0; dv < 9; ++dv) {
-                    acquire(dv);
-                    const uint32_t ta = row_taddr(dv);
-                    uint32_t v[40];
-                    tmem_ld16(ta, v); tmem_ld16(ta + 16, v + 16); tmem_ld8(ta + 32, v + 32);
-                    tmem_ld_wait();
-                    release(dv);
-                    process(v, dv);
-                }
-            }
-            // ---- 32 pixels x 81 floats -> HBM as 324-byte runs; scale and leaky applied here
-            if (yy < p.H) {
-                float* orow = p.out + (((size_t)b * p.H + yy) * p.W + x0) * cs;
-                const int npx = min(32, p.W - x0);
-                if (p.vec) {
-                    int pix = lane / 21, k = lane - pix * 21;                   // unit u = lane + 32 m: pixel u / 21, float4 (or tail scalar) u % 21
-#pragma unroll 3
-                    for (int m = 0; m < 21; ++m) {
-                        if (pix < npx) {
-                            const float* src = out_slab + pix * R_OUT_PITCH + 4 * k;
-                            float* dst = orow + (size_t)pix * cs + 4 * k;
-                            if (k < 20) {
-                                float4 w = *reinterpret_cast<const float4*>(src);
-                                w.x *= scale; w.y *= scale; w.z *= scale; w.w *= scale;
-                                w.x = fmaxf(w.x, alpha * w.x); w.y = fmaxf(w.y, alpha * w.y);
-                                w.z = fmaxf(w.z, alpha * w.z); w.w = fmaxf(w.w, alpha * w.w);
-                                *reinterpret_cast<float4*>(dst) = w;
-                            } else {
-                                const float w = *src * scale;
-                                *dst = fmaxf(w, alpha * w);
-                            }
-                        }
-                        k += 11; pix += 1;                  // u += 32 = 21 + 11
-                        if (k >= 21) { k -= 21; pix += 1; }
-                    }
-                } else {
-                    int pix = 0, k = lane;                  // 32 pixels x 81 scalars
-#pragma unroll 3
-                    for (int m = 0; m < 81; ++m) {
-                        if (pix < npx) {
-                            const float w = out_slab[pix * R_OUT_PITCH + k] * scale;
-                            orow[(size_t)pix * cs + k] = fmaxf(w, alpha * w);
-                        }
-                        k += 32;
-                        if (k >= 81) { k -= 81; pix += 1; }
+                for (int pix = 0; pix < 16; ++pix) {                // scalar path: destination not 16-byte aligned
+                    const int yy = ybase + (pix >> 3), xx = pix & 7;
+                    if (yy >= p.H || xx >= npx) continue;
+                    float* g = grow + (pix >> 3) * gpitch + (size_t)xx * cs;
+                    for (int k = lane; k < 81; k += 32) {
+                        const float w = srow[pix * Q_PITCH + k] * scale;
+                        g[k] = fmaxf(w, alpha * w);
                     }
                 }
             }
-            __syncwarp();                                   // the slabs are rewritten by the next tile
+            if (warp == 2 && lane == 0) S_DBG(7, tcount);
         }
     }
     __syncwarp();
@@ -627,26 +652,47 @@ extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float
     PWC_REQUIRE((C % 32) == 0 && aligned16(f0s) && aligned16(f1s), PWC_E_ALIGN,
                 "cost_volume_split: C must be a multiple of 32 and the operands 16-byte aligned");
     CUtensorMap tm0, tm1;
-    {   // experimental 4 x 32 tiling (not validated on hardware yet: opt-in only)
-        const char* ev = getenv("PWC_CV_SPLIT");
-        if (ev && (!strcmp(ev, "row32") || !strcmp(ev, "row32p"))) {
-            const bool pipe = !strcmp(ev, "row32p");       // row32p: TMEM loads of the next row overlap the current row
-            PWC_REQUIRE(make_map_split(&tm0, f0s, B, H, W, C, R_TW, R_TH) && make_map_split(&tm1, f1s, B, H, W, C, R_FW, R_FH),
+    {   // quadrant-block tiling (16 x 8 pixel tiles, register-resident band extraction): default; PWC_CV_SPLIT=scatter
+        // selects the round-1 kernel below
+        const char* ev = getenv("PWC_CV_SPLIT");   // read per call: the tests switch variants in one process
+        if (!(ev && !strcmp(ev, "scatter"))) {
+            PWC_REQUIRE(make_map_split(&tm0, f0s, B, H, W, C, Q_TW, Q_TH) && make_map_split(&tm1, f1s, B, H, W, C, Q_FW, Q_FH),
                         PWC_E_BADARG, "cost_volume_split: cuTensorMapEncodeTiled failed");
             CvSplitParams p{};
             p.out = out; p.out_cs = out_cs; p.B = B; p.H = H; p.W = W; p.kchunks = C / 32;
-            p.tiles_x = (W + R_TW - 1) / R_TW; p.tiles_y = (H + R_TH - 1) / R_TH;
+            p.tiles_x = (W + Q_TW - 1) / Q_TW; p.tiles_y = (H + Q_TH - 1) / Q_TH;
             const long long tiles = (long long)p.tiles_x * p.tiles_y * B;
             PWC_REQUIRE(tiles < (1ll << 30), PWC_E_BADARG, "cost_volume_split: too many tiles");
             p.total_tiles = (int)tiles;
             p.alpha = alpha; p.scale = scale;
             p.vec = aligned16(out) && (out_cs & 3) == 0;
-            auto kern = pipe ? cost_volume_split_row32_kernel<true> : cost_volume_split_row32_kernel<false>;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_BYTES);
-            if (e != cudaSuccess) { set_error("cost_volume_split(row32): smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-            const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
-            kern<<<grid, R_THREADS, R_SMEM_BYTES, (cudaStream_t)stream>>>(tm0, tm1, p);
-            PWC_CHECK_LAUNCH("cost_volume_split_row32_kernel");
+            cudaError_t e = cudaFuncSetAttribute(cost_volume_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
+            if (e != cudaSuccess) { set_error("cost_volume_split(quad): smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+            const int nsm = sm_count();
+            const int grid = p.total_tiles < nsm ? p.total_tiles : nsm;
+            static unsigned long long* qdbg = nullptr;
+            if (getenv("PWC_CV_DEBUG")) {
+                if (!qdbg) cudaMalloc(&qdbg, 256 * 64 * 8);
+                cudaMemsetAsync(qdbg, 0, 256 * 64 * 8, (cudaStream_t)stream);
+                p.dbg = qdbg;
+            }
+            cost_volume_quad_kernel<<<grid, Q_THREADS, Q_SMEM_BYTES, (cudaStream_t)stream>>>(tm0, tm1, p);
+            PWC_CHECK_LAUNCH("cost_volume_quad_kernel");
+            if (p.dbg) {   // debugging aid only (synchronises): timeline of the first tiles of one CTA
+                cudaStreamSynchronize((cudaStream_t)stream);
+                static int printed = 0;
+                if (printed++ < 2) {
+                    unsigned long long h[64];
+                    const char* names[8] = {"tma_issue", "full_seen", "acce_seen", "accf_seen(w2)", "extract_done(w2)", "extract_done(w6)", "bar_passed(w2)", "stored(w2)"};
+                    cudaMemcpy(h, p.dbg + 64 * (grid / 2), 64 * 8, cudaMemcpyDeviceToHost);
+                    fprintf(stderr, "[cv_quad dbg] cta %d (clk from first tma issue), tiles 0..7\n", grid / 2);
+                    for (int e = 0; e < 8; ++e) {
+                        fprintf(stderr, "   %-17s", names[e]);
+                        for (int t = 0; t < 8; ++t) fprintf(stderr, " %7lld", (long long)(h[e * 8 + t] - h[0]));
+                        fprintf(stderr, "\n");
+                    }
+                }
+            }
             return 0;
         }
     }

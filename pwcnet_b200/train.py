@@ -18,6 +18,7 @@ Only `use_dc=False` (every BASELINE config and every reference checkpoint) is tr
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -354,13 +355,24 @@ class Trainer(object):
         return sd
 
     def load_state_dict(self, sd) -> None:
-        """Inverse of state_dict(); `sd` may also be the prefix of a checkpoint written by the reference's
-        tf.train.Saver (e.g. 'model_250.ckpt'): weights, Adam moments and global_step are resumed."""
+        """Inverse of state_dict(); `sd` may also be the prefix of a checkpoint bundle -- written by save() below or by
+        the reference's tf.train.Saver (e.g. 'model_250.ckpt') -- or the path of a legacy `.npz` written by round-1
+        builds: weights, Adam moments and global_step are resumed.  A bundle that holds only the model variables
+        (train.py's current `Saver(model.vars)`, no 'Variable' / Adam slots) resumes with global_step 0 and zero
+        moments, which is what the reference does on `--resume`.  The Adam bias correction is derived from global_step
+        (t = global_step + 1); stored beta powers are not read."""
         if isinstance(sd, str):
-            from .checkpoint import load_checkpoint, read_scalar
-            prefix = sd
-            sd = load_checkpoint(prefix, self.model.name, include_slots=True)
-            sd["Variable"] = read_scalar(prefix, "Variable")
+            if sd.endswith(".npz") and os.path.exists(sd):
+                sd = dict(np.load(sd))
+            else:
+                from .checkpoint import load_checkpoint, list_variables, read_scalar
+                prefix = sd
+                sd = load_checkpoint(prefix, self.model.name, include_slots=True)
+                names = list_variables(prefix)
+                for gs in ("Variable", "global_step"):
+                    if gs in names:
+                        sd["Variable"] = read_scalar(prefix, gs)
+                        break
         m = self.model
         m.load_weights({k: sd[k] for k in m.var_names})
         off = 0
@@ -369,13 +381,18 @@ class Trainer(object):
             for buf, sfx in ((self.m, "/Adam"), (self.v, "/Adam_1")):
                 if name + sfx in sd:
                     buf[off:off + n].copy_(torch.from_numpy(np.ascontiguousarray(sd[name + sfx], np.float32)).reshape(-1))
+                else:
+                    buf[off:off + n].zero_()
             off += n
-        if "Variable" in sd:
-            self.global_step = int(np.asarray(sd["Variable"]).reshape(-1)[0])
+        self.global_step = int(np.asarray(sd["Variable"]).reshape(-1)[0]) if "Variable" in sd else 0
 
     def save(self, path: str) -> None:
-        """Per-epoch checkpoint (train.py:164-166) as a .npz with the reference's variable names."""
-        np.savez(path, **self.state_dict())
+        """Per-epoch checkpoint (train.py:164-166, `saver.save(sess, 'model_{e+1}.ckpt')`): a TensorFlow checkpoint
+        bundle `<path>.index` + `<path>.data-00000-of-00001` under the reference's variable names, byte-compatible with
+        tf.train.Saver (pwcnet_b200/checkpoint.py:save_checkpoint), so the reference's test.py / train.py --resume and
+        this package's load_weights / load_state_dict / `infer.py --resume` all read it."""
+        from .checkpoint import save_checkpoint
+        save_checkpoint(path, self.state_dict())
 
     def launches_per_step(self) -> int:
         """Kernel launches of ours in one training step, counted: C-ABI calls issued by one step (losses, backward,

@@ -96,23 +96,41 @@ def test_cost_volume_split_pipeline_matches_oracle(P, shape):
     np.testing.assert_allclose(P.ops.cost_volume_split(f0s, f1n, 0.1).cpu().numpy(), refn, atol=1e-5, rtol=1e-5)
 
 
-@pytest.mark.skipif(os.environ.get("PWC_TEST_EXPERIMENTAL") != "1", reason="experimental kernel, written without GPU time "
-                    "left in round 1: run with PWC_TEST_EXPERIMENTAL=1 to validate it (DESIGN.md 3.1, round-2 plan)")
-@pytest.mark.parametrize("variant", ["row32", "row32p"])
-@pytest.mark.parametrize("shape", [(1, 8, 64, 32), (2, 13, 70, 32), (1, 28, 64, 64), (1, 5, 31, 96)])
-def test_cost_volume_split_row32_experimental(P, shape, variant, monkeypatch):
-    """4 x 32-pixel tiling of the split band GEMM (PWC_CV_SPLIT=row32) vs the oracle and the default split kernel."""
+@pytest.mark.parametrize("variant", ["quad", "scatter"])
+@pytest.mark.parametrize("shape", [(1, 8, 64, 32), (2, 13, 70, 32), (1, 28, 64, 64), (1, 5, 31, 96), (1, 33, 9, 32), (2, 16, 8, 32),
+                                   (1, 112, 256, 32), (2, 7, 16, 192)])
+def test_cost_volume_split_variants(P, shape, variant, monkeypatch):
+    """Both tilings of the split band GEMM -- the quadrant-block kernel (default: 16 x 8 tiles, register-resident band
+    extraction) and the round-1 scatter kernel (PWC_CV_SPLIT=scatter) -- vs the oracle, into a strided slot, on ragged
+    shapes (partial tiles right and bottom, images narrower / shorter than one tile)."""
     B, H, W, C = shape
     f0, f1 = _rand(shape, 1), _rand(shape, 2)
-    ref = O.cost_volume(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy()
+    ref = O.cost_volume_closed_form(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy() if H * W > 4000 else \
+        O.cost_volume(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy()
     f0s, f1s = P.ops.split_f16(_cuda(f0)), P.ops.split_f16(_cuda(f1))
-    base = P.ops.cost_volume_split(f0s, f1s, 0.1)
-    monkeypatch.setenv("PWC_CV_SPLIT", variant)     # row32p: TMEM loads of the next row in flight
+    monkeypatch.setenv("PWC_CV_SPLIT", variant)
     buf = torch.full((B, H, W, 88), 7.0, device="cuda")
     P.ops.cost_volume_split(f0s, f1s, 0.1, out=buf[..., :81])
     np.testing.assert_allclose(buf[..., :81].cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
-    np.testing.assert_allclose(buf[..., :81].cpu().numpy(), base.cpu().numpy(), atol=2e-6, rtol=0)
     assert float((buf[..., 81:] - 7.0).abs().max()) == 0
+    # unaligned destination (scalar store path): channel offset 1 inside the buffer
+    buf2 = torch.full((B, H, W, 88), 7.0, device="cuda")
+    P.ops.cost_volume_split(f0s, f1s, 0.1, out=buf2[..., 1:82])
+    np.testing.assert_array_equal(buf2[..., 1:82].cpu().numpy(), buf[..., :81].cpu().numpy())
+    assert float((buf2[..., 82:] - 7.0).abs().max()) == 0 and float((buf2[..., :1] - 7.0).abs().max()) == 0
+
+
+def test_cost_volume_split_all_81_displacements_at_corners(P):
+    """Impulses in the four corners through the tcgen05 split path: every displacement channel picks exactly the
+    reference's (v outer, h inner) neighbour and zero-pads outside the image."""
+    C, H, W = 32, 19, 35
+    f0 = np.zeros((1, H, W, C), np.float32); f1 = _rand((1, H, W, C), 5)
+    for (y, x) in [(0, 0), (0, W - 1), (H - 1, 0), (H - 1, W - 1), (9, 17)]:
+        f0[0, y, x, :4] = [1.0, -2.0, 0.5, 3.0]
+    ref = O.cost_volume(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy()
+    out = P.ops.cost_volume_split(P.ops.split_f16(_cuda(f0)), P.ops.split_f16(_cuda(f1)), 0.1).cpu().numpy()
+    np.testing.assert_allclose(out, ref, atol=1e-6)
+    assert (out[0, 0, 0, :4 * 9] == 0).all()
 
 
 def test_cost_volume_all_81_displacements_at_corners(P):

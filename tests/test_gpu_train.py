@@ -457,12 +457,18 @@ def test_trainer_state_dict_roundtrip_resumes_identically(P, tmp_path):
     gt = np.random.default_rng(3).normal(0, 3, (1, 64, 64, 2)).astype(np.float32)
     tr = Trainer(P.PWCDCNet(weights=W, precision="fp32"))
     tr.step(im0, im1, gt); tr.step(im0, im1, gt)
-    path = str(tmp_path / "model_2.npz")
-    tr.save(path)
-    sd = dict(np.load(path))
+    path = str(tmp_path / "model_2.ckpt")
+    tr.save(path)                                   # a TF checkpoint bundle, as train.py:166 writes
+    from pwcnet_b200.checkpoint import load_all
+    sd = load_all(path)
     assert int(sd["Variable"]) == 2 and "pwcdcnet/context/conv2d_6/kernel/Adam_1" in sd and len(sd) == 110 * 3 + 3
+    assert sd["Variable"].dtype == np.int32 and sd["Variable"].shape == ()
     tr2 = Trainer(P.PWCDCNet(precision="fp32"))
-    tr2.load_state_dict(sd)
+    tr2.load_state_dict(path)                       # resume by path (train.py:97-99)
+    # ... and inference by path (test.py:40-42)
+    ffa, _ = P.PWCDCNet(weights=path, precision="fp32")(im0, im1)
+    ffb, _ = tr.model(im0, im1)
+    assert torch.equal(ffa, ffb)
     assert tr2.global_step == 2
     tr.step(im0, im1, gt); tr2.step(im0, im1, gt)
     # wgrad accumulates with float atomics: summation order is not fixed, so compare to 1e-6 instead of bit-for-bit

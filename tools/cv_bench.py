@@ -16,6 +16,10 @@ f1 = torch.randn((B, h, w, C), device="cuda", generator=g)
 flow = torch.randn((B, h, w, 2), device="cuda", generator=g) * 3
 cv = torch.empty((B, h, w, 148), device="cuda")[..., :81] if slot else torch.empty((B, h, w, 81), device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+# PWC_FLUSH=clean: after the write-flush, READ a second 256 MiB buffer so that L2 holds only clean lines when the timed
+# kernel starts (a write-only flush leaves ~126 MB of dirty lines whose write-back is charged to the timed kernel)
+clean = os.environ.get("PWC_FLUSH") == "clean"
+flush2 = torch.ones(64 << 20, dtype=torch.float32, device="cuda") if clean else None
 split = len(sys.argv) > 3 and sys.argv[3] in ("split", "splitslot")
 if split:
     if sys.argv[3] == "splitslot":
@@ -33,6 +37,8 @@ for _ in range(3):
 ts = []
 for _ in range(iters):
     flush.fill_(1)
+    if clean:
+        flush2.sum()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(); run(); e.record()
     torch.cuda.synchronize()
@@ -40,4 +46,4 @@ for _ in range(iters):
 alg = 4 * h * w * (2 * C + 81 + (2 if fused else 0)) * B
 import statistics
 us = statistics.mean(ts)
-print(f"cost_volume level-2 B={B} fused={fused} slot={slot}: {us:.1f} us/launch (min {min(ts):.1f}), {alg/us/1e3:.0f} GB/s algorithmic, frac of 6550 = {alg/us/1e3/6550:.3f}")
+print(f"cost_volume level-2 B={B} mode={sys.argv[3] if len(sys.argv) > 3 else 'dense'} split={os.environ.get('PWC_CV_SPLIT', '-')} flush={'clean' if clean else 'dirty'}: {us:.1f} us/launch (min {min(ts):.1f}), {alg/us/1e3:.0f} GB/s algorithmic, frac of 6550 = {alg/us/1e3/6550:.3f}")
