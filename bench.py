@@ -309,10 +309,177 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def _init_dist(dev):
+    """NCCL prints its version banner on stdout at communicator creation; keep stdout = the one JSON line."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
+def _bind_to_gpu_numa_node(local: int):
+    """Pin this rank's host threads to the CPUs of its GPU's NUMA node, so pinned staging buffers are allocated there
+    (first touch) and the copy threads do not cross sockets.  Best effort: silently skipped when sysfs has no answer."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        out = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not out:
+            return None
+        bdf = out[-12:] if len(out) >= 12 else out          # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, ids)
+        return node
+    except Exception:
+        return None
+
+
+def roofline_cost_volume(P, torch, dev, B, n_sets=4, reps=12):
+    """Level-2 cost volume as the model runs it (tcgen05 quadrant-block kernel, split fp16 operands, whole-sector writes
+    into the 81+2+5-word head of the 152-wide estimator concat buffer), timed live: `n_sets` rotating operand / output
+    sets (n_sets x 140 MB > 126 MB L2: every launch misses L2 for all of its inputs, and pays the write-back of its
+    predecessor's output), launches back to back, CUDA events around the whole sequence."""
+    h2, w2, C = H // 4, W // 4, 32
+    g = torch.Generator(device=dev).manual_seed(0)
+    sets = []
+    for _ in range(n_sets):
+        f0 = torch.randn((B, h2, w2, C), device=dev, generator=g)
+        f1 = torch.randn((B, h2, w2, C), device=dev, generator=g)
+        tail = torch.randn((B, h2, w2, 2), device=dev, generator=g)
+        buf = torch.zeros((B, h2, w2, 152), device=dev)
+        sets.append((P.ops.split_f16(f0, scale=1.0 / C), P.ops.split_f16(f1), tail, buf[..., :81]))
+    def launch(i):
+        a, b, t, o = sets[i % n_sets]
+        P.ops.cost_volume_split(a, b, 0.1, out=o, prescaled=True, slot=True, tail=t)
+    for i in range(2 * n_sets):
+        launch(i)
+    torch.cuda.synchronize()
+    n = reps * n_sets
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        launch(i)
+    e1.record()
+    torch.cuda.synchronize()
+    cv_us = 1e3 * e0.elapsed_time(e1) / n
+    alg_bytes = 4 * h2 * w2 * (2 * C + 81) * B
+    peak, peak_src = _peaks()
+    achieved = alg_bytes / (cv_us * 1e-6) / 1e9
+    traffic, tsrc = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_cost_volume_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, tsrc = tj.get("dram_bytes_per_launch"), tj.get("source")
+    return {"kernel": "cost_volume_quad_kernel (tcgen05 band GEMM, 3 x fp16 split, fp32 accumulate) level-2 112x256x32 -> 81-ch "
+                      "slot of the 152-wide concat buffer, B=%d" % B,
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": tsrc, "us_per_launch": cv_us, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+            "launches_timed": n,
+            "method": f"{n_sets} rotating operand/output sets ({n_sets} x 140 MB > L2), {n} back-to-back launches between two CUDA events"}
+
+
+def roofline_conv(P, torch, dev, B, flush):
+    """The kernel that dominates the step by time: the halo-resident tcgen05 conv, level-4 estimator layer 128 -> 128."""
+    from pwcnet_b200 import ops_tc
+    h2, w2 = H // 4, W // 4
+    g = torch.Generator(device=dev).manual_seed(1)
+    xc = torch.randn((B, h2, w2, 128), device=dev, generator=g)
+    kc = torch.randn((3, 3, 128, 128), device=dev, generator=g) / 34.0
+    bc = torch.zeros(128, device=dev)
+    yc = torch.empty((B, h2, w2, 128), device=dev)
+    wpk = ops_tc.pack_weights_f16(kc)
+    for _ in range(3):
+        ops_tc.conv3x3_tc_f16(xc, wpk, bc, 128, 128, alpha=0.1, out=yc)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+    for s_, e_ in ev:
+        flush.fill_(3)
+        s_.record()
+        ops_tc.conv3x3_tc_f16(xc, wpk, bc, 128, 128, alpha=0.1, out=yc)
+        e_.record()
+    torch.cuda.synchronize()
+    conv_us = 1e3 * float(np.mean([s_.elapsed_time(e_) for s_, e_ in ev]))
+    conv_flops = 2.0 * 9 * 128 * 128 * B * h2 * w2
+    tpeak, tpeak_src = _tensor_peak()
+    conv_tflops = conv_flops / (conv_us * 1e-6) / 1e12
+    return {"kernel": "conv3x3_tc_halo_kernel, level-4 estimator conv 128->128 at 112x256, B=%d (3 x fp16 split: every useful "
+                      "flop costs 3 fp16 MMA flops)" % B,
+            "bound": "tensor", "achieved": conv_tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": conv_tflops / tpeak,
+            "mma_issue_tflops": 3 * conv_tflops, "mma_issue_frac": 3 * conv_tflops / tpeak, "traffic": None,
+            "us_per_launch": conv_us, "algorithmic_flops": conv_flops, "peak_source": tpeak_src}
+
+
+def train_object(P, torch, dist, dev, rank, world, B, steps, warmup, precision):
+    """BASELINE config 5 inside the default line: training step at 384x1024, B pairs per GPU, NCCL all-reduce of the flat
+    gradient at world > 1.  Device-timed like `value`; `allreduce_exposed_ms` = step time minus the same step with the
+    collective skipped."""
+    h, w = TRAIN_H, TRAIN_W
+    model = P.PWCDCNet(weights=P.glorot_init(2), precision=precision, device=dev, cv_pipeline="default")
+    trainer = P.Trainer(model, lr=1e-4, gamma=4e-4)
+    rng = np.random.default_rng(2000 + rank)
+    d0 = torch.from_numpy(rng.integers(0, 256, (B, h, w, 3), dtype=np.uint8)).to(dev)
+    d1 = torch.from_numpy(rng.integers(0, 256, (B, h, w, 3), dtype=np.uint8)).to(dev)
+    dg = torch.from_numpy(rng.normal(0, 5, (B, h, w, 2)).astype(np.float32)).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = trainer.step(d0, d1, dg)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n, out
+
+    for _ in range(warmup):
+        trainer.step(d0, d1, dg)
+    ms, out = timed(steps)
+    ms_noar = None
+    if world > 1:
+        trainer.skip_allreduce = True          # measurement only: same step without the collective
+        timed(2)
+        ms_noar, _ = timed(steps)
+        trainer.skip_allreduce = False
+    t = torch.tensor([ms, ms_noar if ms_noar is not None else ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_noar = t.tolist()
+    return {"metric": TRAIN_METRIC, "value": B * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "batch_per_gpu": B, "global_batch": B * world, "ranks": world,
+            "allreduce": "bucketed NCCL SUM all-reduce of the flat fp32 gradient (20.1 MB) on a side stream, overlapped with "
+                         "the pyramid backward" if world > 1 else "none (1 rank)",
+            "allreduce_exposed_ms": (ms - ms_noar) if world > 1 else 0.0,
+            "loss": float(out[0].item()), "gpu_launches_per_step": trainer.launches_per_step(),
+            "workload": "PWCDCNet(use_dc=False) training step (forward, multiscale L2 loss + 4e-4 l2 regulariser, backward, gradient "
+                        "all-reduce, TF-Adam), synthetic uint8 384x1024 pairs + random GT flow (BASELINE config 5; 436x1024 is "
+                        "not divisible by 64)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
-                    help="infer = the headline metric (default); train = BASELINE config 5")
+                    help="infer = the headline metric (default; carries a `train` object); train = BASELINE config 5 alone")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -321,6 +488,9 @@ def main():
     ap.add_argument("--precision", default=None, choices=["fp32", "3xf16", "3xtf32", "tf32", "cudnn"])
     ap.add_argument("--cpu-pairs", type=int, default=20, help="pairs timed for cpu_baseline (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the `train` object of the default line")
+    ap.add_argument("--min-seconds", type=float, default=2.0,
+                    help="each of the K timed steps repeats the batch so that the timed region lasts at least this long")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.mode == "train":
@@ -331,28 +501,17 @@ def main():
     import torch
     import torch.distributed as dist
     import pwcnet_b200 as P
-    from pwcnet_b200.model import PRECISIONS  # noqa: F401
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    numa = _bind_to_gpu_numa_node(local)          # before any pinned allocation
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        # NCCL prints its version banner on stdout at communicator creation; keep stdout = the one JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        _init_dist(dev)
     if args.gpus != world and rank == 0 and world > 1:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
@@ -360,8 +519,10 @@ def main():
     precision = args.precision or P.model.DEFAULT_PRECISION
     model = P.PWCDCNet(weights=P.glorot_init(2), precision=precision, device=dev)
     rng = np.random.default_rng(1000 + rank)
-    host0 = torch.from_numpy(rng.random((B, H, W, 3), dtype=np.float32)).pin_memory()
-    host1 = torch.from_numpy(rng.random((B, H, W, 3), dtype=np.float32)).pin_memory()
+    # the reference's inputs are uint8 images divided by 255 on the host (test.py:31-33, train.py:122): the host API takes
+    # the bytes and does the division on the device (bit-identical), so a quarter of the bytes cross PCIe
+    host0 = torch.from_numpy(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)).pin_memory()
+    host1 = torch.from_numpy(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)).pin_memory()
     dev0, dev1 = host0.to(dev), host1.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -370,24 +531,50 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---------------------------------------------------------------- N-GPU == 1-GPU evidence: every rank runs the same
+    # seed-0 probe pair and reports a checksum of its flow (bit-for-bit comparable across ranks and across --gpus runs)
+    pr = np.random.default_rng(0)
+    p0 = pr.integers(0, 256, (1, H, W, 3), dtype=np.uint8)
+    p1 = np.roll(p0, (3, -5), axis=(1, 2))
+    pf, _ = model(p0, p1)
+    import hashlib
+    digest = hashlib.sha256(pf.cpu().numpy().tobytes()).hexdigest()[:16]
+    csum = torch.tensor([int(digest, 16) % (1 << 52)], dtype=torch.float64, device=dev)
+    all_cs = [csum.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(all_cs, csum)
+    probe_equal = all(float(c.item()) == float(csum.item()) for c in all_cs)
+
     # ---------------------------------------------------------------- value: inputs resident in HBM
     for _ in range(args.warmup):
         model(dev0, dev1)
     barrier()
+    # inner repeats so that the timed region is >= --min-seconds (thermal / power steady state, not a 70 ms burst)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); model(dev0, dev1); model(dev0, dev1); e1.record(); torch.cuda.synchronize()
+    est_ms = e0.elapsed_time(e1) / 2
+    inner = max(1, int(np.ceil(args.min_seconds * 1e3 / (est_ms * args.steps))))
+    if world > 1:
+        ti = torch.tensor([inner], dtype=torch.int64, device=dev)
+        dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+        inner = int(ti.item())
+    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps * inner)]
     for s, e in ev:
         flush.fill_(1)                       # evict L2 between timed iterations (outside the event pair)
         s.record()
         model(dev0, dev1)
         e.record()
     barrier()
-    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    times = [s.elapsed_time(e) for s, e in ev]
+    dev_ms = sum(times)
+    burst_ms = sum(times[:args.steps])       # the first K passes: what a K-step run without repeats would report
 
     # ---------------------------------------------------------------- e2e: host buffers through the public API
-    # (a) synchronous call: model(host images) then copy the results back, one request at a time
+    # (a) synchronous reference-shaped call: model(host uint8 images) then copy the results back, one request at a time
     ff, pyr = model(host0, host1)
     outs_dev = [ff] + list(pyr)
     out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs_dev]   # pinned result buffers
@@ -415,14 +602,15 @@ def main():
     for _ in range(2):
         stream.collect(stream.submit(host0, host1))
     barrier()
+    n_e2e = args.steps * max(1, inner // 4)
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     prev = None
-    for _ in range(args.steps):
+    for _ in range(n_e2e):
         tk = stream.submit(host0, host1)
         if prev is not None:
-            out_host = list(stream.collect(prev)[1]) + [stream._slots[prev % 2]["out_host"][0]]
+            stream.collect(prev)
         prev = tk
     res = stream.collect(prev)
     out_host = [res[0]] + list(res[1])
@@ -431,72 +619,26 @@ def main():
     e2e_ms = e0.elapsed_time(e1)
     wall_e2e = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    h2d = int(host0.numel() + host1.numel()) * 4
-    d2h = int(sum(t.numel() for t in out_host)) * 4
+    h2d = int(host0.numel() * host0.element_size() + host1.numel() * host1.element_size())
+    d2h = int(sum(t.numel() * t.element_size() for t in out_host))
 
-    t = torch.tensor([dev_ms, e2e_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms / n_e2e, e2e_sync_ms, burst_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_sync_ms = t.tolist()
-    total_pairs = B * world * args.steps
-    value = total_pairs / (dev_ms * 1e-3)
-    e2e_val = total_pairs / (e2e_ms * 1e-3)
+    dev_ms, e2e_step_ms, e2e_sync_ms, burst_ms = t.tolist()
+    n_timed = args.steps * inner
+    value = B * world * n_timed / (dev_ms * 1e-3)
+    e2e_val = B * world / (e2e_step_ms * 1e-3)
+
+    # ---------------------------------------------------------------- training (BASELINE config 5) in the same line
+    train = None
+    if not args.no_train and precision != "cudnn":
+        del stream
+        train = train_object(P, torch, dist, dev, rank, world, B, max(5, min(args.steps, 20)), 3, precision)
 
     if rank == 0:
-        # ------------------------------------------------------------ roofline: level-2 cost volume, live
-        peak, peak_src = _peaks()
-        h2, w2, C = H // 4, W // 4, 32
-        g = torch.Generator(device=dev).manual_seed(0)
-        f0 = torch.randn((B, h2, w2, C), device=dev, generator=g)
-        f1 = torch.randn((B, h2, w2, C), device=dev, generator=g)
-        # destination = the 81-channel slot of level 2's 148-wide estimator concat buffer, as in the model
-        cv = torch.empty((B, h2, w2, 148), device=dev)[..., :81]
-        for _ in range(5):
-            P.ops.cost_volume(f0, f1, out=cv)
-        n_cv = 30
-        cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_cv)]
-        for s, e in cev:
-            flush.fill_(2)
-            s.record()
-            P.ops.cost_volume(f0, f1, out=cv)
-            e.record()
-        torch.cuda.synchronize()
-        cv_us = 1e3 * float(np.mean([s.elapsed_time(e) for s, e in cev]))
-        alg_bytes = 4 * h2 * w2 * (2 * C + 81) * B
-        achieved = alg_bytes / (cv_us * 1e-6) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "cost_volume_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        roofline = {"kernel": "cost_volume_tma_kernel<true> level-2 112x256x32 -> 81-ch slot of the 148-wide concat buffer, B=%d" % B, "bound": "hbm",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "us_per_launch": cv_us, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}
-        # ------------------------------------------------------------ the kernel that dominates the step by time (77 %):
-        # the halo-resident tcgen05 conv, measured on the level-4 estimator layer 128 -> 128 (tensor roofline)
-        from pwcnet_b200 import ops_tc
-        xc = torch.randn((B, h2, w2, 128), device=dev, generator=g)
-        kc = torch.randn((3, 3, 128, 128), device=dev, generator=g) / 34.0
-        bc = torch.zeros(128, device=dev)
-        yc = torch.empty((B, h2, w2, 128), device=dev)
-        wpk = ops_tc.pack_weights_f16(kc)
-        for _ in range(3):
-            ops_tc.conv3x3_tc_f16(xc, wpk, bc, 128, 128, alpha=0.1, out=yc)
-        cev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
-        for s_, e_ in cev2:
-            flush.fill_(3)
-            s_.record()
-            ops_tc.conv3x3_tc_f16(xc, wpk, bc, 128, 128, alpha=0.1, out=yc)
-            e_.record()
-        torch.cuda.synchronize()
-        conv_us = 1e3 * float(np.mean([s_.elapsed_time(e_) for s_, e_ in cev2]))
-        conv_flops = 2.0 * 9 * 128 * 128 * B * h2 * w2
-        tpeak, tpeak_src = _tensor_peak()
-        conv_tflops = conv_flops / (conv_us * 1e-6) / 1e12
-        roofline_conv = {"kernel": "conv3x3_tc_halo_kernel, level-4 estimator conv 128->128 at 112x256, B=%d (3 x fp16 split: every "
-                                   "useful flop costs 3 fp16 MMA flops)" % B,
-                         "bound": "tensor", "achieved": conv_tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": conv_tflops / tpeak,
-                         "mma_issue_tflops": 3 * conv_tflops, "mma_issue_frac": 3 * conv_tflops / tpeak, "traffic": None,
-                         "us_per_launch": conv_us, "algorithmic_flops": conv_flops, "peak_source": tpeak_src}
+        roofline = roofline_cost_volume(P, torch, dev, B)
+        roof_conv = roofline_conv(P, torch, dev, B, flush)
         cpu_baseline = None
         if not args.no_cpu_baseline:
             pps, cores, _ = cpu_oracle_pairs_per_s(args.cpu_pairs)
@@ -505,21 +647,28 @@ def main():
                                       "weights); restated reference on torch-CPU, not TensorFlow 1.8"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dev_ms / n_timed, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if precision in ("fp32", "cudnn") else precision, "data": "synthetic",
             "config": {"workload": "PWCDCNet(use_dc=False) inference, batch=%d synthetic 448x1024 pairs per GPU "
                                    "(BASELINE config 2 shape), random-init glorot weights" % B,
                        "global_batch": B * world, "parallelism": f"dp{world} (no data-path collective)",
-                       "conv_path": precision, "cuda_graph": True,
-                       "l2": "256 MiB write between timed iterations; per-step CUDA-event intervals summed"},
+                       "conv_path": precision, "cuda_graph": True, "inner_repeats": inner,
+                       "timed_region": f"each of the {args.steps} timed steps runs {inner} passes over the batch ({n_timed} passes, "
+                                       f"{dev_ms / 1e3:.2f} s of device time); value and ms_per_step are per pass",
+                       "l2": "256 MiB write between timed passes; per-pass CUDA-event intervals summed"},
+            "burst_value": B * world * args.steps / (burst_ms * 1e-3),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps,
-                    "sync_value": total_pairs / (e2e_sync_ms * 1e-3),
-                    "what": "InferenceStream(model, depth=2).submit/collect: pinned host images -> flows_final + 5 pyramid "
-                            "flows in pinned host memory, H2D/D2H of neighbouring requests overlapped with the forward; "
-                            "sync_value = one PWCDCNet.__call__ at a time, no overlap"},
-            "gpu_launches": args.steps * model.launches_per_forward(),
-            "clocks": clocks, "roofline": roofline, "roofline_conv": roofline_conv, "cpu_baseline": cpu_baseline,
+                    "ms_per_step": e2e_step_ms, "wall_ms_per_step": 1e3 * wall_e2e / n_e2e, "steps_timed": n_e2e,
+                    "h2d_gbs_per_rank": h2d / (e2e_step_ms * 1e-3) / 1e9, "d2h_gbs_per_rank": d2h / (e2e_step_ms * 1e-3) / 1e9,
+                    "numa_node_bound": numa,
+                    "sync_value": B * world * args.steps / (e2e_sync_ms * 1e-3),
+                    "what": "InferenceStream(model, depth=2).submit/collect: pinned host uint8 images (the reference's input before "
+                            "its /255.0) -> flows_final + 5 pyramid flows (float32) in pinned host memory, H2D/D2H of neighbouring "
+                            "requests overlapped with the forward; sync_value = one PWCDCNet.__call__(host uint8) at a time + D2H, no overlap"},
+            "gpu_launches": n_timed * (model.launches_per_forward() + 0),
+            "probe": {"sha256_16": digest, "equal_across_ranks": probe_equal,
+                      "what": "flows_final of a fixed seed-0 uint8 pair (1x448x1024), identical on every rank and for every --gpus"},
+            "clocks": clocks, "roofline": roofline, "roofline_conv": roof_conv, "cpu_baseline": cpu_baseline, "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

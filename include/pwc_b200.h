@@ -203,6 +203,11 @@ int pwc_conv3x3_tc_f16_dgrad(const float* dy, int dy_cs, const void* w_rot_packe
  * h = fp16(x), l = fp16(x - h): the same bytes as the fp32 row, dense (B,H,W,2C) fp16.
  * ------------------------------------------------------------------------------------------------ */
 
+/* uint8 RGB images -> float32 in [0,1]: y[i] = lut256[x[i]].  Replaces the reference's host-side
+ * `np.array(images)/255.0` + float32 placeholder feed (test.py:31-33, train.py:122, test_continuous.py:49); with
+ * lut256[v] = float32(float64(v)/255.0) the result is bit-identical to that feed.  x, y 16-byte aligned. */
+int pwc_u8_to_f32_fwd(const unsigned char* x, float* y, long long n, const float* lut256, void* stream);
+
 /* scale * x (fp32, channel stride x_cs) -> split tensor `out`; if copy != NULL the UNSCALED x is also copied to `copy`
  * (fp32, channel stride copy_cs: the f0 slot of the estimator's concat buffer, modules.py:262).  C % 32 == 0.
  * The pipeline passes scale = 1/C for f0, so the mean over channels (modules.py:181) costs nothing later. */
@@ -218,6 +223,13 @@ int pwc_warp_split_fwd(const float* x, int x_cs, const float* flow, int flow_cs,
  * produced with scale 1/C.  fp32-class (3 x fp16 products, fp32 accumulation). */
 int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float* out, int out_cs,
                               int B, int H, int W, int C, float scale, float alpha, void* stream);
+
+/* Same kernel writing the head of a concat-buffer pixel row in whole 32-byte sectors: words [0,81) = cost volume,
+ * [81,83) = tail[b,y,x,0:2] (the up-sampled flow the estimator concatenates next, modules.py:262-264; zeros when tail is
+ * NULL), [83,88) = zeros (padding channels whose weights are zero).  Partial-sector writes of 324-byte runs cost this
+ * kernel 30 % on B200; out must be 32-byte aligned and out_cs a multiple of 8 floats, >= 88. */
+int pwc_cost_volume_split_slot_fwd(const void* f0s, const void* f1s, float* out, int out_cs, const float* tail,
+                                   int B, int H, int W, int C, float scale, float alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv2DBackpropFilter on tcgen05 (wgrad_tc.cu).  Operands are first transposed to channel-major fp16 planes

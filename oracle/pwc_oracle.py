@@ -486,3 +486,72 @@ def synthetic_textured_pair(B: int, H: int, W: int, seed: int = 0, max_disp: flo
         im1[b] = ((src[y0, x0] * (1 - wx) + src[y0, x1] * wx) * (1 - wy) +
                   (src[y1, x0] * (1 - wx) + src[y1, x1] * wx) * wy).astype(np.float32)
     return im0, im1, flow
+
+
+# ------------------------------------------------------------------ PWCNet (model.py:6-71), repaired
+# The reference's `PWCNet` cannot be instantiated.  This restates its INTENDED design with the minimal
+# repairs listed in SURVEY 2.4 -- parity unpinned against the reference (nothing executable, no checkpoint, no GraphDef):
+#   model.py:19  OpticalFlowEstimator(self.batch_norm, ...)  -> OpticalFlowEstimator(name=...) (batch_norm False, modules.py:210)
+#   model.py:23  self.context (never set)                    -> 'final' (one ContextNetwork applied at output_level)
+#   model.py:50  of_estimators[l](feature_0, cost, flow)      -> kept as written: positional (cost, x, flow) = (feature_0,
+#                                                               cost, flow), i.e. concat [feature_0, cost, flow] (modules.py:216)
+#   model.py:56  context_net(feature, flow)                  -> context_net(flow, feature) (ContextNetwork.__call__(flows, features))
+def pwcnet_layer_table(num_levels: int = 6, search_range: int = 4, output_level: int = 4, name: str = "pwcnet"):
+    rows, cin = [], 3
+    for l in range(num_levels):                      # FeaturePyramidExtractor (modules.py:19-39): two convs per level
+        for j in range(2):
+            idx = 2 * l + j
+            rows.append((f"{name}/fp_extractor/conv2d" + (f"_{idx}" if idx else ""), cin, PYRAMID_FILTERS[l]))
+            cin = PYRAMID_FILTERS[l]
+    ncv = (2 * search_range + 1) ** 2
+    deep_first = PYRAMID_FILTERS[:num_levels][::-1]
+    for l in range(output_level + 1):                # OpticalFlowEstimator (modules.py:208-224)
+        c = deep_first[l] + ncv + 2
+        for i, f in enumerate(ESTIMATOR_FILTERS + [2]):
+            rows.append((f"{name}/optflow_{l}/conv2d" + (f"_{i}" if i else ""), c, f))
+            c = f
+    cin = 2 + ESTIMATOR_FILTERS[-1]
+    for i, cout in enumerate([128, 128, 128, 96, 64, 32, 2]):
+        rows.append((f"{name}/context/conv2d" + (f"_{i}" if i else ""), cin, cout))
+        cin = cout
+    return rows
+
+
+def pwcnet_glorot_weights(seed: int = 2, gain: float = 1.0, bias_scale: float = 0.0, **kw) -> Dict[str, np.ndarray]:
+    rng = np.random.default_rng(seed)
+    W = {}
+    for scope, cin, cout in pwcnet_layer_table(**kw):
+        lim = math.sqrt(6.0 / (9 * cin + 9 * cout)) * gain
+        W[scope + "/kernel"] = rng.uniform(-lim, lim, size=(3, 3, cin, cout)).astype(np.float32)
+        W[scope + "/bias"] = (rng.standard_normal(cout) * bias_scale).astype(np.float32)
+    return W
+
+
+def pwcnet_forward(W, images_0, images_1, num_levels: int = 6, search_range: int = 4, warp_type: str = "bilinear",
+                   output_level: int = 4, name: str = "pwcnet", dtype=torch.float32):
+    """PWCNet.__call__ (model.py:30-67) with the repairs above -> (finalflow, flows, pyramid_0)."""
+    def pyramid(x):
+        feats = []
+        for l in range(num_levels):                  # modules.py:31-36
+            x = leaky_relu(_conv(W, f"{name}/fp_extractor", 2 * l, x, stride=2), 0.1)
+            x = leaky_relu(_conv(W, f"{name}/fp_extractor", 2 * l + 1, x, stride=1), 0.1)
+            feats.append(x)
+        return feats[::-1]
+    pyr0, pyr1 = pyramid(_t(images_0, dtype)), pyramid(_t(images_1, dtype))
+    flows, flow = [], None
+    for l, (f0, f1) in enumerate(zip(pyr0, pyr1)):
+        b, h, w, _ = f0.shape
+        flow = torch.zeros((b, h, w, 2), dtype=dtype) if l == 0 else resize_bilinear_legacy(flow, h, w) * 2   # model.py:42-45
+        f1w = warping_layer(f1, flow, warp_type)                                                              # model.py:48
+        cost = cost_volume(f0, f1w, search_range)
+        x = torch.cat([f0, cost, flow], dim=3)                                                                 # modules.py:216 via model.py:50
+        for i in range(len(ESTIMATOR_FILTERS)):
+            x = leaky_relu(_conv(W, f"{name}/optflow_{l}", i, x), 0.2)                                        # _conv_block, modules.py:7-15
+        feature = x
+        flow = _conv(W, f"{name}/optflow_{l}", len(ESTIMATOR_FILTERS), feature)                               # modules.py:222
+        if l == output_level:
+            flow = context_network(W, flow, feature, f"{name}/context")                                        # model.py:55-56 (repaired)
+        flows.append(flow)
+        if l == output_level:
+            upscale = 2 ** (num_levels - output_level)
+            return resize_bilinear_legacy(flow, h * upscale, w * upscale) * upscale, flows, pyr0               # model.py:62-64,67

@@ -51,6 +51,9 @@ struct CvSplitParams {
     float alpha, scale;
     int vec;
     unsigned long long* dbg;   // optional timeline (clock64), 64 slots per CTA: 8 events x 8 tiles
+    int exp;                   // experiments (PWC_CV_EXP, wrong results): 1 = no global stores, 2 = no copy-out at all
+    int wide;                  // quad kernel: also write words [81, 88) of every pixel = [tail 2 | zeros 5] (whole 32-byte sectors)
+    const float* tail;         // wide: dense (B,H,W,2) source of words 81, 82 (the up-sampled flow); NULL = zeros
 };
 
 #define S_DBG(ev, tile) do { if (dbg && (tile) < 8) dbg[(ev) * 8 + (tile)] = clock64(); } while (0)
@@ -260,23 +263,28 @@ cost_volume_split_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Quadrant-block kernel (round 2; PWC_CV_SPLIT=quad).  Same band GEMM, re-tiled so that the band
-// extraction never touches shared memory:
+// Quadrant-block kernel (round 2, the default).  Same band GEMM, re-tiled so that the band extraction
+// needs no shared-memory scatter and the output leaves through dedicated store warps:
 //   tile = 16 image rows x 8 pixels (M = 128, A row m = 8 y + x: ONE TMA box), f1 patch 24 rows x 16 columns = 384
 //   accumulator columns n = 16 fy + fx in two halves of 192 (one box, two N = 192 MMAs per K step).
 //   TMEM lane quadrant q = image rows 4q .. 4q+3 of the tile (a 4 x 8 pixel block, lane = 8 yy + xx): the block's
 //   windows span patch rows 4q .. 4q+11 x all 16 columns = 192 CONTIGUOUS accumulator columns [64 q, 64 q + 192).
-//   Two epilogue warps per quadrant: role 0 extracts displacement rows dv = 0..4 (patch rows 4q..4q+7, 128 columns),
-//   role 1 dv = 5..8 (patch rows 4q+5..4q+11, 112 columns), with tcgen05.ld x64/x32/x16 straight into registers;
-//   the accumulator is handed back to the MMA warp as soon as the loads have landed.  The lane-dependent window
-//   offset (yy in 0..3, xx in 0..7) is resolved by a 5-stage select network IN REGISTERS (shift by 4/2/1 columns, then
-//   2/1 rows; ~300 SEL per lane and role) instead of the predicated shared-memory scatter of the kernel above (which is
-//   shared-memory-port bound: TMA writes 64 KB + UMMA operand reads 120 KB + scatter per 128-pixel tile).  Only the
-//   81 useful values per pixel go through shared memory, once, to leave as coalesced 324-byte runs (two slab buffers:
-//   one named barrier per tile and quadrant).
-// Measured on B200 (profiles/r02_tmem_ld_bench.log): tcgen05.ld is latency- not bandwidth-bound (218 clk per isolated
-// x16 load, >450 B/clk/SM with 16 warps x 4 loads in flight), fma.rn.f32x2 issues at the FMA-pipe rate of scalar FFMA,
-// and 16-byte-per-lane stores of 324-byte runs are 2.2x slower than coalesced float4 units -- hence the slab.
+//   warp 0      TMA producer (2 stages of 64 KB)
+//   warp 1      MMA issuer (h.h + l.h + h.l, 12 x M128 N192 K16 per 32 channels)
+//   warps 2-13  extract: three per quadrant, ROLE r owns patch rows 4r .. 4r+3 (64 columns, ONE tcgen05.ld x64 straight
+//               into registers; the accumulator goes back to the MMA warp as soon as the load has landed).  The
+//               lane-dependent window offset is resolved without a scatter: columns by a 3-stage select network in
+//               registers (shift by xx = 4/2/1: 31 SEL per row), rows by the ADDRESS of the store into the lane's slab row
+//               (word 9 (J - yy) + i = lane-constant base + immediate; rows outside the window predicated off).
+//               (rows outside the window predicated off); scale and the leaky slope are applied to those nine words.
+//   warps 14-15 store: two quadrants each, a pure copy slab (32 pixels x 81 words, pitch 84, two buffers) -> HBM as
+//               float4 units of the 324-byte pixel runs (20 float4 + the 81st word per pixel; lane <-> unit map and
+//               offsets precomputed once, 10 LDS.128 in flight per batch).
+// Measured on B200 (profiles/r02_tmem_ld_bench.log, r02_cv_quad_timeline.log): tcgen05.ld is latency- not bandwidth-bound
+// (218 clk per isolated x16 load, >450 B/clk/SM with 16 warps x 4 loads in flight); fma.rn.f32x2 issues at the FMA-pipe
+// rate of scalar FFMA; 16-byte-per-lane stores of 324-byte runs are 2.2x slower than coalesced float4 units (hence the
+// slab); with the extract warps also doing the copy-out a tile took 4.6 k clk of which the copy-out 3.3 k (2.2 k without
+// the global stores: the LDS / FP / STG chain of a warp that owns the accumulator hand-over), 1.7 k without it.
 constexpr int Q_TW = 8, Q_TH = 16, Q_FW = Q_TW + 8, Q_FH = Q_TH + 8;
 constexpr int Q_M = Q_TW * Q_TH;                   // 128
 constexpr int Q_NH = Q_FW * (Q_FH / 2);            // 192 columns per accumulator half
@@ -284,9 +292,10 @@ constexpr uint32_t Q_F0_BYTES = Q_M * 128;         // 16 KB
 constexpr uint32_t Q_F1_BYTES = 2 * Q_NH * 128;    // 48 KB
 constexpr uint32_t Q_STAGE_BYTES = Q_F0_BYTES + Q_F1_BYTES;
 constexpr int Q_STAGES = 2;
-constexpr int Q_EPI_WARPS = 8;
-constexpr int Q_THREADS = 64 + Q_EPI_WARPS * 32;   // 320
-constexpr int Q_PITCH = 84;                        // slab row pitch in words: STS.128 / LDS.128 conflict-free
+constexpr int Q_ROLES = 3;                            // extract warps per quadrant, four patch rows (one tcgen05.ld x64) each
+constexpr int Q_XWARPS = 4 * Q_ROLES, Q_SWARPS = 2;   // 16 warps = 4 per SM sub-partition: 128 registers per thread
+constexpr int Q_THREADS = 64 + (Q_XWARPS + Q_SWARPS) * 32;   // 512
+constexpr int Q_PITCH = 84;                        // slab row pitch in words (LDS.128 of a pixel run is conflict-free)
 constexpr uint32_t Q_SLAB_BYTES = 4 * 32 * Q_PITCH * 4;   // one buffer: 4 quadrants x 32 pixels
 constexpr uint32_t Q_SMEM_BYTES = Q_STAGES * Q_STAGE_BYTES + 2 * Q_SLAB_BYTES + 1024;
 static_assert(Q_SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -314,18 +323,16 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
                  : "r"(taddr));
 }
 
-// Band extraction of one epilogue warp: ROLE r owns patch rows J = 6r .. 6r+5 of the quadrant's twelve (96 accumulator
-// columns, tcgen05.ld x64 + x32).  Row J holds displacement row dv = J - yy of the lane's pixel (if 0 <= dv <= 8): its 16
-// words are shifted left by xx in registers (three select stages, 31 SEL) and the nine window words are stored to the
-// lane's slab row at word 9 dv + i = (9 J + i) - 9 yy, i.e. a lane-constant base plus an immediate: the ROW shift costs
-// nothing, rows outside the lane's window are predicated off.  (bank of the store = 20 xx - 9 yy + const mod 32: the 32
-// lanes hit 32 different banks.)
-template <int ROLE>
-__device__ __forceinline__ void q_extract(uint32_t tq, int q, int lane, uint32_t* slab_lane, uint32_t bar_acce) {
-    uint32_t v[96];
-    const uint32_t t0 = tq + (uint32_t)((4 * q + 6 * ROLE) * Q_FW);
-    tmem_ld64(t0, v);
-    tmem_ld32(t0 + 64, v + 64);
+// Band extraction of one extract warp: ROLE r owns patch rows J = 4r .. 4r+3 of the quadrant's twelve -- ONE tcgen05.ld
+// x64, so nothing can be scheduled between the TMEM reads and the hand-back of the accumulator (with two loads per warp
+// ptxas sank the second one below the select network of the first and the MMA warp waited ~900 clk instead of ~400).  Row J
+// holds displacement row dv = J - yy of the lane's pixel (if 0 <= dv <= 8): its 16 words are shifted left by xx in
+// registers and the nine window words are scaled, passed through the leaky slope and stored to the lane's slab row at word
+// 9 dv + i = (9 J + i) - 9 yy.  (Bank of the store = 20 xx - 9 yy + const mod 32: the 32 lanes hit 32 different banks.)
+template <int ROLE, bool SCALED>
+__device__ __forceinline__ void q_extract(uint32_t tq, int q, int lane, uint32_t* slab_lane, uint32_t bar_acce, float scale, float alpha) {
+    uint32_t v[64];
+    tmem_ld64(tq + (uint32_t)((4 * q + 4 * ROLE) * Q_FW), v);
     tmem_ld_wait();
     // the accumulator words are in registers: hand this warp's share of the accumulator back to the MMA warp
     tc_fence_before();
@@ -335,9 +342,8 @@ __device__ __forceinline__ void q_extract(uint32_t tq, int q, int lane, uint32_t
     const int yy = lane >> 3;
     uint32_t* dst = slab_lane - 9 * yy;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        constexpr int dummy = 0; (void)dummy;
-        const int J = 6 * ROLE + j;
+    for (int j = 0; j < 4; ++j) {
+        const int J = 4 * ROLE + j;
         uint32_t a[12], b[10], w[9];
 #pragma unroll
         for (int i = 0; i < 12; ++i) a[i] = c4 ? v[16 * j + i + 4] : v[16 * j + i];
@@ -346,8 +352,13 @@ __device__ __forceinline__ void q_extract(uint32_t tq, int q, int lane, uint32_t
 #pragma unroll
         for (int i = 0; i < 9; ++i) w[i] = c1 ? b[i + 1] : b[i];
         if ((unsigned)(J - yy) <= 8u) {
+            // scale (1/C unless folded into the f0 operand) and the leaky slope, on the nine useful words only
 #pragma unroll
-            for (int i = 0; i < 9; ++i) dst[9 * J + i] = w[i];
+            for (int i = 0; i < 9; ++i) {
+                float x = __uint_as_float(w[i]);
+                if (SCALED) x *= scale;
+                dst[9 * J + i] = __float_as_uint(fmaxf(x, alpha * x));
+            }
         }
     }
 }
@@ -357,12 +368,14 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    __shared__ __align__(8) uint64_t bars[2 * Q_STAGES + 2];   // full[2], empty[2], acc_full, acc_empty
+    // full[2], empty[2], acc_full, acc_empty, slab_full[4 quadrants][2 buffers], slab_empty[4][2]
+    __shared__ __align__(8) uint64_t bars[2 * Q_STAGES + 2 + 16];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[Q_STAGES]);
     const uint32_t bar_accf = smem_u32(&bars[2 * Q_STAGES]), bar_acce = smem_u32(&bars[2 * Q_STAGES + 1]);
+    const uint32_t bar_sfull = smem_u32(&bars[2 * Q_STAGES + 2]), bar_sempty = smem_u32(&bars[2 * Q_STAGES + 10]);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Q_STAGES; ++s) {
@@ -370,7 +383,11 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_accf, 1);
-        mbar_init(bar_acce, Q_EPI_WARPS);
+        mbar_init(bar_acce, Q_XWARPS);
+        for (int i = 0; i < 8; ++i) {
+            mbar_init(bar_sfull + 8 * i, Q_ROLES);   // the extract warps of the quadrant
+            mbar_init(bar_sempty + 8 * i, 1);     // its store warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -415,7 +432,7 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
                     const int s = it % Q_STAGES;
                     mbar_wait(bar_full + 8 * s, (it / Q_STAGES) & 1);
                     S_DBG(1, it);
-                    if (c == 0 && tcount > 0) mbar_wait(bar_acce, (tcount - 1) & 1);   // all eight warps hold the previous tile in registers
+                    if (c == 0 && tcount > 0) mbar_wait(bar_acce, (tcount - 1) & 1);   // all extract warps hold the previous tile in registers
                     S_DBG(2, it);
                     tc_fence_after();
                     const uint32_t st = base + s * Q_STAGE_BYTES;
@@ -437,80 +454,111 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
                 }
             }
         }
-    } else {
-        // ===================== epilogue: warps 2..9, TMEM lane quadrant q = warp % 4, role = (warp - 2) / 4 ==========
+    } else if (warp < 2 + Q_XWARPS) {
+        // ===================== extract: warps 2..13, TMEM lane quadrant q = warp % 4, role = (warp - 2) / 4 ==========
         const int q = warp & 3, role = (warp - 2) >> 2;
-        float* slabs = reinterpret_cast<float*>(base_ptr + Q_STAGES * Q_STAGE_BYTES);
+        uint32_t* slabs = reinterpret_cast<uint32_t*>(base_ptr + Q_STAGES * Q_STAGE_BYTES);
         const uint32_t tq = tmem_acc + ((uint32_t)(q * 32) << 16);
-        const int cs = p.out_cs;
         const float scale = p.scale, alpha = p.alpha;
+        const bool scaled = scale != 1.0f;
         int tcount = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
-            const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
-            const int x0 = tx * Q_TW, y0 = ty * Q_TH;
-            float* slab = slabs + (tcount & 1) * (Q_SLAB_BYTES / 4) + q * 32 * Q_PITCH;
+            const int buf = tcount & 1;
+            uint32_t* slab_lane = slabs + buf * (Q_SLAB_BYTES / 4) + (q * 32 + lane) * Q_PITCH;
+            if (tcount >= 2) mbar_wait(bar_sempty + 8 * (2 * q + buf), ((tcount >> 1) - 1) & 1);   // the store warp has drained this buffer
             mbar_wait(bar_accf, tcount & 1);
             if (warp == 2 && lane == 0) S_DBG(3, tcount);
             tc_fence_after();
-            if (role == 0) q_extract<0>(tq, q, lane, reinterpret_cast<uint32_t*>(slab) + lane * Q_PITCH, bar_acce);
-            else           q_extract<1>(tq, q, lane, reinterpret_cast<uint32_t*>(slab) + lane * Q_PITCH, bar_acce);
+            if (scaled) {
+                if (role == 0)      q_extract<0, true>(tq, q, lane, slab_lane, bar_acce, scale, alpha);
+                else if (role == 1) q_extract<1, true>(tq, q, lane, slab_lane, bar_acce, scale, alpha);
+                else                q_extract<2, true>(tq, q, lane, slab_lane, bar_acce, scale, alpha);
+            } else {
+                if (role == 0)      q_extract<0, false>(tq, q, lane, slab_lane, bar_acce, scale, alpha);
+                else if (role == 1) q_extract<1, false>(tq, q, lane, slab_lane, bar_acce, scale, alpha);
+                else                q_extract<2, false>(tq, q, lane, slab_lane, bar_acce, scale, alpha);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sfull + 8 * (2 * q + buf));
             if (warp == 2 && lane == 0) S_DBG(4, tcount);
             if (warp == 6 && lane == 0) S_DBG(5, tcount);
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // both roles of the quadrant have filled the slab
-            if (warp == 2 && lane == 0) S_DBG(6, tcount);
-            // ---- slab -> HBM: this warp writes image rows y0 + 4q + 2 role + {0, 1}, 8 pixels each (slab rows 16 role ..
-            //      + 15), one pixel (324 contiguous bytes) per step: lanes 0..19 a float4 each, lane 20 the 81st word.
-            //      scale and the leaky slope are applied here.
-            const int ybase = y0 + 4 * q + 2 * role;
-            const int npx = min(Q_TW, p.W - x0);
-            const float* srow = slab + 16 * role * Q_PITCH;
-            float* grow = p.out + (((size_t)b * p.H + ybase) * p.W + x0) * cs;
-            const size_t gpitch = (size_t)p.W * cs;
-            if (p.vec) {
-                const float* sl = srow + 4 * lane;
-                float* gl = grow + 4 * lane;
-                if (lane < 20) {
+        }
+    } else {
+        // ===================== store: the last two warps: quadrants {0, 1} and {2, 3} =====================
+        // A pure copy (scale and leaky were applied by the extract warps): per quadrant 32 pixels x 20 float4 units, unit
+        // u = lane + 32 m -> pixel u / 20, unit u % 20 (20 iterations, no divergence), then the 81st word of pixel = lane.
+        const float* slabs = reinterpret_cast<const float*>(base_ptr + Q_STAGES * Q_STAGE_BYTES);
+        const int cs = p.out_cs;
+        const int gpitch = p.W * cs;                          // < 2^31 / H (checked by the launcher)
+        int soff[20], goff[20];                               // words into the quadrant's slab / bytes from the quadrant's first pixel
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        if (ybase + half < p.H) {
-                            float4 w[8];
+        for (int m = 0; m < 20; ++m) {
+            const int u = lane + 32 * m, pix = u / 20, k = u - pix * 20;
+            soff[m] = pix * Q_PITCH + 4 * k;
+            goff[m] = ((pix >> 3) * gpitch + (pix & 7) * cs + 4 * k) * 4;
+        }
+        const int goff_t = ((lane >> 3) * gpitch + (lane & 7) * cs + 80) * 4;
+        int tcount = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+            const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+            const int buf = tcount & 1;
+#pragma unroll 1
+            for (int qi = 0; qi < 2; ++qi) {
+                const int q = 2 * (warp - 2 - Q_XWARPS) + qi;
+                const int x0 = tx * Q_TW, y0 = ty * Q_TH + 4 * q;
+                const float* slab = slabs + buf * (Q_SLAB_BYTES / 4) + q * 32 * Q_PITCH;
+                char* gbase = reinterpret_cast<char*>(p.out + (((size_t)b * p.H + y0) * p.W + x0) * cs);
+                const bool interior = y0 + 4 <= p.H && x0 + Q_TW <= p.W;
+                const bool lane_ok = y0 + (lane >> 3) < p.H && x0 + (lane & 7) < p.W;      // pixel = lane (81st word, wide tail)
+                float2 tl = make_float2(0.f, 0.f);
+                if (p.wide && p.tail && lane_ok)       // issued before the wait: the 8 bytes arrive while the slab fills
+                    tl = __ldg(reinterpret_cast<const float2*>(p.tail) + (((size_t)b * p.H + y0 + (lane >> 3)) * p.W + x0 + (lane & 7)));
+                mbar_wait(bar_sfull + 8 * (2 * q + buf), (tcount >> 1) & 1);
+                if (warp == 2 + Q_XWARPS && lane == 0 && qi == 0) S_DBG(6, tcount);
+                if (!(p.exp & 2)) {
+                    if (p.vec && interior && !(p.exp & 1)) {
 #pragma unroll
-                            for (int x = 0; x < 8; ++x) w[x] = *reinterpret_cast<const float4*>(sl + (8 * half + x) * Q_PITCH);
+                        for (int m0 = 0; m0 < 20; m0 += 10) {
+                            float4 w[10];
 #pragma unroll
-                            for (int x = 0; x < 8; ++x) {
-                                w[x].x *= scale; w[x].y *= scale; w[x].z *= scale; w[x].w *= scale;
-                                w[x].x = fmaxf(w[x].x, alpha * w[x].x); w[x].y = fmaxf(w[x].y, alpha * w[x].y);
-                                w[x].z = fmaxf(w[x].z, alpha * w[x].z); w[x].w = fmaxf(w[x].w, alpha * w[x].w);
-                                if (x < npx) *reinterpret_cast<float4*>(gl + half * gpitch + (size_t)x * cs) = w[x];
+                            for (int i = 0; i < 10; ++i) w[i] = *reinterpret_cast<const float4*>(slab + soff[m0 + i]);
+#pragma unroll
+                            for (int i = 0; i < 10; ++i) *reinterpret_cast<float4*>(gbase + goff[m0 + i]) = w[i];
+                        }
+                        if (p.wide) {        // complete the pixel's sectors: words [80, 88) = [cv 80 | tail 2 | zeros 5]
+                            *reinterpret_cast<float4*>(gbase + goff_t) = make_float4(slab[lane * Q_PITCH + 80], tl.x, tl.y, 0.f);
+                            *reinterpret_cast<float4*>(gbase + goff_t + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else {
+                            *reinterpret_cast<float*>(gbase + goff_t) = slab[lane * Q_PITCH + 80];
+                        }
+                    } else if (p.vec && !(p.exp & 1)) {
+#pragma unroll
+                        for (int m = 0; m < 20; ++m) {              // edge tile: per-unit validity
+                            const int pix = (lane + 32 * m) / 20;
+                            if (y0 + (pix >> 3) < p.H && x0 + (pix & 7) < p.W)
+                                *reinterpret_cast<float4*>(gbase + goff[m]) = *reinterpret_cast<const float4*>(slab + soff[m]);
+                        }
+                        if (lane_ok) {
+                            if (p.wide) {
+                                *reinterpret_cast<float4*>(gbase + goff_t) = make_float4(slab[lane * Q_PITCH + 80], tl.x, tl.y, 0.f);
+                                *reinterpret_cast<float4*>(gbase + goff_t + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            } else {
+                                *reinterpret_cast<float*>(gbase + goff_t) = slab[lane * Q_PITCH + 80];
                             }
                         }
-                    }
-                } else if (lane == 20) {
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        if (ybase + half < p.H) {
-                            float w[8];
-#pragma unroll
-                            for (int x = 0; x < 8; ++x) w[x] = sl[(8 * half + x) * Q_PITCH] * scale;
-#pragma unroll
-                            for (int x = 0; x < 8; ++x)
-                                if (x < npx) gl[half * gpitch + (size_t)x * cs] = fmaxf(w[x], alpha * w[x]);
+                    } else if (!(p.exp & 1)) {
+#pragma unroll 1
+                        for (int pix = 0; pix < 32; ++pix) {            // scalar path: destination not 16-byte aligned
+                            if (y0 + (pix >> 3) >= p.H || x0 + (pix & 7) >= p.W) continue;
+                            float* gp = reinterpret_cast<float*>(gbase) + (size_t)(pix >> 3) * gpitch + (pix & 7) * cs;
+                            for (int k = lane; k < 81; k += 32) gp[k] = slab[pix * Q_PITCH + k];
                         }
                     }
                 }
-            } else {
-#pragma unroll 1
-                for (int pix = 0; pix < 16; ++pix) {                // scalar path: destination not 16-byte aligned
-                    const int yy = ybase + (pix >> 3), xx = pix & 7;
-                    if (yy >= p.H || xx >= npx) continue;
-                    float* g = grow + (pix >> 3) * gpitch + (size_t)xx * cs;
-                    for (int k = lane; k < 81; k += 32) {
-                        const float w = srow[pix * Q_PITCH + k] * scale;
-                        g[k] = fmaxf(w, alpha * w);
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sempty + 8 * (2 * q + buf));
             }
-            if (warp == 2 && lane == 0) S_DBG(7, tcount);
+            if (warp == 2 + Q_XWARPS && lane == 0) S_DBG(7, tcount);
         }
     }
     __syncwarp();
@@ -645,8 +693,24 @@ extern "C" int pwc_warp_split_fwd(const float* x, int x_cs, const float* flow, i
     return 0;
 }
 
+static int cv_split_launch(const void* f0s, const void* f1s, float* out, int out_cs, int wide, const float* tail,
+                           int B, int H, int W, int C, float scale, float alpha, void* stream);
+
 extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float* out, int out_cs,
                                          int B, int H, int W, int C, float scale, float alpha, void* stream) {
+    return cv_split_launch(f0s, f1s, out, out_cs, 0, nullptr, B, H, W, C, scale, alpha, stream);
+}
+
+extern "C" int pwc_cost_volume_split_slot_fwd(const void* f0s, const void* f1s, float* out, int out_cs, const float* tail,
+                                              int B, int H, int W, int C, float scale, float alpha, void* stream) {
+    PWC_REQUIRE(out_cs >= 88 && (out_cs & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0, PWC_E_ALIGN,
+                "cost_volume_split_slot: the slot must be 32-byte aligned with a pixel pitch that is a multiple of 8 floats, >= 88");
+    PWC_REQUIRE(!tail || (reinterpret_cast<uintptr_t>(tail) & 7u) == 0, PWC_E_ALIGN, "cost_volume_split_slot: tail must be 8-byte aligned");
+    return cv_split_launch(f0s, f1s, out, out_cs, 1, tail, B, H, W, C, scale, alpha, stream);
+}
+
+static int cv_split_launch(const void* f0s, const void* f1s, float* out, int out_cs, int wide, const float* tail,
+                           int B, int H, int W, int C, float scale, float alpha, void* stream) {
     PWC_REQUIRE(f0s && f1s && out, PWC_E_BADARG, "cost_volume_split: null pointer");
     PWC_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && out_cs >= 81 && scale > 0.f, PWC_E_BADARG, "cost_volume_split: bad dims");
     PWC_REQUIRE((C % 32) == 0 && aligned16(f0s) && aligned16(f1s), PWC_E_ALIGN,
@@ -655,7 +719,7 @@ extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float
     {   // quadrant-block tiling (16 x 8 pixel tiles, register-resident band extraction): default; PWC_CV_SPLIT=scatter
         // selects the round-1 kernel below
         const char* ev = getenv("PWC_CV_SPLIT");   // read per call: the tests switch variants in one process
-        if (!(ev && !strcmp(ev, "scatter"))) {
+        if (wide || !(ev && !strcmp(ev, "scatter"))) {
             PWC_REQUIRE(make_map_split(&tm0, f0s, B, H, W, C, Q_TW, Q_TH) && make_map_split(&tm1, f1s, B, H, W, C, Q_FW, Q_FH),
                         PWC_E_BADARG, "cost_volume_split: cuTensorMapEncodeTiled failed");
             CvSplitParams p{};
@@ -666,11 +730,14 @@ extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float
             p.total_tiles = (int)tiles;
             p.alpha = alpha; p.scale = scale;
             p.vec = aligned16(out) && (out_cs & 3) == 0;
+            p.wide = wide; p.tail = tail;
+            PWC_REQUIRE((long long)H * W * out_cs < (1ll << 31), PWC_E_BADARG, "cost_volume_split: image too large for 32-bit offsets");
             cudaError_t e = cudaFuncSetAttribute(cost_volume_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
             if (e != cudaSuccess) { set_error("cost_volume_split(quad): smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             const int nsm = sm_count();
             const int grid = p.total_tiles < nsm ? p.total_tiles : nsm;
             static unsigned long long* qdbg = nullptr;
+            if (const char* ex = getenv("PWC_CV_EXP")) p.exp = atoi(ex);
             if (getenv("PWC_CV_DEBUG")) {
                 if (!qdbg) cudaMalloc(&qdbg, 256 * 64 * 8);
                 cudaMemsetAsync(qdbg, 0, 256 * 64 * 8, (cudaStream_t)stream);
@@ -683,7 +750,7 @@ extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float
                 static int printed = 0;
                 if (printed++ < 2) {
                     unsigned long long h[64];
-                    const char* names[8] = {"tma_issue", "full_seen", "acce_seen", "accf_seen(w2)", "extract_done(w2)", "extract_done(w6)", "bar_passed(w2)", "stored(w2)"};
+                    const char* names[8] = {"tma_issue", "full_seen", "acce_seen", "accf_seen(w2)", "extract_done(w2)", "extract_done(w6)", "slab_full(w10)", "stored(w10)"};
                     cudaMemcpy(h, p.dbg + 64 * (grid / 2), 64 * 8, cudaMemcpyDeviceToHost);
                     fprintf(stderr, "[cv_quad dbg] cta %d (clk from first tma issue), tiles 0..7\n", grid / 2);
                     for (int e = 0; e < 8; ++e) {

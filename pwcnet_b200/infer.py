@@ -32,7 +32,8 @@ class Tester(object):
         img1, img2 = (factor_crop(_imread(p)) for p in args.input_images)
         if img1.shape != img2.shape:
             raise ValueError(f"input images differ in shape: {img1.shape} vs {img2.shape}")
-        self.images = (np.array([img1, img2]) / 255.0).astype(np.float32)      # (2, h, w, 3), test.py:32
+        # uint8 (2, h, w, 3): the `/255.0` of test.py:32 runs on the device (bit-identical, see PWCDCNet.__call__)
+        self.images = np.ascontiguousarray(np.array([img1, img2]))
         self.model = PWCDCNet()
         if args.resume is not None:
             print(f'Loading learned model from checkpoint {args.resume}')

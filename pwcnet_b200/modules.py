@@ -31,6 +31,63 @@ def _layer(params: Dict[str, torch.Tensor], scope: str, idx: int):
         raise KeyError(f"missing variable {e} (expected the reference's checkpoint naming)") from None
 
 
+def _conv_block(filters, kernel_size=(3, 3), strides=(1, 1), batch_norm=False, *, kernel=None, bias=None):
+    """modules.py:7-15: Conv2D(filters, 3x3, strides, 'same') [+ BatchNormalization] + leaky_relu(0.2).  TF creates the
+    variables when the closure runs; here they are passed in (`kernel` HWIO with `filters` output channels, `bias`).
+    batch_norm=True is not supported (no caller in the reference sets it: modules.py:210 fixes it to False)."""
+    if tuple(kernel_size) != (3, 3):
+        raise NotImplementedError("_conv_block: only 3x3 kernels exist in the reference")
+    if batch_norm:
+        raise NotImplementedError("_conv_block: batch_norm=True has no caller in the reference (modules.py:210)")
+
+    def f(x):
+        if kernel is None or bias is None or kernel.shape[3] != filters:
+            raise ValueError("_conv_block: pass kernel (3,3,Cin,filters) and bias (filters,)")
+        return ops.conv3x3(x, kernel, bias, stride=strides[0], alpha=0.2)
+    return f
+
+
+class FeaturePyramidExtractor(object):
+    """Feature pyramid extractor module simple/original (modules.py:19-39): two convs per level."""
+
+    def __init__(self, num_levels=6, name='fp_extractor', params=None, scope='pwcnet'):
+        self.num_levels = num_levels
+        self.filters = list(PYRAMID_FILTERS)
+        self.name = name
+        self.params = params
+        self.scope = f"{scope}/{name}"
+
+    def __call__(self, x, reuse=True):
+        feature_pyramid = []
+        for l in range(self.num_levels):
+            for j, stride in enumerate((2, 1)):
+                k, b = _layer(self.params, self.scope, 2 * l + j)
+                x = ops.conv3x3(x, k, b, stride=stride, alpha=0.1)
+            feature_pyramid.append(x)
+        return feature_pyramid[::-1]
+
+
+class OpticalFlowEstimator(object):
+    """Optical flow estimator module simple/original (modules.py:208-224): concat [cost, x, flow] -> five
+    _conv_block (leaky 0.2) -> 2-channel conv; returns (feature, flow)."""
+
+    def __init__(self, name='of_estimator', params=None, scope='pwcnet'):
+        self.batch_norm = False
+        self.name = name
+        self.params = params
+        self.scope = f"{scope}/{name}"
+
+    def __call__(self, cost, x, flow):
+        x = torch.cat([cost, x, flow.to(torch.float32)], dim=3)
+        for i, f in enumerate(ESTIMATOR_FILTERS):
+            k, b = _layer(self.params, self.scope, i)
+            x = _conv_block(f, (3, 3), (1, 1), self.batch_norm, kernel=k, bias=b)(x)
+        feature = x
+        k, b = _layer(self.params, self.scope, len(ESTIMATOR_FILTERS))
+        flow = ops.conv3x3(feature, k, b, alpha=1.0)
+        return feature, flow
+
+
 class FeaturePyramidExtractor_custom(object):
     """Feature pyramid extractor module (modules.py:42-71)."""
 

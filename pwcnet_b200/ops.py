@@ -219,9 +219,12 @@ def warp_split(x, flow, flow_scale: float = 1.0, warp_type: str = "bilinear", ou
     return out
 
 
-def cost_volume_split(f0s, f1s, alpha: float = 0.1, out=None, prescaled: bool = False):
+def cost_volume_split(f0s, f1s, alpha: float = 0.1, out=None, prescaled: bool = False, slot: bool = False, tail=None):
     """CostVolumeLayer.__call__ (modules.py:189-204, search_range 4) from split operands, on the tensor cores.
-    prescaled=True: f0s was produced by split_f16(..., scale=1/C), the kernel skips the 1/C multiply."""
+    prescaled=True: f0s was produced by split_f16(..., scale=1/C), the kernel skips the 1/C multiply.
+    slot=True: `out` is the head of a concat-buffer pixel row and the kernel writes whole 32-byte sectors: words [0,81) =
+    cost volume, [81,83) = `tail` (dense (B,H,W,2), e.g. the up-sampled flow; zeros if None), [83,88) = zeros; `out` must be
+    the (B,H,W,81) view at channel 0 of a 32-byte aligned buffer whose pixel pitch is a multiple of 8 floats, >= 88."""
     for t, nm in ((f0s, "f0s"), (f1s, "f1s")):
         if t.dtype != torch.float16 or t.dim() != 4 or not t.is_cuda or not t.is_contiguous():
             raise ValueError(f"cost_volume_split: {nm} must be a contiguous CUDA fp16 (B,H,W,2C) split tensor")
@@ -229,10 +232,45 @@ def cost_volume_split(f0s, f1s, alpha: float = 0.1, out=None, prescaled: bool = 
         raise ValueError("cost_volume_split: operand shapes differ or 2C is not a multiple of 64")
     B, H, W, C2 = f0s.shape
     if out is None:
-        out = new_nhwc(B, H, W, 81, f0s.device)
+        out = new_nhwc(B, H, W, 81, f0s.device, cs=88 if slot else None)
     Bo, Ho, Wo, Co, out_cs = _nhwc(out, "out")
     if (Bo, Ho, Wo, Co) != (B, H, W, 81):
         raise ValueError("cost_volume_split: out shape mismatch")
-    check(lib().pwc_cost_volume_split_fwd(f0s.data_ptr(), f1s.data_ptr(), out.data_ptr(), out_cs, B, H, W, C2 // 2,
-                                          1.0 if prescaled else 2.0 / C2, float(alpha), _stream()), "pwc_cost_volume_split_fwd")
+    scale = 1.0 if prescaled else 2.0 / C2
+    if slot:
+        tp = 0
+        if tail is not None:
+            if tuple(tail.shape) != (B, H, W, 2) or tail.dtype != torch.float32 or not tail.is_cuda or not tail.is_contiguous():
+                raise ValueError("cost_volume_split: tail must be a contiguous CUDA float32 (B,H,W,2) tensor")
+            tp = tail.data_ptr()
+        check(lib().pwc_cost_volume_split_slot_fwd(f0s.data_ptr(), f1s.data_ptr(), out.data_ptr(), out_cs, tp, B, H, W, C2 // 2,
+                                                   scale, float(alpha), _stream()), "pwc_cost_volume_split_slot_fwd")
+    else:
+        if tail is not None:
+            raise ValueError("cost_volume_split: tail needs slot=True")
+        check(lib().pwc_cost_volume_split_fwd(f0s.data_ptr(), f1s.data_ptr(), out.data_ptr(), out_cs, B, H, W, C2 // 2,
+                                              scale, float(alpha), _stream()), "pwc_cost_volume_split_fwd")
+    return out
+
+
+_U8_LUT = {}
+
+
+def u8_lut(device) -> torch.Tensor:
+    """float32(float64(v) / 255.0) for v = 0..255: the values the reference's `images/255.0` feed holds."""
+    key = str(device)
+    if key not in _U8_LUT:
+        import numpy as np
+        _U8_LUT[key] = torch.from_numpy((np.arange(256, dtype=np.float64) / 255.0).astype(np.float32)).to(device)
+    return _U8_LUT[key]
+
+
+def u8_to_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """uint8 images -> float32 in [0,1], bit-identical to the reference's host-side /255.0 (test.py:31-33)."""
+    if not (x.is_cuda and out.is_cuda) or x.dtype != torch.uint8 or out.dtype != torch.float32:
+        raise TypeError("u8_to_f32: x must be a CUDA uint8 tensor and out a CUDA float32 tensor")
+    if not (x.is_contiguous() and out.is_contiguous()) or x.numel() != out.numel():
+        raise ValueError("u8_to_f32: x and out must be contiguous and of equal size")
+    check(lib().pwc_u8_to_f32_fwd(x.data_ptr(), out.data_ptr(), x.numel(), u8_lut(x.device).data_ptr(), _stream()),
+          "pwc_u8_to_f32_fwd")
     return out

@@ -19,11 +19,19 @@ import torch
 
 
 class InferenceStream:
-    def __init__(self, model, depth: int = 2):
+    """`outputs` selects what travels back to the host: "final" (flows_final, full resolution) and/or "pyramid" (the five
+    per-scale flows -- all the reference's test.py fetches, test.py:51).  Images may be float32 RGB/255 or uint8 RGB bytes
+    (then the reference's host-side `/255.0` runs on the device, bit-identically, and a quarter of the bytes cross PCIe)."""
+
+    def __init__(self, model, depth: int = 2, outputs=("final", "pyramid")):
         if depth < 1:
             raise ValueError("depth must be >= 1")
+        outputs = tuple(outputs)
+        if not outputs or any(o not in ("final", "pyramid") for o in outputs):
+            raise ValueError("outputs must be a non-empty subset of ('final', 'pyramid')")
         self.model = model
         self.depth = depth
+        self.outputs = outputs
         self.dev = model.device
         self.s_in = torch.cuda.Stream(device=self.dev)
         self.s_out = torch.cuda.Stream(device=self.dev)
@@ -32,73 +40,82 @@ class InferenceStream:
         self._next = 0
         self._pending = {}
 
-    def _alloc(self, B, H, W):
+    def _alloc(self, B, H, W, dtype):
         plan = self.model.plan(B, H, W)
-        outs = [plan.flows_final] + list(plan.flows)
+        outs = ([plan.flows_final] if "final" in self.outputs else []) + (list(plan.flows) if "pyramid" in self.outputs else [])
         self._slots = []
         for _ in range(self.depth):
             self._slots.append(dict(
-                in_dev=torch.empty((2 * B, H, W, 3), dtype=torch.float32, device=self.dev),
+                in_dev=torch.empty((2 * B, H, W, 3), dtype=dtype, device=self.dev),
                 out_dev=[torch.empty_like(t) for t in outs],
                 out_host=[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs],
                 ev_in=torch.cuda.Event(), ev_taken=torch.cuda.Event(), ev_fwd=torch.cuda.Event(),
                 ev_out=torch.cuda.Event(), used=False, ticket=None))
-        self._shape = (B, H, W)
+        self._shape = (B, H, W, dtype)
 
     @staticmethod
     def _host(a, name):
         if isinstance(a, np.ndarray):
-            if a.dtype != np.float32:
-                raise TypeError(f"{name}: dtype must be float32")
+            if a.dtype not in (np.float32, np.uint8):
+                raise TypeError(f"{name}: dtype must be float32 or uint8")
             a = torch.from_numpy(np.ascontiguousarray(a))
-        if not isinstance(a, torch.Tensor) or a.is_cuda or a.dtype != torch.float32 or a.dim() != 4:
-            raise TypeError(f"{name}: expected a float32 host array/tensor of shape (B,H,W,3)")
+        if not isinstance(a, torch.Tensor) or a.is_cuda or a.dtype not in (torch.float32, torch.uint8) or a.dim() != 4:
+            raise TypeError(f"{name}: expected a float32 or uint8 host array/tensor of shape (B,H,W,3)")
         return a
 
     def submit(self, images_0, images_1) -> int:
         i0, i1 = self._host(images_0, "images_0"), self._host(images_1, "images_1")
-        if i0.shape != i1.shape:
-            raise ValueError("images_0 and images_1 differ in shape")
-        B, H, W, _ = i0.shape
-        if self._shape != (B, H, W):
-            self.drain()
-            self._alloc(B, H, W)
-        ticket = self._next
-        self._next += 1
-        sl = self._slots[ticket % self.depth]
-        if sl["used"] and sl["ticket"] in self._pending:
-            raise RuntimeError(f"slot still holds uncollected ticket {sl['ticket']}: collect() it first (depth={self.depth})")
-        cur = torch.cuda.current_stream(self.dev)
-        # ---- H2D on the input stream (waits until the previous user of this slot was consumed)
-        with torch.cuda.stream(self.s_in):
+        if i0.shape != i1.shape or i0.dtype != i1.dtype:
+            raise ValueError("images_0 and images_1 differ in shape or dtype")
+        B, H, W, C = i0.shape
+        with torch.cuda.device(self.dev):
+            if self._shape != (B, H, W, i0.dtype):
+                self.model._check_shape(B, H, W, C)          # before any allocation
+                if self._pending:
+                    raise RuntimeError("submit: input shape/dtype changed while tickets are pending; collect() them first")
+                self._alloc(B, H, W, i0.dtype)
+            ticket = self._next
+            self._next += 1
+            sl = self._slots[ticket % self.depth]
+            if sl["used"] and sl["ticket"] in self._pending:
+                raise RuntimeError(f"slot still holds uncollected ticket {sl['ticket']}: collect() it first (depth={self.depth})")
+            cur = torch.cuda.current_stream(self.dev)
+            # ---- H2D on the input stream (waits until the previous user of this slot was consumed)
+            with torch.cuda.stream(self.s_in):
+                if sl["used"]:
+                    self.s_in.wait_event(sl["ev_taken"])
+                sl["in_dev"][:B].copy_(i0, non_blocking=True)
+                sl["in_dev"][B:].copy_(i1, non_blocking=True)
+                sl["ev_in"].record(self.s_in)
+            # ---- forward on the caller's stream
+            cur.wait_event(sl["ev_in"])
+            flows_final, pyr = self.model._run_device(sl["in_dev"], B, H, W)
+            sl["ev_taken"].record(cur)
             if sl["used"]:
-                self.s_in.wait_event(sl["ev_taken"])
-            sl["in_dev"][:B].copy_(i0, non_blocking=True)
-            sl["in_dev"][B:].copy_(i1, non_blocking=True)
-            sl["ev_in"].record(self.s_in)
-        # ---- forward on the caller's stream
-        cur.wait_event(sl["ev_in"])
-        flows_final, pyr = self.model._run_device(sl["in_dev"], B, H, W)
-        sl["ev_taken"].record(cur)
-        if sl["used"]:
-            cur.wait_event(sl["ev_out"])            # previous D2H out of this slot's staging has finished
-        for d, s in zip(sl["out_dev"], [flows_final] + list(pyr)):
-            d.copy_(s, non_blocking=True)
-        sl["ev_fwd"].record(cur)
-        # ---- D2H on the output stream
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(sl["ev_fwd"])
-            for h, d in zip(sl["out_host"], sl["out_dev"]):
-                h.copy_(d, non_blocking=True)
-            sl["ev_out"].record(self.s_out)
-        sl["used"], sl["ticket"] = True, ticket
-        self._pending[ticket] = sl
+                cur.wait_event(sl["ev_out"])            # previous D2H out of this slot's staging has finished
+            srcs = ([flows_final] if "final" in self.outputs else []) + (list(pyr) if "pyramid" in self.outputs else [])
+            for d, s in zip(sl["out_dev"], srcs):
+                d.copy_(s, non_blocking=True)
+            sl["ev_fwd"].record(cur)
+            # ---- D2H on the output stream
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(sl["ev_fwd"])
+                for h, d in zip(sl["out_host"], sl["out_dev"]):
+                    h.copy_(d, non_blocking=True)
+                sl["ev_out"].record(self.s_out)
+            sl["used"], sl["ticket"] = True, ticket
+            self._pending[ticket] = sl
         return ticket
 
-    def collect(self, ticket: int) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    def collect(self, ticket: int):
+        """-> (flows_final, flows_pyramid) as pinned host tensors (valid until the slot is reused); an entry that was not
+        requested through `outputs` is None."""
         sl = self._pending.pop(ticket)
         sl["ev_out"].synchronize()
-        return sl["out_host"][0], sl["out_host"][1:]
+        oh = sl["out_host"]
+        final = oh[0] if "final" in self.outputs else None
+        pyr = (oh[1:] if "final" in self.outputs else oh) if "pyramid" in self.outputs else None
+        return final, pyr
 
     def drain(self):
         for t in list(self._pending):
@@ -106,8 +123,8 @@ class InferenceStream:
 
 
 class TrainStream:
-    """Input side of the training loop (the reference feeds its step from a prefetching tf.data pipeline,
-    train.py:33-47): `submit()` starts the H2D copy of a (pinned) host batch into one of `depth` device staging sets on
+    """Input side of the training loop (the reference feeds its step from a torch DataLoader with worker processes and
+    pinned batches, train.py:36-41): `submit()` starts the H2D copy of a (pinned) host batch into one of `depth` device staging sets on
     a copy stream, `step()` runs `Trainer.step` on the oldest staged batch.  With depth >= 2 the copy of batch i+1
     overlaps the step of batch i; the bytes moved per step are those of the synchronous `Trainer.step(host...)`.
 
@@ -130,13 +147,13 @@ class TrainStream:
         self._head = 0          # next slot to fill
         self._tail = 0          # next slot to train on
 
-    def _alloc(self, B, H, W):
-        self._slots = [dict(im0=torch.empty((B, H, W, 3), dtype=torch.float32, device=self.dev),
-                            im1=torch.empty((B, H, W, 3), dtype=torch.float32, device=self.dev),
+    def _alloc(self, B, H, W, dtype=torch.float32):
+        self._slots = [dict(im0=torch.empty((B, H, W, 3), dtype=dtype, device=self.dev),
+                            im1=torch.empty((B, H, W, 3), dtype=dtype, device=self.dev),
                             gt=torch.empty((B, H, W, 2), dtype=torch.float32, device=self.dev),
                             ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), used=False)
                        for _ in range(self.depth)]
-        self._shape = (B, H, W)
+        self._shape = (B, H, W, dtype)
         self._head = self._tail = 0
 
     def pending(self) -> int:
@@ -146,12 +163,12 @@ class TrainStream:
         i0, i1 = InferenceStream._host(images_0, "images_0"), InferenceStream._host(images_1, "images_1")
         gt = flows_gt if isinstance(flows_gt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(flows_gt))
         B, H, W, _ = i0.shape
-        if i1.shape != i0.shape or gt.is_cuda or gt.dtype != torch.float32 or tuple(gt.shape) != (B, H, W, 2):
-            raise ValueError("submit: images_0/images_1 (B,H,W,3) and flows_gt (B,H,W,2) must be float32 host arrays of one batch")
-        if self._shape != (B, H, W):
+        if i1.shape != i0.shape or i1.dtype != i0.dtype or gt.is_cuda or gt.dtype != torch.float32 or tuple(gt.shape) != (B, H, W, 2):
+            raise ValueError("submit: images_0/images_1 (B,H,W,3; float32 or uint8) and flows_gt (B,H,W,2) float32 must be host arrays of one batch")
+        if self._shape != (B, H, W, i0.dtype):
             if self.pending():
                 raise RuntimeError("submit: batch shape changed while staged batches are pending; step() them first")
-            self._alloc(B, H, W)
+            self._alloc(B, H, W, i0.dtype)
         if self.pending() >= self.depth:
             raise RuntimeError(f"submit: all {self.depth} staging sets hold batches that were not trained on yet")
         sl = self._slots[self._head % self.depth]

@@ -26,7 +26,7 @@ import torch
 
 from . import ops, ops_bwd
 from ._abi import PwcError
-from .model import PWCDCNet
+from .model import PWCDCNet, on_device
 from .modules import CONTEXT_DILATIONS, CONTEXT_FILTERS, ESTIMATOR_FILTERS
 
 DEFAULT_LOSS_WEIGHTS = [0.32, 0.08, 0.02, 0.01, 0.005]          # train.py:220-222
@@ -56,14 +56,19 @@ class Trainer(object):
         if model.use_dc:
             raise NotImplementedError("Trainer: use_dc=True is inference-only in this build (no reference checkpoint "
                                       "or BASELINE config trains it)")
-        if model.fuse_warp or getattr(model, "cv_split", False):
-            raise PwcError("Trainer needs the warped features in memory: construct the model with fuse_warp=False and "
-                           "the default cost-volume pipeline")
+        if model.fuse_warp:
+            raise PwcError("Trainer needs the warped features in memory: construct the model with fuse_warp=False")
+        if getattr(model, "cv_split", False):
+            # the backward pass reads the warped fp32 features the split (inference) pipeline never materialises: training
+            # runs the default cost-volume pipeline; plans made for inference are dropped
+            model.cv_split = False
+            model._plans.clear()
         if model.precision == "cudnn":
             raise PwcError("Trainer: the cuDNN baseline arm has no backward path")
         if len(weights) != model.output_level + 1:
             raise ValueError(f"need {model.output_level + 1} loss weights (one per pyramid flow), got {len(weights)}")
         self.model = model
+        self.device = model.device
         self.lr, self.gamma = float(lr), float(gamma)
         self.loss_weights = [float(w) for w in weights]
         self.beta1, self.beta2, self.eps = float(beta1), float(beta2), float(eps)
@@ -81,6 +86,18 @@ class Trainer(object):
             t = model.params[name]
             self.grads[name] = self.grad_flat[off:off + t.numel()].view(t.shape)
             off += t.numel()
+        self._var_off: Dict[str, tuple] = {}            # variable name -> (begin, end) in the flat buffers
+        off = 0
+        for name in model.var_names:
+            cnt = model.params[name].numel()
+            self._var_off[name] = (off, off + cnt)
+            off += cnt
+        # data parallel: the gradient all-reduce is issued in buckets as soon as a range of the flat gradient is final
+        # (context + estimator level by level, then pyramid level by level, deepest first) on a side stream, so only the
+        # last small bucket (pyramid level 1: 5 k floats) is exposed; skip_allreduce is a measurement switch (bench.py)
+        self.skip_allreduce = False
+        self._ar_stream = None
+        self._ar_works: list = []
         self._lr_t = torch.zeros(1, dtype=torch.float32, device=dev)
         self._scalars = torch.zeros(3, dtype=torch.float32, device=dev)   # multiscale loss, l2 term, epe
         self._gbufs: Dict[tuple, _Grads] = {}
@@ -199,6 +216,7 @@ class Trainer(object):
         return parts
 
     # ------------------------------------------------------------------ backward
+    @on_device
     def backward(self, p, flows_gt) -> None:
         """Gradient of multiscale_loss(flows_gt, flows_pyramid) w.r.t. every variable -> self.grad_flat
         (the regulariser's gradient gamma*var is added inside the Adam kernel)."""
@@ -271,6 +289,9 @@ class Trainer(object):
                                  warp_type=m.warp_type)
                 ops_bwd.resize_bilinear_bwd(flow_slot_g, g.flows[l - 1])
                 ops_bwd.resize_bilinear_bwd(gS[..., lv["off_feat"]:lv["off_feat"] + nf], g.tmp[l - 1][-1][..., 0:nf])
+            # this level's estimator (and, at the output level, the context network) gradients are final
+            last = f"{n}/context/conv2d_{len(CONTEXT_FILTERS) - 1}/bias" if l == L else f"{n}/optflow_{l}/conv2d_{nest}/bias"
+            self._allreduce_range(f"{n}/optflow_{l}/conv2d/kernel", last)
 
         # ---- feature pyramid, both images as one batch of 2B (modules.py:49-71)
         for lev in range(m.num_levels - 1, -1, -1):
@@ -284,6 +305,42 @@ class Trainer(object):
                 self._conv_bwd(scope(0), p.pyr[lev - 1][2], g.pyr[lev][0], g.pyr[lev - 1][2], stride=2, accumulate=True)
             else:
                 self._conv_bwd(scope(0), p.im, g.pyr[lev][0], None, stride=2)
+            self._allreduce_range(scope(0) + "/kernel", scope(2) + "/bias")
+
+    # ------------------------------------------------------------------ gradient all-reduce, bucketed
+    def _world(self) -> int:
+        import torch.distributed as dist
+        if self.skip_allreduce or not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.pg)
+
+    def _allreduce_range(self, first_var: str, last_var: str) -> None:
+        """SUM all-reduce of grad_flat[begin(first_var) : end(last_var)] on the side stream, after everything enqueued so far."""
+        if self._world() == 1:
+            return
+        import torch.distributed as dist
+        lo, hi = self._var_off[first_var][0], self._var_off[last_var][1]
+        cur = torch.cuda.current_stream(self.device)
+        if self._ar_stream is None:
+            self._ar_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self._ar_stream):
+            self._ar_stream.wait_event(ev)
+            self._ar_works.append(dist.all_reduce(self.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def _allreduce_finish(self) -> int:
+        """Wait (on the current stream) for the buckets; all-reduce the three logged scalars.  Returns the world size."""
+        world = self._world()
+        if world == 1:
+            return 1
+        import torch.distributed as dist
+        for w in self._ar_works:
+            w.wait()
+        self._ar_works.clear()
+        dist.all_reduce(self._scalars, op=dist.ReduceOp.SUM, group=self.pg)
+        self._scalars /= world
+        return world
 
     # ------------------------------------------------------------------ losses
     def _losses(self, p, flows_gt) -> None:
@@ -300,6 +357,7 @@ class Trainer(object):
         lr = piecewise_lr(self.global_step, self.lr, self.lr_boundaries)
         return lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
 
+    @on_device
     def forward_backward(self, images_0, images_1, flows_gt):
         m = self.model
         i0, i1 = m._as_input(images_0, "images_0"), m._as_input(images_1, "images_1")
@@ -311,26 +369,46 @@ class Trainer(object):
         if gt.dtype != torch.float32 or tuple(gt.shape) != (B, H, W, 2):
             raise ValueError(f"flows_gt must be float32 (B,H,W,2) = {(B, H, W, 2)}, got {tuple(gt.shape)} {gt.dtype}")
         gt = gt.to(m.device, non_blocking=True).contiguous()
+        if i0.dtype != i1.dtype:
+            raise ValueError("images_0 and images_1 differ in dtype")
         p = m.plan(B, H, W)
-        p.im[:B].copy_(i0, non_blocking=True)
-        p.im[B:].copy_(i1, non_blocking=True)
+        m._stage(p, i0, i1)              # float32 RGB/255 or uint8 bytes (train.py:122's /255.0 then happens on the device)
         m._launch(p)
         self._losses(p, gt)
         self.backward(p, gt)
         return p
 
+    @on_device
     def step(self, images_0, images_1, flows_gt):
         """One optimisation step (train.py:143-147).  Returns (loss, multiscale_loss, epe) as 0-dim CUDA tensors;
         with a process group the three scalars are averaged over ranks like the gradient."""
-        from .parallel import allreduce_gradients
         self.forward_backward(images_0, images_1, flows_gt)
-        world = allreduce_gradients(self.grad_flat, self._scalars, self.pg)      # the one data-path collective
+        world = self._allreduce_finish()                 # the one data-path collective: buckets issued during backward()
         t = self.global_step + 1
         self._lr_t.fill_(self.lr_t(t))
         ops_bwd.adam_step(self.model.flat, self.grad_flat, self.m, self.v, self._lr_t, self.beta1, self.beta2, self.eps,
                           gamma=self.gamma, grad_scale=1.0 / world)
         self.global_step += 1                                                         # train.py:91-92
         self.model.refresh_derived()
+        s = self._scalars
+        return s[0] + self.gamma * s[1], s[0].clone(), s[2].clone()
+
+    @on_device
+    def evaluate(self, images_0, images_1, flows_gt):
+        """Forward + losses without an update: what `sess.run(self.merged)` computes for the summaries and the
+        validation pass (train.py:128-141).  Returns (loss, multiscale_loss, epe) like step()."""
+        m = self.model
+        i0, i1 = m._as_input(images_0, "images_0"), m._as_input(images_1, "images_1")
+        B, H, W, C = i0.shape
+        m._check_shape(B, H, W, C)
+        gt = flows_gt if isinstance(flows_gt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(flows_gt))
+        if gt.dtype != torch.float32 or tuple(gt.shape) != (B, H, W, 2):
+            raise ValueError(f"flows_gt must be float32 (B,H,W,2) = {(B, H, W, 2)}, got {tuple(gt.shape)} {gt.dtype}")
+        gt = gt.to(m.device, non_blocking=True).contiguous()
+        p = m.plan(B, H, W)
+        m._stage(p, i0, i1)
+        m._launch(p)
+        self._losses(p, gt)
         s = self._scalars
         return s[0] + self.gamma * s[1], s[0].clone(), s[2].clone()
 
@@ -354,6 +432,7 @@ class Trainer(object):
         sd["beta2_power"] = np.array(self.beta2 ** (self.global_step + 1), np.float32)
         return sd
 
+    @on_device
     def load_state_dict(self, sd) -> None:
         """Inverse of state_dict(); `sd` may also be the prefix of a checkpoint bundle -- written by save() below or by
         the reference's tf.train.Saver (e.g. 'model_250.ckpt') -- or the path of a legacy `.npz` written by round-1
@@ -394,6 +473,7 @@ class Trainer(object):
         from .checkpoint import save_checkpoint
         save_checkpoint(path, self.state_dict())
 
+    @on_device
     def launches_per_step(self) -> int:
         """Kernel launches of ours in one training step, counted: C-ABI calls issued by one step (losses, backward,
         optimizer, derived-weight refresh) plus the forward's launches (replayed from its CUDA graph)."""
