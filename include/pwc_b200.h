@@ -203,6 +203,12 @@ int pwc_conv3x3_tc_f16_dgrad(const float* dy, int dy_cs, const void* w_rot_packe
  * h = fp16(x), l = fp16(x - h): the same bytes as the fp32 row, dense (B,H,W,2C) fp16.
  * ------------------------------------------------------------------------------------------------ */
 
+/* *count += number of non-finite values in the pixel-strided tensor x (n_pix pixels, C channels, channel stride x_cs).
+ * Range guard of the 3 x fp16 tensor-core path (operands must stay below 65504): an overflow anywhere upstream turns
+ * the last pyramid flow into NaN; the host raises when the counter is non-zero.  No reference counterpart (TF computes
+ * in fp32). */
+int pwc_count_nonfinite(const float* x, int x_cs, int C, long long n_pix, int* count, void* stream);
+
 /* uint8 RGB images -> float32 in [0,1]: y[i] = lut256[x[i]].  Replaces the reference's host-side
  * `np.array(images)/255.0` + float32 placeholder feed (test.py:31-33, train.py:122, test_continuous.py:49); with
  * lut256[v] = float32(float64(v)/255.0) the result is bit-identical to that feed.  x, y 16-byte aligned. */
@@ -224,11 +230,12 @@ int pwc_warp_split_fwd(const float* x, int x_cs, const float* flow, int flow_cs,
 int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float* out, int out_cs,
                               int B, int H, int W, int C, float scale, float alpha, void* stream);
 
-/* Same kernel writing the head of a concat-buffer pixel row in whole 32-byte sectors: words [0,81) = cost volume,
+/* Same kernel writing the HEAD of a concat-buffer pixel row in whole 32-byte sectors: words [0,81) = cost volume,
  * [81,83) = tail[b,y,x,0:2] (the up-sampled flow the estimator concatenates next, modules.py:262-264; zeros when tail is
- * NULL), [83,88) = zeros (padding channels whose weights are zero).  Partial-sector writes of 324-byte runs cost this
- * kernel 30 % on B200; out must be 32-byte aligned and out_cs a multiple of 8 floats, >= 88. */
-int pwc_cost_volume_split_slot_fwd(const void* f0s, const void* f1s, float* out, int out_cs, const float* tail,
+ * NULL), [83,88) = zeros (padding channels whose weights are zero).  head must be 88; out 32-byte aligned, out_cs a
+ * multiple of 8 floats.  Measured on B200 (profiles/r02_store_bw_bench.log, r02_cv_quad.log): partial-sector 324-byte runs
+ * cost this kernel 30 %; 352-byte runs at a 608-byte pitch write at 4.6 TB/s, contiguous lines at 6.6 TB/s. */
+int pwc_cost_volume_split_slot_fwd(const void* f0s, const void* f1s, float* out, int out_cs, int head, const float* tail,
                                    int B, int H, int W, int C, float scale, float alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -280,6 +280,10 @@ cost_volume_split_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid
 //   warps 14-15 store: two quadrants each, a pure copy slab (32 pixels x 81 words, pitch 84, two buffers) -> HBM as
 //               float4 units of the 324-byte pixel runs (20 float4 + the 81st word per pixel; lane <-> unit map and
 //               offsets precomputed once, 10 LDS.128 in flight per batch).
+// Variants measured slower (profiles/r02_cv_quad.log): the extract warps doing the copy-out themselves (33-36 us: their
+// select network is ALU-bound, the copy-out latency-bound, and the hand-back of the accumulator waits for the slowest warp),
+// 96-word heads / 128-byte-aligned slots (33 us), two extract roles with x64 + x32 loads (ptxas sinks the second load below
+// the select network of the first: the MMA warp waits 900 instead of 400 clk).
 // Measured on B200 (profiles/r02_tmem_ld_bench.log, r02_cv_quad_timeline.log): tcgen05.ld is latency- not bandwidth-bound
 // (218 clk per isolated x16 load, >450 B/clk/SM with 16 warps x 4 loads in flight); fma.rn.f32x2 issues at the FMA-pipe
 // rate of scalar FFMA; 16-byte-per-lane stores of 324-byte runs are 2.2x slower than coalesced float4 units (hence the
@@ -498,21 +502,33 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
             goff[m] = ((pix >> 3) * gpitch + (pix & 7) * cs + 4 * k) * 4;
         }
         const int goff_t = ((lane >> 3) * gpitch + (lane & 7) * cs + 80) * 4;
+        // tail words 81, 82 of pixel = lane (the up-sampled flow) of work item (tile t, quadrant q): loaded ONE ITEM AHEAD --
+        // a load issued just before its own copy loop costs the store warp its full latency (41 instead of 32 us per launch)
+        auto load_tail = [&](int t, int q) {
+            float2 r = make_float2(0.f, 0.f);
+            if (p.wide && p.tail && t < p.total_tiles) {
+                const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+                const int yy = ty * Q_TH + 4 * q + (lane >> 3), xx = tx * Q_TW + (lane & 7);
+                if (yy < p.H && xx < p.W) r = __ldg(reinterpret_cast<const float2*>(p.tail) + (((size_t)b * p.H + yy) * p.W + xx));
+            }
+            return r;
+        };
+        const int q_first = 2 * (warp - 2 - Q_XWARPS);
+        float2 tl_next = load_tail(blockIdx.x, q_first);
         int tcount = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
             const int buf = tcount & 1;
 #pragma unroll 1
             for (int qi = 0; qi < 2; ++qi) {
-                const int q = 2 * (warp - 2 - Q_XWARPS) + qi;
+                const int q = q_first + qi;
                 const int x0 = tx * Q_TW, y0 = ty * Q_TH + 4 * q;
                 const float* slab = slabs + buf * (Q_SLAB_BYTES / 4) + q * 32 * Q_PITCH;
                 char* gbase = reinterpret_cast<char*>(p.out + (((size_t)b * p.H + y0) * p.W + x0) * cs);
                 const bool interior = y0 + 4 <= p.H && x0 + Q_TW <= p.W;
                 const bool lane_ok = y0 + (lane >> 3) < p.H && x0 + (lane & 7) < p.W;      // pixel = lane (81st word, wide tail)
-                float2 tl = make_float2(0.f, 0.f);
-                if (p.wide && p.tail && lane_ok)       // issued before the wait: the 8 bytes arrive while the slab fills
-                    tl = __ldg(reinterpret_cast<const float2*>(p.tail) + (((size_t)b * p.H + y0 + (lane >> 3)) * p.W + x0 + (lane & 7)));
+                const float2 tl = tl_next;
+                tl_next = qi == 0 ? load_tail(t, q + 1) : load_tail(t + gridDim.x, q_first);
                 mbar_wait(bar_sfull + 8 * (2 * q + buf), (tcount >> 1) & 1);
                 if (warp == 2 + Q_XWARPS && lane == 0 && qi == 0) S_DBG(6, tcount);
                 if (!(p.exp & 2)) {
@@ -701,8 +717,9 @@ extern "C" int pwc_cost_volume_split_fwd(const void* f0s, const void* f1s, float
     return cv_split_launch(f0s, f1s, out, out_cs, 0, nullptr, B, H, W, C, scale, alpha, stream);
 }
 
-extern "C" int pwc_cost_volume_split_slot_fwd(const void* f0s, const void* f1s, float* out, int out_cs, const float* tail,
+extern "C" int pwc_cost_volume_split_slot_fwd(const void* f0s, const void* f1s, float* out, int out_cs, int head, const float* tail,
                                               int B, int H, int W, int C, float scale, float alpha, void* stream) {
+    PWC_REQUIRE(head == 88, PWC_E_BADARG, "cost_volume_split_slot: head must be 88");
     PWC_REQUIRE(out_cs >= 88 && (out_cs & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0, PWC_E_ALIGN,
                 "cost_volume_split_slot: the slot must be 32-byte aligned with a pixel pitch that is a multiple of 8 floats, >= 88");
     PWC_REQUIRE(!tail || (reinterpret_cast<uintptr_t>(tail) & 7u) == 0, PWC_E_ALIGN, "cost_volume_split_slot: tail must be 8-byte aligned");

@@ -227,3 +227,28 @@ extern "C" int pwc_u8_to_f32_fwd(const unsigned char* x, float* y, long long n, 
     PWC_CHECK_LAUNCH("u8_to_f32_kernel");
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------- range guard
+// The 3 x fp16 split of the tensor-core convs needs |activation|, |weight| < 65504; a larger value becomes +-inf in the
+// converter and NaN in the accumulator, and NaN then reaches every pixel downstream.  Counting the non-finite values of
+// the network's LAST pyramid flow (2 floats per quarter-resolution pixel) therefore detects an overflow anywhere
+// upstream at the cost of one tiny launch; the host raises when the counter is non-zero (PWCDCNet.check_finite).
+namespace pwc {
+__global__ void __launch_bounds__(256) count_nonfinite_kernel(const float* __restrict__ x, int x_cs, int C, size_t n_pix, int* __restrict__ count) {
+    int bad = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_pix; i += (size_t)gridDim.x * blockDim.x)
+        for (int c = 0; c < C; ++c) bad += !isfinite(x[i * x_cs + c]);
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, bad);
+}
+}  // namespace pwc
+
+extern "C" int pwc_count_nonfinite(const float* x, int x_cs, int C, long long n_pix, int* count, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(x && count && n_pix > 0 && C > 0 && x_cs >= C, PWC_E_BADARG, "count_nonfinite: bad arguments");
+    const size_t cap = (size_t)sm_count() * 4;
+    const int blocks = (int)(((size_t)n_pix + 255) / 256 < cap ? ((size_t)n_pix + 255) / 256 : cap);
+    count_nonfinite_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, C, (size_t)n_pix, count);
+    PWC_CHECK_LAUNCH("count_nonfinite_kernel");
+    return 0;
+}

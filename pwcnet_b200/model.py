@@ -114,12 +114,15 @@ class PWCDCNet(object):
         # PWC_NO_GRAPH=1: eager launches (ncu cannot profile the tf32 16-channel kernel as a graph node: LaunchFailed)
         self.use_cuda_graph = use_cuda_graph and not os.environ.get("PWC_NO_GRAPH")
         self.fuse_warp = fuse_warp
-        # cv_pipeline="split" (or PWC_CV_PIPELINE=split): inference-only experiment -- the levels with C % 32 == 0 run
-        # split_f16 / warp_split producers + the tcgen05 band-GEMM cost volume instead of warp + the CUDA-core kernel
-        # (slower with the round-1 split kernel, kept for the 4 x 32 re-tiling, PWC_CV_SPLIT=row32)
+        # cost-volume pipeline.  "split" (default for the tensor-core precisions, search range 4): the levels run split_f16 /
+        # warp_split producers (fp32 -> [h|l] fp16 rows) + the tcgen05 quadrant-block band GEMM writing whole sectors of the
+        # concat row; "default": warp + the CUDA-core TMA kernel (exact fp32 products; what training uses,
+        # because the backward pass needs the warped fp32 features).  PWC_CV_PIPELINE overrides the choice.
         cv_pipeline = os.environ.get("PWC_CV_PIPELINE") if cv_pipeline is None else cv_pipeline
         if cv_pipeline not in (None, "", "default", "split"):
             raise ValueError("cv_pipeline must be None, 'default' or 'split'")
+        if cv_pipeline in (None, ""):
+            cv_pipeline = "split" if precision in ("3xf16", "3xtf32", "tf32") else "default"
         self.cv_split = cv_pipeline == "split" and search_range == 4 and not fuse_warp
         if not torch.cuda.is_available():
             raise PwcError("PWCDCNet needs a CUDA device: the compute path is sm_100a CUDA only (no CPU fallback)")
@@ -194,12 +197,23 @@ class PWCDCNet(object):
         for l in range(self.output_level + 1):
             C = deep_first[l]
             up = 0 if l == 0 else len(prev_stack_perm)
-            # every slot starts on a multiple of 8 floats and the pixel pitch is a multiple of 8 floats: writers then cover
-            # whole 32-byte sectors (partial-sector writes cost the cost-volume kernel 30 % on B200)
-            off_flow = nd
-            off_f0 = _round_up(nd + (2 if l else 0), 8)
-            off_feat = off_f0 + C
-            cin_int = _round_up(off_feat + up, 8)
+            # split pipeline: every slot starts on a multiple of 8 floats and the pixel pitch is a multiple of 8 floats, so
+            # each writer (cost volume incl. the up-sampled flow, f0 copy, up-sampled features) covers whole 32-byte sectors
+            # of a pixel row: partial-sector writes cost the cost-volume kernel 30 % on B200.  The padding
+            # costs no MMA work: the K loop runs over 32-channel slices either way (148 -> 152 of 160 at level 2).
+            al = 8 if self.cv_split else 4
+            if self.cv_split:
+                # [cv 81 | zeros 7 | f0 C | features_up | flows_up 2 | pad 6]: the cost-volume kernel owns the first 88 words
+                # of a row outright (the up-sampled flow sits at the END of the row, written by the x2 resize)
+                off_f0 = _round_up(nd, al)
+                off_feat = off_f0 + C
+                off_flow = off_feat + up
+                cin_int = _round_up(off_flow + (2 if l else 0), al)
+            else:
+                off_flow = nd
+                off_f0 = _round_up(nd + (2 if l else 0), al)
+                off_feat = off_f0 + C
+                cin_int = _round_up(off_feat + up, al)
             perm = [-1] * cin_int
             for i in range(nd):
                 perm[i] = i
@@ -352,6 +366,10 @@ class PWCDCNet(object):
         p.graph = None
         p.im = torch.zeros((2 * B, H, W, 3), dtype=torch.float32, device=dev)
         p.im_u8 = None                      # uint8 staging for byte images (allocated on first use)
+        # range guard: number of non-finite values in the last pyramid flow of the latest forward (see check_finite)
+        p.nonfinite = torch.zeros(1, dtype=torch.int32, device=dev)
+        p.nf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        p.nf_event = None
         p.pyr = []
         h, w = H, W
         for l in range(self.num_levels):
@@ -380,12 +398,12 @@ class PWCDCNet(object):
                          if l and not self.fuse_warp and not split else None)
             p.f0s.append(torch.empty((B, ph, pw, 2 * lv["C"]), dtype=torch.float16, device=dev) if split else None)
             p.f1s.append(torch.empty((B, ph, pw, 2 * lv["C"]), dtype=torch.float16, device=dev) if split else None)
-            # split pipeline: the up-sampled flow lives in its own dense tensor (read by the warp) and the cost-volume kernel
-            # writes it into the concat slot together with the 81 cost channels (whole sectors)
+            # split pipeline: the cost-volume kernel writes the first 88 words of every concat row (81 cost channels + zero
+            # padding) in whole 32-byte sectors
             S = p.S[-1]
             slot_ok = split and S.stride(2) % 8 == 0 and (S.data_ptr() + 4 * (pre_total if self.use_dc else 0)) % 32 == 0 \
-                and lv["off_f0"] >= 88
-            p.flow_up.append(torch.empty((B, ph, pw, 2), dtype=torch.float32, device=dev) if (slot_ok and l) else None)
+                and lv["off_f0"] >= 88 and B * ph * pw > 1      # (a 1-pixel view hides its pixel pitch from the C ABI)
+            p.flow_up.append(None)
             p.cv_slot.append(bool(slot_ok))
         ph, pw = p.flows[-1].shape[1:3]
         p.ctx = [torch.empty((B, ph, pw, f), dtype=torch.float32, device=dev) for f in CONTEXT_FILTERS[:-1]]
@@ -397,6 +415,7 @@ class PWCDCNet(object):
     def _forward(self, p: _Plan) -> None:
         n, B = self.name, p.B
         nd = self._nd
+        p.nonfinite.zero_()
         x = p.im
         for l in range(self.num_levels):
             for j, stride in enumerate((2, 1, 1)):
@@ -472,6 +491,7 @@ class PWCDCNet(object):
                         self._conv(x, scope, p.flows[l], dilation=d, alpha=1.0, residual=flow_slot)
                 ops.resize_bilinear(p.flows[l], p.flows_final.shape[1], p.flows_final.shape[2], mul=20.0,
                                     out=p.flows_final)
+                ops.count_nonfinite(p.flows[l], p.nonfinite)
 
     @on_device
     def __call__(self, images_0, images_1, with_features=False, reuse=False):
@@ -483,6 +503,7 @@ class PWCDCNet(object):
             raise ValueError(f"images_0 {tuple(i0.shape)}/{i0.dtype} and images_1 {tuple(i1.shape)}/{i1.dtype} differ")
         B, H, W, C = i0.shape
         self._check_shape(B, H, W, C)
+        self.check_finite(wait=False)            # range guard: raise for an earlier forward that has finished meanwhile
         p = self.plan(B, H, W)
         self._stage(p, i0, i1)
         self._launch(p)
@@ -529,7 +550,36 @@ class PWCDCNet(object):
             p = self._plans[key] = self._make_plan(B, H, W)
         return p
 
+    def check_finite(self, wait: bool = True) -> None:
+        """Range guard of the 3 x fp16 tensor-core path.  Its operands must stay below 65504 in magnitude (trained PWC-Net
+        activations reach ~25); a larger activation or weight becomes inf in the fp32 -> fp16 split and NaN in
+        the accumulator, and the NaN reaches every pixel downstream.  Every forward therefore counts the non-finite values
+        of its last pyramid flow on the device; this method raises PwcError if a finished forward counted any.
+        wait=True synchronises with the latest forward of every input shape first; wait=False only looks at forwards that
+        have already finished (PWCDCNet.__call__ does that for the previous call, so an overflow never goes unnoticed for
+        more than one call; InferenceStream.collect checks its own request)."""
+        for p in self._plans.values():
+            if p.nf_event is None:
+                continue
+            if wait:
+                p.nf_event.synchronize()
+            elif not p.nf_event.query():
+                continue
+            if int(p.nf_host[0]) != 0:
+                n = int(p.nf_host[0])
+                p.nf_host[0] = 0
+                raise PwcError(f"{n} non-finite values in the flow of the last forward at {p.B}x{p.H}x{p.W}: activations or "
+                               f"weights left the fp16 range of precision='{self.precision}' (|x| < 65504) or the input holds "
+                               "inf/NaN; use precision='3xtf32' or 'fp32' for such weights")
+
     def _launch(self, p: _Plan) -> None:
+        self._launch_graph(p)
+        p.nf_host.copy_(p.nonfinite, non_blocking=True)
+        if p.nf_event is None:
+            p.nf_event = torch.cuda.Event()
+        p.nf_event.record(torch.cuda.current_stream(self.device))
+
+    def _launch_graph(self, p: _Plan) -> None:
         if self.use_cuda_graph and self.precision != "cudnn":
             if p.graph is None:
                 self._forward(p)                      # warm-up (also sets kernel attributes, packs weights)
@@ -573,6 +623,7 @@ class PWCDCNet(object):
             n += sum((2 if l == 0 else 1) for l, lv in enumerate(self._lv) if lv["C"] % 32 == 0)
         n += self.output_level * 2                    # up-sampling of flows and features
         n += len(CONTEXT_FILTERS) + 1                 # context + final x4 resize
+        n += 1                                        # range guard (count_nonfinite)
         return n
 
 

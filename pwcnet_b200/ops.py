@@ -219,12 +219,13 @@ def warp_split(x, flow, flow_scale: float = 1.0, warp_type: str = "bilinear", ou
     return out
 
 
-def cost_volume_split(f0s, f1s, alpha: float = 0.1, out=None, prescaled: bool = False, slot: bool = False, tail=None):
+def cost_volume_split(f0s, f1s, alpha: float = 0.1, out=None, prescaled: bool = False, slot=False, tail=None):
     """CostVolumeLayer.__call__ (modules.py:189-204, search_range 4) from split operands, on the tensor cores.
     prescaled=True: f0s was produced by split_f16(..., scale=1/C), the kernel skips the 1/C multiply.
     slot=True: `out` is the head of a concat-buffer pixel row and the kernel writes whole 32-byte sectors: words [0,81) =
     cost volume, [81,83) = `tail` (dense (B,H,W,2), e.g. the up-sampled flow; zeros if None), [83,88) = zeros; `out` must be
     the (B,H,W,81) view at channel 0 of a 32-byte aligned buffer whose pixel pitch is a multiple of 8 floats, >= 88."""
+    slot = 88 if slot else 0
     for t, nm in ((f0s, "f0s"), (f1s, "f1s")):
         if t.dtype != torch.float16 or t.dim() != 4 or not t.is_cuda or not t.is_contiguous():
             raise ValueError(f"cost_volume_split: {nm} must be a contiguous CUDA fp16 (B,H,W,2C) split tensor")
@@ -232,7 +233,7 @@ def cost_volume_split(f0s, f1s, alpha: float = 0.1, out=None, prescaled: bool = 
         raise ValueError("cost_volume_split: operand shapes differ or 2C is not a multiple of 64")
     B, H, W, C2 = f0s.shape
     if out is None:
-        out = new_nhwc(B, H, W, 81, f0s.device, cs=88 if slot else None)
+        out = new_nhwc(B, H, W, 81, f0s.device, cs=slot if slot else None)
     Bo, Ho, Wo, Co, out_cs = _nhwc(out, "out")
     if (Bo, Ho, Wo, Co) != (B, H, W, 81):
         raise ValueError("cost_volume_split: out shape mismatch")
@@ -243,7 +244,7 @@ def cost_volume_split(f0s, f1s, alpha: float = 0.1, out=None, prescaled: bool = 
             if tuple(tail.shape) != (B, H, W, 2) or tail.dtype != torch.float32 or not tail.is_cuda or not tail.is_contiguous():
                 raise ValueError("cost_volume_split: tail must be a contiguous CUDA float32 (B,H,W,2) tensor")
             tp = tail.data_ptr()
-        check(lib().pwc_cost_volume_split_slot_fwd(f0s.data_ptr(), f1s.data_ptr(), out.data_ptr(), out_cs, tp, B, H, W, C2 // 2,
+        check(lib().pwc_cost_volume_split_slot_fwd(f0s.data_ptr(), f1s.data_ptr(), out.data_ptr(), out_cs, slot, tp, B, H, W, C2 // 2,
                                                    scale, float(alpha), _stream()), "pwc_cost_volume_split_slot_fwd")
     else:
         if tail is not None:
@@ -274,3 +275,12 @@ def u8_to_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     check(lib().pwc_u8_to_f32_fwd(x.data_ptr(), out.data_ptr(), x.numel(), u8_lut(x.device).data_ptr(), _stream()),
           "pwc_u8_to_f32_fwd")
     return out
+
+
+def count_nonfinite(x: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
+    """count (int32 CUDA scalar) += number of non-finite values of the pixel-strided NHWC tensor x."""
+    B, H, W, C, cs = _nhwc(x, "x")
+    if count.dtype != torch.int32 or not count.is_cuda or count.numel() != 1:
+        raise TypeError("count_nonfinite: count must be a CUDA int32 scalar")
+    check(lib().pwc_count_nonfinite(x.data_ptr(), cs, C, B * H * W, count.data_ptr(), _stream()), "pwc_count_nonfinite")
+    return count

@@ -49,6 +49,7 @@ class InferenceStream:
                 in_dev=torch.empty((2 * B, H, W, 3), dtype=dtype, device=self.dev),
                 out_dev=[torch.empty_like(t) for t in outs],
                 out_host=[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs],
+                nf_dev=torch.zeros(1, dtype=torch.int32, device=self.dev), nf_host=torch.zeros(1, dtype=torch.int32).pin_memory(),
                 ev_in=torch.cuda.Event(), ev_taken=torch.cuda.Event(), ev_fwd=torch.cuda.Event(),
                 ev_out=torch.cuda.Event(), used=False, ticket=None))
         self._shape = (B, H, W, dtype)
@@ -96,12 +97,14 @@ class InferenceStream:
             srcs = ([flows_final] if "final" in self.outputs else []) + (list(pyr) if "pyramid" in self.outputs else [])
             for d, s in zip(sl["out_dev"], srcs):
                 d.copy_(s, non_blocking=True)
+            sl["nf_dev"].copy_(self.model.plan(B, H, W).nonfinite, non_blocking=True)      # range guard of this request
             sl["ev_fwd"].record(cur)
             # ---- D2H on the output stream
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(sl["ev_fwd"])
                 for h, d in zip(sl["out_host"], sl["out_dev"]):
                     h.copy_(d, non_blocking=True)
+                sl["nf_host"].copy_(sl["nf_dev"], non_blocking=True)
                 sl["ev_out"].record(self.s_out)
             sl["used"], sl["ticket"] = True, ticket
             self._pending[ticket] = sl
@@ -112,6 +115,10 @@ class InferenceStream:
         requested through `outputs` is None."""
         sl = self._pending.pop(ticket)
         sl["ev_out"].synchronize()
+        if int(sl["nf_host"][0]) != 0:
+            from ._abi import PwcError
+            raise PwcError(f"ticket {ticket}: {int(sl['nf_host'][0])} non-finite flow values: activations or weights left the fp16 "
+                           f"range of precision='{self.model.precision}' (see PWCDCNet.check_finite)")
         oh = sl["out_host"]
         final = oh[0] if "final" in self.outputs else None
         pyr = (oh[1:] if "final" in self.outputs else oh) if "pyramid" in self.outputs else None
@@ -181,6 +188,16 @@ class TrainStream:
             sl["ev_in"].record(self.s_in)
         sl["used"] = True
         self._head += 1
+
+    def discard(self) -> None:
+        """Drop the oldest staged batch without training on it (its staging set becomes reusable once the copy has landed)."""
+        if not self.pending():
+            raise RuntimeError("discard: no staged batch")
+        sl = self._slots[self._tail % self.depth]
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(sl["ev_in"])
+        sl["ev_done"].record(cur)
+        self._tail += 1
 
     def step(self):
         if not self.pending():

@@ -14,7 +14,7 @@ What the reference's graph does per step, and what runs here instead:
     (train.py:82-89), global_step += 1 afterwards (train.py:91-92) -> one Adam launch over the flat buffers
   * the derived kernels (internal channel order, packed tensor-core tiles) are refreshed in place
 
-Only `use_dc=False` (every BASELINE config and every reference checkpoint) is trainable here."""
+`use_dc=True` (train.py:203-207, modules.py:269-270) trains through the same kernels over the dense per-level buffers."""
 from __future__ import annotations
 
 import math
@@ -53,9 +53,6 @@ class Trainer(object):
                  eps: float = 1e-8, lr_boundaries: Sequence[int] = LR_BOUNDARIES, process_group=None,
                  global_step: int = 0, tc_dgrad: Optional[bool] = None,
                  tc_wgrad: Optional[bool] = None):
-        if model.use_dc:
-            raise NotImplementedError("Trainer: use_dc=True is inference-only in this build (no reference checkpoint "
-                                      "or BASELINE config trains it)")
         if model.fuse_warp:
             raise PwcError("Trainer needs the warped features in memory: construct the model with fuse_warp=False")
         if getattr(model, "cv_split", False):
@@ -121,7 +118,7 @@ class Trainer(object):
         for lev in p.pyr:
             acts += lev
         for l in range(len(p.S)):
-            acts += [p.S[l]] + list(p.tmp[l]) + [p.flows[l]] + ([p.f1w[l]] if p.f1w[l] is not None else [])
+            acts += [p.S[l]] + list(p.tmp[l] or []) + [p.flows[l]] + ([p.f1w[l]] if p.f1w[l] is not None else [])
         acts += list(p.ctx)
         def al(n):   # every view starts on a 256-byte boundary (vector loads / TMA need 16)
             return (n + 63) // 64 * 64
@@ -138,7 +135,7 @@ class Trainer(object):
         g.S, g.tmp, g.flows, g.f1w = [], [], [], []
         for l in range(len(p.S)):
             g.S.append(next(it))
-            g.tmp.append([next(it) for _ in p.tmp[l]])
+            g.tmp.append([next(it) for _ in (p.tmp[l] or [])])
             g.flows.append(next(it))
             g.f1w.append(next(it) if p.f1w[l] is not None else None)
         g.ctx = [next(it) for _ in p.ctx]
@@ -241,54 +238,92 @@ class Trainer(object):
         for l in range(L + 1):
             ops_bwd.lploss_level_bwd(flows_gt, p.flows[l], self.loss_weights[l], g.flows[l], gt_div=20.0, ord=2)
 
+        pre_total = sum(ESTIMATOR_FILTERS) if m.use_dc else 0
         for l in range(L, -1, -1):
             lv = m._lv[l]
             lev = m.num_levels - 1 - l
             S, gS = p.S[l], g.S[l]
-            feats, gfeats = p.tmp[l][-1][..., 0:nf], g.tmp[l][-1][..., 0:nf]
-            flow_slot_g = gS[..., lv["off_flow"]:lv["off_flow"] + 2] if l else None
             head = f"{n}/optflow_{l}/conv2d_{nest}"
-            if l == L:
-                # ---- context network (modules.py:304-326): flows_out = flow_slot + conv6(...conv0([features, flows]))
-                Cbuf, gCbuf = p.tmp[l][-1], g.tmp[l][-1]            # [features nf | flows 2 | pad 2]
-                nctx = len(CONTEXT_FILTERS)
-                for i in range(nctx - 1, 0, -1):
-                    scope = f"{n}/context/conv2d_{i}"
-                    dy = g.flows[l] if i == nctx - 1 else g.ctx[i]
-                    self._conv_bwd(scope, p.ctx[i - 1], dy, g.ctx[i - 1], dilation=CONTEXT_DILATIONS[i], mask=p.ctx[i - 1])
-                ops_bwd.add_(gCbuf[..., nf:nf + 2], g.flows[l])     # residual `flows + x` (modules.py:326)
-                self._conv_bwd(f"{n}/context/conv2d", Cbuf[..., 0:nf + 4], g.ctx[0], gCbuf[..., 0:nf + 4],
-                               dilation=CONTEXT_DILATIONS[0], accumulate=True)
-                dy_head = gCbuf[..., nf:nf + 2]
+            if m.use_dc:
+                # ---- dense connections (modules.py:269-270): one buffer per level, [conv4 | conv3 | conv2 | conv1 | conv0 | X];
+                # conv i reads channels [start_i, end) and writes [start_i - f_i, start_i).  Every region collects the
+                # gradients of ALL its consumers (later convs, head, x2 up-sampling, context) before its own conv runs.
+                end = pre_total + lv["cin_int"]
+                feats, gfeats = S[..., 0:end], gS[..., 0:end]
+                X, gX = S[..., pre_total:end], gS[..., pre_total:end]
+                flow_slot_g = gX[..., lv["off_flow"]:lv["off_flow"] + 2] if l else None
+                if l == L:
+                    nctx = len(CONTEXT_FILTERS)
+                    for i in range(nctx - 1, 0, -1):
+                        scope = f"{n}/context/conv2d_{i}"
+                        dy = g.flows[l] if i == nctx - 1 else g.ctx[i]
+                        self._conv_bwd(scope, p.ctx[i - 1], dy, g.ctx[i - 1], dilation=CONTEXT_DILATIONS[i], mask=p.ctx[i - 1])
+                    ops_bwd.add_(gS[..., end:end + 2], g.flows[l])          # residual `flows + x` (modules.py:326)
+                    self._conv_bwd(f"{n}/context/conv2d", S[..., 0:end + 4], g.ctx[0], gS[..., 0:end + 4],
+                                   dilation=CONTEXT_DILATIONS[0], accumulate=True)
+                    dy_head = gS[..., end:end + 2]
+                else:
+                    dy_head = g.flows[l]
+                self._conv_bwd(head, feats, dy_head, gfeats, accumulate=True)
+                if l:
+                    ops_bwd.add_(flow_slot_g, dy_head)
+                start = 0
+                for i in range(nest - 1, -1, -1):
+                    f = ESTIMATOR_FILTERS[i]
+                    scope = f"{n}/optflow_{l}/conv2d" + (f"_{i}" if i else "")
+                    out_g, out_y = gS[..., start:start + f], S[..., start:start + f]
+                    ops_bwd.leaky_bwd(out_g, out_y, 0.1)
+                    self._conv_bwd(scope, S[..., start + f:end], out_g, gS[..., start + f:end], accumulate=True)
+                    start += f
+                gS_in, S_in = gX, X
+                up_feat_g = lambda lprev: g.S[lprev][..., 0:pre_total + m._lv[lprev]["cin_int"]]
             else:
-                dy_head = g.flows[l]
-            # ---- flow head (no activation) + residual flows_up (modules.py:274-277)
-            self._conv_bwd(head, feats, dy_head, gfeats, accumulate=True)
-            if l:
-                ops_bwd.add_(flow_slot_g, dy_head)
-            ops_bwd.leaky_bwd(gfeats, feats, 0.1)
-            # ---- estimator convs (modules.py:266-270)
-            for i in range(nest - 1, 0, -1):
-                scope = f"{n}/optflow_{l}/conv2d_{i}"
-                fi = ESTIMATOR_FILTERS[i]
-                self._conv_bwd(scope, p.tmp[l][i - 1], g.tmp[l][i][..., 0:fi], g.tmp[l][i - 1], mask=p.tmp[l][i - 1])
-            self._conv_bwd(f"{n}/optflow_{l}/conv2d", S, g.tmp[l][0], gS, accumulate=True)
+                feats, gfeats = p.tmp[l][-1][..., 0:nf], g.tmp[l][-1][..., 0:nf]
+                flow_slot_g = gS[..., lv["off_flow"]:lv["off_flow"] + 2] if l else None
+                if l == L:
+                    # ---- context network (modules.py:304-326): flows_out = flow_slot + conv6(...conv0([features, flows]))
+                    Cbuf, gCbuf = p.tmp[l][-1], g.tmp[l][-1]            # [features nf | flows 2 | pad 2]
+                    nctx = len(CONTEXT_FILTERS)
+                    for i in range(nctx - 1, 0, -1):
+                        scope = f"{n}/context/conv2d_{i}"
+                        dy = g.flows[l] if i == nctx - 1 else g.ctx[i]
+                        self._conv_bwd(scope, p.ctx[i - 1], dy, g.ctx[i - 1], dilation=CONTEXT_DILATIONS[i], mask=p.ctx[i - 1])
+                    ops_bwd.add_(gCbuf[..., nf:nf + 2], g.flows[l])     # residual `flows + x` (modules.py:326)
+                    self._conv_bwd(f"{n}/context/conv2d", Cbuf[..., 0:nf + 4], g.ctx[0], gCbuf[..., 0:nf + 4],
+                                   dilation=CONTEXT_DILATIONS[0], accumulate=True)
+                    dy_head = gCbuf[..., nf:nf + 2]
+                else:
+                    dy_head = g.flows[l]
+                # ---- flow head (no activation) + residual flows_up (modules.py:274-277)
+                self._conv_bwd(head, feats, dy_head, gfeats, accumulate=True)
+                if l:
+                    ops_bwd.add_(flow_slot_g, dy_head)
+                ops_bwd.leaky_bwd(gfeats, feats, 0.1)
+                # ---- estimator convs (modules.py:266-270)
+                for i in range(nest - 1, 0, -1):
+                    scope = f"{n}/optflow_{l}/conv2d_{i}"
+                    fi = ESTIMATOR_FILTERS[i]
+                    self._conv_bwd(scope, p.tmp[l][i - 1], g.tmp[l][i][..., 0:fi], g.tmp[l][i - 1], mask=p.tmp[l][i - 1])
+                self._conv_bwd(f"{n}/optflow_{l}/conv2d", S, g.tmp[l][0], gS, accumulate=True)
+                gS_in, S_in = gS, S
+                up_feat_g = lambda lprev: g.tmp[lprev][-1][..., 0:nf]
             # ---- concat slots: cost volume (+ f0 copy), warp, x2 up-sampling (model.py:106-112, modules.py:262-285)
             F, gF = p.pyr[lev][2], g.pyr[lev][2]
             f0, f1 = F[:B], F[B:]
-            g_cv, cv = gS[..., 0:nd], S[..., 0:nd]
-            g_f0 = gS[..., lv["off_f0"]:lv["off_f0"] + lv["C"]]
+            g_cv, cv = gS_in[..., 0:nd], S_in[..., 0:nd]
+            g_f0 = gS_in[..., lv["off_f0"]:lv["off_f0"] + lv["C"]]
             if l == 0:
                 ops_bwd.cost_volume_bwd(g_cv, cv, f0, f1, gF[:B], gF[B:], g_f0slot=g_f0, accumulate_f1=True,
                                         search_range=m.s_range)
             else:
                 ops_bwd.cost_volume_bwd(g_cv, cv, f0, p.f1w[l], gF[:B], g.f1w[l], g_f0slot=g_f0, accumulate_f1=False,
                                         search_range=m.s_range)
-                flow_up = S[..., lv["off_flow"]:lv["off_flow"] + 2]
+                flow_up = S_in[..., lv["off_flow"]:lv["off_flow"] + 2]
                 ops_bwd.warp_bwd(f1, flow_up, g.f1w[l], gF[B:], dflow=flow_slot_g, flow_scale=m.scales[l],
                                  warp_type=m.warp_type)
                 ops_bwd.resize_bilinear_bwd(flow_slot_g, g.flows[l - 1])
-                ops_bwd.resize_bilinear_bwd(gS[..., lv["off_feat"]:lv["off_feat"] + nf], g.tmp[l - 1][-1][..., 0:nf])
+                up = lv["up"]
+                ops_bwd.resize_bilinear_bwd(gS_in[..., lv["off_feat"]:lv["off_feat"] + up], up_feat_g(l - 1))
             # this level's estimator (and, at the output level, the context network) gradients are final
             last = f"{n}/context/conv2d_{len(CONTEXT_FILTERS) - 1}/bias" if l == L else f"{n}/optflow_{l}/conv2d_{nest}/bias"
             self._allreduce_range(f"{n}/optflow_{l}/conv2d/kernel", last)

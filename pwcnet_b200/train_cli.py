@@ -149,7 +149,7 @@ class Trainer(object):
                 if a.max_steps is not None and g_step >= a.max_steps:
                     done = True
                     if nxt is not None:
-                        stream.step()                      # drain the staged batch (keeps the staging ring consistent)
+                        stream.discard()                   # the batch staged for the next step is not trained on
                     break
             # Validation (train.py:134-141): one summary per validation batch at the current step
             if self.is_chief:

@@ -137,3 +137,36 @@ def test_training_step_384x1024_vs_oracle_autograd(P):
         assert err < 1e-3, f"{name}: relative max-abs gradient error {err:.3e}"
     print(f"[parity train 384x1024] loss {s[0]:.6f} vs {ref_total:.6f}  EPE {s[2]:.5f} vs {ref_epe:.5f}  "
           f"worst relative gradient error {worst:.2e} ({worst_name})")
+
+
+def test_fp16_range_guard_fails_loudly(P):
+    """VERDICT r1 weak point 3: the 3 x fp16 split needs |x| < 65504.  Activations of ~1e5 (first conv scaled up) must not
+    silently turn into garbage: the forward counts non-finite flow values and check_finite / the next call / collect raise;
+    the fp32-operand precisions handle the same weights."""
+    W = O.glorot_weights(2)
+    W = {k: v.copy() for k, v in W.items()}
+    W["pwcdcnet/fp_extractor/conv2d/kernel"] *= 4e5          # level-1 activations of ~1e5, beyond fp16
+    W["pwcdcnet/fp_extractor/conv2d_1/kernel"] *= 1e-5       # ... scaled back by the next layer: fp32 arithmetic is unaffected
+    im0, im1 = O.synthetic_pair(1, 64, 192, 0)      # level-1 rows of 96 pixels: the 16 -> 16 layer runs on the fp16 halo kernel
+    rff, _ = O.pwcdcnet_forward(W, im0, im1)
+    assert float(O.pyramid_extractor(torch.from_numpy(im0), W)[-1].abs().max()) < 1e3      # the oracle stays finite and small
+    model = P.PWCDCNet(weights=W)                               # default: 3xf16
+    ff, _ = model(im0, im1)
+    with pytest.raises(P.PwcError, match="non-finite"):
+        model.check_finite()
+    model(im0, im1)
+    torch.cuda.synchronize()
+    with pytest.raises(P.PwcError, match="non-finite"):
+        model(im0, im1)                                         # the previous call's overflow surfaces on the next call
+    model.check_finite()                                        # consumed
+    st = P.InferenceStream(model, depth=2)
+    with pytest.raises(P.PwcError, match="non-finite"):
+        st.collect(st.submit(im0, im1))
+    for precision in ("fp32", "3xtf32"):
+        m2 = P.PWCDCNet(weights=W, precision=precision)
+        ff2, _ = m2(im0, im1)
+        m2.check_finite()
+        np.testing.assert_allclose(ff2.cpu().numpy(), rff.numpy(), atol=1e-3, rtol=0)
+    ok = P.PWCDCNet(weights=O.glorot_weights(2))
+    ok(im0, im1)
+    ok.check_finite()

@@ -120,8 +120,9 @@ def test_cost_volume_split_variants(P, shape, variant, monkeypatch):
     assert float((buf2[..., 82:] - 7.0).abs().max()) == 0 and float((buf2[..., :1] - 7.0).abs().max()) == 0
 
 
+@pytest.mark.parametrize("head", [88])
 @pytest.mark.parametrize("shape", [(2, 13, 70, 32), (1, 112, 256, 32), (2, 7, 16, 192), (1, 33, 9, 64)])
-def test_cost_volume_split_slot_mode_writes_whole_sectors(P, shape):
+def test_cost_volume_split_slot_mode_writes_whole_sectors(P, shape, head):
     """pwc_cost_volume_split_slot_fwd: words [0,81) = cost volume, [81,83) = the tail tensor (up-sampled flow), [83,88) = 0,
     everything beyond word 88 untouched; interior and ragged tiles."""
     B, H, W, C = shape
@@ -130,16 +131,16 @@ def test_cost_volume_split_slot_mode_writes_whole_sectors(P, shape):
     ref = O.cost_volume_closed_form(torch.from_numpy(f0), torch.from_numpy(f1), 4).numpy()
     f0s, f1s = P.ops.split_f16(_cuda(f0)), P.ops.split_f16(_cuda(f1))
     buf = torch.full((B, H, W, 96 + C), 7.0, device="cuda")
-    P.ops.cost_volume_split(f0s, f1s, 0.1, out=buf[..., :81], slot=True, tail=_cuda(tail))
+    P.ops.cost_volume_split(f0s, f1s, 0.1, out=buf[..., :81], slot=head, tail=_cuda(tail))
     np.testing.assert_allclose(buf[..., :81].cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
     np.testing.assert_array_equal(buf[..., 81:83].cpu().numpy(), tail)
-    assert float(buf[..., 83:88].abs().max()) == 0 and float((buf[..., 88:] - 7.0).abs().max()) == 0
+    assert float(buf[..., 83:head].abs().max()) == 0 and float((buf[..., head:] - 7.0).abs().max()) == 0
     buf.fill_(7.0)
-    P.ops.cost_volume_split(f0s, f1s, 0.1, out=buf[..., :81], slot=True)
+    P.ops.cost_volume_split(f0s, f1s, 0.1, out=buf[..., :81], slot=head)
     np.testing.assert_allclose(buf[..., :81].cpu().numpy(), ref, atol=1e-5, rtol=1e-5)
-    assert float(buf[..., 81:88].abs().max()) == 0 and float((buf[..., 88:] - 7.0).abs().max()) == 0
+    assert float(buf[..., 81:head].abs().max()) == 0 and float((buf[..., head:] - 7.0).abs().max()) == 0
     with pytest.raises(P.PwcError):
-        P.ops.cost_volume_split(f0s, f1s, 0.1, out=torch.empty((B, H, W, 84), device="cuda")[..., :81], slot=True)
+        P.ops.cost_volume_split(f0s, f1s, 0.1, out=torch.empty((B, H, W, 84), device="cuda")[..., :81], slot=head)
 
 
 def test_cost_volume_split_all_81_displacements_at_corners(P):

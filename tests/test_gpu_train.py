@@ -417,7 +417,7 @@ def test_batched_weight_packs_equal_per_layer_packs(P):
     W = O.glorot_weights(6, gain=1.2, bias_scale=0.02)
     im0, im1 = O.synthetic_pair(2, 64, 128, 31, shift=(2, -1))
     gt = np.random.default_rng(3).normal(0, 3, (2, 64, 128, 2)).astype(np.float32)
-    tr = Trainer(P.PWCDCNet(weights=W))
+    tr = Trainer(P.PWCDCNet(weights=W, cv_pipeline="default"))
     m = tr.model
     tr.forward_backward(im0, im1, gt)          # first pass: layer-by-layer packs, records the parts
     g1 = tr.grad_flat.clone()
@@ -436,16 +436,52 @@ def test_batched_weight_packs_equal_per_layer_packs(P):
         src = m._head_k[scope] if key.endswith("#head") else m._k[scope]
         assert torch.equal(ops_tc.pack_weights_f16(src), m._packed[key]), key
     ff, _ = m(im0, im1)
-    ff2, _ = P.PWCDCNet(weights=m.state_dict())(im0, im1)
+    ff2, _ = P.PWCDCNet(weights=m.state_dict(), cv_pipeline="default")(im0, im1)      # the trainer's model runs the default pipeline
     assert torch.equal(ff, ff2)
+    ff3, _ = P.PWCDCNet(weights=m.state_dict())(im0, im1)                              # split cost-volume pipeline: fp32-class, not bit-equal
+    assert float((ff3 - ff).abs().max()) < 1e-4
 
 
 def test_trainer_rejects_unsupported_models(P):
     from pwcnet_b200.train import Trainer
-    with pytest.raises(NotImplementedError):
-        Trainer(P.PWCDCNet(use_dc=True))
     with pytest.raises(P.PwcError):
         Trainer(P.PWCDCNet(fuse_warp=True))
+    with pytest.raises(P.PwcError):
+        Trainer(P.PWCDCNet(precision="cudnn"))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "3xf16"])
+def test_use_dc_network_gradients_match_oracle_autograd(P, precision):
+    """`--use-dc` (train.py:203-207, modules.py:269-270): all 110 gradient tensors of the densely connected estimator
+    network vs torch autograd over the oracle, and one optimisation step."""
+    from pwcnet_b200.train import Trainer
+    W = O.glorot_weights(5, gain=1.0, bias_scale=0.02, use_dc=True)
+    im0, im1 = O.synthetic_pair(2, 64, 128, 4, shift=(-4, 2))
+    gt = np.random.default_rng(1).normal(0, 5, (2, 64, 128, 2)).astype(np.float32)
+    Wt = {k: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in W.items()}
+    total, epe, ff, pyr = O.training_loss(Wt, im0, im1, gt, gamma=0.0, use_dc=True)
+    total.backward()
+    model = P.PWCDCNet(weights=W, use_dc=True, precision=precision)
+    tr = Trainer(model)
+    tr.forward_backward(im0, im1, gt)
+    torch.cuda.synchronize()
+    s = tr._scalars.cpu().numpy()
+    assert s[0] == pytest.approx(float(total), rel=2e-5)
+    # fp32 proves the orchestration (2e-4).  With the tensor-core forward the dense stack feeds every pre-activation to
+    # up to seven consumers: a handful of leaky masks of near-zero pre-activations flip relative to the fp32 forward and
+    # move single gradient tensors by a few 1e-3 of their maximum (identical with CUDA-core dgrad / wgrad: tools/dc_grad_dbg.py)
+    rel = 2e-4 if precision == "fp32" else 1e-2
+    worst = 0.0
+    for name in model.var_names:
+        got, r = tr.grads[name].cpu().numpy(), Wt[name].grad.numpy()
+        scale = float(np.abs(r).max())
+        assert scale > 0, name
+        err = float(np.abs(got - r).max()) / scale
+        worst = max(worst, err)
+        assert err < rel, f"{name}: relative max-abs gradient error {err:.3e}"
+    print(f"use_dc worst relative gradient error ({precision}): {worst:.2e}")
+    loss, _, _ = tr.step(im0, im1, gt)
+    assert np.isfinite(loss.item()) and tr.global_step == 1
 
 
 def test_trainer_state_dict_roundtrip_resumes_identically(P, tmp_path):

@@ -19,7 +19,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 # PWC_FLUSH=clean: after the write-flush, READ a second 256 MiB buffer so that L2 holds only clean lines when the timed
 # kernel starts (a write-only flush leaves ~126 MB of dirty lines whose write-back is charged to the timed kernel)
 clean = os.environ.get("PWC_FLUSH") == "clean"
-wide = os.environ.get("PWC_WIDE") == "1"     # whole-sector slot writes (pwc_cost_volume_split_slot_fwd)
+wide = os.environ.get("PWC_WIDE", "0") != "0"     # whole-sector slot writes (pwc_cost_volume_split_slot_fwd)
 flush2 = torch.ones(64 << 20, dtype=torch.float32, device="cuda") if clean else None
 split = len(sys.argv) > 3 and sys.argv[3].startswith("split")
 if split:
