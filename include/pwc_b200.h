@@ -203,6 +203,14 @@ int pwc_conv3x3_tc_f16_dgrad(const float* dy, int dy_cs, const void* w_rot_packe
  * h = fp16(x), l = fp16(x - h): the same bytes as the fp32 row, dense (B,H,W,2C) fp16.
  * ------------------------------------------------------------------------------------------------ */
 
+/* First pyramid convolution (modules.py:62-63, l = 0): 3 -> 16 channels, 3x3, stride 2, SAME, + bias + leaky, exact fp32 on
+ * the CUDA cores, reading either float32 RGB/255 images or (x_is_u8) the uint8 RGB bytes themselves through lut256
+ * (= float32(float64(v)/255.0): the reference's `images/255.0`, test.py:31-33).  x: dense (B,H,W,3); y: (B,H/2,W/2,16)
+ * with channel stride y_cs.  H even, W a multiple of 4.  Uploads the 448 weights to a module-global constant buffer in
+ * stream order: calls with different weights on different streams must be serialised by the caller. */
+int pwc_conv_first_fwd(const void* x, int x_is_u8, const float* lut256, const float* w_hwio, const float* bias,
+                       float* y, int y_cs, int B, int H, int W, float alpha, void* stream);
+
 /* *count += number of non-finite values in the pixel-strided tensor x (n_pix pixels, C channels, channel stride x_cs).
  * Range guard of the 3 x fp16 tensor-core path (operands must stay below 65504): an overflow anywhere upstream turns
  * the last pyramid flow into NaN; the host raises when the counter is non-zero.  No reference counterpart (TF computes

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpwc_b200.so")
-SOURCES = ["abi.cu", "cost_volume.cu", "cost_volume_tma.cu", "cost_volume_tc.cu", "cost_volume_tcs.cu", "warp_resize_loss.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc_f16.cu", "conv_tc_halo.cu", "backward.cu", "wgrad_tc.cu"]
+SOURCES = ["abi.cu", "cost_volume.cu", "cost_volume_tma.cu", "cost_volume_tc.cu", "cost_volume_tcs.cu", "warp_resize_loss.cu", "conv_direct.cu", "conv_first.cu", "conv_tc.cu", "conv_tc_f16.cu", "conv_tc_halo.cu", "backward.cu", "wgrad_tc.cu"]
 EXTRA = os.environ.get("PWC_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

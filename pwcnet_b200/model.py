@@ -359,13 +359,14 @@ class PWCDCNet(object):
         return out
 
     # ------------------------------------------------------------------ workspace
-    def _make_plan(self, B, H, W) -> _Plan:
+    def _make_plan(self, B, H, W, u8=False) -> _Plan:
         dev = self.device
         p = _Plan()
-        p.B, p.H, p.W = B, H, W
+        p.B, p.H, p.W, p.u8 = B, H, W, u8
         p.graph = None
-        p.im = torch.zeros((2 * B, H, W, 3), dtype=torch.float32, device=dev)
-        p.im_u8 = None                      # uint8 staging for byte images (allocated on first use)
+        # both images as one batch of 2B: float32 RGB/255, or (u8 plans) the RGB bytes the first conv reads directly
+        p.im = None if u8 else torch.zeros((2 * B, H, W, 3), dtype=torch.float32, device=dev)
+        p.im_u8 = torch.zeros((2 * B, H, W, 3), dtype=torch.uint8, device=dev) if u8 else None
         # range guard: number of non-finite values in the last pyramid flow of the latest forward (see check_finite)
         p.nonfinite = torch.zeros(1, dtype=torch.int32, device=dev)
         p.nf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -416,11 +417,15 @@ class PWCDCNet(object):
         n, B = self.name, p.B
         nd = self._nd
         p.nonfinite.zero_()
-        x = p.im
+        x = p.im_u8 if p.u8 else p.im
         for l in range(self.num_levels):
             for j, stride in enumerate((2, 1, 1)):
                 idx = 3 * l + j
                 scope = f"{n}/fp_extractor/conv2d" + (f"_{idx}" if idx else "")
+                if idx == 0 and self.precision != "cudnn" and PYRAMID_FILTERS[0] == 16:
+                    # Cin = 3: exact fp32 on the CUDA cores, from float32 or uint8 images (csrc/conv_first.cu)
+                    x = ops.conv_first(x, self.params[scope + "/kernel"], self.params[scope + "/bias"], 0.1, out=p.pyr[l][j])
+                    continue
                 x = self._conv(x, scope, p.pyr[l][j], stride=stride, alpha=0.1)
         pre_total = sum(ESTIMATOR_FILTERS) if self.use_dc else 0
         nest = len(ESTIMATOR_FILTERS)
@@ -504,7 +509,7 @@ class PWCDCNet(object):
         B, H, W, C = i0.shape
         self._check_shape(B, H, W, C)
         self.check_finite(wait=False)            # range guard: raise for an earlier forward that has finished meanwhile
-        p = self.plan(B, H, W)
+        p = self.plan(B, H, W, u8=i0.dtype == torch.uint8 and self.precision != "cudnn")
         self._stage(p, i0, i1)
         self._launch(p)
         flows_pyramid = list(p.flows)
@@ -516,24 +521,25 @@ class PWCDCNet(object):
     def _stage(self, p: _Plan, i0, i1=None) -> None:
         """Copy one request into the plan's input buffer; i1 None: i0 already holds both images (2B,H,W,3)."""
         B = p.B
-        if i0.dtype == torch.uint8:
-            if p.im_u8 is None:
-                p.im_u8 = torch.empty((2 * B, p.H, p.W, 3), dtype=torch.uint8, device=self.device)
-            if i1 is None:
-                src = i0 if (i0.is_cuda and i0.is_contiguous()) else None
-                if src is None:
-                    p.im_u8.copy_(i0, non_blocking=True)
-                    src = p.im_u8
-            else:
-                p.im_u8[:B].copy_(i0, non_blocking=True)
-                p.im_u8[B:].copy_(i1, non_blocking=True)
-                src = p.im_u8
-            ops.u8_to_f32(src, p.im)
-        elif i1 is None:
-            p.im.copy_(i0, non_blocking=True)
+        u8 = i0.dtype == torch.uint8
+        if p.u8:
+            if not u8:
+                raise TypeError("this plan reads uint8 images")
+            dst = p.im_u8
+        elif u8:
+            # float32 plan (training, cuDNN arm) fed with bytes: expand through the /255.0 table into the float32 buffer
+            if getattr(p, "im_stage_u8", None) is None:
+                p.im_stage_u8 = torch.empty((2 * B, p.H, p.W, 3), dtype=torch.uint8, device=self.device)
+            dst = p.im_stage_u8
         else:
-            p.im[:B].copy_(i0, non_blocking=True)
-            p.im[B:].copy_(i1, non_blocking=True)
+            dst = p.im
+        if i1 is None:
+            dst.copy_(i0, non_blocking=True)
+        else:
+            dst[:B].copy_(i0, non_blocking=True)
+            dst[B:].copy_(i1, non_blocking=True)
+        if u8 and not p.u8:
+            ops.u8_to_f32(dst, p.im)
 
     def _check_shape(self, B, H, W, C=3) -> None:
         m = 2 ** self.num_levels
@@ -542,12 +548,14 @@ class PWCDCNet(object):
                              f"got {(B, H, W, C)}")
 
     @on_device
-    def plan(self, B, H, W) -> _Plan:
-        """Workspace (buffers + CUDA graph) for one input shape; created on first use."""
-        key = (B, H, W)
+    def plan(self, B, H, W, u8: bool = False) -> _Plan:
+        """Workspace (buffers + CUDA graph) for one input shape; created on first use.  u8: the plan's first convolution
+        reads the uint8 image bytes directly (inference requests that arrive as uint8); the float32 plan is the one the
+        trainer uses (its backward pass reads the float32 images)."""
+        key = (B, H, W, bool(u8))
         p = self._plans.get(key)
         if p is None:
-            p = self._plans[key] = self._make_plan(B, H, W)
+            p = self._plans[key] = self._make_plan(B, H, W, bool(u8))
         return p
 
     def check_finite(self, wait: bool = True) -> None:
@@ -596,7 +604,7 @@ class PWCDCNet(object):
     def _run_device(self, images_2b, B, H, W):
         """Forward on a device tensor (2B,H,W,3) holding images_0 then images_1, float32 or uint8 (used by InferenceStream)."""
         self._check_shape(B, H, W, images_2b.shape[3])
-        p = self.plan(B, H, W)
+        p = self.plan(B, H, W, u8=images_2b.dtype == torch.uint8 and self.precision != "cudnn")
         self._stage(p, images_2b)
         self._launch(p)
         return p.flows_final, list(p.flows)

@@ -284,3 +284,24 @@ def count_nonfinite(x: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
         raise TypeError("count_nonfinite: count must be a CUDA int32 scalar")
     check(lib().pwc_count_nonfinite(x.data_ptr(), cs, C, B * H * W, count.data_ptr(), _stream()), "pwc_count_nonfinite")
     return count
+
+
+def conv_first(x: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor, alpha: float = 0.1, out=None) -> torch.Tensor:
+    """First pyramid conv (3 -> 16, stride 2, SAME, + bias + leaky; modules.py:62-63) from dense float32 RGB/255 or uint8
+    RGB images (B,H,W,3); uint8 values pass through the reference's /255.0 table on the fly."""
+    if not x.is_cuda or x.dim() != 4 or x.shape[3] != 3 or not x.is_contiguous() or x.dtype not in (torch.float32, torch.uint8):
+        raise ValueError("conv_first: x must be a contiguous CUDA (B,H,W,3) float32 or uint8 tensor")
+    if tuple(kernel.shape) != (3, 3, 3, 16) or tuple(bias.shape) != (16,) or not kernel.is_contiguous():
+        raise ValueError("conv_first: kernel must be (3,3,3,16) HWIO and bias (16,)")
+    B, H, W, _ = x.shape
+    if H % 2 or W % 4:
+        raise ValueError("conv_first: H must be even and W a multiple of 4")
+    if out is None:
+        out = new_nhwc(B, H // 2, W // 2, 16, x.device)
+    Bo, Ho, Wo, Co, y_cs = _nhwc(out, "out")
+    if (Bo, Ho, Wo, Co) != (B, H // 2, W // 2, 16):
+        raise ValueError("conv_first: out shape mismatch")
+    u8 = x.dtype == torch.uint8
+    check(lib().pwc_conv_first_fwd(x.data_ptr(), int(u8), u8_lut(x.device).data_ptr() if u8 else 0, kernel.data_ptr(), bias.data_ptr(),
+                                   out.data_ptr(), y_cs, B, H, W, float(alpha), _stream()), "pwc_conv_first_fwd")
+    return out

@@ -41,7 +41,7 @@ class InferenceStream:
         self._pending = {}
 
     def _alloc(self, B, H, W, dtype):
-        plan = self.model.plan(B, H, W)
+        plan = self.model.plan(B, H, W, u8=dtype == torch.uint8 and self.model.precision != "cudnn")
         outs = ([plan.flows_final] if "final" in self.outputs else []) + (list(plan.flows) if "pyramid" in self.outputs else [])
         self._slots = []
         for _ in range(self.depth):
@@ -97,7 +97,7 @@ class InferenceStream:
             srcs = ([flows_final] if "final" in self.outputs else []) + (list(pyr) if "pyramid" in self.outputs else [])
             for d, s in zip(sl["out_dev"], srcs):
                 d.copy_(s, non_blocking=True)
-            sl["nf_dev"].copy_(self.model.plan(B, H, W).nonfinite, non_blocking=True)      # range guard of this request
+            sl["nf_dev"].copy_(self.model.plan(B, H, W, u8=i0.dtype == torch.uint8 and self.model.precision != "cudnn").nonfinite, non_blocking=True)      # range guard of this request
             sl["ev_fwd"].record(cur)
             # ---- D2H on the output stream
             with torch.cuda.stream(self.s_out):

@@ -515,7 +515,7 @@ class Trainer(object):
         from . import _abi
         if not self._gbufs:
             raise RuntimeError("launches_per_step() needs one step to have run")
-        p = next(iter(self.model._plans.values()))
+        p = next(pl for pl in self.model._plans.values() if not pl.u8)
         gt = torch.zeros((p.B, p.H, p.W, 2), dtype=torch.float32, device=self.model.device)
         n0 = _abi.LAUNCHES
         self._losses(p, gt)

@@ -453,3 +453,26 @@ def test_conv3x3_f16x3_small_and_large_magnitudes(P):
         ref = O.conv2d_same(torch.from_numpy(x), torch.from_numpy(k), torch.from_numpy(b)).numpy()
         out = ops_tc.conv3x3_tc_f16(_cuda(x), ops_tc.pack_weights_f16(_cuda(k)), _cuda(b), 64, 64, alpha=1.0)
         np.testing.assert_allclose(out.cpu().numpy(), ref, atol=2e-5 * scale, rtol=0)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 70, 132), (3, 18, 260), (1, 448, 1024)])
+@pytest.mark.parametrize("u8", [False, True])
+def test_conv_first_matches_oracle(P, shape, u8):
+    """First pyramid conv (3 -> 16, stride 2, SAME, leaky 0.1; modules.py:62-63) from float32 or uint8 images: exact-fp32 class
+    vs the oracle's conv, ragged tiles, strided destination; the uint8 path equals the float path on the /255.0 feed bit for bit."""
+    B, H, W = shape
+    rng = np.random.default_rng(H + W)
+    k = rng.uniform(-0.3, 0.3, (3, 3, 3, 16)).astype(np.float32)
+    b = rng.normal(0, 0.1, 16).astype(np.float32)
+    xu = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    xf = (xu / 255.0).astype(np.float32)
+    ref = O.leaky_relu(O.conv2d_same(torch.from_numpy(xf), torch.from_numpy(k), torch.from_numpy(b), stride=2), 0.1).numpy()
+    buf = torch.full((B, H // 2, W // 2, 20), 7.0, device="cuda")
+    x = torch.from_numpy(xu if u8 else xf).cuda()
+    out = P.ops.conv_first(x, _cuda(k), _cuda(b), 0.1, out=buf[..., 2:18])
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=2e-6, rtol=1e-6)
+    assert float((buf[..., :2] - 7.0).abs().max()) == 0 and float((buf[..., 18:] - 7.0).abs().max()) == 0
+    dense = P.ops.conv_first(torch.from_numpy(xf).cuda(), _cuda(k), _cuda(b), 0.1)
+    assert torch.equal(dense, out.contiguous())
+    with pytest.raises(ValueError):
+        P.ops.conv_first(torch.zeros((1, 63, 128, 3), device="cuda"), _cuda(k), _cuda(b))
