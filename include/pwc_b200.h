@@ -203,6 +203,15 @@ int pwc_conv3x3_tc_f16_dgrad(const float* dy, int dy_cs, const void* w_rot_packe
  * h = fp16(x), l = fp16(x - h): the same bytes as the fp32 row, dense (B,H,W,2C) fp16.
  * ------------------------------------------------------------------------------------------------ */
 
+/* The same stride-1 conv (tf.layers.Conv2D + leaky, modules.py:266-270, 306-323) inside a conv -> conv chain whose
+ * intermediate tensors are kept as SPLIT rows: per pixel and 32-channel slice [h: 32 x fp16 | l: 32 x fp16 * 2^11] (the bytes
+ * of 32 floats; the row layout of pwc_split_f16_fwd, whose l is unscaled), written by the producer's epilogue (y_split) and read by the consumer without its fp32 -> fp16 converter
+ * pass (x_split).  Bit-identical to pwc_conv3x3_tc_f16_fwd on fp32 tensors.  Cout <= 128, dilation 1..16; x_cs / ys_cs count
+ * halfs per pixel for split tensors; y and y_split may both be given (y may be NULL). */
+int pwc_conv3x3_tc_f16_split_fwd(const void* x, int x_split, int x_cs, const void* w_packed, const float* bias,
+                                 float* y, int y_cs, void* y_split, int ys_cs,
+                                 int B, int H, int W, int Cin, int Cout, int dilation, float alpha, void* stream);
+
 /* First pyramid convolution (modules.py:62-63, l = 0): 3 -> 16 channels, 3x3, stride 2, SAME, + bias + leaky, exact fp32 on
  * the CUDA cores, reading either float32 RGB/255 images or (x_is_u8) the uint8 RGB bytes themselves through lut256
  * (= float32(float64(v)/255.0): the reference's `images/255.0`, test.py:31-33).  x: dense (B,H,W,3); y: (B,H/2,W/2,16)

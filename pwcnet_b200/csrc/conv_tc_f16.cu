@@ -367,7 +367,8 @@ struct F16Extra { const float* mask; int mask_cs; float mask_alpha; int accumula
 // conv_tc_halo.cu: halo-resident variant for stride 1, dilation 1, wide rows, Cout <= 128
 int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
                      int B, int H, int W, int Cin, int Cout, int dilation, float alpha, const float* mask, int mask_cs,
-                     float mask_alpha, int accumulate, int cout_valid, const float* res, int res_cs, cudaStream_t st);
+                     float mask_alpha, int accumulate, int cout_valid, const float* res, int res_cs, cudaStream_t st,
+                     int in_split = 0, void* y_split = nullptr, int ys_cs = 0);
 }
 
 static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const float* bias,
@@ -514,4 +515,28 @@ extern "C" int pwc_conv3x3_tc_f16_dgrad(const float* dy, int dy_cs, const void* 
     PWC_REQUIRE(!mask || mask_cs >= Cdx, PWC_E_BADARG, "conv3x3_tc_f16_dgrad: mask channel stride smaller than Cdx");
     const pwc::F16Extra ex{mask, mask_cs, mask_alpha, accumulate, Cdx, nullptr, 0};
     return launch_conv_f16(dy, dy_cs, w_rot_packed, nullptr, dx, dx_cs, B, H, W, Cdy, Cdx_pad, 1, dilation, 1.f, ex, stream);
+}
+
+// Stride-1 conv of a conv -> conv chain with SPLIT activations (conv_tc_halo.cu): the input and/or the output tensor holds,
+// per pixel and 32-channel slice, the 128-byte row [h: 32 x fp16 | l: 32 x fp16 scaled by 2^11] instead of 32 floats (the
+// same bytes; what the converter warps of the consumer would otherwise produce from the fp32 tensor on every tile).
+//   x_split != 0: x points to a split tensor, x_cs = halfs per pixel (>= 2 * Cin), Cin % 32 == 0.
+//   y (fp32, may be NULL) and/or y_split (split, may be NULL; Cout % 32 == 0, ys_cs halfs per pixel, 16-byte aligned).
+// Results are bit-identical to pwc_conv3x3_tc_f16_fwd on the fp32 tensors.  Cout <= 128, dilation 1..16.
+extern "C" int pwc_conv3x3_tc_f16_split_fwd(const void* x, int x_split, int x_cs, const void* w_packed, const float* bias,
+                                            float* y, int y_cs, void* y_split, int ys_cs,
+                                            int B, int H, int W, int Cin, int Cout, int dilation, float alpha, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(x && w_packed && bias && (y || y_split), PWC_E_BADARG, "conv3x3_tc_f16_split: null pointer");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0 && Cin >= 16 && Cout > 0 && Cout % 16 == 0 && Cout <= 128 && dilation >= 1 && dilation <= 16,
+                PWC_E_BADARG, "conv3x3_tc_f16_split: bad dims (stride 1, Cout <= 128, dilation 1..16)");
+    PWC_REQUIRE(aligned16(x) && aligned16(w_packed) && (!y || y_cs >= Cout), PWC_E_ALIGN, "conv3x3_tc_f16_split: alignment / strides");
+    PWC_REQUIRE(x_split ? (Cin % 32 == 0 && x_cs >= 2 * Cin && x_cs % 8 == 0) : (x_cs >= Cin && x_cs % 4 == 0), PWC_E_BADARG,
+                "conv3x3_tc_f16_split: input channel stride");
+    PWC_REQUIRE(!y_split || (Cout % 32 == 0 && ys_cs >= 2 * Cout && ys_cs % 16 == 0 && aligned16(y_split)), PWC_E_BADARG,
+                "conv3x3_tc_f16_split: split output needs Cout % 32 == 0 and a 32-byte pixel pitch");
+    const int rc = launch_conv_halo(static_cast<const float*>(x), x_cs, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, dilation, alpha,
+                                    nullptr, 0, 1.f, 0, Cout, nullptr, 0, (cudaStream_t)stream, x_split ? 1 : 0, y_split, ys_cs);
+    PWC_REQUIRE(rc != -1000, PWC_E_BADARG, "conv3x3_tc_f16_split: shape not supported by the halo kernel");
+    return rc;
 }

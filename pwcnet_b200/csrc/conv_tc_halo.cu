@@ -53,6 +53,12 @@ struct HaloParams {
     int w_resident;       // all 9 * kchunks weight images stay in shared memory (small layers): loaded once per CTA
     float alpha, mask_alpha;
     unsigned long long* dbg;   // optional timeline (clock64): 8 events x 8 tiles per CTA; nullptr in production
+    // split activations (round 2): conv -> conv chains keep their intermediate tensors as [h | l * 2^11] fp16 rows (per
+    // pixel and 32-channel slice 128 bytes: exactly what the converter warps produce; the cost volume's operands use the same
+    // row layout with an unscaled l),
+    // written by the producer's epilogue and landed by TMA ready for the MMAs: the consumer's converter pass disappears.
+    int in_split;              // the input tensor map is over split rows (fp16): the converter warps only forward the barrier
+    __half* ys; int ys_cs;     // optional split output (halfs per pixel = 2 * channels of that tensor); y may then be null
 };
 
 #define HL_DBG(ev, tile) do { if (dbg && (tile) < 8) dbg[(ev) * 8 + (tile)] = clock64(); } while (0)
@@ -127,12 +133,13 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                     mbar_wait(bar_aempty + 8 * s, ((it / AS) & 1) ^ 1);
                     HL_DBG(0, it);
                     mbar_expect_tx(bar_afull + 8 * s, (uint32_t)n_rows * 128);
+                    const int c0 = c * (p.in_split ? 2 * HL_BK : HL_BK);      // element offset of the slice (fp32 or halfs)
                     if (p.row_loads == 1) {
-                        tma_load_4d(base + s * p.act_stage, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - p.dil, y - p.dil, b);
+                        tma_load_4d(base + s * p.act_stage, &tmX, bar_afull + 8 * s, c0, x0 - p.dil, y - p.dil, b);
                     } else {
 #pragma unroll
                         for (int r2 = 0; r2 < HL_BH; ++r2)
-                            tma_load_4d(base + s * p.act_stage + r2 * p.bw * 128, &tmX, bar_afull + 8 * s, c * HL_BK, x0 - p.dil,
+                            tma_load_4d(base + s * p.act_stage + r2 * p.bw * 128, &tmX, bar_afull + 8 * s, c0, x0 - p.dil,
                                         y + (r2 - 1) * p.dil, b);
                     }
                 }
@@ -270,7 +277,25 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = leaky(acc[j], p.alpha);
-                    if (vec) {
+                    if (p.ys) {
+                        // 16 channels of this pixel as split rows: h at half (n0 / 32) * 64 + n0 % 32 of the pixel, l 32 halfs later
+                        __half* hp = p.ys + pix * p.ys_cs + (n0 >> 5) * 64 + (n0 & 31);
+                        uint32_t hw[8], lw[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const __half2 h2 = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+                            const float2 f2 = __half22float2(h2);
+                            const __half2 l2 = __floats2half2_rn((acc[2 * j] - f2.x) * HL_SCALE, (acc[2 * j + 1] - f2.y) * HL_SCALE);
+                            hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                            lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                        uint4* hq = reinterpret_cast<uint4*>(hp);
+                        uint4* lq = reinterpret_cast<uint4*>(hp + 32);
+                        hq[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); hq[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                        lq[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); lq[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                    }
+                    if (!p.y) {
+                    } else if (vec) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             if (n0 + j >= p.cout_valid) break;
@@ -315,7 +340,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int R = ct + rr * HL_CONV_THREADS;
-                    if (R < n_rows && !p.exp_skip_conv) {
+                    if (R < n_rows && !p.exp_skip_conv && !p.in_split) {
                         uint8_t* row = stp + (size_t)R * 128;
                         const int sw = R & 7;              // 128B swizzle: logical 16-byte chunk j sits at chunk j ^ (R & 7)
                         float4 v[8];
@@ -361,24 +386,29 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
 // Returns CONV_HALO_UNSUPPORTED when the arguments need the streaming kernel of conv_tc_f16.cu.
 int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
                      int B, int H, int W, int Cin, int Cout, int dilation, float alpha, const float* mask, int mask_cs,
-                     float mask_alpha, int accumulate, int cout_valid, const float* res, int res_cs, cudaStream_t st) {
+                     float mask_alpha, int accumulate, int cout_valid, const float* res, int res_cs, cudaStream_t st,
+                     int in_split, void* y_split, int ys_cs) {
     EncodeTiledFn enc = get_encode();
+    if (in_split && (Cin & 31)) return -1000;                   // split rows come in whole 32-channel slices
+    if (y_split && ((Cout & 31) || (ys_cs & 15) || !aligned16(y_split))) return -1000;
     if (!enc || Cout > 128 || (Cout & 7) || dilation < 1 || dilation > 16) return -1000;   // two accumulator sets of 2*Cout columns must fit 512
     // rows narrower than a tile: flat mode (d = 1 only) packs several rows into the 128 MMA rows
     const int flat = (W < HL_M && dilation == 1 && !getenv("PWC_HALO_NO_FLAT")) ? 1 : 0;
     const int nr = flat ? (HL_M - 1 + (W + 2) - 1) / (W + 2) + 3 : 0;
     CUtensorMap tmX;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)x_cs * 4, (cuuint64_t)W * x_cs * 4, (cuuint64_t)H * W * x_cs * 4};
+        // x_cs counts elements of the input tensor: floats, or halfs of a split tensor (2 * its channel count)
+        const cuuint64_t esz = in_split ? 2 : 4;
+        cuuint64_t dims[4] = {(cuuint64_t)(in_split ? 2 * Cin : Cin), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)x_cs * esz, (cuuint64_t)W * x_cs * esz, (cuuint64_t)H * W * x_cs * esz};
         // rows y-d, y, y+d through the traversal stride of the row dimension (TMA allows strides up to 8); larger
         // dilations use one single-row box per row (their row pitch (128+2d)*128 B must keep the 1024-byte swizzle phase)
         const bool strided = dilation <= 8;
         if (!strided && (((HL_M + 2 * dilation) * 128) & 1023)) return -1000;
-        cuuint32_t box[4] = {HL_BK, (cuuint32_t)(HL_M + 2 * dilation), (cuuint32_t)(strided ? HL_BH * dilation : 1), 1};
+        cuuint32_t box[4] = {(cuuint32_t)(in_split ? 2 * HL_BK : HL_BK), (cuuint32_t)(HL_M + 2 * dilation), (cuuint32_t)(strided ? HL_BH * dilation : 1), 1};
         cuuint32_t es[4] = {1, 1, (cuuint32_t)(strided ? dilation : 1), 1};
         if (flat) { box[1] = (cuuint32_t)(W + 2); box[2] = (cuuint32_t)nr; es[2] = 1; }
-        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
+        CUresult r = enc(&tmX, in_split ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return PWC_E_BADARG; }
@@ -396,6 +426,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.b_bytes = Cout * 64;
     p.w_stage_bytes = (2 * p.b_bytes + 1023) / 1024 * 1024;
     p.accumulate = accumulate; p.alpha = alpha; p.mask_alpha = mask_alpha;
+    p.in_split = in_split; p.ys = (__half*)y_split; p.ys_cs = ys_cs;
     p.dil = dilation; p.bw = flat ? W + 2 : HL_M + 2 * dilation; p.row_loads = dilation <= 8 ? 1 : HL_BH;
     p.act_stage = ((flat ? nr : HL_BH) * p.bw * 128 + 1023) / 1024 * 1024;
     p.desc_mode = 0;

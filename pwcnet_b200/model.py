@@ -124,6 +124,11 @@ class PWCDCNet(object):
         if cv_pipeline in (None, ""):
             cv_pipeline = "split" if precision in ("3xf16", "3xtf32", "tf32") else "default"
         self.cv_split = cv_pipeline == "split" and search_range == 4 and not fuse_warp
+        # split activations (inference, 3xf16): the intermediate tensors of conv -> conv chains (estimator convs 0..3, context
+        # convs 0..4, the middle conv of pyramid levels 2..5) are stored as [h | l] fp16 rows by the producer's epilogue, so
+        # the consumer's fp32 -> fp16 converter pass disappears (bit-identical results).  The trainer turns it
+        # off: its backward pass reads the float32 activations.  PWC_SPLIT_ACT=0 disables it.
+        self.split_act = precision == "3xf16" and not use_dc and os.environ.get("PWC_SPLIT_ACT", "1") != "0"
         if not torch.cuda.is_available():
             raise PwcError("PWCDCNet needs a CUDA device: the compute path is sm_100a CUDA only (no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -297,6 +302,16 @@ class PWCDCNet(object):
         k = self._k[scope]
         b = self.params[scope + "/bias"]
         cin, cout = k.shape[2], k.shape[3]
+        if x.dtype == torch.float16 or out.dtype == torch.float16:
+            # conv -> conv chain with split activations (only planned for layers the halo kernel takes)
+            from . import ops_tc
+            assert self.precision == "3xf16" and stride == 1 and residual is None
+            if scope not in self._packed:
+                self._packed[scope] = ops_tc.pack_weights_f16(k)
+            osplit = out.dtype == torch.float16
+            ops_tc.conv3x3_tc_f16_split(x, self._packed[scope], b, cin, cout, dilation=dilation, alpha=alpha,
+                                        out=None if osplit else out, out_split=out if osplit else None)
+            return out
         if self.precision == "cudnn":
             return self._conv_cudnn(x, k, b, out, stride, dilation, alpha, residual)
         if self.precision == "3xf16" and cout == 2 and stride == 1 and cin >= 16 and cin % 4 == 0 \
@@ -358,6 +373,11 @@ class PWCDCNet(object):
         out.copy_(y)
         return out
 
+    def _split_ok(self, c_mid: int, c_next: int, width: int) -> bool:
+        """May a tensor with c_mid channels that is consumed ONLY by the next stride-1 conv (c_next outputs) be kept as split rows?
+        Both convs must run on the halo kernel (Cout <= 128, rows >= PWC_HALO_MINW) and own whole 32-channel slices."""
+        return bool(self.split_act and c_mid % 32 == 0 and c_mid <= 128 and c_next <= 128 and width >= 8)
+
     # ------------------------------------------------------------------ workspace
     def _make_plan(self, B, H, W, u8=False) -> _Plan:
         dev = self.device
@@ -376,7 +396,10 @@ class PWCDCNet(object):
         for l in range(self.num_levels):
             h, w = h // 2, w // 2
             C = PYRAMID_FILTERS[l]
-            p.pyr.append([torch.empty((2 * B, h, w, C), dtype=torch.float32, device=dev) for _ in range(3)])
+            lvl = [torch.empty((2 * B, h, w, C), dtype=torch.float32, device=dev) for _ in range(3)]
+            if self._split_ok(C, C, w):          # conv(l,1) -> conv(l,2): the middle tensor is only read by the next conv
+                lvl[1] = torch.empty((2 * B, h, w, 2 * C), dtype=torch.float16, device=dev)
+            p.pyr.append(lvl)
         pre_total = sum(ESTIMATOR_FILTERS) if self.use_dc else 0
         p.S, p.tmp, p.flows, p.f1w = [], [], [], []
         p.f0s, p.f1s, p.flow_up, p.cv_slot = [], [], [], []
@@ -390,7 +413,9 @@ class PWCDCNet(object):
                 p.tmp.append(None)
             else:
                 p.S.append(torch.zeros((B, ph, pw, lv["cin_int"]), dtype=torch.float32, device=dev))
-                tmps = [torch.empty((B, ph, pw, f), dtype=torch.float32, device=dev) for f in ESTIMATOR_FILTERS[:-1]]
+                tmps = [torch.empty((B, ph, pw, 2 * f), dtype=torch.float16, device=dev) if self._split_ok(f, fn, pw)
+                        else torch.empty((B, ph, pw, f), dtype=torch.float32, device=dev)
+                        for f, fn in zip(ESTIMATOR_FILTERS[:-1], ESTIMATOR_FILTERS[1:])]
                 last = torch.zeros((B, ph, pw, ESTIMATOR_FILTERS[-1] + (4 if is_out else 0)), dtype=torch.float32, device=dev)
                 p.tmp.append(tmps + [last])
             p.flows.append(torch.empty((B, ph, pw, 2), dtype=torch.float32, device=dev))
@@ -407,7 +432,9 @@ class PWCDCNet(object):
             p.flow_up.append(None)
             p.cv_slot.append(bool(slot_ok))
         ph, pw = p.flows[-1].shape[1:3]
-        p.ctx = [torch.empty((B, ph, pw, f), dtype=torch.float32, device=dev) for f in CONTEXT_FILTERS[:-1]]
+        p.ctx = [torch.empty((B, ph, pw, 2 * f), dtype=torch.float16, device=dev) if (fn != 2 and self._split_ok(f, fn, pw))
+                 else torch.empty((B, ph, pw, f), dtype=torch.float32, device=dev)
+                 for f, fn in zip(CONTEXT_FILTERS[:-1], CONTEXT_FILTERS[1:])]
         up = 2 ** (self.num_levels - self.output_level)
         p.flows_final = torch.empty((B, ph * up, pw * up, 2), dtype=torch.float32, device=dev)
         return p
@@ -469,7 +496,8 @@ class PWCDCNet(object):
                 feats = X
                 for i, f in enumerate(ESTIMATOR_FILTERS):
                     scope = f"{n}/optflow_{l}/conv2d" + (f"_{i}" if i else "")
-                    feats = self._conv(feats, scope, p.tmp[l][i][..., 0:f], alpha=0.1)
+                    t = p.tmp[l][i]
+                    feats = self._conv(feats, scope, t if t.dtype == torch.float16 else t[..., 0:f], alpha=0.1)
             head = f"{n}/optflow_{l}/conv2d_{nest}"
             if not is_out:
                 flows = self._conv(feats, head, p.flows[l], alpha=1.0, residual=flow_up)

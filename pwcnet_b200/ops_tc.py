@@ -127,6 +127,40 @@ def conv3x3_tc_f16(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, al
     return out
 
 
+def conv3x3_tc_f16_split(x, w_packed, bias, cin: int, cout: int, dilation: int = 1, alpha: float = 1.0, out=None, out_split=None):
+    """Stride-1 conv of a conv -> conv chain with split activations (halo kernel): `x` is a float32 NHWC view or a split
+    tensor (contiguous fp16 (B,H,W,2*cin): per pixel and 32-channel slice [h x32 | l x32]); the result goes to `out` (float32
+    NHWC view) and/or `out_split` (contiguous fp16 (B,H,W,2*cout)).  Bit-identical to conv3x3_tc_f16 on float32 tensors."""
+    if x.dtype == torch.float16:
+        if x.dim() != 4 or not x.is_contiguous() or x.shape[3] != 2 * cin or cin % 32:
+            raise ValueError("conv3x3_tc_f16_split: split input must be contiguous fp16 (B,H,W,2*cin), cin % 32 == 0")
+        B, H, W, _ = x.shape
+        x_split, x_cs = 1, 2 * cin
+    else:
+        B, H, W, C, x_cs = _nhwc(x, "x")
+        if C != cin:
+            raise ValueError(f"conv3x3_tc_f16_split: x has {C} channels, weights expect {cin}")
+        x_split = 0
+    if bias.shape != (cout,) or w_packed.dtype != torch.float16 or w_packed.numel() * 2 != lib().pwc_conv3x3_packed_bytes_f16(cin, cout):
+        raise ValueError("conv3x3_tc_f16_split: bias / w_packed do not match (Cin, Cout)")
+    if out is None and out_split is None:
+        out = new_nhwc(B, H, W, cout, x.device)
+    yp, y_cs = 0, 0
+    if out is not None:
+        Bo, Ho, Wo, Co, y_cs = _nhwc(out, "out")
+        if (Bo, Ho, Wo, Co) != (B, H, W, cout):
+            raise ValueError("conv3x3_tc_f16_split: out shape mismatch")
+        yp = out.data_ptr()
+    sp, ys_cs = 0, 0
+    if out_split is not None:
+        if out_split.dtype != torch.float16 or tuple(out_split.shape) != (B, H, W, 2 * cout) or not out_split.is_contiguous() or cout % 32:
+            raise ValueError("conv3x3_tc_f16_split: out_split must be contiguous fp16 (B,H,W,2*cout), cout % 32 == 0")
+        sp, ys_cs = out_split.data_ptr(), 2 * cout
+    check(lib().pwc_conv3x3_tc_f16_split_fwd(x.data_ptr(), x_split, x_cs, w_packed.data_ptr(), bias.data_ptr(), yp, y_cs, sp, ys_cs,
+                                             B, H, W, cin, cout, dilation, float(alpha), _stream()), "pwc_conv3x3_tc_f16_split_fwd")
+    return out if out is not None else out_split
+
+
 def conv3x3_tc_f16_head(x, w_packed_pad, bias_pad, cin: int, cout: int, cout_pad: int, dilation: int = 1, alpha: float = 1.0,
                         residual=None, out=None):
     """Narrow-output conv (the 2-channel flow heads, modules.py:274-277, 325-326) on tcgen05: kernel and bias are

@@ -55,10 +55,12 @@ class Trainer(object):
                  tc_wgrad: Optional[bool] = None):
         if model.fuse_warp:
             raise PwcError("Trainer needs the warped features in memory: construct the model with fuse_warp=False")
-        if getattr(model, "cv_split", False):
-            # the backward pass reads the warped fp32 features the split (inference) pipeline never materialises: training
-            # runs the default cost-volume pipeline; plans made for inference are dropped
+        if getattr(model, "cv_split", False) or getattr(model, "split_act", False):
+            # the backward pass reads the warped fp32 features and the fp32 activations that the inference pipeline (split
+            # cost volume, split conv -> conv chains) never materialises: training runs the default pipeline; plans made for
+            # inference are dropped
             model.cv_split = False
+            model.split_act = False
             model._plans.clear()
         if model.precision == "cudnn":
             raise PwcError("Trainer: the cuDNN baseline arm has no backward path")

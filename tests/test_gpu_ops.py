@@ -476,3 +476,29 @@ def test_conv_first_matches_oracle(P, shape, u8):
     assert torch.equal(dense, out.contiguous())
     with pytest.raises(ValueError):
         P.ops.conv_first(torch.zeros((1, 63, 128, 3), device="cuda"), _cuda(k), _cuda(b))
+
+
+@pytest.mark.parametrize("shape,cmid,cout,dil", [((2, 20, 140, 36), 128, 96, 1), ((1, 56, 128, 128), 64, 32, 4), ((1, 9, 17, 64), 32, 32, 1),
+                                                  ((1, 40, 160, 96), 96, 64, 16)])
+def test_conv_chain_with_split_activations_is_bit_identical(P, shape, cmid, cout, dil):
+    """conv -> conv with the intermediate tensor stored as [h | l] fp16 rows (pwc_conv3x3_tc_f16_split_fwd): the split tensor
+    reproduces the fp32 intermediate to fp32 precision and the chain's result equals the fp32-tensor chain bit for bit."""
+    from pwcnet_b200 import ops_tc
+    B, H, W, C = shape
+    x = _cuda(_rand(shape, 1))
+    k1, b1 = _cuda(_rand((3, 3, C, cmid), 2, 0.05)), _cuda(_rand((cmid,), 3, 0.1))
+    k2, b2 = _cuda(_rand((3, 3, cmid, cout), 4, 0.05)), _cuda(_rand((cout,), 5, 0.1))
+    w1, w2 = ops_tc.pack_weights_f16(k1), ops_tc.pack_weights_f16(k2)
+    mid = ops_tc.conv3x3_tc_f16(x, w1, b1, C, cmid, dilation=dil, alpha=0.1)
+    ref = ops_tc.conv3x3_tc_f16(mid, w2, b2, cmid, cout, dilation=dil, alpha=0.1)
+    mid_s = torch.empty((B, H, W, 2 * cmid), dtype=torch.float16, device="cuda")
+    mid_f = torch.empty((B, H, W, cmid), device="cuda")
+    ops_tc.conv3x3_tc_f16_split(x, w1, b1, C, cmid, dilation=dil, alpha=0.1, out=mid_f, out_split=mid_s)
+    assert torch.equal(mid_f, mid)
+    hl = mid_s.float().view(B, H, W, cmid // 32, 2, 32)
+    rec = (hl[..., 0, :] + hl[..., 1, :] / 2048.0).reshape(B, H, W, cmid)
+    np.testing.assert_allclose(rec.cpu().numpy(), mid.cpu().numpy(), rtol=2e-7, atol=1e-9)
+    out = ops_tc.conv3x3_tc_f16_split(mid_s, w2, b2, cmid, cout, dilation=dil, alpha=0.1)
+    assert torch.equal(out, ref)
+    with pytest.raises(ValueError):
+        ops_tc.conv3x3_tc_f16_split(mid_s[..., :cmid], w2, b2, cmid, cout)
