@@ -20,6 +20,7 @@
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <cstring>
 
 namespace pwc {
 
@@ -29,6 +30,7 @@ constexpr int HL_BK = 32;
 constexpr int HL_MAX_ACT_STAGES = 4, HL_W_STAGES = 4;   // activation stages: 2, up to 4 for layers with resident weights
 constexpr int HL_CONV_THREADS = 256;
 constexpr int HL_THREADS = 64 + 128 + HL_CONV_THREADS + 32;   // act TMA, MMA, 4 epilogue, 8 converter, weight producer
+constexpr size_t HL_SMEM_BUDGET = 226 * 1024;         // dynamic shared memory: 227 KB per CTA minus the static barriers + bias
 constexpr float HL_SCALE = 2048.f, HL_INV_SCALE = 1.f / 2048.f;
 
 struct HaloParams {
@@ -41,6 +43,11 @@ struct HaloParams {
     int w_stage_bytes;    // 2 * b_bytes rounded up to 1024
     int accumulate, desc_mode;
     int exp_skip_conv;    // experiment (PWC_HALO_EXP=1): converters do nothing -> wrong results, upper bound of a split-input variant
+    int tma_y, tma_ys;    // the epilogue stores the fp32 / split output through TMA (shared-memory staging + bulk tensor store)
+    int epi_off;          // byte offset of the epilogue staging area: 4 warps x 2 buffers x (32 pixels x 128 or 64 bytes)
+    int contig;           // experiment (PWC_HALO_CONTIG=1): contiguous tile runs per CTA
+    int exp_direct_store; // experiment (PWC_HALO_EXP=3): 16-byte-per-lane stores (round-1 pattern)
+    int exp_skip_store;   // experiment (PWC_HALO_EXP=2): the epilogue stores nothing -> upper bound of the store path
     int dil, bw;          // dilation d; box width in pixels (128 + 2d, or W + 2 in flat mode)
     int flat, nr;         // flat mode (W < 128, d = 1): a tile is 128 consecutive SLOTS of the padded row-major space
                           // (rows of bw = W + 2 slots); nr = box rows.  Tap (ky,kx) is still one uniform shift ky*bw + kx.
@@ -48,8 +55,6 @@ struct HaloParams {
     int row_loads;        // 1: one box with row traversal stride d (d <= 8); 3: one single-row box per row (d > 8)
     int act_stage;        // bytes per activation stage (3 * bw * 128 rounded up to 1024)
     int act_stages;       // 2..4
-    int n_sets;           // independent (main | corr) accumulator sets per tile that the taps rotate over: consecutive MMAs
-                          // into ONE accumulator serialise on its latency (~125 clk measured), which dominates narrow layers
     int w_resident;       // all 9 * kchunks weight images stay in shared memory (small layers): loaded once per CTA
     float alpha, mask_alpha;
     unsigned long long* dbg;   // optional timeline (clock64): 8 events x 8 tiles per CTA; nullptr in production
@@ -63,23 +68,283 @@ struct HaloParams {
 
 #define HL_DBG(ev, tile) do { if (dbg && (tile) < 8) dbg[(ev) * 8 + (tile)] = clock64(); } while (0)
 
-__device__ __forceinline__ void hl_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+// tcgen05.mma with the shared-memory descriptors given as (lo, hi) words: only the low word (start address) changes
+// between the MMAs of a tile, so the issuing thread does 32-bit adds instead of 64-bit descriptor arithmetic.
+constexpr uint32_t HL_ADESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // A: 128-byte K-major rows, 128B swizzle, 8-row groups 1024 B apart
+constexpr uint32_t HL_BDESC_HI = (512u >> 4) | (1u << 14) | (4u << 29);    // B: 64-byte K-major rows, 64B swizzle, 8-row groups 512 B apart
+template <bool ACC>
+__device__ __forceinline__ void hl_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    if (ACC) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b64 da, db;\n\t"
+            "setp.eq.u32 p, 1, 1;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+            "}" ::"r"(d_tmem), "r"(a_lo), "r"(HL_ADESC_HI), "r"(b_lo), "r"(HL_BDESC_HI), "r"(idesc) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+            "}" ::"r"(d_tmem), "r"(a_lo), "r"(HL_ADESC_HI), "r"(b_lo), "r"(HL_BDESC_HI), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+
+struct IssueCtx {
+    uint32_t idesc_n, idesc_w, tapoff[9], wsb16, cout, bar_wfull, bar_wempty, w_lo0;
+};
+
+// The MMAs of one 32-channel slice of a tile: nine taps x (A_h x [W_h|W_l] -> main|corr, A_l x W_h -> corr) x one or two
+// K = 16 steps.  The issuing thread is the critical path of the narrow layers (a 16 -> 16 tile is 18 tiny MMAs: the
+// round-1 loop spent ~55 instructions per tap, ~90 clk per MMA -- as long as a 128 x 256 x 16 MMA executes, so it also
+// held the wide layers below the tensor pipe's rate; profiles/r02_halo_epilogue.log), so everything per tap is a 32-bit add.
+template <bool RESIDENT, bool KS2>
+__device__ __forceinline__ void hl_issue_chunk(const IssueCtx& cx, uint32_t d_main, uint32_t a_lo, uint32_t b_lo, uint32_t first, uint32_t& wt) {
+    const uint32_t d_corr = d_main + cx.cout;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        if (!RESIDENT) {
+            const uint32_t ws = wt & (HL_W_STAGES - 1);
+            mbar_wait(cx.bar_wfull + 8 * ws, (wt / HL_W_STAGES) & 1);
+            tc_fence_after();
+            b_lo = cx.w_lo0 + ws * cx.wsb16;
+        }
+        const uint32_t al = a_lo + cx.tapoff[tap];
+        if (tap == 0) hl_mma_lo<false>(d_main, al, b_lo, cx.idesc_w, first);      // A_h x [W_h | W_l] -> main | corr
+        else hl_mma_lo<true>(d_main, al, b_lo, cx.idesc_w, 1u);
+        if (KS2) hl_mma_lo<true>(d_main, al + 2, b_lo + 2, cx.idesc_w, 1u);
+        hl_mma_lo<true>(d_corr, al + 4, b_lo, cx.idesc_n, 1u);                      // A_l x W_h -> corr
+        if (KS2) hl_mma_lo<true>(d_corr, al + 6, b_lo + 2, cx.idesc_n, 1u);
+        if (RESIDENT) b_lo += cx.wsb16;
+        else { tc_commit(cx.bar_wempty + 8 * (wt & (HL_W_STAGES - 1))); ++wt; }
+    }
+}
+
+__device__ __forceinline__ void hl_tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// TMA-store epilogue pass (round 2).  Plain stores from the epilogue warps cost ~275 clk per STG.128 whatever their
+// pattern (16 bytes per lane, 32-byte lane pairs, or fully coalesced after a shared-memory transpose: all measured,
+// profiles/r02_halo_epilogue.log) -- the SM's store path accepts ~7 B/clk from these warps, and the epilogue, not the
+// MMAs, set the tile period of the narrow layers.  Here a warp writes its 32 pixels x G channels into a private,
+// swizzled staging buffer (conflict-free STS.128: the swizzle the tensor map undoes), and lane 0 hands the 32-pixel box
+// to the TMA engine; the warp goes on with the next pass / tile while the engine drains it (two buffers per warp,
+// cp.async.bulk.wait_group.read before a buffer is rewritten).  Pixels beyond the row end are clipped by the tensor map.
+template <int G>
+__device__ __forceinline__ void hl_stage_and_store(const CUtensorMap* map, uint8_t* buf, const uint32_t (&w)[G], int lane,
+                                                   int c0, int x, int y, int b) {
+    constexpr int NCH = G / 4;                                // 16-byte chunks per pixel row (8: 128 B, 4: 64 B)
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the store that last read this buffer is done
+    __syncwarp();
+    const int sw = NCH == 8 ? (lane & 7) : ((lane >> 1) & 3);  // 128B / 64B swizzle of row `lane` (buffers are 1024-byte aligned)
+    uint8_t* row = buf + lane * (16 * NCH);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+        *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        hl_tma_store_4d(map, smem_u32(buf), c0, x, y, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+
+// Stores of one pass, 32 contiguous bytes per lane PAIR: after tcgen05.ld a lane holds one pixel's channels, and a plain
+// 16-byte store per lane puts 32 half-written sectors per instruction on the wire (the other half follows an instruction
+// later; measured ~375 clk per such instruction, profiles/r02_halo_epilogue.log).  Lanes 2k / 2k+1 swap every second
+// 16-byte chunk instead: store A covers chunks (c, c+1) of the even lane's pixel, store B the same chunks of the odd
+// lane's pixel -- every request is a whole 32-byte sector.  `own` / `oth` point at this lane's / the partner's pixel
+// (at the pass's first channel); the mask (dgrad: leaky derivative of the forward activation) and the accumulate
+// operand are read at the stored positions.  Executed by all 32 lanes (shuffles); invalid pixels only skip the stores.
+template <int NCH>
+__device__ __forceinline__ void hl_store_pairs(const uint32_t (&w)[4 * NCH], char* own, char* oth, bool valid, bool valid_o, bool odd,
+                                               const float* mask_own, const float* mask_oth, float mask_alpha, bool accumulate) {
+    char* row_e = odd ? oth : own;                     // the even lane's pixel, the odd lane's pixel
+    char* row_o = odd ? own : oth;
+    const bool ok_e = odd ? valid_o : valid, ok_o = odd ? valid : valid_o;
+    const char* m_e = reinterpret_cast<const char*>(odd ? mask_oth : mask_own);
+    const char* m_o = reinterpret_cast<const char*>(odd ? mask_own : mask_oth);
+#pragma unroll
+    for (int c = 0; c < NCH; c += 2) {
+        uint4 mine_e, mine_o;                          // even lane keeps chunk c, sends c+1; odd lane keeps c+1, sends c
+        uint4 snd;
+        snd.x = odd ? w[4 * c] : w[4 * c + 4]; snd.y = odd ? w[4 * c + 1] : w[4 * c + 5];
+        snd.z = odd ? w[4 * c + 2] : w[4 * c + 6]; snd.w = odd ? w[4 * c + 3] : w[4 * c + 7];
+        uint4 rcv;
+        rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, 1); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
+        rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, 1); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
+        const uint4 keep = odd ? make_uint4(w[4 * c + 4], w[4 * c + 5], w[4 * c + 6], w[4 * c + 7])
+                               : make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        mine_e = odd ? rcv : keep;                     // -> even pixel, chunk c + odd
+        mine_o = odd ? keep : rcv;                     // -> odd pixel,  chunk c + odd
+        const int off = (c + (odd ? 1 : 0)) * 16;
+        if (mask_own) {
+            if (ok_e) {
+                const float4 mk = __ldg(reinterpret_cast<const float4*>(m_e + off));
+                mine_e.x = __float_as_uint(__uint_as_float(mine_e.x) * (mk.x > 0.f ? 1.f : mask_alpha));
+                mine_e.y = __float_as_uint(__uint_as_float(mine_e.y) * (mk.y > 0.f ? 1.f : mask_alpha));
+                mine_e.z = __float_as_uint(__uint_as_float(mine_e.z) * (mk.z > 0.f ? 1.f : mask_alpha));
+                mine_e.w = __float_as_uint(__uint_as_float(mine_e.w) * (mk.w > 0.f ? 1.f : mask_alpha));
+            }
+            if (ok_o) {
+                const float4 mk = __ldg(reinterpret_cast<const float4*>(m_o + off));
+                mine_o.x = __float_as_uint(__uint_as_float(mine_o.x) * (mk.x > 0.f ? 1.f : mask_alpha));
+                mine_o.y = __float_as_uint(__uint_as_float(mine_o.y) * (mk.y > 0.f ? 1.f : mask_alpha));
+                mine_o.z = __float_as_uint(__uint_as_float(mine_o.z) * (mk.z > 0.f ? 1.f : mask_alpha));
+                mine_o.w = __float_as_uint(__uint_as_float(mine_o.w) * (mk.w > 0.f ? 1.f : mask_alpha));
+            }
+        }
+        if (accumulate) {
+            if (ok_e) {
+                const uint4 o = *reinterpret_cast<const uint4*>(row_e + off);
+                mine_e.x = __float_as_uint(__uint_as_float(mine_e.x) + __uint_as_float(o.x)); mine_e.y = __float_as_uint(__uint_as_float(mine_e.y) + __uint_as_float(o.y));
+                mine_e.z = __float_as_uint(__uint_as_float(mine_e.z) + __uint_as_float(o.z)); mine_e.w = __float_as_uint(__uint_as_float(mine_e.w) + __uint_as_float(o.w));
+            }
+            if (ok_o) {
+                const uint4 o = *reinterpret_cast<const uint4*>(row_o + off);
+                mine_o.x = __float_as_uint(__uint_as_float(mine_o.x) + __uint_as_float(o.x)); mine_o.y = __float_as_uint(__uint_as_float(mine_o.y) + __uint_as_float(o.y));
+                mine_o.z = __float_as_uint(__uint_as_float(mine_o.z) + __uint_as_float(o.z)); mine_o.w = __float_as_uint(__uint_as_float(mine_o.w) + __uint_as_float(o.w));
+            }
+        }
+        if (ok_e) *reinterpret_cast<uint4*>(row_e + off) = mine_e;
+        if (ok_o) *reinterpret_cast<uint4*>(row_o + off) = mine_o;
+    }
+}
+
+// One epilogue pass over G channels of one pixel (a lane of the accumulator quadrant): TMEM -> registers, main + 2^-11 x
+// correction, bias (from shared memory: a global load here sits on the tile's critical path at L2 latency -- measured
+// ~1k clk per pass, profiles/r02_halo_epilogue.log), leaky, stores.  G = 32 when the layer has whole 32-channel groups:
+// half the TMEM round trips (~0.5-1k clk each under MMA load) and a lane writes whole 128-byte lines (its pixel's fp32
+// channels, or the [h | l] split row of the slice).  A shared-memory transpose for fully coalesced stores was measured
+// SLOWER (same log): shared memory is this kernel's saturated resource.
+template <int G>
+__device__ __forceinline__ void hl_epilogue_pass(const HaloParams& p, const float* s_bias, uint32_t tbase, int n0, bool valid,
+                                                 size_t pix, bool valid_o, size_t pix_o, bool odd, bool vec,
+                                                 unsigned long long* dbg, int tcount,
+                                                 const CUtensorMap* tmY, const CUtensorMap* tmYS, uint8_t* stage, int& nbuf,
+                                                 int lane, int wx, int wy, int wb, uint32_t release_bar) {
+    float acc[G];
+    {
+        uint32_t rm[G], rc[G];
+#pragma unroll
+        for (int g = 0; g < G; g += 16) {
+            tmem_ld16(tbase + p.Cout + n0 + g, rc + g);
+            tmem_ld16(tbase + n0 + g, rm + g);
+        }
+        tmem_ld_wait();
+        if (release_bar) {
+            // last pass of the tile: the accumulators are in registers, hand the TMEM set back to the MMA issuer now
+            // (not after the stores: the narrow layers' tile period is the epilogue's latency chain)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(release_bar);
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) acc[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]) * HL_INV_SCALE;
+    }
+    if (n0 == 0) HL_DBG(7, tcount);
+    if (p.exp_skip_store) return;
+#pragma unroll
+    for (int j = 0; j < G; j += 4) {
+        const float4 bq = *reinterpret_cast<const float4*>(s_bias + n0 + j);
+        acc[j] = leaky(acc[j] + bq.x, p.alpha); acc[j + 1] = leaky(acc[j + 1] + bq.y, p.alpha);
+        acc[j + 2] = leaky(acc[j + 2] + bq.z, p.alpha); acc[j + 3] = leaky(acc[j + 3] + bq.w, p.alpha);
+    }
+    if (n0 == 0) HL_DBG(8, tcount);
+    if (p.ys) {
+        // channels as split rows: h at half (n0 / 32) * 64 + n0 % 32 of the pixel, l 32 halfs later (G = 32: one whole 128-byte row)
+        uint32_t w[G];
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) {
+            const __half2 h2 = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+            const float2 f2 = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn((acc[2 * j] - f2.x) * HL_SCALE, (acc[2 * j + 1] - f2.y) * HL_SCALE);
+            w[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            w[G / 2 + j] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        if (p.tma_ys && G == 32) {
+            hl_stage_and_store<G>(tmYS, stage + (nbuf & 1) * (32 * 4 * G), w, lane, (n0 >> 5) * 64, wx, wy, wb);
+            ++nbuf;
+        } else if (G == 32 && !p.exp_direct_store) {
+            char* own = reinterpret_cast<char*>(p.ys + pix * p.ys_cs + (n0 >> 5) * 64);
+            char* oth = reinterpret_cast<char*>(p.ys + pix_o * p.ys_cs + (n0 >> 5) * 64);
+            hl_store_pairs<G / 4>(w, own, oth, valid, valid_o, odd, nullptr, nullptr, 0.f, false);
+        } else if (valid) {
+            __half* hp = p.ys + pix * p.ys_cs + (n0 >> 5) * 64 + (n0 & 31);
+            uint4* hq = reinterpret_cast<uint4*>(hp);
+            uint4* lq = reinterpret_cast<uint4*>(hp + 32);
+#pragma unroll
+            for (int j = 0; j < G / 8; ++j) hq[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+#pragma unroll
+            for (int j = 0; j < G / 8; ++j) lq[j] = make_uint4(w[G / 2 + 4 * j], w[G / 2 + 4 * j + 1], w[G / 2 + 4 * j + 2], w[G / 2 + 4 * j + 3]);
+        }
+    }
+    if (p.y) {
+        float* yrow = p.y + pix * p.y_cs;
+        const float* mrow = p.mask ? p.mask + pix * p.mask_cs : nullptr;
+        const float* rrow = p.res ? p.res + pix * p.res_cs : nullptr;
+        if (p.tma_y) {
+            uint32_t w[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) w[j] = __float_as_uint(acc[j]);
+            hl_stage_and_store<G>(tmY, stage + (nbuf & 1) * (32 * 4 * G), w, lane, n0, wx, wy, wb);
+            ++nbuf;
+        } else if (vec && p.cout_valid == p.Cout && (p.Cout % G) == 0 && !p.exp_direct_store) {
+            uint32_t w[G];
+#pragma unroll
+            for (int j = 0; j < G; ++j) w[j] = __float_as_uint(acc[j]);
+            hl_store_pairs<G / 4>(w, reinterpret_cast<char*>(yrow + n0), reinterpret_cast<char*>(p.y + pix_o * p.y_cs + n0), valid, valid_o, odd,
+                                  mrow ? mrow + n0 : nullptr, p.mask ? p.mask + pix_o * p.mask_cs + n0 : nullptr, p.mask_alpha,
+                                  p.accumulate != 0);
+        } else if (!valid) {
+        } else if (vec) {
+#pragma unroll
+            for (int j = 0; j < G; j += 4) {
+                if (n0 + j >= p.cout_valid) break;
+                float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                if (mrow) {
+                    const float4 mk = ldg4(mrow + n0 + j);
+                    v.x *= mk.x > 0.f ? 1.f : p.mask_alpha; v.y *= mk.y > 0.f ? 1.f : p.mask_alpha;
+                    v.z *= mk.z > 0.f ? 1.f : p.mask_alpha; v.w *= mk.w > 0.f ? 1.f : p.mask_alpha;
+                }
+                float4* dst = reinterpret_cast<float4*>(yrow + n0 + j);
+                if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                *dst = v;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                if (n0 + j >= p.cout_valid) break;
+                float v = acc[j];
+                if (mrow) v *= __ldg(mrow + n0 + j) > 0.f ? 1.f : p.mask_alpha;
+                if (rrow) v += __ldg(rrow + n0 + j);
+                if (p.accumulate) v += yrow[n0 + j];
+                yrow[n0 + j] = v;
+            }
+        }
+    }
+    if (n0 == 0) HL_DBG(9, tcount);
 }
 
 __global__ void __launch_bounds__(HL_THREADS, 1)
-conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams p) {
+conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                       const __grid_constant__ CUtensorMap tmYS, const HaloParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     // barriers: act_full[2], act_conv[2], act_empty[2], w_full[4], w_empty[4], acc_full[2], acc_empty[2]
     __shared__ __align__(8) uint64_t bars[3 * HL_MAX_ACT_STAGES + 2 * HL_W_STAGES + 4];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float s_bias[128 + 16];   // Cout <= 128; a 16-channel pass of a Cout % 16 == 8 layer reads 8 past the end
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int MS = HL_MAX_ACT_STAGES;
@@ -106,6 +371,10 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 144) {
+        const int c = threadIdx.x - 64;
+        s_bias[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -116,21 +385,27 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
     const uint32_t tmem_acc = tmem_base_slot;
     const int KC = p.kchunks;
     const int tiles_per_img = p.tiles_img;
-    unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+    // tile walk of this CTA: strided (t = cta, cta + grid, ...) or, PWC_HALO_CONTIG=1, one contiguous run of tiles
+    int t_begin = blockIdx.x, t_end = p.total_tiles, t_step = gridDim.x;
+    if (p.contig) {
+        const int per = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+        t_begin = blockIdx.x * per; t_end = min(p.total_tiles, t_begin + per); t_step = 1;
+    }
+    unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 128 : nullptr;
 
     if (warp == 0) {
         // ===================== activation producer =====================
         if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-            int it = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            int it = 0, s = 0;
+            uint32_t ph = 0;                                   // stage index and ring phase as counters: no division per slice
+            for (int t = t_begin; t < t_end; t += t_step) {
                 const int b = t / tiles_per_img, r = t - b * tiles_per_img;
                 int y, x0;
                 if (p.flat) { y = (r * HL_M) / p.bw; x0 = 0; }           // first row touched by the tile's slots
                 else { y = r / p.tiles_x; x0 = (r - y * p.tiles_x) * HL_M; }
                 for (int c = 0; c < KC; ++c, ++it) {
-                    const int s = it % AS;
-                    mbar_wait(bar_aempty + 8 * s, ((it / AS) & 1) ^ 1);
+                    mbar_wait(bar_aempty + 8 * s, ph ^ 1);
                     HL_DBG(0, it);
                     mbar_expect_tx(bar_afull + 8 * s, (uint32_t)n_rows * 128);
                     const int c0 = c * (p.in_split ? 2 * HL_BK : HL_BK);      // element offset of the slice (fp32 or halfs)
@@ -142,6 +417,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                             tma_load_4d(base + s * p.act_stage + r2 * p.bw * 128, &tmX, bar_afull + 8 * s, c0, x0 - p.dil,
                                         y + (r2 - 1) * p.dil, b);
                     }
+                    if (++s == AS) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -158,7 +434,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                     for (int tap = 0; tap < 9; ++tap)
                         bulk_load_1d(w_base + (c * 9 + tap) * p.w_stage_bytes, p.w + (size_t)(tap * KC + c) * bytes, bytes, bar_wfull);
             } else {
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int t = t_begin; t < t_end; t += t_step) {
                 for (int c = 0; c < KC; ++c) {
                     for (int tap = 0; tap < 9; ++tap, ++wt) {
                         const int s = wt & (HL_W_STAGES - 1);
@@ -173,168 +449,113 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            const bool leader = true;
-            const uint32_t tmem_u = tmem_acc, base_u = base, w_base_u = w_base;
-            const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
-            const uint32_t idesc_w = (1u << 4) | ((uint32_t)((2 * p.Cout) >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
-            // A: K-major rows of 128 bytes ([h | l]), 128B swizzle, 8-row groups 1024 bytes apart
-            const uint64_t adesc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-            // B: K-major rows of 64 bytes, 64B swizzle, 8-row groups 512 bytes apart
-            const uint64_t bdesc_hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
-            // Everything that does not change is hoisted out of the issue loop (the nine tap offsets of the A descriptor,
-            // the accumulator-set stride, the weight-image stride): on narrow layers the issuing thread is the critical path.
-            uint32_t tapoff[9];
+            IssueCtx cx;
+            cx.idesc_n = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
+            cx.idesc_w = (1u << 4) | ((uint32_t)((2 * p.Cout) >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (uint32_t)((tap / 3) * p.bw + (tap % 3) * p.dil) * 8;   // 128-byte rows, >> 4
-            const uint32_t setmask = (uint32_t)p.n_sets - 1, cout2 = 2 * p.Cout, n_sets = p.n_sets;
-            const uint32_t wsb16 = (uint32_t)p.w_stage_bytes >> 4;
+            for (int tap = 0; tap < 9; ++tap) cx.tapoff[tap] = (uint32_t)((tap / 3) * p.bw + (tap % 3) * p.dil) * 8;   // 128-byte rows, >> 4
+            cx.wsb16 = (uint32_t)p.w_stage_bytes >> 4;
+            cx.cout = (uint32_t)p.Cout;
+            cx.bar_wfull = bar_wfull; cx.bar_wempty = bar_wempty;
+            cx.w_lo0 = ((w_base >> 4) & 0x3FFF) | (1u << 16);
             const bool resident = p.w_resident != 0;
-            int it = 0, wt = 0, tcount = 0;
+            int it = 0, tcount = 0, s = 0;
+            uint32_t wt = 0, ph = 0;
             if (resident) { mbar_wait(bar_wfull, 0); tc_fence_after(); }
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+            for (int t = t_begin; t < t_end; t += t_step, ++tcount) {
                 const int a = tcount & 1, u = tcount >> 1;
                 if (u > 0) {                       // the epilogue has drained this accumulator set
                     mbar_wait(bar_acce + 8 * a, (u - 1) & 1);
                     tc_fence_after();
                 }
-                const uint32_t d_tile = tmem_u + a * 256;
+                const uint32_t d_tile = tmem_acc + a * 256;
                 uint32_t c0off = 0;                                   // flat mode: the tile starts c0 slots into its first row
                 if (p.flat) { const int r = t % tiles_per_img; c0off = (uint32_t)((r * HL_M) % p.bw) * 8; }
                 for (int c = 0; c < KC; ++c, ++it) {
-                    const int s = it % AS;
-                    mbar_wait(bar_aconv + 8 * s, (it / AS) & 1);
-                    if (leader) HL_DBG(3, it);
+                    mbar_wait(bar_aconv + 8 * s, ph);
+                    HL_DBG(3, it);
                     tc_fence_after();
-                    const uint32_t ast = base_u + s * p.act_stage;
+                    const uint32_t ast = base + s * p.act_stage;
+                    const uint32_t a_lo = (((ast >> 4) & 0x3FFF) | (1u << 16)) + c0off;
                     const bool ks2 = p.Cin - c * HL_BK > 16;             // channels 16..31 of the slice are zero padding otherwise
-                    const uint64_t ad0 = (adesc_hi | (uint64_t)(((ast >> 4) & 0x3FFF) | (1u << 16))) + c0off;
-                    uint64_t bd = bdesc_hi | (uint64_t)((((w_base_u + (resident ? c * 9 * p.w_stage_bytes : 0)) >> 4) & 0x3FFF) | (1u << 16));
-                    const uint32_t use0 = (uint32_t)c * 9;
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        if (!resident) {
-                            const int ws = wt & (HL_W_STAGES - 1);
-                            mbar_wait(bar_wfull + 8 * ws, (wt / HL_W_STAGES) & 1);
-                            tc_fence_after();
-                            bd = bdesc_hi | (uint64_t)((((w_base_u + ws * p.w_stage_bytes) >> 4) & 0x3FFF) | (1u << 16));
-                        }
-                        const uint64_t ad = ad0 + tapoff[tap];
-                        const uint32_t use = use0 + tap;
-                        const uint32_t d_main = d_tile + (use & setmask) * cout2, d_corr = d_main + p.Cout;
-                        if (leader) hl_mma(d_main, ad, bd, idesc_w, use < n_sets ? 0u : 1u);          // A_h x [W_h | W_l] -> main | corr
-                        if (ks2 && leader) hl_mma(d_main, ad + 2, bd + 2, idesc_w, 1u);
-                        if (leader) hl_mma(d_corr, ad + 4, bd, idesc_n, 1u);                            // A_l x W_h -> corr
-                        if (ks2 && leader) hl_mma(d_corr, ad + 6, bd + 2, idesc_n, 1u);
-                        if (resident) bd += wsb16;
-                        else { if (leader) tc_commit(bar_wempty + 8 * (wt & (HL_W_STAGES - 1))); ++wt; }
+                    const uint32_t first = c == 0 ? 0u : 1u;
+                    if (resident) {
+                        const uint32_t b_lo = cx.w_lo0 + (uint32_t)c * 9 * cx.wsb16;
+                        if (ks2) hl_issue_chunk<true, true>(cx, d_tile, a_lo, b_lo, first, wt);
+                        else hl_issue_chunk<true, false>(cx, d_tile, a_lo, b_lo, first, wt);
+                    } else {
+                        if (ks2) hl_issue_chunk<false, true>(cx, d_tile, a_lo, 0, first, wt);
+                        else hl_issue_chunk<false, false>(cx, d_tile, a_lo, 0, first, wt);
                     }
-                    if (leader) tc_commit(bar_aempty + 8 * s);
-                    if (leader) HL_DBG(4, it);
+                    tc_commit(bar_aempty + 8 * s);
+                    HL_DBG(4, it);
+                    if (++s == AS) { s = 0; ph ^= 1; }
                 }
-                if (leader) tc_commit(bar_accf + 8 * a);
+                tc_commit(bar_accf + 8 * a);
             }
         }
     } else if (warp < 6) {
         // ===================== epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =====================
         const int q = warp & 3;
         const int m = q * 32 + lane;
+        uint8_t* stage = base_ptr + p.epi_off + q * 8192;      // this warp's two staging buffers (TMA-store epilogue)
+        int nbuf = 0;
+        if ((p.tma_y || p.tma_ys) && lane == 0) {
+            if (p.tma_y) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+            if (p.tma_ys) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmYS) : "memory");
+        }
         int tcount = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
-            const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+        // tile coordinates advance by the (constant) tile step without divisions: image b, tile r of the image =
+        // (row ty, column tile tx) in row mode
+        const int d_b = t_step / tiles_per_img, d_r = t_step - d_b * tiles_per_img;
+        const int d_y = d_r / p.tiles_x, d_x = d_r - d_y * p.tiles_x;
+        int b = t_begin / tiles_per_img, r = t_begin - b * tiles_per_img;
+        int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        for (int t = t_begin; t < t_end; t += t_step, ++tcount) {
             int y, x;
             if (p.flat) { const int slot = r * HL_M + m; y = slot / p.bw; x = slot - y * p.bw; }
-            else { y = r / p.tiles_x; x = (r - y * p.tiles_x) * HL_M + m; }
+            else { y = ty; x = tx * HL_M + m; }
+            const int b_now = b;
+            r += d_r; b += d_b;
+            if (r >= tiles_per_img) { r -= tiles_per_img; ++b; }
+            tx += d_x; ty += d_y;
+            if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+            if (ty >= p.H) ty -= p.H;                      // row mode: tiles_per_img = tiles_x * H, the image carry is in b
             const int a = tcount & 1, u = tcount >> 1;
             mbar_wait(bar_accf + 8 * a, u & 1);
             if (threadIdx.x == 64) HL_DBG(5, tcount);
             tc_fence_after();
             const bool valid = x < p.W && y < p.H;
-            const size_t pix = ((size_t)b * p.H + y) * p.W + x;
-            float* yrow = p.y + pix * p.y_cs;
-            const float* mrow = p.mask ? p.mask + pix * p.mask_cs : nullptr;
-            const float* rrow = p.res ? p.res + pix * p.res_cs : nullptr;
+            const size_t pix = ((size_t)b_now * p.H + y) * p.W + x;
             const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y) && ((p.cout_valid & 3) == 0) && !p.res &&
                              (!p.mask || (((p.mask_cs & 3) == 0) && aligned16(p.mask)));
             const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + a * 256;
-            for (int n0 = 0; n0 < p.Cout; n0 += 16) {
-                uint32_t rm[16], rc[16];
-                float acc[16], accc[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { acc[j] = 0.f; accc[j] = 0.f; }
-                for (int st = 0; st < p.n_sets; ++st) {
-                    tmem_ld16(tbase + st * 2 * p.Cout + p.Cout + n0, rc);
-                    tmem_ld16(tbase + st * 2 * p.Cout + n0, rm);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { acc[j] += __uint_as_float(rm[j]); accc[j] += __uint_as_float(rc[j]); }
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += accc[j] * HL_INV_SCALE;
-                if (valid) {
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] += __ldg(p.bias + n0 + j);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = leaky(acc[j], p.alpha);
-                    if (p.ys) {
-                        // 16 channels of this pixel as split rows: h at half (n0 / 32) * 64 + n0 % 32 of the pixel, l 32 halfs later
-                        __half* hp = p.ys + pix * p.ys_cs + (n0 >> 5) * 64 + (n0 & 31);
-                        uint32_t hw[8], lw[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const __half2 h2 = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-                            const float2 f2 = __half22float2(h2);
-                            const __half2 l2 = __floats2half2_rn((acc[2 * j] - f2.x) * HL_SCALE, (acc[2 * j + 1] - f2.y) * HL_SCALE);
-                            hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
-                            lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
-                        }
-                        uint4* hq = reinterpret_cast<uint4*>(hp);
-                        uint4* lq = reinterpret_cast<uint4*>(hp + 32);
-                        hq[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); hq[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-                        lq[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); lq[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-                    }
-                    if (!p.y) {
-                    } else if (vec) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            if (n0 + j >= p.cout_valid) break;
-                            float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                            if (mrow) {
-                                const float4 mk = ldg4(mrow + n0 + j);
-                                v.x *= mk.x > 0.f ? 1.f : p.mask_alpha; v.y *= mk.y > 0.f ? 1.f : p.mask_alpha;
-                                v.z *= mk.z > 0.f ? 1.f : p.mask_alpha; v.w *= mk.w > 0.f ? 1.f : p.mask_alpha;
-                            }
-                            float4* dst = reinterpret_cast<float4*>(yrow + n0 + j);
-                            if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                            *dst = v;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (n0 + j >= p.cout_valid) break;
-                            float v = acc[j];
-                            if (mrow) v *= __ldg(mrow + n0 + j) > 0.f ? 1.f : p.mask_alpha;
-                            if (rrow) v += __ldg(rrow + n0 + j);
-                            if (p.accumulate) v += yrow[n0 + j];
-                            yrow[n0 + j] = v;
-                        }
-                    }
-                }
+            unsigned long long* edbg = threadIdx.x == 64 ? dbg : nullptr;
+            const bool odd = lane & 1;
+            const bool valid_o = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
+            const size_t pix_o = (size_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)pix, 1);
+            if ((p.Cout & 31) == 0) {
+                for (int n0 = 0; n0 < p.Cout; n0 += 32) hl_epilogue_pass<32>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 32 >= p.Cout ? bar_acce + 8 * a : 0u);
+            } else {
+                for (int n0 = 0; n0 < p.Cout; n0 += 16) hl_epilogue_pass<16>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 16 >= p.Cout ? bar_acce + 8 * a : 0u);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acce + 8 * a);
             if (threadIdx.x == 64) HL_DBG(6, tcount);
+            if (threadIdx.x == 64 && dbg) {
+                unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+                dbg[80] = clock64(); dbg[81] = tcount + 1; dbg[83] = ns;
+                if (tcount == 0) dbg[82] = ns;      // wall clock at the first tile's epilogue
+                if (tcount == 0) dbg[84] = dbg[80];
+            }
         }
+        if ((p.tma_y || p.tma_ys) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging buffers must outlive their reads
     } else {
         // ===================== converters (warps 6..13): fp32 pixel row -> [h | l * 2^11] fp16, in place =====================
         const int ct = threadIdx.x - 192;   // 0..255
-        int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int it = 0, s = 0;
+        uint32_t ph = 0;
+        for (int t = t_begin; t < t_end; t += t_step) {
             for (int c = 0; c < KC; ++c, ++it) {
-                const int s = it % AS;
-                mbar_wait(bar_afull + 8 * s, (it / AS) & 1);
+                mbar_wait(bar_afull + 8 * s, ph);
                 if (ct == 0) HL_DBG(1, it);
                 uint8_t* stp = base_ptr + (size_t)s * p.act_stage;
 #pragma unroll
@@ -372,6 +593,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const HaloParams
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 if (ct == 0) HL_DBG(2, it);
                 mbar_arrive(bar_aconv + 8 * s);
+                if (++s == AS) { s = 0; ph ^= 1; }
             }
         }
     }
@@ -430,56 +652,93 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.dil = dilation; p.bw = flat ? W + 2 : HL_M + 2 * dilation; p.row_loads = dilation <= 8 ? 1 : HL_BH;
     p.act_stage = ((flat ? nr : HL_BH) * p.bw * 128 + 1023) / 1024 * 1024;
     p.desc_mode = 0;
-    p.exp_skip_conv = getenv("PWC_HALO_EXP") ? 1 : 0;
+    p.contig = getenv("PWC_HALO_CONTIG") ? 1 : 0;
+    // TMA-store epilogue: row tiles (not the flat mode: its tiles hold padding slots between rows), whole passes, plain
+    // stores (no dgrad mask / residual / accumulate)
+    CUtensorMap tmY, tmYS;
+    memset(&tmY, 0, sizeof(tmY)); memset(&tmYS, 0, sizeof(tmYS));
+    const bool tma_ok = !flat && !mask && !res && !accumulate && cout_valid == Cout && (Cout == 16 || (Cout & 31) == 0) &&
+                        !getenv("PWC_HALO_NO_TMA_STORE");
+    if (tma_ok && y && (y_cs & 3) == 0 && aligned16(y)) {
+        const cuuint32_t G = Cout == 16 ? 16 : 32;
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)y_cs * 4, (cuuint64_t)W * y_cs * 4, (cuuint64_t)H * W * y_cs * 4};
+        cuuint32_t box[4] = {G, 32, 1, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         G == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(y) failed with %d", (int)r); return PWC_E_BADARG; }
+        p.tma_y = 1;
+    }
+    if (tma_ok && y_split && (Cout & 31) == 0) {
+        cuuint64_t dims[4] = {(cuuint64_t)2 * Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)ys_cs * 2, (cuuint64_t)W * ys_cs * 2, (cuuint64_t)H * W * ys_cs * 2};
+        cuuint32_t box[4] = {64, 32, 1, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmYS, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, y_split, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(y_split) failed with %d", (int)r); return PWC_E_BADARG; }
+        p.tma_ys = 1;
+    }
+    const size_t epi_bytes = (p.tma_y || p.tma_ys) ? 4 * 8192 : 0;
+    if (const char* e = getenv("PWC_HALO_EXP")) { p.exp_skip_conv = atoi(e) == 1; p.exp_skip_store = atoi(e) == 2; p.exp_direct_store = atoi(e) == 3; }
     if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
-    // Rotating accumulator sets (power of two, <= 8, n_sets * 2 * Cout <= 256 columns per tile) paid off while the MMA
-    // issue was slowed by the lane-0 wrapper; with elect.sync one set is fastest (the epilogue reads every set back:
-    // 2.4k clk per 16-channel tile with 8 sets), so 1 is the default and PWC_HALO_SETS selects more.
-    int max_sets = 1;
-    while (max_sets < 8 && 2 * max_sets * 2 * Cout <= 256) max_sets *= 2;
-    p.n_sets = 1;
-    if (const char* e = getenv("PWC_HALO_SETS")) { int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v <= max_sets) p.n_sets = v; }
+    // (Rotating accumulator sets over the taps were tried in round 1 and again in round 2 with a separate A_l x W_h chain:
+    // no gain -- the issue loop, not the accumulator latency, was the limit; profiles/r02_halo_epilogue.log.)
     p.act_stages = 2;   // measured: a third activation stage does not help (174.6 vs 171.5 us at 128->128), the limit is operand bandwidth
     int want_stages = 0;
     if (const char* e = getenv("PWC_HALO_STAGES")) want_stages = atoi(e);
     if (want_stages == 3) p.act_stages = 3;
     const size_t w_all = (size_t)9 * p.kchunks * p.w_stage_bytes;
-    p.w_resident = (2 * (size_t)p.act_stage + w_all + 1024 <= 227 * 1024) && !getenv("PWC_HALO_NO_RESIDENT");
+    p.w_resident = (2 * (size_t)p.act_stage + w_all + epi_bytes + 1024 <= HL_SMEM_BUDGET) && !getenv("PWC_HALO_NO_RESIDENT");
     if (p.w_resident) {
         // small layers (resident weights): a stage is held from the TMA issue to the last MMA that reads it (~5k clk
         // at 16->16: 1.9k TMA latency + 1.4k conversion + 1.7k MMAs), so two stages cap the tile period at ~2.5k clk
         p.act_stages = 2;
-        const int fit = (int)((227 * 1024 - 1024 - w_all) / p.act_stage);
+        const int fit = (int)((HL_SMEM_BUDGET - 1024 - w_all - epi_bytes) / p.act_stage);
         const int lim = want_stages >= 2 && want_stages <= HL_MAX_ACT_STAGES ? want_stages : HL_MAX_ACT_STAGES;
         if (fit > 2) p.act_stages = fit < lim ? fit : lim;
     }
-    size_t smem = (size_t)p.act_stages * p.act_stage + (p.w_resident ? w_all : (size_t)HL_W_STAGES * p.w_stage_bytes) + 1024;
-    if (smem > 227 * 1024) { p.act_stages = 2; smem = (size_t)2 * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + 1024; }
-    if (smem > 227 * 1024) return -1000;
+    size_t smem = (size_t)p.act_stages * p.act_stage + (p.w_resident ? w_all : (size_t)HL_W_STAGES * p.w_stage_bytes) + epi_bytes + 1024;
+    if (smem > HL_SMEM_BUDGET) { p.act_stages = 2; smem = (size_t)2 * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + epi_bytes + 1024; }
+    if (smem > HL_SMEM_BUDGET && epi_bytes) { smem -= epi_bytes; p.tma_y = p.tma_ys = 0; }    // no room for the staging buffers: plain stores
+    if (smem > HL_SMEM_BUDGET) return -1000;
+    p.epi_off = (int)(smem - 1024 - ((p.tma_y || p.tma_ys) ? epi_bytes : 0));               // 1024-byte aligned: every part before it is
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc_halo: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
     static unsigned long long* dbg_buf = nullptr;
     if (getenv("PWC_HALO_DEBUG")) {
-        if (!dbg_buf) cudaMalloc(&dbg_buf, 148 * 64 * 8);
-        cudaMemsetAsync(dbg_buf, 0, 148 * 64 * 8, st);
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 148 * 128 * 8);
+        cudaMemsetAsync(dbg_buf, 0, 148 * 128 * 8, st);
         p.dbg = dbg_buf;
     }
-    conv3x3_tc_halo_kernel<<<grid, HL_THREADS, smem, st>>>(tmX, p);
+    conv3x3_tc_halo_kernel<<<grid, HL_THREADS, smem, st>>>(tmX, tmY, tmYS, p);
     PWC_CHECK_LAUNCH("conv3x3_tc_halo_kernel");
     if (p.dbg) {   // debugging aid only (synchronises): timeline of the first chunks / tiles of one CTA
         cudaStreamSynchronize(st);
         static int printed = 0;
         if (printed++ < 1) {
-            unsigned long long h[64];
-            const char* names[8] = {"act_tma", "full_seen", "conv_done", "mma_start", "mma_issued", "acc_seen", "epi_done", "-"};
-            cudaMemcpy(h, p.dbg + 64 * (grid / 2), 64 * 8, cudaMemcpyDeviceToHost);
+            unsigned long long h[128];
+            const char* names[10] = {"act_tma", "full_seen", "conv_done", "mma_start", "mma_issued", "acc_seen", "epi_done", "ld_done", "math_done", "stores_out"};
+            cudaMemcpy(h, p.dbg + 128 * (grid / 2), 128 * 8, cudaMemcpyDeviceToHost);
             fprintf(stderr, "[halo dbg] cta %d Cin %d Cout %d kchunks %d resident %d (clk from first TMA issue; columns = chunks / tiles 0..7)\n", grid / 2, Cin, Cout, p.kchunks, p.w_resident);
-            for (int e = 0; e < 7; ++e) {
+            for (int e = 0; e < 10; ++e) {
                 fprintf(stderr, "   %-10s", names[e]);
                 for (int t = 0; t < 8; ++t) fprintf(stderr, " %7lld", (long long)(h[e * 8 + t] - h[0]));
                 fprintf(stderr, "\n");
             }
+            fprintf(stderr, "   last epilogue done at %lld clk after %lld tiles; first -> last epilogue: %lld clk in %lld ns = %.3f GHz\n",
+                    (long long)(h[80] - h[0]), (long long)h[81], (long long)(h[80] - h[84]), (long long)(h[83] - h[82]),
+                    (double)(h[80] - h[84]) / (double)(h[83] - h[82]));
+            // per-CTA totals: slowest CTA
+            unsigned long long* all = (unsigned long long*)malloc((size_t)grid * 128 * 8);
+            cudaMemcpy(all, p.dbg, (size_t)grid * 128 * 8, cudaMemcpyDeviceToHost);
+            long long worst = 0, best = 1ll << 60; int wc = 0;
+            for (int c = 0; c < grid; ++c) { const long long d = (long long)(all[c * 128 + 80] - all[c * 128]); if (d > worst) { worst = d; wc = c; } if (d < best) best = d; }
+            fprintf(stderr, "   CTA life (first TMA -> last epilogue): min %lld max %lld clk (cta %d, %lld tiles)\n", best, worst, wc, (long long)all[wc * 128 + 81]);
+            free(all);
         }
     }
     return 0;
