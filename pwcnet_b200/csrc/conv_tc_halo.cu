@@ -27,7 +27,9 @@ namespace pwc {
 constexpr int HL_M = 128;                          // output pixels per tile (one row segment)
 constexpr int HL_BH = 3;                           // halo box: 3 rows (y-d, y, y+d) x (128 + 2d) pixels
 constexpr int HL_BK = 32;
-constexpr int HL_MAX_ACT_STAGES = 4, HL_W_STAGES = 4;   // activation stages: 2, up to 4 for layers with resident weights
+constexpr int HL_MAX_ACT_STAGES = 4;                   // activation stages: 2, up to 4 for layers with resident weights
+constexpr int HL_W_STAGES = 16;                        // barriers of the weight ring; the ring itself is p.w_stages (4..16, power of two) deep
+constexpr int HL_W_MIN_STAGES = 4;
 constexpr int HL_CONV_THREADS = 256;
 constexpr int HL_THREADS = 64 + 128 + HL_CONV_THREADS + 32;   // act TMA, MMA, 4 epilogue, 8 converter, weight producer
 constexpr size_t HL_SMEM_BUDGET = 226 * 1024;         // dynamic shared memory: 227 KB per CTA minus the static barriers + bias
@@ -39,13 +41,17 @@ struct HaloParams {
     int res_cs;
     int y_cs, mask_cs, B, H, W, Cin, Cout, cout_valid;
     int tiles_x, total_tiles, kchunks;
+    // Work items: CTA i processes the whole tiles i, i + grid, ... (`rounds` of them), then at most one item of the TAIL -- the
+    // last total_tiles - rounds * grid tiles, each split n_split ways along the output channels (cn_split channels per item,
+    // tail_items = tail tiles * n_split <= grid) so that the partly filled last round costs 1 / n_split of a tile time (layers
+    // with fewer tiles than SMs are all tail).  n_split = 1: no split possible (tail_items = tail tiles, cn_split = Cout).
+    int rounds, tail_items, n_split, cn_split;
     int b_bytes;          // Cout * 64: one fp16 weight tile (h or l) of a (tap, slice)
     int w_stage_bytes;    // 2 * b_bytes rounded up to 1024
     int accumulate, desc_mode;
     int exp_skip_conv;    // experiment (PWC_HALO_EXP=1): converters do nothing -> wrong results, upper bound of a split-input variant
     int tma_y, tma_ys;    // the epilogue stores the fp32 / split output through TMA (shared-memory staging + bulk tensor store)
     int epi_off;          // byte offset of the epilogue staging area: 4 warps x 2 buffers x (32 pixels x 128 or 64 bytes)
-    int contig;           // experiment (PWC_HALO_CONTIG=1): contiguous tile runs per CTA
     int exp_direct_store; // experiment (PWC_HALO_EXP=3): 16-byte-per-lane stores (round-1 pattern)
     int exp_skip_store;   // experiment (PWC_HALO_EXP=2): the epilogue stores nothing -> upper bound of the store path
     int dil, bw;          // dilation d; box width in pixels (128 + 2d, or W + 2 in flat mode)
@@ -55,6 +61,7 @@ struct HaloParams {
     int row_loads;        // 1: one box with row traversal stride d (d <= 8); 3: one single-row box per row (d > 8)
     int act_stage;        // bytes per activation stage (3 * bw * 128 rounded up to 1024)
     int act_stages;       // 2..4
+    int w_stages, w_shift; // depth of the weight ring (streaming layers) and its log2
     int w_resident;       // all 9 * kchunks weight images stay in shared memory (small layers): loaded once per CTA
     float alpha, mask_alpha;
     unsigned long long* dbg;   // optional timeline (clock64): 8 events x 8 tiles per CTA; nullptr in production
@@ -98,7 +105,7 @@ __device__ __forceinline__ void hl_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32
 }
 
 struct IssueCtx {
-    uint32_t idesc_n, idesc_w, tapoff[9], wsb16, cout, bar_wfull, bar_wempty, w_lo0;
+    uint32_t idesc_n, idesc_w, tapoff[9], wsb16, cout, bar_wfull, bar_wempty, w_lo0, w_mask, w_shift;
 };
 
 // The MMAs of one 32-channel slice of a tile: nine taps x (A_h x [W_h|W_l] -> main|corr, A_l x W_h -> corr) x one or two
@@ -111,8 +118,8 @@ __device__ __forceinline__ void hl_issue_chunk(const IssueCtx& cx, uint32_t d_ma
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
         if (!RESIDENT) {
-            const uint32_t ws = wt & (HL_W_STAGES - 1);
-            mbar_wait(cx.bar_wfull + 8 * ws, (wt / HL_W_STAGES) & 1);
+            const uint32_t ws = wt & cx.w_mask;
+            mbar_wait(cx.bar_wfull + 8 * ws, (wt >> cx.w_shift) & 1);
             tc_fence_after();
             b_lo = cx.w_lo0 + ws * cx.wsb16;
         }
@@ -123,7 +130,7 @@ __device__ __forceinline__ void hl_issue_chunk(const IssueCtx& cx, uint32_t d_ma
         hl_mma_lo<true>(d_corr, al + 4, b_lo, cx.idesc_n, 1u);                      // A_l x W_h -> corr
         if (KS2) hl_mma_lo<true>(d_corr, al + 6, b_lo + 2, cx.idesc_n, 1u);
         if (RESIDENT) b_lo += cx.wsb16;
-        else { tc_commit(cx.bar_wempty + 8 * (wt & (HL_W_STAGES - 1))); ++wt; }
+        else { tc_commit(cx.bar_wempty + 8 * (wt & cx.w_mask)); ++wt; }
     }
 }
 
@@ -231,13 +238,13 @@ __device__ __forceinline__ void hl_epilogue_pass(const HaloParams& p, const floa
                                                  size_t pix, bool valid_o, size_t pix_o, bool odd, bool vec,
                                                  unsigned long long* dbg, int tcount,
                                                  const CUtensorMap* tmY, const CUtensorMap* tmYS, uint8_t* stage, int& nbuf,
-                                                 int lane, int wx, int wy, int wb, uint32_t release_bar) {
+                                                 int lane, int wx, int wy, int wb, uint32_t release_bar, int ch0, int cn) {
     float acc[G];
     {
         uint32_t rm[G], rc[G];
 #pragma unroll
         for (int g = 0; g < G; g += 16) {
-            tmem_ld16(tbase + p.Cout + n0 + g, rc + g);
+            tmem_ld16(tbase + cn + n0 + g, rc + g);
             tmem_ld16(tbase + n0 + g, rm + g);
         }
         tmem_ld_wait();
@@ -255,7 +262,7 @@ __device__ __forceinline__ void hl_epilogue_pass(const HaloParams& p, const floa
     if (p.exp_skip_store) return;
 #pragma unroll
     for (int j = 0; j < G; j += 4) {
-        const float4 bq = *reinterpret_cast<const float4*>(s_bias + n0 + j);
+        const float4 bq = *reinterpret_cast<const float4*>(s_bias + ch0 + n0 + j);
         acc[j] = leaky(acc[j] + bq.x, p.alpha); acc[j + 1] = leaky(acc[j + 1] + bq.y, p.alpha);
         acc[j + 2] = leaky(acc[j + 2] + bq.z, p.alpha); acc[j + 3] = leaky(acc[j + 3] + bq.w, p.alpha);
     }
@@ -272,14 +279,14 @@ __device__ __forceinline__ void hl_epilogue_pass(const HaloParams& p, const floa
             w[G / 2 + j] = *reinterpret_cast<const uint32_t*>(&l2);
         }
         if (p.tma_ys && G == 32) {
-            hl_stage_and_store<G>(tmYS, stage + (nbuf & 1) * (32 * 4 * G), w, lane, (n0 >> 5) * 64, wx, wy, wb);
+            hl_stage_and_store<G>(tmYS, stage + (nbuf & 1) * (32 * 4 * G), w, lane, ((ch0 + n0) >> 5) * 64, wx, wy, wb);
             ++nbuf;
         } else if (G == 32 && !p.exp_direct_store) {
-            char* own = reinterpret_cast<char*>(p.ys + pix * p.ys_cs + (n0 >> 5) * 64);
-            char* oth = reinterpret_cast<char*>(p.ys + pix_o * p.ys_cs + (n0 >> 5) * 64);
+            char* own = reinterpret_cast<char*>(p.ys + pix * p.ys_cs + ((ch0 + n0) >> 5) * 64);
+            char* oth = reinterpret_cast<char*>(p.ys + pix_o * p.ys_cs + ((ch0 + n0) >> 5) * 64);
             hl_store_pairs<G / 4>(w, own, oth, valid, valid_o, odd, nullptr, nullptr, 0.f, false);
         } else if (valid) {
-            __half* hp = p.ys + pix * p.ys_cs + (n0 >> 5) * 64 + (n0 & 31);
+            __half* hp = p.ys + pix * p.ys_cs + ((ch0 + n0) >> 5) * 64 + ((ch0 + n0) & 31);
             uint4* hq = reinterpret_cast<uint4*>(hp);
             uint4* lq = reinterpret_cast<uint4*>(hp + 32);
 #pragma unroll
@@ -289,21 +296,21 @@ __device__ __forceinline__ void hl_epilogue_pass(const HaloParams& p, const floa
         }
     }
     if (p.y) {
-        float* yrow = p.y + pix * p.y_cs;
-        const float* mrow = p.mask ? p.mask + pix * p.mask_cs : nullptr;
-        const float* rrow = p.res ? p.res + pix * p.res_cs : nullptr;
+        float* yrow = p.y + pix * p.y_cs + ch0;
+        const float* mrow = p.mask ? p.mask + pix * p.mask_cs + ch0 : nullptr;
+        const float* rrow = p.res ? p.res + pix * p.res_cs + ch0 : nullptr;
         if (p.tma_y) {
             uint32_t w[G];
 #pragma unroll
             for (int j = 0; j < G; ++j) w[j] = __float_as_uint(acc[j]);
-            hl_stage_and_store<G>(tmY, stage + (nbuf & 1) * (32 * 4 * G), w, lane, n0, wx, wy, wb);
+            hl_stage_and_store<G>(tmY, stage + (nbuf & 1) * (32 * 4 * G), w, lane, ch0 + n0, wx, wy, wb);
             ++nbuf;
         } else if (vec && p.cout_valid == p.Cout && (p.Cout % G) == 0 && !p.exp_direct_store) {
             uint32_t w[G];
 #pragma unroll
             for (int j = 0; j < G; ++j) w[j] = __float_as_uint(acc[j]);
-            hl_store_pairs<G / 4>(w, reinterpret_cast<char*>(yrow + n0), reinterpret_cast<char*>(p.y + pix_o * p.y_cs + n0), valid, valid_o, odd,
-                                  mrow ? mrow + n0 : nullptr, p.mask ? p.mask + pix_o * p.mask_cs + n0 : nullptr, p.mask_alpha,
+            hl_store_pairs<G / 4>(w, reinterpret_cast<char*>(yrow + n0), reinterpret_cast<char*>(p.y + pix_o * p.y_cs + ch0 + n0), valid, valid_o, odd,
+                                  mrow ? mrow + n0 : nullptr, p.mask ? p.mask + pix_o * p.mask_cs + ch0 + n0 : nullptr, p.mask_alpha,
                                   p.accumulate != 0);
         } else if (!valid) {
         } else if (vec) {
@@ -385,12 +392,11 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const uint32_t tmem_acc = tmem_base_slot;
     const int KC = p.kchunks;
     const int tiles_per_img = p.tiles_img;
-    // tile walk of this CTA: strided (t = cta, cta + grid, ...) or, PWC_HALO_CONTIG=1, one contiguous run of tiles
-    int t_begin = blockIdx.x, t_end = p.total_tiles, t_step = gridDim.x;
-    if (p.contig) {
-        const int per = (p.total_tiles + gridDim.x - 1) / gridDim.x;
-        t_begin = blockIdx.x * per; t_end = min(p.total_tiles, t_begin + per); t_step = 1;
-    }
+    // work items of this CTA (HaloParams): `rounds` whole tiles, then possibly one channel-split item of the tail
+    const int n_items = p.rounds + ((int)blockIdx.x < p.tail_items ? 1 : 0);
+    const int tail_q = blockIdx.x / p.n_split;
+    const int tail_t = p.rounds * gridDim.x + tail_q;
+    const int tail_ch0 = (blockIdx.x - tail_q * p.n_split) * p.cn_split;
     unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 128 : nullptr;
 
     if (warp == 0) {
@@ -399,7 +405,8 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
             int it = 0, s = 0;
             uint32_t ph = 0;                                   // stage index and ring phase as counters: no division per slice
-            for (int t = t_begin; t < t_end; t += t_step) {
+            for (int j = 0; j < n_items; ++j) {
+                const int t = j < p.rounds ? (int)blockIdx.x + j * (int)gridDim.x : tail_t;
                 const int b = t / tiles_per_img, r = t - b * tiles_per_img;
                 int y, x0;
                 if (p.flat) { y = (r * HL_M) / p.bw; x0 = 0; }           // first row touched by the tile's slots
@@ -429,21 +436,35 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             if (p.w_resident) {
                 // small layers: the weight stream would be latency-bound (a tap's MMAs are shorter than an L2 round trip),
                 // so every (slice, tap) image is loaded ONCE per persistent CTA
-                mbar_expect_tx(bar_wfull, (uint32_t)(9 * KC) * bytes);
-                for (int c = 0; c < KC; ++c)
-                    for (int tap = 0; tap < 9; ++tap)
-                        bulk_load_1d(w_base + (c * 9 + tap) * p.w_stage_bytes, p.w + (size_t)(tap * KC + c) * bytes, bytes, bar_wfull);
-            } else {
-            for (int t = t_begin; t < t_end; t += t_step) {
+                // one barrier per slice (the last one takes every slice beyond HL_W_STAGES): the MMAs of slice 0 start as
+                // soon as ITS nine images have landed, not after the whole set (5k clk at 128 -> 128)
                 for (int c = 0; c < KC; ++c) {
-                    for (int tap = 0; tap < 9; ++tap, ++wt) {
-                        const int s = wt & (HL_W_STAGES - 1);
-                        mbar_wait(bar_wempty + 8 * s, ((wt / HL_W_STAGES) & 1) ^ 1);
-                        mbar_expect_tx(bar_wfull + 8 * s, bytes);
-                        bulk_load_1d(w_base + s * p.w_stage_bytes, p.w + (size_t)(tap * KC + c) * bytes, bytes, bar_wfull + 8 * s);
+                    if (c < HL_W_STAGES) mbar_expect_tx(bar_wfull + 8 * c, (uint32_t)(9 * (c == HL_W_STAGES - 1 ? KC - c : 1)) * bytes);
+                    const uint32_t bar_c = bar_wfull + 8 * (c < HL_W_STAGES ? c : HL_W_STAGES - 1);
+                    for (int tap = 0; tap < 9; ++tap)
+                        bulk_load_1d(w_base + (c * 9 + tap) * p.w_stage_bytes, p.w + (size_t)(tap * KC + c) * bytes, bytes, bar_c);
+                }
+            } else {
+                for (int j = 0; j < n_items; ++j) {
+                    const bool tail = j >= p.rounds;
+                    const int ch0 = tail ? tail_ch0 : 0, cn = tail ? p.cn_split : p.Cout;
+                    const uint32_t part = (uint32_t)cn * 64;          // rows ch0 .. ch0 + cn of the W_h and of the W_l image
+                    for (int c = 0; c < KC; ++c) {
+                        for (int tap = 0; tap < 9; ++tap, ++wt) {
+                            const int s = wt & (p.w_stages - 1);
+                            mbar_wait(bar_wempty + 8 * s, ((wt >> p.w_shift) & 1) ^ 1);
+                            mbar_expect_tx(bar_wfull + 8 * s, 2 * part);
+                            const uint8_t* img = p.w + (size_t)(tap * KC + c) * bytes + (size_t)ch0 * 64;
+                            const uint32_t dst = w_base + s * p.w_stage_bytes;
+                            if (cn != p.Cout) {
+                                bulk_load_1d(dst, img, part, bar_wfull + 8 * s);
+                                bulk_load_1d(dst + part, img + p.b_bytes, part, bar_wfull + 8 * s);
+                            } else {
+                                bulk_load_1d(dst, img, bytes, bar_wfull + 8 * s);
+                            }
+                        }
                     }
                 }
-            }
             }
         }
     } else if (warp == 1) {
@@ -457,12 +478,18 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             cx.wsb16 = (uint32_t)p.w_stage_bytes >> 4;
             cx.cout = (uint32_t)p.Cout;
             cx.bar_wfull = bar_wfull; cx.bar_wempty = bar_wempty;
+            cx.w_mask = (uint32_t)p.w_stages - 1; cx.w_shift = (uint32_t)p.w_shift;
             cx.w_lo0 = ((w_base >> 4) & 0x3FFF) | (1u << 16);
             const bool resident = p.w_resident != 0;
             int it = 0, tcount = 0, s = 0;
             uint32_t wt = 0, ph = 0;
-            if (resident) { mbar_wait(bar_wfull, 0); tc_fence_after(); }
-            for (int t = t_begin; t < t_end; t += t_step, ++tcount) {
+            for (int j = 0; j < n_items; ++j, ++tcount) {
+                const int t = j < p.rounds ? (int)blockIdx.x + j * (int)gridDim.x : tail_t;
+                if (j >= p.rounds && p.cn_split != p.Cout) {          // channel-split tail item: narrower MMAs
+                    cx.cout = (uint32_t)p.cn_split;
+                    cx.idesc_n = (1u << 4) | ((uint32_t)(p.cn_split >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
+                    cx.idesc_w = (1u << 4) | ((uint32_t)((2 * p.cn_split) >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
+                }
                 const int a = tcount & 1, u = tcount >> 1;
                 if (u > 0) {                       // the epilogue has drained this accumulator set
                     mbar_wait(bar_acce + 8 * a, (u - 1) & 1);
@@ -472,6 +499,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 uint32_t c0off = 0;                                   // flat mode: the tile starts c0 slots into its first row
                 if (p.flat) { const int r = t % tiles_per_img; c0off = (uint32_t)((r * HL_M) % p.bw) * 8; }
                 for (int c = 0; c < KC; ++c, ++it) {
+                    if (resident && tcount == 0) mbar_wait(bar_wfull + 8 * (c < HL_W_STAGES ? c : HL_W_STAGES - 1), 0);   // this slice's weights
                     mbar_wait(bar_aconv + 8 * s, ph);
                     HL_DBG(3, it);
                     tc_fence_after();
@@ -507,11 +535,18 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         int tcount = 0;
         // tile coordinates advance by the (constant) tile step without divisions: image b, tile r of the image =
         // (row ty, column tile tx) in row mode
+        const int t_step = gridDim.x;
         const int d_b = t_step / tiles_per_img, d_r = t_step - d_b * tiles_per_img;
         const int d_y = d_r / p.tiles_x, d_x = d_r - d_y * p.tiles_x;
-        int b = t_begin / tiles_per_img, r = t_begin - b * tiles_per_img;
+        int b = (int)blockIdx.x / tiles_per_img, r = (int)blockIdx.x - b * tiles_per_img;
         int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        for (int t = t_begin; t < t_end; t += t_step, ++tcount) {
+        for (int j = 0; j < n_items; ++j, ++tcount) {
+            const bool tail = j >= p.rounds;
+            const int ch0 = tail ? tail_ch0 : 0, cn = tail ? p.cn_split : p.Cout;
+            if (tail) {                                   // the tail item is not on the strided walk
+                b = tail_t / tiles_per_img; r = tail_t - b * tiles_per_img;
+                ty = r / p.tiles_x; tx = r - ty * p.tiles_x;
+            }
             int y, x;
             if (p.flat) { const int slot = r * HL_M + m; y = slot / p.bw; x = slot - y * p.bw; }
             else { y = ty; x = tx * HL_M + m; }
@@ -535,9 +570,9 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const bool valid_o = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
             const size_t pix_o = (size_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)pix, 1);
             if ((p.Cout & 31) == 0) {
-                for (int n0 = 0; n0 < p.Cout; n0 += 32) hl_epilogue_pass<32>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 32 >= p.Cout ? bar_acce + 8 * a : 0u);
+                for (int n0 = 0; n0 < cn; n0 += 32) hl_epilogue_pass<32>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 32 >= cn ? bar_acce + 8 * a : 0u, ch0, cn);
             } else {
-                for (int n0 = 0; n0 < p.Cout; n0 += 16) hl_epilogue_pass<16>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 16 >= p.Cout ? bar_acce + 8 * a : 0u);
+                for (int n0 = 0; n0 < p.Cout; n0 += 16) hl_epilogue_pass<16>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 16 >= p.Cout ? bar_acce + 8 * a : 0u, 0, p.Cout);
             }
             if (threadIdx.x == 64) HL_DBG(6, tcount);
             if (threadIdx.x == 64 && dbg) {
@@ -553,7 +588,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int ct = threadIdx.x - 192;   // 0..255
         int it = 0, s = 0;
         uint32_t ph = 0;
-        for (int t = t_begin; t < t_end; t += t_step) {
+        for (int j = 0; j < n_items; ++j) {
             for (int c = 0; c < KC; ++c, ++it) {
                 mbar_wait(bar_afull + 8 * s, ph);
                 if (ct == 0) HL_DBG(1, it);
@@ -645,6 +680,20 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     if (tiles >= (1ll << 30)) return -1000;
     p.total_tiles = (int)tiles;
     p.kchunks = (Cin + HL_BK - 1) / HL_BK;
+    // Work items (HaloParams): whole rounds of tiles, then the tail split along the output channels when that shortens the
+    // last, partly filled round (or the only round of a layer with fewer tiles than SMs) by a useful amount.
+    const int sms = sm_count();
+    const int G = p.total_tiles < sms ? p.total_tiles : sms;
+    p.rounds = p.total_tiles >= sms ? p.total_tiles / sms : 0;
+    const int tail = p.total_tiles - p.rounds * G;
+    p.n_split = 1;
+    if (tail > 0 && p.rounds <= 32 && (Cout & 31) == 0 && cout_valid == Cout && !getenv("PWC_HALO_NO_NSPLIT")) {
+        for (int k = 4; k >= 2; --k)
+            if (Cout % (32 * k) == 0 && tail * k <= sms) { p.n_split = k; break; }
+    }
+    p.cn_split = Cout / p.n_split;
+    p.tail_items = tail * p.n_split;
+    const int grid = p.rounds > 0 ? sms : p.tail_items;
     p.b_bytes = Cout * 64;
     p.w_stage_bytes = (2 * p.b_bytes + 1023) / 1024 * 1024;
     p.accumulate = accumulate; p.alpha = alpha; p.mask_alpha = mask_alpha;
@@ -652,7 +701,6 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.dil = dilation; p.bw = flat ? W + 2 : HL_M + 2 * dilation; p.row_loads = dilation <= 8 ? 1 : HL_BH;
     p.act_stage = ((flat ? nr : HL_BH) * p.bw * 128 + 1023) / 1024 * 1024;
     p.desc_mode = 0;
-    p.contig = getenv("PWC_HALO_CONTIG") ? 1 : 0;
     // TMA-store epilogue: row tiles (not the flat mode: its tiles hold padding slots between rows), whole passes, plain
     // stores (no dgrad mask / residual / accumulate)
     CUtensorMap tmY, tmYS;
@@ -691,7 +739,8 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     if (const char* e = getenv("PWC_HALO_STAGES")) want_stages = atoi(e);
     if (want_stages == 3) p.act_stages = 3;
     const size_t w_all = (size_t)9 * p.kchunks * p.w_stage_bytes;
-    p.w_resident = (2 * (size_t)p.act_stage + w_all + epi_bytes + 1024 <= HL_SMEM_BUDGET) && !getenv("PWC_HALO_NO_RESIDENT");
+    // (a channel-split tail needs [W_h | W_l] sub-images side by side: streamed, not cut out of resident full images)
+    p.w_resident = (2 * (size_t)p.act_stage + w_all + epi_bytes + 1024 <= HL_SMEM_BUDGET) && p.n_split == 1 && !getenv("PWC_HALO_NO_RESIDENT");
     if (p.w_resident) {
         // small layers (resident weights): a stage is held from the TMA issue to the last MMA that reads it (~5k clk
         // at 16->16: 1.9k TMA latency + 1.4k conversion + 1.7k MMAs), so two stages cap the tile period at ~2.5k clk
@@ -700,14 +749,21 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         const int lim = want_stages >= 2 && want_stages <= HL_MAX_ACT_STAGES ? want_stages : HL_MAX_ACT_STAGES;
         if (fit > 2) p.act_stages = fit < lim ? fit : lim;
     }
-    size_t smem = (size_t)p.act_stages * p.act_stage + (p.w_resident ? w_all : (size_t)HL_W_STAGES * p.w_stage_bytes) + epi_bytes + 1024;
-    if (smem > HL_SMEM_BUDGET) { p.act_stages = 2; smem = (size_t)2 * p.act_stage + (size_t)HL_W_STAGES * p.w_stage_bytes + epi_bytes + 1024; }
+    // streaming layers: the weight ring takes what the activation stages leave (4..16 images in flight: with small images --
+    // narrow or channel-split layers -- four are not enough to cover the L2 latency of one image per tap)
+    p.w_stages = HL_W_MIN_STAGES; p.w_shift = 2;
+    if (!p.w_resident) {
+        while (p.w_stages < HL_W_STAGES && (size_t)p.act_stages * p.act_stage + (size_t)2 * p.w_stages * p.w_stage_bytes + epi_bytes + 1024 <= HL_SMEM_BUDGET) {
+            p.w_stages *= 2; ++p.w_shift;
+        }
+    }
+    size_t smem = (size_t)p.act_stages * p.act_stage + (p.w_resident ? w_all : (size_t)p.w_stages * p.w_stage_bytes) + epi_bytes + 1024;
+    if (smem > HL_SMEM_BUDGET) { p.act_stages = 2; smem = (size_t)2 * p.act_stage + (size_t)p.w_stages * p.w_stage_bytes + epi_bytes + 1024; }
     if (smem > HL_SMEM_BUDGET && epi_bytes) { smem -= epi_bytes; p.tma_y = p.tma_ys = 0; }    // no room for the staging buffers: plain stores
     if (smem > HL_SMEM_BUDGET) return -1000;
     p.epi_off = (int)(smem - 1024 - ((p.tma_y || p.tma_ys) ? epi_bytes : 0));               // 1024-byte aligned: every part before it is
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc_halo: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
     static unsigned long long* dbg_buf = nullptr;
     if (getenv("PWC_HALO_DEBUG")) {
         if (!dbg_buf) cudaMalloc(&dbg_buf, 148 * 128 * 8);
