@@ -212,6 +212,15 @@ int pwc_conv3x3_tc_f16_split_fwd(const void* x, int x_split, int x_cs, const voi
                                  float* y, int y_cs, void* y_split, int ys_cs,
                                  int B, int H, int W, int Cin, int Cout, int dilation, float alpha, void* stream);
 
+/* Stride-2 3x3 convolution + bias + leaky on the halo kernel (replaces modules.py:62-63, the first convolution of every
+ * pyramid level: tf.layers.Conv2D(filters, (3,3), (2,2), 'same') + tf.nn.leaky_relu) as a 2x2 convolution over the
+ * space-to-depth view of x, read in place through a 5-D tensor map.  x: [B,H,W,Cin] dense fp32, even H and W, Cin % 16 == 0,
+ * Cout % 16 == 0, Cout <= 128; y / y_split as in pwc_conv3x3_tc_f16_split_fwd at [B,H/2,W/2].  w_packed =
+ * pwc_conv3x3_pack_weights_f16(pwc_conv3x3_s2d_reindex(w_hwio), Cin' = 4*Cin, Cout). */
+int pwc_conv3x3_s2d_reindex(const float* w_hwio, float* w_s2d, int Cin, int Cout, void* stream);
+int pwc_conv3x3_s2_tc_f16_fwd(const float* x, const void* w_packed, const float* bias, float* y, int y_cs,
+                              void* y_split, int ys_cs, int B, int H, int W, int Cin, int Cout, float alpha, void* stream);
+
 /* First pyramid convolution (modules.py:62-63, l = 0): 3 -> 16 channels, 3x3, stride 2, SAME, + bias + leaky, exact fp32 on
  * the CUDA cores, reading either float32 RGB/255 images or (x_is_u8) the uint8 RGB bytes themselves through lut256
  * (= float32(float64(v)/255.0): the reference's `images/255.0`, test.py:31-33).  x: dense (B,H,W,3); y: (B,H/2,W/2,16)

@@ -54,6 +54,8 @@ SIGNATURES = {
     "pwc_tsplit_bytes": (C.c_longlong, [_i, _i, _i, _i, _i]),
     "pwc_tsplit_f16": (_i, [_f32p, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _f32p, _vp]),
     "pwc_conv3x3_wgrad_tc": (_i, [_vp, _vp, _f32p, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "pwc_conv3x3_s2d_reindex": (_i, [_f32p, _f32p, _i, _i, _vp]),
+    "pwc_conv3x3_s2_tc_f16_fwd": (_i, [_f32p, _vp, _f32p, _f32p, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "pwc_conv3x3_tc_f16_split_fwd": (_i, [_vp, _i, _i, _f32p, _f32p, _f32p, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "pwc_conv_first_fwd": (_i, [_vp, _i, _f32p, _f32p, _f32p, _f32p, _i, _i, _i, _i, _f, _vp]),
     "pwc_count_nonfinite": (_i, [_f32p, _i, _i, _ll, _vp, _vp]),

@@ -62,6 +62,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     __shared__ __align__(8) uint64_t bars[3 * 8 + 1];   // full[8], conv[8], empty[8], acc_full
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_bias[256 + 16];                  // bias (or zeros): a global load per pass would sit on the epilogue's critical path
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -91,6 +92,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int c = threadIdx.x; c < 256 + 16; c += F16_THREADS) s_bias[c] = (p.bias && c < p.cout_valid) ? __ldg(p.bias + c) : 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -111,17 +113,17 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                 const int tap = it / p.kchunks, kc = it - tap * p.kchunks, ky = tap / 3, kx = tap - ky * 3;
                 tma_prefetch_4d(&tmX, kc * F16_BK, x0 * p.stride - p.pad_l + kx * p.dil, y0 * p.stride - p.pad_t + ky * p.dil, b);
             }
+            // ring stage / phase and the (tap, slice) pairs of the load and of the prefetch as counters: the integer divisions
+            // they replace (~40 instructions each) were a visible part of every K iteration of this single thread
+            int s = 0, kc = 0, kx = 0, ky = 0;
+            uint32_t ph = 0;
+            int pkc = PF % p.kchunks, ptap = PF / p.kchunks, pky = ptap / 3, pkx = ptap - pky * 3;
             for (int it = 0; it < KT; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (it / S) & 1;
                 if (it + PF < KT) {
-                    const int itp = it + PF;
-                    const int tap = itp / p.kchunks, kc = itp - tap * p.kchunks, ky = tap / 3, kx = tap - ky * 3;
-                    tma_prefetch_4d(&tmX, kc * F16_BK, x0 * p.stride - p.pad_l + kx * p.dil, y0 * p.stride - p.pad_t + ky * p.dil, b);
+                    tma_prefetch_4d(&tmX, pkc * F16_BK, x0 * p.stride - p.pad_l + pkx * p.dil, y0 * p.stride - p.pad_t + pky * p.dil, b);
+                    if (++pkc == p.kchunks) { pkc = 0; if (++pkx == 3) { pkx = 0; ++pky; } }
                 }
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                const int ky = tap / 3, kx = tap - ky * 3;
                 const uint32_t st = base + s * p.stage_bytes;
                 if (dbg && it >= 8 && it < 24) dbg[8 + (it - 8)] = clock64();
                 mbar_expect_tx(bar_full + 8 * s, tx_bytes);
@@ -129,6 +131,8 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                             y0 * p.stride - p.pad_t + ky * p.dil, b);
                 // [h tile | l tile] of this (tap, slice): one linear bulk copy
                 bulk_load_1d(st + off_bh, p.w + (size_t)it * 2 * p.b_bytes, 2 * p.b_bytes, bar_full + 8 * s);
+                if (++kc == p.kchunks) { kc = 0; if (++kx == 3) { kx = 0; ++ky; } }
+                if (++s == S) { s = 0; ph ^= 1; }
             }
             if (dbg) dbg[2] = clock64();   // last TMA issued
         }
@@ -140,9 +144,9 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
             // 64-byte-row K-major tiles: 8-row atoms 512 bytes apart, SWIZZLE_64B (layout type 4)
             const uint64_t desc_hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
             const uint32_t d_corr = tmem_acc + p.n_main * p.Cout;
+            int s = 0, am = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < KT; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (it / S) & 1;
                 mbar_wait(bar_conv + 8 * s, ph);
                 if (dbg && it == 0) dbg[3] = clock64();   // first stage converted
                 if (dbg && it >= 8 && it < 24) dbg[56 + (it - 8)] = clock64();
@@ -152,7 +156,6 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                 const uint32_t al = (((st + off_al) >> 4) & 0x3FFF) | (1u << 16);
                 const uint32_t bh = (((st + off_bh) >> 4) & 0x3FFF) | (1u << 16);
                 const uint32_t bl = (((st + off_bl) >> 4) & 0x3FFF) | (1u << 16);
-                const int am = it % p.n_main;
                 const uint32_t d_main = tmem_acc + am * p.Cout;
 #pragma unroll
                 for (int k = 0; k < F16_BK / 16; ++k)   // K = 16 fp16 = 32 bytes per instruction
@@ -164,6 +167,8 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                 for (int k = 0; k < F16_BK / 16; ++k)
                     tc_mma_f16(d_corr, desc_hi | (ah + 2 * k), desc_hi | (bl + 2 * k), idesc, 1u);
                 tc_commit(bar_empty + 8 * s);
+                if (++s == S) { s = 0; ph ^= 1; }
+                if (++am == p.n_main) am = 0;
             }
             tc_commit(bar_acc);
             if (dbg) dbg[4] = clock64();   // last MMA issued
@@ -171,9 +176,9 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
     } else {
         // ===================== converter, then epilogue =====================
         const int ct = threadIdx.x - 64;   // 0..255
+        int s = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < KT; ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
             mbar_wait(bar_full + 8 * s, ph);
             if (dbg && ct == 0 && it >= 8 && it < 24) dbg[24 + (it - 8)] = clock64();
             if (dbg && ct == 0 && it == 12) dbg[72] = clock64();
@@ -204,6 +209,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
             if (dbg && ct == 0 && it >= 8 && it < 24) dbg[40 + (it - 8)] = clock64();
             mbar_arrive(bar_conv + 8 * s);
             if (dbg && ct == 0 && it == 12) dbg[75] = clock64();
+            if (++s == S) { s = 0; ph ^= 1; }
         }
         // ---- epilogue: warps 2..5 (TMEM lane quadrant = warp % 4); the other converter warps are done
         if (warp < 6) {
@@ -235,10 +241,8 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                     for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
                 }
                 if (valid) {
-                    if (p.bias) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] += __ldg(p.bias + n0 + j);
-                    }
+                    for (int j = 0; j < 16; ++j) acc[j] += s_bias[n0 + j];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = leaky(acc[j], p.alpha);
                     if (vec) {
@@ -368,7 +372,7 @@ struct F16Extra { const float* mask; int mask_cs; float mask_alpha; int accumula
 int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
                      int B, int H, int W, int Cin, int Cout, int dilation, float alpha, const float* mask, int mask_cs,
                      float mask_alpha, int accumulate, int cout_valid, const float* res, int res_cs, cudaStream_t st,
-                     int in_split = 0, void* y_split = nullptr, int ys_cs = 0);
+                     int in_split = 0, void* y_split = nullptr, int ys_cs = 0, int s2d = 0);
 }
 
 static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const float* bias,
@@ -538,5 +542,55 @@ extern "C" int pwc_conv3x3_tc_f16_split_fwd(const void* x, int x_split, int x_cs
     const int rc = launch_conv_halo(static_cast<const float*>(x), x_cs, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, dilation, alpha,
                                     nullptr, 0, 1.f, 0, Cout, nullptr, 0, (cudaStream_t)stream, x_split ? 1 : 0, y_split, ys_cs);
     PWC_REQUIRE(rc != -1000, PWC_E_BADARG, "conv3x3_tc_f16_split: shape not supported by the halo kernel");
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stride-2 3x3 convolution (tf.layers.Conv2D(filters,(3,3),(2,2),'same') + bias + leaky: the first convolution of every
+// pyramid level, modules.py:62-63) on the halo kernel, as a stride-1 2 x 2 convolution over the space-to-depth view
+//     X'[y][x][(py, px, c)] = X[2y + py][2x + px][c]            (read in place through a 5-D tensor map: no copy),
+//     Y[y][x] = sum_{dy,dx in {0,1}} W'[dy][dx] . X'[y + dy][x + dx],   W'[dy][dx][(py,px,c)] = W[2dy+py][2dx+px][c] or 0.
+// TF 'SAME' with even H, W and stride 2 pads one row / column AFTER the image only, which is the tensor map's zero fill.
+// The streaming kernel this replaces loads nine shifted stride-2 boxes per 32-channel slice (one CTA per 128 outputs);
+// here a persistent CTA loads each input element once per tile.  Needs a dense input (x_cs == Cin), even H and W,
+// Cin % 16 == 0, Cout % 16 == 0, Cout <= 128.
+//   pwc_conv3x3_s2d_reindex : (3,3,Cin,Cout) HWIO -> (3,3,4*Cin,Cout) with W' in taps (0..1, 0..1) and zeros elsewhere; the
+//                             result goes through pwc_conv3x3_pack_weights_f16 (Cin' = 4*Cin) like any other kernel.
+namespace pwc {
+__global__ void s2d_reindex_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int Cout) {
+    const size_t total = (size_t)9 * 4 * C * Cout;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int n = idx % Cout; size_t r = idx / Cout;
+        const int k = r % (4 * C); const int tap = r / (4 * C);
+        const int dy = tap / 3, dx = tap % 3;
+        const int py = k / (2 * C), px = (k % (2 * C)) / C, c = k % C;
+        const int ky = 2 * dy + py, kx = 2 * dx + px;
+        out[idx] = (dy < 2 && dx < 2 && ky < 3 && kx < 3) ? w[((size_t)(ky * 3 + kx) * C + c) * Cout + n] : 0.f;
+    }
+}
+}  // namespace pwc
+
+extern "C" int pwc_conv3x3_s2d_reindex(const float* w_hwio, float* w_s2d, int Cin, int Cout, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(w_hwio && w_s2d && Cin > 0 && Cout > 0, PWC_E_BADARG, "conv3x3_s2d_reindex: bad arguments");
+    s2d_reindex_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(w_hwio, w_s2d, Cin, Cout);
+    PWC_CHECK_LAUNCH("s2d_reindex_kernel");
+    return 0;
+}
+
+// x: [B, H, W, Cin] dense fp32; w_packed: pwc_conv3x3_pack_weights_f16 of the re-indexed kernel (Cin' = 4 * Cin);
+// y (fp32, may be NULL) and/or y_split (split rows, may be NULL; Cout % 32 == 0): [B, H/2, W/2, ...].
+extern "C" int pwc_conv3x3_s2_tc_f16_fwd(const float* x, const void* w_packed, const float* bias, float* y, int y_cs,
+                                         void* y_split, int ys_cs, int B, int H, int W, int Cin, int Cout, float alpha, void* stream) {
+    using namespace pwc;
+    PWC_REQUIRE(x && w_packed && bias && (y || y_split), PWC_E_BADARG, "conv3x3_s2_tc_f16: null pointer");
+    PWC_REQUIRE(B > 0 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0 && Cin >= 16 && Cin % 16 == 0 && Cout > 0 && Cout % 16 == 0 && Cout <= 128,
+                PWC_E_BADARG, "conv3x3_s2_tc_f16: bad dims (even H and W, Cin % 16 == 0, Cout % 16 == 0, Cout <= 128)");
+    PWC_REQUIRE(aligned16(x) && aligned16(w_packed) && (!y || y_cs >= Cout), PWC_E_ALIGN, "conv3x3_s2_tc_f16: alignment / strides");
+    PWC_REQUIRE(!y_split || (Cout % 32 == 0 && ys_cs >= 2 * Cout && ys_cs % 16 == 0 && aligned16(y_split)), PWC_E_BADARG,
+                "conv3x3_s2_tc_f16: split output needs Cout % 32 == 0 and a 32-byte pixel pitch");
+    const int rc = launch_conv_halo(x, Cin, w_packed, bias, y, y_cs, B, H, W, Cin, Cout, 1, alpha, nullptr, 0, 1.f, 0, Cout, nullptr, 0,
+                                    (cudaStream_t)stream, 0, y_split, ys_cs, 1);
+    PWC_REQUIRE(rc != -1000, PWC_E_BADARG, "conv3x3_s2_tc_f16: shape not supported by the halo kernel");
     return rc;
 }

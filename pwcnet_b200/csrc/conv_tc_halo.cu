@@ -50,6 +50,13 @@ struct HaloParams {
     int w_stage_bytes;    // 2 * b_bytes rounded up to 1024
     int accumulate, desc_mode;
     int exp_skip_conv;    // experiment (PWC_HALO_EXP=1): converters do nothing -> wrong results, upper bound of a split-input variant
+    // Tap set.  Stride 1: the nine taps (ky, kx) of a 3 x 3 kernel, box rows y-d, y, y+d.  Stride 2 ("space to depth", s2d = 1):
+    // the input is read through a 5-D tensor map as X'[y][x][(py, px, c)] = X[2y+py][2x+px][c] (4 * Cin channels at half the
+    // resolution), on which the stride-2 3 x 3 convolution is a stride-1 2 x 2 one: taps (dy, dx) in {0,1}^2, box rows y, y+1,
+    // no padding before (TF 'SAME' with even sizes pads one row / column AFTER), weights re-indexed host-side with zeros
+    // where 2*dy+py or 2*dx+px would be 3.  A K slice is 32 consecutive (px, c) values of one row phase py.
+    int n_taps, box_rows, pad, s2d, kc_per_py;
+    int tap_dy[9], tap_dx[9], tap_id[9];     // tap offsets in box rows / pixels (times dil for dx), and the tap's index in the packed weights
     int tma_y, tma_ys;    // the epilogue stores the fp32 / split output through TMA (shared-memory staging + bulk tensor store)
     int epi_off;          // byte offset of the epilogue staging area: 4 warps x 2 buffers x (32 pixels x 128 or 64 bytes)
     int exp_direct_store; // experiment (PWC_HALO_EXP=3): 16-byte-per-lane stores (round-1 pattern)
@@ -112,11 +119,11 @@ struct IssueCtx {
 // K = 16 steps.  The issuing thread is the critical path of the narrow layers (a 16 -> 16 tile is 18 tiny MMAs: the
 // round-1 loop spent ~55 instructions per tap, ~90 clk per MMA -- as long as a 128 x 256 x 16 MMA executes, so it also
 // held the wide layers below the tensor pipe's rate; profiles/r02_halo_epilogue.log), so everything per tap is a 32-bit add.
-template <bool RESIDENT, bool KS2>
+template <bool RESIDENT, bool KS2, int NT>
 __device__ __forceinline__ void hl_issue_chunk(const IssueCtx& cx, uint32_t d_main, uint32_t a_lo, uint32_t b_lo, uint32_t first, uint32_t& wt) {
     const uint32_t d_corr = d_main + cx.cout;
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
+    for (int tap = 0; tap < NT; ++tap) {
         if (!RESIDENT) {
             const uint32_t ws = wt & cx.w_mask;
             mbar_wait(cx.bar_wfull + 8 * ws, (wt >> cx.w_shift) & 1);
@@ -132,6 +139,12 @@ __device__ __forceinline__ void hl_issue_chunk(const IssueCtx& cx, uint32_t d_ma
         if (RESIDENT) b_lo += cx.wsb16;
         else { tc_commit(cx.bar_wempty + 8 * (wt & cx.w_mask)); ++wt; }
     }
+}
+
+__device__ __forceinline__ void hl_tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
 __device__ __forceinline__ void hl_tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -360,7 +373,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const uint32_t bar_accf = smem_u32(&bars[3 * MS + 2 * HL_W_STAGES]), bar_acce = smem_u32(&bars[3 * MS + 2 * HL_W_STAGES + 2]);
     const int AS = p.act_stages;
     const uint32_t w_base = base + p.act_stages * p.act_stage;
-    const int n_rows = (p.flat ? p.nr : HL_BH) * p.bw;
+    const int n_rows = (p.flat ? p.nr : p.box_rows) * p.bw;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < HL_MAX_ACT_STAGES; ++s) {
@@ -416,12 +429,15 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     HL_DBG(0, it);
                     mbar_expect_tx(bar_afull + 8 * s, (uint32_t)n_rows * 128);
                     const int c0 = c * (p.in_split ? 2 * HL_BK : HL_BK);      // element offset of the slice (fp32 or halfs)
-                    if (p.row_loads == 1) {
-                        tma_load_4d(base + s * p.act_stage, &tmX, bar_afull + 8 * s, c0, x0 - p.dil, y - p.dil, b);
+                    if (p.s2d) {
+                        const int py = c / p.kc_per_py;                         // row phase; the slice is 32 (px, c) values of it
+                        hl_tma_load_5d(base + s * p.act_stage, &tmX, bar_afull + 8 * s, (c - py * p.kc_per_py) * HL_BK, py, x0, y, b);
+                    } else if (p.row_loads == 1) {
+                        tma_load_4d(base + s * p.act_stage, &tmX, bar_afull + 8 * s, c0, x0 - p.pad, y - p.pad, b);
                     } else {
 #pragma unroll
                         for (int r2 = 0; r2 < HL_BH; ++r2)
-                            tma_load_4d(base + s * p.act_stage + r2 * p.bw * 128, &tmX, bar_afull + 8 * s, c0, x0 - p.dil,
+                            tma_load_4d(base + s * p.act_stage + r2 * p.bw * 128, &tmX, bar_afull + 8 * s, c0, x0 - p.pad,
                                         y + (r2 - 1) * p.dil, b);
                     }
                     if (++s == AS) { s = 0; ph ^= 1; }
@@ -439,10 +455,10 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 // one barrier per slice (the last one takes every slice beyond HL_W_STAGES): the MMAs of slice 0 start as
                 // soon as ITS nine images have landed, not after the whole set (5k clk at 128 -> 128)
                 for (int c = 0; c < KC; ++c) {
-                    if (c < HL_W_STAGES) mbar_expect_tx(bar_wfull + 8 * c, (uint32_t)(9 * (c == HL_W_STAGES - 1 ? KC - c : 1)) * bytes);
+                    if (c < HL_W_STAGES) mbar_expect_tx(bar_wfull + 8 * c, (uint32_t)(p.n_taps * (c == HL_W_STAGES - 1 ? KC - c : 1)) * bytes);
                     const uint32_t bar_c = bar_wfull + 8 * (c < HL_W_STAGES ? c : HL_W_STAGES - 1);
-                    for (int tap = 0; tap < 9; ++tap)
-                        bulk_load_1d(w_base + (c * 9 + tap) * p.w_stage_bytes, p.w + (size_t)(tap * KC + c) * bytes, bytes, bar_c);
+                    for (int tap = 0; tap < p.n_taps; ++tap)
+                        bulk_load_1d(w_base + (c * p.n_taps + tap) * p.w_stage_bytes, p.w + (size_t)(p.tap_id[tap] * KC + c) * bytes, bytes, bar_c);
                 }
             } else {
                 for (int j = 0; j < n_items; ++j) {
@@ -450,11 +466,11 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     const int ch0 = tail ? tail_ch0 : 0, cn = tail ? p.cn_split : p.Cout;
                     const uint32_t part = (uint32_t)cn * 64;          // rows ch0 .. ch0 + cn of the W_h and of the W_l image
                     for (int c = 0; c < KC; ++c) {
-                        for (int tap = 0; tap < 9; ++tap, ++wt) {
+                        for (int tap = 0; tap < p.n_taps; ++tap, ++wt) {
                             const int s = wt & (p.w_stages - 1);
                             mbar_wait(bar_wempty + 8 * s, ((wt >> p.w_shift) & 1) ^ 1);
                             mbar_expect_tx(bar_wfull + 8 * s, 2 * part);
-                            const uint8_t* img = p.w + (size_t)(tap * KC + c) * bytes + (size_t)ch0 * 64;
+                            const uint8_t* img = p.w + (size_t)(p.tap_id[tap] * KC + c) * bytes + (size_t)ch0 * 64;
                             const uint32_t dst = w_base + s * p.w_stage_bytes;
                             if (cn != p.Cout) {
                                 bulk_load_1d(dst, img, part, bar_wfull + 8 * s);
@@ -474,7 +490,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             cx.idesc_n = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
             cx.idesc_w = (1u << 4) | ((uint32_t)((2 * p.Cout) >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) cx.tapoff[tap] = (uint32_t)((tap / 3) * p.bw + (tap % 3) * p.dil) * 8;   // 128-byte rows, >> 4
+            for (int tap = 0; tap < 9; ++tap) cx.tapoff[tap] = (uint32_t)(p.tap_dy[tap] * p.bw + p.tap_dx[tap]) * 8;   // 128-byte rows, >> 4
             cx.wsb16 = (uint32_t)p.w_stage_bytes >> 4;
             cx.cout = (uint32_t)p.Cout;
             cx.bar_wfull = bar_wfull; cx.bar_wempty = bar_wempty;
@@ -507,13 +523,16 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     const uint32_t a_lo = (((ast >> 4) & 0x3FFF) | (1u << 16)) + c0off;
                     const bool ks2 = p.Cin - c * HL_BK > 16;             // channels 16..31 of the slice are zero padding otherwise
                     const uint32_t first = c == 0 ? 0u : 1u;
-                    if (resident) {
+                    if (p.n_taps == 4) {                                 // stride 2 as a 2 x 2 convolution (slices are always full)
+                        if (resident) hl_issue_chunk<true, true, 4>(cx, d_tile, a_lo, cx.w_lo0 + (uint32_t)c * 4 * cx.wsb16, first, wt);
+                        else hl_issue_chunk<false, true, 4>(cx, d_tile, a_lo, 0, first, wt);
+                    } else if (resident) {
                         const uint32_t b_lo = cx.w_lo0 + (uint32_t)c * 9 * cx.wsb16;
-                        if (ks2) hl_issue_chunk<true, true>(cx, d_tile, a_lo, b_lo, first, wt);
-                        else hl_issue_chunk<true, false>(cx, d_tile, a_lo, b_lo, first, wt);
+                        if (ks2) hl_issue_chunk<true, true, 9>(cx, d_tile, a_lo, b_lo, first, wt);
+                        else hl_issue_chunk<true, false, 9>(cx, d_tile, a_lo, b_lo, first, wt);
                     } else {
-                        if (ks2) hl_issue_chunk<false, true>(cx, d_tile, a_lo, 0, first, wt);
-                        else hl_issue_chunk<false, false>(cx, d_tile, a_lo, 0, first, wt);
+                        if (ks2) hl_issue_chunk<false, true, 9>(cx, d_tile, a_lo, 0, first, wt);
+                        else hl_issue_chunk<false, false, 9>(cx, d_tile, a_lo, 0, first, wt);
                     }
                     tc_commit(bar_aempty + 8 * s);
                     HL_DBG(4, it);
@@ -644,16 +663,33 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float* bias, float* y, int y_cs,
                      int B, int H, int W, int Cin, int Cout, int dilation, float alpha, const float* mask, int mask_cs,
                      float mask_alpha, int accumulate, int cout_valid, const float* res, int res_cs, cudaStream_t st,
-                     int in_split, void* y_split, int ys_cs) {
+                     int in_split, void* y_split, int ys_cs, int s2d) {
     EncodeTiledFn enc = get_encode();
+    // Stride 2 (s2d): H, W, Cin arrive as the INPUT's; from here on they describe the half-resolution 2 x 2 problem.
+    const int Hin = H, Win = W, Cin_in = Cin;
+    if (s2d) {
+        if ((H & 1) || (W & 1) || (Cin & 15) || x_cs != Cin || in_split || mask || res || accumulate || dilation != 1) return -1000;
+        H /= 2; W /= 2; Cin *= 4;
+    }
     if (in_split && (Cin & 31)) return -1000;                   // split rows come in whole 32-channel slices
     if (y_split && ((Cout & 31) || (ys_cs & 15) || !aligned16(y_split))) return -1000;
     if (!enc || Cout > 128 || (Cout & 7) || dilation < 1 || dilation > 16) return -1000;   // two accumulator sets of 2*Cout columns must fit 512
     // rows narrower than a tile: flat mode (d = 1 only) packs several rows into the 128 MMA rows
     const int flat = (W < HL_M && dilation == 1 && !getenv("PWC_HALO_NO_FLAT")) ? 1 : 0;
-    const int nr = flat ? (HL_M - 1 + (W + 2) - 1) / (W + 2) + 3 : 0;
+    const int span = s2d ? 1 : 2 * dilation;                    // extra box columns (and, in rows, box rows - 1) around a tile
+    const int fbw = W + span;                                   // flat mode: slots per padded row
+    const int nr = flat ? (HL_M - 1 + fbw - 1) / fbw + 1 + span : 0;
     CUtensorMap tmX;
-    {
+    if (s2d) {
+        cuuint64_t dims[5] = {(cuuint64_t)2 * Cin_in, 2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[4] = {(cuuint64_t)Win * Cin_in * 4, (cuuint64_t)2 * Cin_in * 4, (cuuint64_t)2 * Win * Cin_in * 4,
+                                 (cuuint64_t)Hin * Win * Cin_in * 4};
+        cuuint32_t box[5] = {HL_BK, 1, (cuuint32_t)(flat ? fbw : HL_M + 1), (cuuint32_t)(flat ? nr : 2), 1};
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(x, s2d) failed with %d", (int)r); return PWC_E_BADARG; }
+    } else {
         // x_cs counts elements of the input tensor: floats, or halfs of a split tensor (2 * its channel count)
         const cuuint64_t esz = in_split ? 2 : 4;
         cuuint64_t dims[4] = {(cuuint64_t)(in_split ? 2 * Cin : Cin), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -664,7 +700,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         if (!strided && (((HL_M + 2 * dilation) * 128) & 1023)) return -1000;
         cuuint32_t box[4] = {(cuuint32_t)(in_split ? 2 * HL_BK : HL_BK), (cuuint32_t)(HL_M + 2 * dilation), (cuuint32_t)(strided ? HL_BH * dilation : 1), 1};
         cuuint32_t es[4] = {1, 1, (cuuint32_t)(strided ? dilation : 1), 1};
-        if (flat) { box[1] = (cuuint32_t)(W + 2); box[2] = (cuuint32_t)nr; es[2] = 1; }
+        if (flat) { box[1] = (cuuint32_t)fbw; box[2] = (cuuint32_t)nr; es[2] = 1; }
         CUresult r = enc(&tmX, in_split ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -675,7 +711,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.y_cs = y_cs; p.mask_cs = mask_cs; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.cout_valid = cout_valid;
     p.tiles_x = (W + HL_M - 1) / HL_M;
     p.flat = flat; p.nr = nr;
-    p.tiles_img = flat ? (H * (W + 2) + HL_M - 1) / HL_M : p.tiles_x * H;
+    p.tiles_img = flat ? (H * fbw + HL_M - 1) / HL_M : p.tiles_x * H;
     const long long tiles = (long long)p.tiles_img * B;
     if (tiles >= (1ll << 30)) return -1000;
     p.total_tiles = (int)tiles;
@@ -698,8 +734,14 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.w_stage_bytes = (2 * p.b_bytes + 1023) / 1024 * 1024;
     p.accumulate = accumulate; p.alpha = alpha; p.mask_alpha = mask_alpha;
     p.in_split = in_split; p.ys = (__half*)y_split; p.ys_cs = ys_cs;
-    p.dil = dilation; p.bw = flat ? W + 2 : HL_M + 2 * dilation; p.row_loads = dilation <= 8 ? 1 : HL_BH;
-    p.act_stage = ((flat ? nr : HL_BH) * p.bw * 128 + 1023) / 1024 * 1024;
+    p.dil = dilation; p.bw = flat ? fbw : HL_M + span; p.row_loads = dilation <= 8 ? 1 : HL_BH;
+    p.s2d = s2d; p.pad = s2d ? 0 : dilation; p.box_rows = s2d ? 2 : HL_BH; p.kc_per_py = s2d ? (2 * Cin_in) / HL_BK : 0;
+    p.n_taps = s2d ? 4 : 9;
+    for (int t = 0; t < p.n_taps; ++t) {
+        if (s2d) { p.tap_dy[t] = t >> 1; p.tap_dx[t] = t & 1; p.tap_id[t] = (t >> 1) * 3 + (t & 1); }   // packed as the top-left 2 x 2 of a 3 x 3 kernel
+        else { p.tap_dy[t] = t / 3; p.tap_dx[t] = (t % 3) * dilation; p.tap_id[t] = t; }
+    }
+    p.act_stage = ((flat ? nr : p.box_rows) * p.bw * 128 + 1023) / 1024 * 1024;
     p.desc_mode = 0;
     // TMA-store epilogue: row tiles (not the flat mode: its tiles hold padding slots between rows), whole passes, plain
     // stores (no dgrad mask / residual / accumulate)
@@ -738,7 +780,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     int want_stages = 0;
     if (const char* e = getenv("PWC_HALO_STAGES")) want_stages = atoi(e);
     if (want_stages == 3) p.act_stages = 3;
-    const size_t w_all = (size_t)9 * p.kchunks * p.w_stage_bytes;
+    const size_t w_all = (size_t)p.n_taps * p.kchunks * p.w_stage_bytes;
     // (a channel-split tail needs [W_h | W_l] sub-images side by side: streamed, not cut out of resident full images)
     p.w_resident = (2 * (size_t)p.act_stage + w_all + epi_bytes + 1024 <= HL_SMEM_BUDGET) && p.n_split == 1 && !getenv("PWC_HALO_NO_RESIDENT");
     if (p.w_resident) {

@@ -129,6 +129,8 @@ class PWCDCNet(object):
         # the consumer's fp32 -> fp16 converter pass disappears (bit-identical results).  The trainer turns it
         # off: its backward pass reads the float32 activations.  PWC_SPLIT_ACT=0 disables it.
         self.split_act = precision == "3xf16" and not use_dc and os.environ.get("PWC_SPLIT_ACT", "1") != "0"
+        # stride-2 convs as 2x2 convs over the space-to-depth view on the halo kernel (PWC_S2D=0: streaming kernel, round 1)
+        self.s2d = os.environ.get("PWC_S2D", "1") != "0"
         if not torch.cuda.is_available():
             raise PwcError("PWCDCNet needs a CUDA device: the compute path is sm_100a CUDA only (no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -278,9 +280,13 @@ class PWCDCNet(object):
                 scope = key.split("#")[0]
                 if key.endswith("#head"):     # 2-channel head: zero-padded to 16 output channels by the pack itself
                     self._pack_jobs.add_forward(self._k[scope], self._packed[key], cout_pad=16)
+                elif key.endswith("#s2d"):    # stride-2 conv as a 2x2 conv over the space-to-depth view: re-indexed kernel
+                    self._pack_jobs.add_forward(self._k_s2d[scope], self._packed[key])
                 else:
                     self._pack_jobs.add_forward(self._k[scope], self._packed[key])
             self._pack_keys = keys
+        for scope, k2 in getattr(self, "_k_s2d", {}).items():
+            ops_tc.s2d_reindex(self._k[scope], out=k2)
         if keys:
             self._pack_jobs.run()
         for key, packed in self._packed.items():
@@ -305,7 +311,11 @@ class PWCDCNet(object):
         if x.dtype == torch.float16 or out.dtype == torch.float16:
             # conv -> conv chain with split activations (only planned for layers the halo kernel takes)
             from . import ops_tc
-            assert self.precision == "3xf16" and stride == 1 and residual is None
+            assert self.precision == "3xf16" and residual is None
+            if stride == 2:
+                assert self._s2d_ok(cin, cout) and x.dtype == torch.float32
+                return self._conv_s2d(x, scope, k, b, cin, cout, alpha, out)
+            assert stride == 1
             if scope not in self._packed:
                 self._packed[scope] = ops_tc.pack_weights_f16(k)
             osplit = out.dtype == torch.float16
@@ -326,6 +336,9 @@ class PWCDCNet(object):
                 self._packed[key] = ops_tc.pack_weights_f16(self._head_k[scope])
             return ops_tc.conv3x3_tc_f16_head(x, self._packed[key], self._head_b[scope], cin, 2, 16, dilation=dilation,
                                               alpha=alpha, residual=residual, out=out)
+        if stride == 2 and residual is None and dilation == 1 and self._s2d_ok(cin, cout) and x.is_contiguous() \
+                and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0 and x.data_ptr() % 16 == 0:
+            return self._conv_s2d(x, scope, k, b, cin, cout, alpha, out)
         if self.precision == "3xf16" and cin == 16 and stride in (1, 2) and residual is None and cout % 16 == 0 \
                 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0 and not (stride == 1 and dilation == 1 and x.shape[2] >= 96):
             # 16-channel inputs (pyramid level 1): the tf32 kernel has a native 16-channel K slice (the streaming fp16
@@ -343,6 +356,23 @@ class PWCDCNet(object):
                 and (cin == 16 or cin >= 32) and cout <= 256 and x.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0:
             return self._conv_tc(x, scope, k, b, out, dilation, alpha, stride)
         return ops.conv3x3(x, k, b, stride=stride, dilation=dilation, alpha=alpha, residual=residual, out=out)
+
+    def _s2d_ok(self, cin: int, cout: int) -> bool:
+        """Stride-2 convs on the halo kernel (2x2 conv over the space-to-depth view, csrc/conv_tc_f16.cu): 3xf16 only."""
+        return bool(self.precision == "3xf16" and self.s2d and cin % 16 == 0 and cout % 16 == 0 and cout <= 128)
+
+    def _conv_s2d(self, x, scope, k, b, cin, cout, alpha, out):
+        from . import ops_tc
+        key = scope + "#s2d"
+        if key not in self._packed:
+            if not hasattr(self, "_k_s2d"):
+                self._k_s2d = {}
+            self._k_s2d[scope] = ops_tc.s2d_reindex(k)
+            self._packed[key] = ops_tc.pack_weights_f16(self._k_s2d[scope])
+        osplit = out.dtype == torch.float16
+        ops_tc.conv3x3_s2_tc_f16(x, self._packed[key], b, cin, cout, alpha=alpha, out=None if osplit else out,
+                                 out_split=out if osplit else None)
+        return out
 
     def _conv_tc(self, x, scope, k, b, out, dilation, alpha, stride=1, n_split=None):
         from . import ops_tc
@@ -399,6 +429,8 @@ class PWCDCNet(object):
             lvl = [torch.empty((2 * B, h, w, C), dtype=torch.float32, device=dev) for _ in range(3)]
             if self._split_ok(C, C, w):          # conv(l,1) -> conv(l,2): the middle tensor is only read by the next conv
                 lvl[1] = torch.empty((2 * B, h, w, 2 * C), dtype=torch.float16, device=dev)
+                if l and self._s2d_ok(PYRAMID_FILTERS[l - 1], C):      # so is the stride-2 conv's output (halo kernel: split rows)
+                    lvl[0] = torch.empty((2 * B, h, w, 2 * C), dtype=torch.float16, device=dev)
             p.pyr.append(lvl)
         pre_total = sum(ESTIMATOR_FILTERS) if self.use_dc else 0
         p.S, p.tmp, p.flows, p.f1w = [], [], [], []

@@ -161,6 +161,49 @@ def conv3x3_tc_f16_split(x, w_packed, bias, cin: int, cout: int, dilation: int =
     return out if out is not None else out_split
 
 
+def s2d_reindex(k_hwio, out=None):
+    """(3,3,Cin,Cout) HWIO kernel of a stride-2 conv -> the (3,3,4*Cin,Cout) kernel of the equivalent 2x2 convolution over the
+    space-to-depth view (taps (0..1, 0..1); see pwc_conv3x3_s2_tc_f16_fwd).  Pack the result with pack_weights_f16."""
+    if k_hwio.dim() != 4 or tuple(k_hwio.shape[:2]) != (3, 3) or k_hwio.dtype != torch.float32 or not k_hwio.is_contiguous():
+        raise ValueError("s2d_reindex: kernel must be contiguous float32 (3,3,Cin,Cout)")
+    cin, cout = k_hwio.shape[2], k_hwio.shape[3]
+    if out is None:
+        out = torch.empty((3, 3, 4 * cin, cout), dtype=torch.float32, device=k_hwio.device)
+    if tuple(out.shape) != (3, 3, 4 * cin, cout) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("s2d_reindex: out must be contiguous float32 (3,3,4*Cin,Cout)")
+    check(lib().pwc_conv3x3_s2d_reindex(k_hwio.data_ptr(), out.data_ptr(), cin, cout, _stream()), "pwc_conv3x3_s2d_reindex")
+    return out
+
+
+def conv3x3_s2_tc_f16(x, w_packed_s2d, bias, cin: int, cout: int, alpha: float = 1.0, out=None, out_split=None):
+    """Stride-2 3x3 conv + bias + leaky (modules.py:62-63) on the halo kernel.  `x`: dense float32 NHWC with even H, W;
+    `w_packed_s2d` = pack_weights_f16(s2d_reindex(kernel)); result (B,H/2,W/2,cout) to `out` (float32 view) and/or
+    `out_split` (contiguous fp16 (B,H/2,W/2,2*cout), cout % 32 == 0).  Same numerics class as conv3x3_tc_f16(stride=2)."""
+    B, H, W, C, x_cs = _nhwc(x, "x")
+    if C != cin or x_cs != cin or H % 2 or W % 2 or cin % 16 or cout % 16 or cout > 128:
+        raise ValueError("conv3x3_s2_tc_f16: needs a dense input, even H and W, cin % 16 == 0, cout % 16 == 0, cout <= 128")
+    if bias.shape != (cout,) or w_packed_s2d.dtype != torch.float16 or \
+            w_packed_s2d.numel() * 2 != lib().pwc_conv3x3_packed_bytes_f16(4 * cin, cout):
+        raise ValueError("conv3x3_s2_tc_f16: bias / w_packed_s2d do not match (4*Cin, Cout)")
+    OH, OW = H // 2, W // 2
+    if out is None and out_split is None:
+        out = new_nhwc(B, OH, OW, cout, x.device)
+    yp, y_cs = 0, 0
+    if out is not None:
+        Bo, Ho, Wo, Co, y_cs = _nhwc(out, "out")
+        if (Bo, Ho, Wo, Co) != (B, OH, OW, cout):
+            raise ValueError("conv3x3_s2_tc_f16: out shape mismatch")
+        yp = out.data_ptr()
+    sp, ys_cs = 0, 0
+    if out_split is not None:
+        if out_split.dtype != torch.float16 or tuple(out_split.shape) != (B, OH, OW, 2 * cout) or not out_split.is_contiguous() or cout % 32:
+            raise ValueError("conv3x3_s2_tc_f16: out_split must be contiguous fp16 (B,H/2,W/2,2*cout), cout % 32 == 0")
+        sp, ys_cs = out_split.data_ptr(), 2 * cout
+    check(lib().pwc_conv3x3_s2_tc_f16_fwd(x.data_ptr(), w_packed_s2d.data_ptr(), bias.data_ptr(), yp, y_cs, sp, ys_cs,
+                                          B, H, W, cin, cout, float(alpha), _stream()), "pwc_conv3x3_s2_tc_f16_fwd")
+    return out if out is not None else out_split
+
+
 def conv3x3_tc_f16_head(x, w_packed_pad, bias_pad, cin: int, cout: int, cout_pad: int, dilation: int = 1, alpha: float = 1.0,
                         residual=None, out=None):
     """Narrow-output conv (the 2-channel flow heads, modules.py:274-277, 325-326) on tcgen05: kernel and bias are

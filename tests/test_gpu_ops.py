@@ -502,3 +502,42 @@ def test_conv_chain_with_split_activations_is_bit_identical(P, shape, cmid, cout
     assert torch.equal(out, ref)
     with pytest.raises(ValueError):
         ops_tc.conv3x3_tc_f16_split(mid_s[..., :cmid], w2, b2, cmid, cout)
+
+
+@pytest.mark.parametrize("shape,cout", [((2, 40, 264, 16), 32), ((1, 56, 128, 32), 64), ((2, 28, 64, 64), 96), ((3, 14, 34, 96), 128),
+                                        ((1, 6, 8, 16), 16), ((1, 300, 2, 32), 32)])
+def test_conv_stride2_space_to_depth_matches_oracle(P, shape, cout):
+    """Stride-2 conv + bias + leaky (modules.py:62-63) on the halo kernel as a 2x2 conv over the space-to-depth view
+    (pwc_conv3x3_s2d_reindex + pwc_conv3x3_s2_tc_f16_fwd): vs the oracle's TF-'SAME' stride-2 conv, fp32-class tolerance;
+    the split-row output reproduces the fp32 output.  Covers row tiles with a ragged right edge, the flat mode (rows of
+    fewer than 128 outputs), one-column outputs, every pyramid channel pair."""
+    from pwcnet_b200 import ops_tc
+    B, H, W, C = shape
+    x, k, b = _rand(shape, 11), _rand((3, 3, C, cout), 12, 0.05), _rand((cout,), 13, 0.1)
+    ref = O.leaky_relu(O.conv2d_same(torch.from_numpy(x), torch.from_numpy(k), torch.from_numpy(b), stride=2), 0.1).numpy()
+    k2 = ops_tc.s2d_reindex(_cuda(k))
+    # the re-indexed kernel: taps (0..1, 0..1) hold W[2dy+py][2dx+px], everything else is zero
+    k2n = k2.cpu().numpy().reshape(3, 3, 2, 2, C, cout)
+    for dy in range(3):
+        for dx in range(3):
+            for py in range(2):
+                for px in range(2):
+                    ky, kx = 2 * dy + py, 2 * dx + px
+                    want = k[ky, kx] if (dy < 2 and dx < 2 and ky < 3 and kx < 3) else np.zeros((C, cout), np.float32)
+                    assert np.array_equal(k2n[dy, dx, py, px], want)
+    wp = ops_tc.pack_weights_f16(k2)
+    y = ops_tc.conv3x3_s2_tc_f16(_cuda(x), wp, _cuda(b), C, cout, alpha=0.1)
+    assert tuple(y.shape) == (B, H // 2, W // 2, cout)
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=0, atol=2e-5 * max(1.0, float(np.abs(ref).max())))
+    # into a channel slot of a wider buffer, and as split rows
+    wide = torch.full((B, H // 2, W // 2, cout + 16), 7.0, device="cuda")
+    ops_tc.conv3x3_s2_tc_f16(_cuda(x), wp, _cuda(b), C, cout, alpha=0.1, out=wide[..., 16:])
+    assert torch.equal(wide[..., 16:], y) and bool((wide[..., :16] == 7.0).all())
+    if cout % 32 == 0:
+        ys = torch.empty((B, H // 2, W // 2, 2 * cout), dtype=torch.float16, device="cuda")
+        ops_tc.conv3x3_s2_tc_f16(_cuda(x), wp, _cuda(b), C, cout, alpha=0.1, out_split=ys)
+        hl = ys.float().view(B, H // 2, W // 2, cout // 32, 2, 32)
+        rec = (hl[..., 0, :] + hl[..., 1, :] / 2048.0).reshape(B, H // 2, W // 2, cout)
+        np.testing.assert_allclose(rec.cpu().numpy(), y.cpu().numpy(), rtol=2e-7, atol=1e-9)
+    with pytest.raises(ValueError):
+        ops_tc.conv3x3_s2_tc_f16(_cuda(x)[:, :-1], wp, _cuda(b), C, cout)          # odd height
