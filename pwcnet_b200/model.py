@@ -359,7 +359,11 @@ class PWCDCNet(object):
 
     def _s2d_ok(self, cin: int, cout: int) -> bool:
         """Stride-2 convs on the halo kernel (2x2 conv over the space-to-depth view, csrc/conv_tc_f16.cu): 3xf16 only."""
-        return bool(self.precision == "3xf16" and self.s2d and cin % 16 == 0 and cout % 16 == 0 and cout <= 128)
+        # measured per layer at B = 8 x 448 x 1024 (ncu launch lists, profiles/r02_halo_epilogue.log): 16 -> 32: 120 -> 56 us,
+        # 32 -> 64: 55 -> 54 us (+ 5 us saved in the next conv by the split output); 64 -> 96 and 96 -> 128 (flat mode, 8 / 12
+        # K slices per tile) are no faster than the streaming kernel, so they stay there unless PWC_S2D=all
+        lim = 128 if os.environ.get("PWC_S2D") == "all" else 32
+        return bool(self.precision == "3xf16" and self.s2d and cin % 16 == 0 and cin <= lim and cout % 16 == 0 and cout <= 128)
 
     def _conv_s2d(self, x, scope, k, b, cin, cout, alpha, out):
         from . import ops_tc
