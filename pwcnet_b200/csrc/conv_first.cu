@@ -8,8 +8,8 @@
 //   * CTA = 8 x 64 output pixels; the 17 x 129 x 3 input patch is staged in shared memory once (coalesced 4-byte loads;
 //     uint8 inputs go through the 256-entry table float32(float64(v) / 255.0), i.e. the reference's `images / 255.0`
 //     feed, test.py:31-33, train.py:122 -- the bytes themselves cross PCIe and HBM, nothing is expanded in memory);
-//   * a thread owns two output pixels x 16 channels (32 accumulators); the 27 x 16 weights sit in __constant__ memory so
-//     every FFMA takes its weight as a constant operand (no LDS per FMA: one LDS.32 per input value and 16 FFMAs);
+//   * a thread owns four output pixels x 16 channels (64 accumulators); the 27 x 16 weights sit in __constant__ memory:
+//     one constant load per weight feeds four FFMAs, one LDS.32 per input value feeds 16;
 //   * the 16 results of a pixel go through a shared-memory transpose so that a warp's float4 stores cover 512 contiguous
 //     bytes (16-byte-per-lane stores at a 64-byte stride cost 2.2x, profiles/r02_tmem_ld_bench.log).
 // Exact fp32 (same operation order per output: taps row-major, channels inner), the yard-stick class of conv_direct.cu.
@@ -22,8 +22,11 @@ namespace pwc {
 
 constexpr int F_TH = 8, F_TW = 64, F_CO = 16;
 constexpr int F_PH = 2 * F_TH + 1, F_PW = 2 * F_TW + 1;       // 17 x 129 input pixels
-constexpr int F_THREADS = 256;
-constexpr int F_PATCH = F_PH * F_PW * 3;                      // floats
+constexpr int F_THREADS = 128;                                // 4 output pixels x 16 channels per thread
+constexpr int F_PPT = 4;                                      // (ncu, round 2: with 2 pixels per thread the kernel was instruction-
+                                                              // bound -- one LDC per weight per 2 FFMAs, issue slots 76 % busy, FMA pipe 39 %)
+constexpr int F_ROW = (F_PW * 3 + 3) / 4 * 4;                 // patch row pitch in floats: 388 (97 whole 4-byte-pixel words)
+constexpr int F_PATCH = F_PH * F_ROW;                         // floats
 constexpr int F_OPITCH = F_CO + 4;                            // staging row pitch in floats (conflict-free float4 stores)
 
 __constant__ float c_first_w[27 * F_CO + F_CO];               // HWIO kernel (ky, kx, ci, co) then the bias
@@ -40,7 +43,7 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_kernel(const FirstParams
     __shared__ __align__(16) float stage[F_TH * F_TW * F_OPITCH];
     __shared__ float lut[256];
     float* patch = stage;
-    static_assert(F_PATCH + 3 <= F_TH * F_TW * F_OPITCH, "patch must fit in the staging area");
+    static_assert(F_PATCH <= F_TH * F_TW * F_OPITCH, "patch must fit in the staging area");
     const int tid = threadIdx.x;
     const int tiles_x = (p.OW + F_TW - 1) / F_TW, tiles_y = (p.OH + F_TH - 1) / F_TH;
     const int tile = blockIdx.x;
@@ -49,32 +52,43 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_kernel(const FirstParams
     const int iy0 = 2 * oy0, ix0 = 2 * ox0;                    // SAME padding of an even size with stride 2: 0 before, 1 after
     if (U8) {
         lut[tid] = __ldg(p.lut + tid);
+        lut[tid + F_THREADS] = __ldg(p.lut + tid + F_THREADS);
         __syncthreads();
     }
     // ---- stage the input patch: rows iy0 .. iy0+16, columns ix0 .. ix0+128, 3 channels; zero outside the image
-    const int row_elems = F_PW * 3;                            // 387
+    const int row_elems = F_PW * 3;                            // 387 values per patch row, stored at a pitch of F_ROW
     if (U8) {
         const uint8_t* xb = static_cast<const uint8_t*>(p.x) + (size_t)b * p.H * p.W * 3;
-        const int words = (row_elems + 3) / 4;                 // 97 4-byte words per row (row starts are 4-byte aligned: W % 4 == 0)
-        for (int e = tid; e < F_PH * words; e += F_THREADS) {
+        constexpr int words = F_ROW / 4;                       // 97 4-byte words per row (row starts are 4-byte aligned: W % 4 == 0)
+        // all of a thread's 4-byte loads are issued before the first table lookup (13 independent loads in flight: as a
+        // plain loop the staging phase was 13 serialised global-memory round trips per CTA)
+        constexpr int NIT = (F_PH * words + F_THREADS - 1) / F_THREADS;
+        uint32_t vv[NIT];
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int e = tid + i * F_THREADS;
             const int ry = e / words, w4 = e - ry * words;
             const int iy = iy0 + ry;
             const long long off = ((long long)iy * p.W + ix0) * 3 + 4 * w4;       // byte offset inside the image
-            const long long row_end = ((long long)iy + 1) * p.W * 3;
+            const long long left = ((long long)iy + 1) * p.W * 3 - off;           // bytes up to the end of the image row
             uint32_t v = 0;
-            if (iy < p.H) {
-                if (off + 4 <= row_end) v = __ldg(reinterpret_cast<const uint32_t*>(xb + off));
+            if (e < F_PH * words && iy < p.H && left > 0) {
+                if (left >= 4) v = __ldg(reinterpret_cast<const uint32_t*>(xb + off));
                 else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (off + k < row_end) v |= (uint32_t)xb[off + k] << (8 * k);
+                    for (int k = 0; k < (int)left; ++k) v |= (uint32_t)xb[off + k] << (8 * k);
                 }
             }
-            const bool in_y = iy < p.H;
+            vv[i] = v;
+        }
+        // bytes beyond the image are 0 and the table maps 0 to 0.0f: the zero padding needs no branches
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int col = 4 * w4 + k;
-                if (col < row_elems) patch[ry * row_elems + col] = (in_y && off + k < row_end) ? lut[(v >> (8 * k)) & 0xFF] : 0.f;
-            }
+        for (int i = 0; i < NIT; ++i) {
+            const int e = tid + i * F_THREADS;
+            const int ry = e / words, w4 = e - ry * words;
+            const uint32_t v = vv[i];
+            if (e < F_PH * words)
+                *reinterpret_cast<float4*>(patch + ry * F_ROW + 4 * w4) =
+                    make_float4(lut[v & 0xFF], lut[(v >> 8) & 0xFF], lut[(v >> 16) & 0xFF], lut[v >> 24]);
         }
     } else {
         const float* xb = static_cast<const float*>(p.x) + (size_t)b * p.H * p.W * 3;
@@ -82,15 +96,15 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_kernel(const FirstParams
             const int ry = e / row_elems, col = e - ry * row_elems;
             const int iy = iy0 + ry;
             const long long off = ((long long)iy * p.W + ix0) * 3 + col;
-            patch[e] = (iy < p.H && off < ((long long)iy + 1) * p.W * 3) ? __ldg(xb + off) : 0.f;
+            patch[ry * F_ROW + col] = (iy < p.H && off < ((long long)iy + 1) * p.W * 3) ? __ldg(xb + off) : 0.f;
         }
     }
     __syncthreads();
-    // ---- two output pixels per thread: (oy, ox) and (oy + 4, ox); lanes = consecutive ox
-    const int lx = tid & (F_TW - 1), ly = tid >> 6;            // 64 x 4
-    float acc[2][F_CO];
+    // ---- four output pixels per thread: (oy + 2 h, ox), h = 0..3; lanes = consecutive ox
+    const int lx = tid & (F_TW - 1), ly = tid >> 6;            // 64 x 2
+    float acc[F_PPT][F_CO];
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < F_PPT; ++h)
 #pragma unroll
         for (int j = 0; j < F_CO; ++j) acc[h][j] = 0.f;
 #pragma unroll
@@ -100,19 +114,21 @@ __global__ void __launch_bounds__(F_THREADS) conv_first_kernel(const FirstParams
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
                 const int widx = ((ky * 3 + kx) * 3 + ci) * F_CO;
-                const float x0 = patch[(2 * ly + ky) * row_elems + (2 * lx + kx) * 3 + ci];
-                const float x1 = patch[(2 * (ly + 4) + ky) * row_elems + (2 * lx + kx) * 3 + ci];
+                float xv[F_PPT];
+#pragma unroll
+                for (int h = 0; h < F_PPT; ++h) xv[h] = patch[(2 * (ly + 2 * h) + ky) * F_ROW + (2 * lx + kx) * 3 + ci];
 #pragma unroll
                 for (int j = 0; j < F_CO; ++j) {
-                    acc[0][j] = fmaf(x0, c_first_w[widx + j], acc[0][j]);
-                    acc[1][j] = fmaf(x1, c_first_w[widx + j], acc[1][j]);
+                    const float wv = c_first_w[widx + j];
+#pragma unroll
+                    for (int h = 0; h < F_PPT; ++h) acc[h][j] = fmaf(xv[h], wv, acc[h][j]);
                 }
             }
     // ---- bias, leaky, transpose through shared memory, coalesced float4 stores
     __syncthreads();                                           // every thread is done with the patch
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        float* s = stage + ((ly + 4 * h) * F_TW + lx) * F_OPITCH;
+    for (int h = 0; h < F_PPT; ++h) {
+        float* s = stage + ((ly + 2 * h) * F_TW + lx) * F_OPITCH;
 #pragma unroll
         for (int j = 0; j < F_CO; j += 4) {
             float4 v;

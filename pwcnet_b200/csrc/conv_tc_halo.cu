@@ -141,6 +141,21 @@ __device__ __forceinline__ void hl_issue_chunk(const IssueCtx& cx, uint32_t d_ma
     }
 }
 
+// eight fp32 values -> 8 x fp16 h (16 bytes) and 8 x fp16 l * 2^11 (16 bytes)
+__device__ __forceinline__ void hl_split8(const float4& a, const float4& bq, uint4& hq, uint4& lq) {
+    const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+    const __half2 h2 = __floats2half2_rn(bq.x, bq.y), h3 = __floats2half2_rn(bq.z, bq.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+    const __half2 l0 = __floats2half2_rn((a.x - f0.x) * HL_SCALE, (a.y - f0.y) * HL_SCALE);
+    const __half2 l1 = __floats2half2_rn((a.z - f1.x) * HL_SCALE, (a.w - f1.y) * HL_SCALE);
+    const __half2 l2 = __floats2half2_rn((bq.x - f2.x) * HL_SCALE, (bq.y - f2.y) * HL_SCALE);
+    const __half2 l3 = __floats2half2_rn((bq.z - f3.x) * HL_SCALE, (bq.w - f3.y) * HL_SCALE);
+    hq = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                    *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+    lq = make_uint4(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1),
+                    *reinterpret_cast<const uint32_t*>(&l2), *reinterpret_cast<const uint32_t*>(&l3));
+}
+
 __device__ __forceinline__ void hl_tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -605,6 +620,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     } else {
         // ===================== converters (warps 6..13): fp32 pixel row -> [h | l * 2^11] fp16, in place =====================
         const int ct = threadIdx.x - 192;   // 0..255
+        const bool half_rows = p.Cin <= 16 && !p.s2d;
         int it = 0, s = 0;
         uint32_t ph = 0;
         for (int j = 0; j < n_items; ++j) {
@@ -618,29 +634,32 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     if (R < n_rows && !p.exp_skip_conv && !p.in_split) {
                         uint8_t* row = stp + (size_t)R * 128;
                         const int sw = R & 7;              // 128B swizzle: logical 16-byte chunk j sits at chunk j ^ (R & 7)
-                        float4 v[8];
+                        if (half_rows) {
+                            // 16 input channels (pyramid level 1): channels 16..31 of the slice are the tensor map's zero
+                            // fill and the MMAs only take the first K = 16 step -- read 64 bytes, write h to chunks 0-1 and
+                            // l to chunks 4-5 (half the converter's shared-memory traffic and arithmetic)
+                            float4 v[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
-                        uint4 hq[4], lq[4];
+                            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 a = v[2 * j], bq = v[2 * j + 1];
-                            const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-                            const __half2 h2 = __floats2half2_rn(bq.x, bq.y), h3 = __floats2half2_rn(bq.z, bq.w);
-                            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
-                            const __half2 l0 = __floats2half2_rn((a.x - f0.x) * HL_SCALE, (a.y - f0.y) * HL_SCALE);
-                            const __half2 l1 = __floats2half2_rn((a.z - f1.x) * HL_SCALE, (a.w - f1.y) * HL_SCALE);
-                            const __half2 l2 = __floats2half2_rn((bq.x - f2.x) * HL_SCALE, (bq.y - f2.y) * HL_SCALE);
-                            const __half2 l3 = __floats2half2_rn((bq.z - f3.x) * HL_SCALE, (bq.w - f3.y) * HL_SCALE);
-                            hq[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                                               *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
-                            lq[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1),
-                                               *reinterpret_cast<const uint32_t*>(&l2), *reinterpret_cast<const uint32_t*>(&l3));
-                        }
+                            for (int j = 0; j < 2; ++j) {
+                                uint4 hq, lq;
+                                hl_split8(v[2 * j], v[2 * j + 1], hq, lq);
+                                *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = hq;
+                                *reinterpret_cast<uint4*>(row + (((j + 4) ^ sw) << 4)) = lq;
+                            }
+                        } else {
+                            float4 v[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = hq[j];
-                            *reinterpret_cast<uint4*>(row + (((j + 4) ^ sw) << 4)) = lq[j];
+                            for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
+                            uint4 hq[4], lq[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) hl_split8(v[2 * j], v[2 * j + 1], hq[j], lq[j]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = hq[j];
+                                *reinterpret_cast<uint4*>(row + (((j + 4) ^ sw) << 4)) = lq[j];
+                            }
                         }
                     }
                 }
