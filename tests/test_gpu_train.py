@@ -433,7 +433,11 @@ def test_batched_weight_packs_equal_per_layer_packs(P):
     assert len(m._pack_keys) > 40
     for key in m._pack_keys:
         scope = key.split("#")[0]
-        src = m._head_k[scope] if key.endswith("#head") else m._k[scope]
+        if key.endswith("#s2d"):               # stride-2 conv as a 2x2 conv: the pack's source is the re-indexed kernel
+            assert torch.equal(m._k_s2d[scope], ops_tc.s2d_reindex(m._k[scope])), key
+            src = m._k_s2d[scope]
+        else:
+            src = m._head_k[scope] if key.endswith("#head") else m._k[scope]
         assert torch.equal(ops_tc.pack_weights_f16(src), m._packed[key]), key
     ff, _ = m(im0, im1)
     ff2, _ = P.PWCDCNet(weights=m.state_dict(), cv_pipeline="default")(im0, im1)      # the trainer's model runs the default pipeline
