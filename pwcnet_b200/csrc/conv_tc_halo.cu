@@ -59,6 +59,8 @@ struct HaloParams {
     int tap_dy[9], tap_dx[9], tap_id[9];     // tap offsets in box rows / pixels (times dil for dx), and the tap's index in the packed weights
     int tma_y, tma_ys;    // the epilogue stores the fp32 / split output through TMA (shared-memory staging + bulk tensor store)
     int epi_off;          // byte offset of the epilogue staging area: 4 warps x 2 buffers x (32 pixels x 128 or 64 bytes)
+    int tma_mask;         // dgrad: the leaky-derivative mask tile of a pass is TMA-loaded into a per-warp buffer behind the staging area
+    int tma_red;          // accumulate through the TMA engine's reduce-add store (UTMAREDG) instead of a read-modify-write
     int exp_direct_store; // experiment (PWC_HALO_EXP=3): 16-byte-per-lane stores (round-1 pattern)
     int exp_skip_store;   // experiment (PWC_HALO_EXP=2): the epilogue stores nothing -> upper bound of the store path
     int dil, bw;          // dilation d; box width in pixels (128 + 2d, or W + 2 in flat mode)
@@ -176,7 +178,7 @@ __device__ __forceinline__ void hl_tma_store_4d(const CUtensorMap* map, uint32_t
 // cp.async.bulk.wait_group.read before a buffer is rewritten).  Pixels beyond the row end are clipped by the tensor map.
 template <int G>
 __device__ __forceinline__ void hl_stage_and_store(const CUtensorMap* map, uint8_t* buf, const uint32_t (&w)[G], int lane,
-                                                   int c0, int x, int y, int b) {
+                                                   int c0, int x, int y, int b, bool reduce_add = false) {
     constexpr int NCH = G / 4;                                // 16-byte chunks per pixel row (8: 128 B, 4: 64 B)
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the store that last read this buffer is done
     __syncwarp();
@@ -188,7 +190,10 @@ __device__ __forceinline__ void hl_stage_and_store(const CUtensorMap* map, uint8
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
-        hl_tma_store_4d(map, smem_u32(buf), c0, x, y, b);
+        if (reduce_add)
+            asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(map), "r"(smem_u32(buf)), "r"(c0), "r"(x), "r"(y), "r"(b) : "memory");
+        else hl_tma_store_4d(map, smem_u32(buf), c0, x, y, b);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
 }
@@ -266,7 +271,8 @@ __device__ __forceinline__ void hl_epilogue_pass(const HaloParams& p, const floa
                                                  size_t pix, bool valid_o, size_t pix_o, bool odd, bool vec,
                                                  unsigned long long* dbg, int tcount,
                                                  const CUtensorMap* tmY, const CUtensorMap* tmYS, uint8_t* stage, int& nbuf,
-                                                 int lane, int wx, int wy, int wb, uint32_t release_bar, int ch0, int cn) {
+                                                 int lane, int wx, int wy, int wb, uint32_t release_bar, int ch0, int cn,
+                                                 const CUtensorMap* tmM, uint8_t* mask_buf, uint32_t bar_mask, uint32_t& mask_phase) {
     float acc[G];
     {
         uint32_t rm[G], rc[G];
@@ -328,10 +334,31 @@ __device__ __forceinline__ void hl_epilogue_pass(const HaloParams& p, const floa
         const float* mrow = p.mask ? p.mask + pix * p.mask_cs + ch0 : nullptr;
         const float* rrow = p.res ? p.res + pix * p.res_cs + ch0 : nullptr;
         if (p.tma_y) {
+            if (p.tma_mask) {
+                // dgrad: multiply by leaky'(forward activation); this warp's 32 pixel x G channel tile of the mask tensor was
+                // TMA-loaded (same swizzle as the staging rows) while the MMAs / the previous pass ran
+                mbar_wait(bar_mask, mask_phase);
+                mask_phase ^= 1;
+                constexpr int NCH = G / 4;
+                const int sw = NCH == 8 ? (lane & 7) : ((lane >> 1) & 3);
+                const uint8_t* mrow_s = mask_buf + lane * (16 * NCH);
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const float4 mk = *reinterpret_cast<const float4*>(mrow_s + ((j ^ sw) << 4));
+                    acc[4 * j] *= mk.x > 0.f ? 1.f : p.mask_alpha; acc[4 * j + 1] *= mk.y > 0.f ? 1.f : p.mask_alpha;
+                    acc[4 * j + 2] *= mk.z > 0.f ? 1.f : p.mask_alpha; acc[4 * j + 3] *= mk.w > 0.f ? 1.f : p.mask_alpha;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the reads above before the next TMA write
+                __syncwarp();
+                if (lane == 0 && n0 + G < cn) {                                   // next pass of this tile
+                    mbar_expect_tx(bar_mask, 32 * 4 * G);
+                    tma_load_4d(smem_u32(mask_buf), tmM, bar_mask, ch0 + n0 + G, wx, wy, wb);
+                }
+            }
             uint32_t w[G];
 #pragma unroll
             for (int j = 0; j < G; ++j) w[j] = __float_as_uint(acc[j]);
-            hl_stage_and_store<G>(tmY, stage + (nbuf & 1) * (32 * 4 * G), w, lane, ch0 + n0, wx, wy, wb);
+            hl_stage_and_store<G>(tmY, stage + (nbuf & 1) * (32 * 4 * G), w, lane, ch0 + n0, wx, wy, wb, p.tma_red != 0);
             ++nbuf;
         } else if (vec && p.cout_valid == p.Cout && (p.Cout % G) == 0 && !p.exp_direct_store) {
             uint32_t w[G];
@@ -372,12 +399,12 @@ __device__ __forceinline__ void hl_epilogue_pass(const HaloParams& p, const floa
 
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                       const __grid_constant__ CUtensorMap tmYS, const HaloParams p) {
+                       const __grid_constant__ CUtensorMap tmYS, const __grid_constant__ CUtensorMap tmM, const HaloParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     // barriers: act_full[2], act_conv[2], act_empty[2], w_full[4], w_empty[4], acc_full[2], acc_empty[2]
-    __shared__ __align__(8) uint64_t bars[3 * HL_MAX_ACT_STAGES + 2 * HL_W_STAGES + 4];
+    __shared__ __align__(8) uint64_t bars[3 * HL_MAX_ACT_STAGES + 2 * HL_W_STAGES + 4 + 4];   // ... + mask tile of each epilogue warp
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_bias[128 + 16];   // Cout <= 128; a 16-channel pass of a Cout % 16 == 8 layer reads 8 past the end
 
@@ -404,6 +431,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             mbar_init(bar_accf + 8 * a, 1);
             mbar_init(bar_acce + 8 * a, 4);
         }
+        for (int q = 0; q < 4; ++q) mbar_init(bar_accf + 8 * (4 + q), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + 144) {
@@ -565,7 +593,11 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         if ((p.tma_y || p.tma_ys) && lane == 0) {
             if (p.tma_y) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
             if (p.tma_ys) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmYS) : "memory");
+            if (p.tma_mask) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmM) : "memory");
         }
+        uint8_t* mask_buf = base_ptr + p.epi_off + 4 * 8192 + q * 4096;
+        const uint32_t bar_mask = bar_accf + 8 * (4 + q);
+        uint32_t mask_phase = 0;
         int tcount = 0;
         // tile coordinates advance by the (constant) tile step without divisions: image b, tile r of the image =
         // (row ty, column tile tx) in row mode
@@ -591,6 +623,10 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
             if (ty >= p.H) ty -= p.H;                      // row mode: tiles_per_img = tiles_x * H, the image carry is in b
             const int a = tcount & 1, u = tcount >> 1;
+            if (p.tma_mask && lane == 0) {            // first pass's mask tile: in flight while the MMAs of this tile run
+                mbar_expect_tx(bar_mask, (p.Cout & 31) == 0 ? 4096 : 2048);
+                tma_load_4d(smem_u32(mask_buf), &tmM, bar_mask, ch0, x - lane, y, b_now);
+            }
             mbar_wait(bar_accf + 8 * a, u & 1);
             if (threadIdx.x == 64) HL_DBG(5, tcount);
             tc_fence_after();
@@ -604,9 +640,9 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const bool valid_o = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
             const size_t pix_o = (size_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)pix, 1);
             if ((p.Cout & 31) == 0) {
-                for (int n0 = 0; n0 < cn; n0 += 32) hl_epilogue_pass<32>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 32 >= cn ? bar_acce + 8 * a : 0u, ch0, cn);
+                for (int n0 = 0; n0 < cn; n0 += 32) hl_epilogue_pass<32>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 32 >= cn ? bar_acce + 8 * a : 0u, ch0, cn, &tmM, mask_buf, bar_mask, mask_phase);
             } else {
-                for (int n0 = 0; n0 < p.Cout; n0 += 16) hl_epilogue_pass<16>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 16 >= p.Cout ? bar_acce + 8 * a : 0u, 0, p.Cout);
+                for (int n0 = 0; n0 < p.Cout; n0 += 16) hl_epilogue_pass<16>(p, s_bias, tbase, n0, valid, pix, valid_o, pix_o, odd, vec, edbg, tcount, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now, n0 + 16 >= p.Cout ? bar_acce + 8 * a : 0u, 0, p.Cout, &tmM, mask_buf, bar_mask, mask_phase);
             }
             if (threadIdx.x == 64) HL_DBG(6, tcount);
             if (threadIdx.x == 64 && dbg) {
@@ -764,10 +800,13 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     p.desc_mode = 0;
     // TMA-store epilogue: row tiles (not the flat mode: its tiles hold padding slots between rows), whole passes, plain
     // stores (no dgrad mask / residual / accumulate)
-    CUtensorMap tmY, tmYS;
-    memset(&tmY, 0, sizeof(tmY)); memset(&tmYS, 0, sizeof(tmYS));
-    const bool tma_ok = !flat && !mask && !res && !accumulate && cout_valid == Cout && (Cout == 16 || (Cout & 31) == 0) &&
-                        !getenv("PWC_HALO_NO_TMA_STORE");
+    CUtensorMap tmY, tmYS, tmM;
+    memset(&tmY, 0, sizeof(tmY)); memset(&tmYS, 0, sizeof(tmYS)); memset(&tmM, 0, sizeof(tmM));
+    // (dgrad: the mask tile comes in through TMA as well and `accumulate` becomes a reduce-add store; PWC_HALO_NO_TMA_DGRAD=1
+    //  keeps the register epilogue for those)
+    const bool dgrad_ok = (!mask || ((mask_cs & 3) == 0 && aligned16(mask))) && !getenv("PWC_HALO_NO_TMA_DGRAD");
+    const bool tma_ok = !flat && (!mask || dgrad_ok) && !res && (!accumulate || dgrad_ok) && !(y_split && (mask || accumulate)) &&
+                        cout_valid == Cout && (Cout == 16 || (Cout & 31) == 0) && !getenv("PWC_HALO_NO_TMA_STORE");
     if (tma_ok && y && (y_cs & 3) == 0 && aligned16(y)) {
         const cuuint32_t G = Cout == 16 ? 16 : 32;
         cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -779,6 +818,15 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(y) failed with %d", (int)r); return PWC_E_BADARG; }
         p.tma_y = 1;
+        p.tma_red = accumulate ? 1 : 0;
+        if (mask) {
+            cuuint64_t mstrides[3] = {(cuuint64_t)mask_cs * 4, (cuuint64_t)W * mask_cs * 4, (cuuint64_t)H * W * mask_cs * 4};
+            r = enc(&tmM, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)mask, dims, mstrides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    G == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(mask) failed with %d", (int)r); return PWC_E_BADARG; }
+            p.tma_mask = 1;
+        }
     }
     if (tma_ok && y_split && (Cout & 31) == 0) {
         cuuint64_t dims[4] = {(cuuint64_t)2 * Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -790,7 +838,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(y_split) failed with %d", (int)r); return PWC_E_BADARG; }
         p.tma_ys = 1;
     }
-    const size_t epi_bytes = (p.tma_y || p.tma_ys) ? 4 * 8192 : 0;
+    const size_t epi_bytes = (p.tma_y || p.tma_ys) ? 4 * 8192 + (p.tma_mask ? 4 * 4096 : 0) : 0;
     if (const char* e = getenv("PWC_HALO_EXP")) { p.exp_skip_conv = atoi(e) == 1; p.exp_skip_store = atoi(e) == 2; p.exp_direct_store = atoi(e) == 3; }
     if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
     // (Rotating accumulator sets over the taps were tried in round 1 and again in round 2 with a separate A_l x W_h chain:
@@ -820,7 +868,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     }
     size_t smem = (size_t)p.act_stages * p.act_stage + (p.w_resident ? w_all : (size_t)p.w_stages * p.w_stage_bytes) + epi_bytes + 1024;
     if (smem > HL_SMEM_BUDGET) { p.act_stages = 2; smem = (size_t)2 * p.act_stage + (size_t)p.w_stages * p.w_stage_bytes + epi_bytes + 1024; }
-    if (smem > HL_SMEM_BUDGET && epi_bytes) { smem -= epi_bytes; p.tma_y = p.tma_ys = 0; }    // no room for the staging buffers: plain stores
+    if (smem > HL_SMEM_BUDGET && epi_bytes) { smem -= epi_bytes; p.tma_y = p.tma_ys = p.tma_mask = p.tma_red = 0; }    // no room for the staging buffers: plain stores
     if (smem > HL_SMEM_BUDGET) return -1000;
     p.epi_off = (int)(smem - 1024 - ((p.tma_y || p.tma_ys) ? epi_bytes : 0));               // 1024-byte aligned: every part before it is
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -831,7 +879,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         cudaMemsetAsync(dbg_buf, 0, 148 * 128 * 8, st);
         p.dbg = dbg_buf;
     }
-    conv3x3_tc_halo_kernel<<<grid, HL_THREADS, smem, st>>>(tmX, tmY, tmYS, p);
+    conv3x3_tc_halo_kernel<<<grid, HL_THREADS, smem, st>>>(tmX, tmY, tmYS, tmM, p);
     PWC_CHECK_LAUNCH("conv3x3_tc_halo_kernel");
     if (p.dbg) {   // debugging aid only (synchronises): timeline of the first chunks / tiles of one CTA
         cudaStreamSynchronize(st);
