@@ -6,7 +6,7 @@
 #include <cstdint>
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(1024, 1) st_kernel(float4* out, size_t n_chunks, int mode) {
+__global__ void __launch_bounds__(1024, 1) st_kernel(float4* out, size_t n_chunks, int mode, int pitch) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, nth = blockDim.x;
     if (mode == 0) {
@@ -47,15 +47,15 @@ __global__ void __launch_bounds__(1024, 1) st_kernel(float4* out, size_t n_chunk
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else {
-        // 32 pixels per warp iteration: 22 float4 units each (352 B) at pitch 608 B; unit u = lane + 32 m
+        // 32 pixels per warp iteration: 22 float4 units each (352 B) at `pitch` bytes; unit u = lane + 32 m
         const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
-        const size_t n_pix = n_chunks * 4096 / 608;
+        const size_t n_pix = n_chunks * 4096 / pitch;
         for (size_t p0 = ((size_t)blockIdx.x * nw + warp) * 32; p0 + 32 <= n_pix; p0 += (size_t)gridDim.x * nw * 32) {
-            char* base = reinterpret_cast<char*>(out) + p0 * 608;
+            char* base = reinterpret_cast<char*>(out) + p0 * pitch;
 #pragma unroll
             for (int m = 0; m < 22; ++m) {
                 const int u = lane + 32 * m, pix = u / 22, k = u - pix * 22;
-                *reinterpret_cast<float4*>(base + pix * 608 + 16 * k) = make_float4(1.f, 2.f, 3.f, (float)m);
+                *reinterpret_cast<float4*>(base + (size_t)pix * pitch + 16 * k) = make_float4(1.f, 2.f, 3.f, (float)m);
             }
         }
     }
@@ -66,11 +66,11 @@ int main() {
     float4* buf; cudaMalloc(&buf, bytes);
     cudaFuncSetAttribute(st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    auto run = [&](int mode, int threads, const char* name, double useful_frac) {
+    auto run = [&](int mode, int threads, const char* name, double useful_frac, int pitch = 608) {
         float best = 1e9;
         for (int rep = 0; rep < 4; ++rep) {
             cudaEventRecord(a);
-            st_kernel<<<148, threads, 8192>>>(buf, bytes / 4096, mode);
+            st_kernel<<<148, threads, 8192>>>(buf, bytes / 4096, mode, pitch);
             cudaEventRecord(b); cudaEventSynchronize(b);
             float ms; cudaEventElapsedTime(&ms, a, b); if (rep && ms < best) best = ms;
         }
@@ -82,6 +82,9 @@ int main() {
     run(1, 32, "cp.async.bulk smem->global 4 KB, one thread, 8 in flight", 1.0);
     for (int th : {64, 128, 256, 512}) run(2, th, "STG.128 352-byte runs at 608-byte pitch", 352.0 / 608.0);
     run(3, 32, "cp.async.bulk 352 B per pixel at 608-byte pitch, one thread", 352.0 / 608.0);
+    for (int th : {64, 256}) run(2, th, "STG.128 352-byte runs at 640-byte pitch", 352.0 / 640.0, 640);
+    for (int th : {64, 256}) run(2, th, "STG.128 352-byte runs at 384-byte pitch (dense 96-word rows)", 352.0 / 384.0, 384);
+    for (int th : {64, 256}) run(2, th, "STG.128 352-byte runs at 352-byte pitch (dense 88-word rows)", 1.0, 352);
     // reference: cudaMemsetAsync
     float best = 1e9;
     for (int rep = 0; rep < 4; ++rep) {
