@@ -102,11 +102,13 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base_slot;
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();   // setup done
+    pdl_trigger();                                     // (common.cuh) programmatic dependent launch
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+            pdl_wait();                                // activations of the previous layer
             const uint32_t tx_bytes = F16_A_RAW + 2 * p.b_bytes;
             const int PF = p.prefetch;   // stages of L2 prefetch distance for the activation boxes
             for (int it = 0; it < PF && it < KT; ++it) {
@@ -213,6 +215,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
         }
         // ---- epilogue: warps 2..5 (TMEM lane quadrant = warp % 4); the other converter warps are done
         if (warp < 6) {
+            pdl_wait();                                // mask / residual / accumulate operands
             mbar_wait(bar_acc, 0);
             if (dbg && ct == 0) dbg[5] = clock64();   // accumulator complete
             tc_fence_after();
@@ -466,7 +469,7 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc_f16: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    conv3x3_tc_f16_kernel<<<(unsigned)tiles, F16_THREADS, smem, (cudaStream_t)stream>>>(tmX, p);
+    launch_pdl(conv3x3_tc_f16_kernel, dim3((unsigned)tiles), dim3(F16_THREADS), smem, (cudaStream_t)stream, tmX, p);
     PWC_CHECK_LAUNCH("conv3x3_tc_f16_kernel");
     if (p.dbg) {   // debugging aid only (synchronises!): print the timeline of a few CTAs
         cudaStreamSynchronize((cudaStream_t)stream);

@@ -404,12 +404,14 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
     const uint32_t tmem_acc = tmem_base_slot;
     const int KC = p.kchunks;
     unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+    pdl_trigger();                                             // (common.cuh) the next kernel may start its prologue
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f0) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_f1) : "memory");
+            pdl_wait();                                        // the split operands come from the previous kernels
             int it = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
@@ -491,6 +493,7 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
         // ===================== store: the last two warps: quadrants {0, 1} and {2, 3} =====================
         // A pure copy (scale and leaky were applied by the extract warps): per quadrant 32 pixels x 20 float4 units, unit
         // u = lane + 32 m -> pixel u / 20, unit u % 20 (20 iterations, no divergence), then the 81st word of pixel = lane.
+        pdl_wait();                                            // the tail operand and the output rows themselves
         const float* slabs = reinterpret_cast<const float*>(base_ptr + Q_STAGES * Q_STAGE_BYTES);
         const int cs = p.out_cs;
         const int gpitch = p.W * cs;                          // < 2^31 / H (checked by the launcher)
@@ -589,6 +592,8 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
 // optionally also copies x to a second fp32 destination (the estimator's concat slot, modules.py:262).
 __global__ void split_f16_kernel(const float* __restrict__ x, int x_cs, __half* __restrict__ out, float* __restrict__ copy,
                                  int copy_cs, size_t n_pix, int C, float scale) {
+    pdl_wait();
+    pdl_trigger();
     const int C8 = C >> 3;
     const size_t total = n_pix * C8;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -618,6 +623,8 @@ __global__ void split_f16_kernel(const float* __restrict__ x, int x_cs, __half* 
 template <bool NEAREST>
 __global__ void warp_split_kernel(const float* __restrict__ x, int x_cs, const float* __restrict__ flow, int flow_cs,
                                   float flow_scale, __half* __restrict__ out, int B, int H, int W, int C) {
+    pdl_wait();
+    pdl_trigger();
     const int C8 = C >> 3;
     const size_t total = (size_t)B * H * W * C8;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -689,7 +696,7 @@ extern "C" int pwc_split_f16_fwd(const float* x, int x_cs, void* out, float* cop
                 "split_f16: C must be a multiple of 32, strides multiples of 4, pointers 16-byte aligned");
     const size_t total = (size_t)n_pix * (C / 8);
     const int blocks = (int)((total + 255) / 256 < (size_t)148 * 16 ? (total + 255) / 256 : (size_t)148 * 16);
-    split_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, (__half*)out, copy, copy_cs, (size_t)n_pix, C, scale);
+    launch_pdl(split_f16_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, x_cs, (__half*)out, copy, copy_cs, (size_t)n_pix, C, scale);
     PWC_CHECK_LAUNCH("split_f16_kernel");
     return 0;
 }
@@ -703,8 +710,8 @@ extern "C" int pwc_warp_split_fwd(const float* x, int x_cs, const float* flow, i
                 "warp_split: C must be a multiple of 32, x_cs a multiple of 4, x/out 16-byte aligned");
     const size_t total = (size_t)B * H * W * (C / 8);
     const int blocks = (int)((total + 255) / 256 < (size_t)148 * 16 ? (total + 255) / 256 : (size_t)148 * 16);
-    if (warp_type == 1) warp_split_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, flow, flow_cs, flow_scale, (__half*)out, B, H, W, C);
-    else warp_split_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_cs, flow, flow_cs, flow_scale, (__half*)out, B, H, W, C);
+    if (warp_type == 1) launch_pdl(warp_split_kernel<true>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, x_cs, flow, flow_cs, flow_scale, (__half*)out, B, H, W, C);
+    else launch_pdl(warp_split_kernel<false>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, x_cs, flow, flow_cs, flow_scale, (__half*)out, B, H, W, C);
     PWC_CHECK_LAUNCH("warp_split_kernel");
     return 0;
 }
@@ -760,7 +767,7 @@ static int cv_split_launch(const void* f0s, const void* f1s, float* out, int out
                 cudaMemsetAsync(qdbg, 0, 256 * 64 * 8, (cudaStream_t)stream);
                 p.dbg = qdbg;
             }
-            cost_volume_quad_kernel<<<grid, Q_THREADS, Q_SMEM_BYTES, (cudaStream_t)stream>>>(tm0, tm1, p);
+            launch_pdl(cost_volume_quad_kernel, dim3(grid), dim3(Q_THREADS), Q_SMEM_BYTES, (cudaStream_t)stream, tm0, tm1, p);
             PWC_CHECK_LAUNCH("cost_volume_quad_kernel");
             if (p.dbg) {   // debugging aid only (synchronises): timeline of the first tiles of one CTA
                 cudaStreamSynchronize((cudaStream_t)stream);

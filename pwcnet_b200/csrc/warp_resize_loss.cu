@@ -60,6 +60,8 @@ template <> struct VecT<1> { typedef float type; };
 template <int V>
 __global__ void resize_bilinear_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int y_cs,
                                        int B, int H, int W, int C, int OH, int OW, float sy, float sx, float mul) {
+    pdl_wait();
+    pdl_trigger();
     typedef typename VecT<V>::type vec_t;
     const int CV = C / V;
     const size_t total = (size_t)B * OH * OW * CV;
@@ -98,6 +100,8 @@ __global__ void resize_bilinear_kernel(const float* __restrict__ x, int x_cs, fl
 template <int V, int S>
 __global__ void resize_bilinear_up_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int y_cs,
                                           int B, int H, int W, int C, float sy, float sx, float mul) {
+    pdl_wait();
+    pdl_trigger();
     typedef typename VecT<V>::type vec_t;
     const int CV = C / V, OH = S * H, OW = S * W;
     const size_t total = (size_t)B * OH * W * CV;
@@ -216,18 +220,18 @@ extern "C" int pwc_resize_bilinear_fwd(const float* x, int x_cs, float* y, int y
     if (S && V >= 2 && (V != 2 || y_cs != 2 || (al & 15) == 0)) {
         const size_t work = (size_t)B * OH * W * (C / V);
         const int nb = (int)((work + 255) / 256 < (size_t)148 * 32 ? (work + 255) / 256 : (size_t)148 * 32);
-        if (V == 4 && S == 2) resize_bilinear_up_kernel<4, 2><<<nb, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, sy, sx, mul);
-        else if (V == 4) resize_bilinear_up_kernel<4, 4><<<nb, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, sy, sx, mul);
-        else if (S == 2) resize_bilinear_up_kernel<2, 2><<<nb, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, sy, sx, mul);
-        else resize_bilinear_up_kernel<2, 4><<<nb, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, sy, sx, mul);
+        if (V == 4 && S == 2) launch_pdl(resize_bilinear_up_kernel<4, 2>, dim3(nb), dim3(256), 0, st, x, x_cs, y, y_cs, B, H, W, C, sy, sx, mul);
+        else if (V == 4) launch_pdl(resize_bilinear_up_kernel<4, 4>, dim3(nb), dim3(256), 0, st, x, x_cs, y, y_cs, B, H, W, C, sy, sx, mul);
+        else if (S == 2) launch_pdl(resize_bilinear_up_kernel<2, 2>, dim3(nb), dim3(256), 0, st, x, x_cs, y, y_cs, B, H, W, C, sy, sx, mul);
+        else launch_pdl(resize_bilinear_up_kernel<2, 4>, dim3(nb), dim3(256), 0, st, x, x_cs, y, y_cs, B, H, W, C, sy, sx, mul);
         PWC_CHECK_LAUNCH("resize_bilinear_up_kernel");
         return 0;
     }
     const size_t total = (size_t)B * OH * OW * (C / V);
     const int blocks = (int)((total + 255) / 256 < (size_t)148 * 32 ? (total + 255) / 256 : (size_t)148 * 32);
-    if (V == 4) resize_bilinear_kernel<4><<<blocks, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
-    else if (V == 2) resize_bilinear_kernel<2><<<blocks, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
-    else resize_bilinear_kernel<1><<<blocks, 256, 0, st>>>(x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
+    if (V == 4) launch_pdl(resize_bilinear_kernel<4>, dim3(blocks), dim3(256), 0, st, x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
+    else if (V == 2) launch_pdl(resize_bilinear_kernel<2>, dim3(blocks), dim3(256), 0, st, x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
+    else launch_pdl(resize_bilinear_kernel<1>, dim3(blocks), dim3(256), 0, st, x, x_cs, y, y_cs, B, H, W, C, OH, OW, sy, sx, mul);
     PWC_CHECK_LAUNCH("resize_bilinear_kernel");
     return 0;
 }
