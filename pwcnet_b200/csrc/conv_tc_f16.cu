@@ -36,7 +36,9 @@ struct F16Params {
     int OH, OW, stride, pad_t, pad_l;
     int tiles_x, tiles_y, kchunks, total_tiles;
     float alpha;
-    int b_bytes;       // Cout * 64 (one fp16 weight tile)
+    int b_bytes;       // channels per CTA * 64 (one fp16 weight tile in shared memory)
+    int n_parts, cn, b_bytes_full;   // coarse levels (fewer tiles than SMs): the output channels are split over n_parts CTAs per tile,
+                                     // cn channels each (a multiple of 16); b_bytes_full = Cout * 64 = the packed image's W_h -> W_l distance
     int stage_bytes, stages, tmem_cols, n_main, prefetch, shift;
     unsigned long long* dbg;   // optional per-CTA timeline (clock64), 8 slots per CTA; nullptr in production
     // dgrad use (pwc_conv3x3_tc_f16_dgrad): bias may be null, stores are limited to the first cout_valid channels
@@ -71,7 +73,9 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
     const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[8]), bar_empty = smem_u32(&bars[16]);
     const uint32_t bar_acc = smem_u32(&bars[24]);
 
-    int t = blockIdx.x;
+    int t = blockIdx.x / p.n_parts;
+    const int ch0 = (blockIdx.x - t * p.n_parts) * p.cn;     // first output channel of this CTA
+    const int CN = p.cn;
     const int tx = t % p.tiles_x; t /= p.tiles_x;
     const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
     const int x0 = tx * F16_TW, y0 = ty * F16_TH;
@@ -132,7 +136,13 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                 tma_load_4d(st, &tmX, bar_full + 8 * s, kc * F16_BK, x0 * p.stride - p.pad_l + kx * p.dil,
                             y0 * p.stride - p.pad_t + ky * p.dil, b);
                 // [h tile | l tile] of this (tap, slice): one linear bulk copy
-                bulk_load_1d(st + off_bh, p.w + (size_t)it * 2 * p.b_bytes, 2 * p.b_bytes, bar_full + 8 * s);
+                if (p.n_parts > 1) {   // rows ch0 .. ch0 + cn of the W_h and of the W_l image
+                    const uint8_t* img = p.w + (size_t)it * 2 * p.b_bytes_full + (size_t)ch0 * 64;
+                    bulk_load_1d(st + off_bh, img, p.b_bytes, bar_full + 8 * s);
+                    bulk_load_1d(st + off_bh + p.b_bytes, img + p.b_bytes_full, p.b_bytes, bar_full + 8 * s);
+                } else {
+                    bulk_load_1d(st + off_bh, p.w + (size_t)it * 2 * p.b_bytes, 2 * p.b_bytes, bar_full + 8 * s);
+                }
                 if (++kc == p.kchunks) { kc = 0; if (++kx == 3) { kx = 0; ++ky; } }
                 if (++s == S) { s = 0; ph ^= 1; }
             }
@@ -142,10 +152,10 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
         // ===================== MMA issuer =====================
         if (elect_one()) {
             // kind::f16: D = f32 (bit 4), A = B = F16 (format 0), K-major, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(F16_BM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(F16_BM >> 4) << 24);
             // 64-byte-row K-major tiles: 8-row atoms 512 bytes apart, SWIZZLE_64B (layout type 4)
             const uint64_t desc_hi = ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
-            const uint32_t d_corr = tmem_acc + p.n_main * p.Cout;
+            const uint32_t d_corr = tmem_acc + p.n_main * CN;
             int s = 0, am = 0;
             uint32_t ph = 0;
             for (int it = 0; it < KT; ++it) {
@@ -158,7 +168,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                 const uint32_t al = (((st + off_al) >> 4) & 0x3FFF) | (1u << 16);
                 const uint32_t bh = (((st + off_bh) >> 4) & 0x3FFF) | (1u << 16);
                 const uint32_t bl = (((st + off_bl) >> 4) & 0x3FFF) | (1u << 16);
-                const uint32_t d_main = tmem_acc + am * p.Cout;
+                const uint32_t d_main = tmem_acc + am * CN;
 #pragma unroll
                 for (int k = 0; k < F16_BK / 16; ++k)   // K = 16 fp16 = 32 bytes per instruction
                     tc_mma_f16(d_main, desc_hi | (ah + 2 * k), desc_hi | (bh + 2 * k), idesc, (it >= p.n_main || k > 0) ? 1u : 0u);
@@ -223,35 +233,36 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
             const int m = q * 32 + lane;
             const int oy = y0 + m / F16_TW, ox = x0 + (m % F16_TW);
             const bool valid = oy < p.OH && ox < p.OW;
-            float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs;
-            const float* mrow = p.mask ? p.mask + (((size_t)b * p.OH + oy) * p.OW + ox) * p.mask_cs : nullptr;
-            const float* rrow = p.res ? p.res + (((size_t)b * p.OH + oy) * p.OW + ox) * p.res_cs : nullptr;
+            float* yrow = p.y + (((size_t)b * p.OH + oy) * p.OW + ox) * p.y_cs + ch0;
+            const float* mrow = p.mask ? p.mask + (((size_t)b * p.OH + oy) * p.OW + ox) * p.mask_cs + ch0 : nullptr;
+            const float* rrow = p.res ? p.res + (((size_t)b * p.OH + oy) * p.OW + ox) * p.res_cs + ch0 : nullptr;
+            const int cvalid = p.cout_valid - ch0;                 // valid channels of this CTA's range (may exceed CN)
             const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y) && ((p.cout_valid & 3) == 0) && !p.res &&
                              (!p.mask || (((p.mask_cs & 3) == 0) && aligned16(p.mask)));
-            for (int n0 = 0; n0 < p.Cout; n0 += 16) {
+            for (int n0 = 0; n0 < CN; n0 += 16) {
                 const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + n0;
                 uint32_t r[16];
                 float acc[16];
                 // correction group first (scaled by 2^-11), then the main accumulators, main 0 last
-                tmem_ld16(tbase + p.n_main * p.Cout, r);
+                tmem_ld16(tbase + p.n_main * CN, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]) * F16_INV_SCALE;
                 for (int a2 = p.n_main - 1; a2 >= 0; --a2) {
-                    tmem_ld16(tbase + a2 * p.Cout, r);
+                    tmem_ld16(tbase + a2 * CN, r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
                 }
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += s_bias[n0 + j];
+                    for (int j = 0; j < 16; ++j) acc[j] += s_bias[ch0 + n0 + j];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = leaky(acc[j], p.alpha);
                     if (vec) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            if (n0 + j >= p.cout_valid) break;
+                            if (n0 + j >= cvalid) break;
                             float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
                             if (mrow) {
                                 const float4 m = ldg4(mrow + n0 + j);
@@ -265,7 +276,7 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            if (n0 + j >= p.cout_valid) break;
+                            if (n0 + j >= cvalid) break;
                             float v = acc[j];
                             if (mrow) v *= __ldg(mrow + n0 + j) > 0.f ? 1.f : p.mask_alpha;
                             if (rrow) v += __ldg(rrow + n0 + j);
@@ -432,7 +443,17 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     p.alpha = alpha;
     p.mask = ex.mask; p.mask_cs = ex.mask_cs; p.mask_alpha = ex.mask_alpha; p.accumulate = ex.accumulate; p.cout_valid = ex.cout_valid;
     p.res = ex.res; p.res_cs = ex.res_cs;
-    p.b_bytes = Cout * 64;
+    // channel split for the coarse pyramid levels (16 tiles of 128 pixels at level 6): the serial K loop of a CTA streams
+    // 2 * Cout * 64 bytes of weights per (tap, slice) and issues N = Cout MMAs while 130 SMs idle
+    p.n_parts = 1;
+    if (tiles * 2 <= sm_count() && Cout >= 64 && !getenv("PWC_TC_NO_NSPLIT")) {
+        for (int k = (int)(sm_count() / tiles); k >= 2; --k)
+            if (Cout % k == 0 && (Cout / k) % 16 == 0 && Cout / k >= 32) { p.n_parts = k; break; }
+    }
+    p.cn = Cout / p.n_parts;
+    p.b_bytes_full = Cout * 64;
+    const int Cl = p.cn;
+    p.b_bytes = Cl * 64;
     p.stage_bytes = (int)(F16_A_RAW + 2 * F16_A_HALF) + 1024 + 2 * p.b_bytes;
     p.shift = 0;
     if (const char* e = getenv("PWC_TC_SHIFT")) p.shift = atoi(e) & 0x3C0;
@@ -453,13 +474,13 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     PWC_REQUIRE(p.stages >= 2, PWC_E_BADARG, "conv3x3_tc_f16: tile does not fit in shared memory");
     p.prefetch = 0;   // L2 prefetch of upcoming activation boxes: measured no gain (profiles/r01_f16_prefetch.log)
     if (const char* e = getenv("PWC_TC_PREFETCH")) p.prefetch = atoi(e);
-    p.n_main = 256 / Cout - 1;   // main accumulators the K loop rotates over (+1 correction accumulator)
+    p.n_main = 256 / Cl - 1;   // main accumulators the K loop rotates over (+1 correction accumulator)
     if (p.n_main > 3) p.n_main = 3;
     if (p.n_main < 1) p.n_main = 1;
     if (const char* e = getenv("PWC_TC_NMAIN")) { int v = atoi(e); if (v >= 1 && v <= p.n_main) p.n_main = v; }
     PWC_REQUIRE(p.n_main >= 1, PWC_E_BADARG, "conv3x3_tc_f16: Cout too large for the accumulator layout");
     int cols = 32;
-    while (cols < (p.n_main + 1) * Cout) cols *= 2;
+    while (cols < (p.n_main + 1) * Cl) cols *= 2;
     p.tmem_cols = cols;
     static unsigned long long* dbg_buf = nullptr;
     if (getenv("PWC_TC_DEBUG")) {
@@ -469,7 +490,7 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc_f16: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    launch_pdl(conv3x3_tc_f16_kernel, dim3((unsigned)tiles), dim3(F16_THREADS), smem, (cudaStream_t)stream, tmX, p);
+    launch_pdl(conv3x3_tc_f16_kernel, dim3((unsigned)(tiles * p.n_parts)), dim3(F16_THREADS), smem, (cudaStream_t)stream, tmX, p);
     PWC_CHECK_LAUNCH("conv3x3_tc_f16_kernel");
     if (p.dbg) {   // debugging aid only (synchronises!): print the timeline of a few CTAs
         cudaStreamSynchronize((cudaStream_t)stream);
