@@ -450,7 +450,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     // on idle SMs now; whatever reads or writes activations in THIS kernel first waits for the previous one to complete
     // (griddepcontrol.wait below: the activation producer and the epilogue warps; weights and bias are never written by a
     // kernel that triggers early).  Both instructions are no-ops for a kernel launched without the attribute.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    pdl_trigger();
     const int KC = p.kchunks;
     const int tiles_per_img = p.tiles_img;
     // work items of this CTA (HaloParams): `rounds` whole tiles, then possibly one channel-split item of the tail
@@ -464,7 +464,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         // ===================== activation producer =====================
         if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-            asm volatile("griddepcontrol.wait;" ::: "memory");
+            pdl_wait();
             int it = 0, s = 0;
             uint32_t ph = 0;                                   // stage index and ring phase as counters: no division per slice
             for (int j = 0; j < n_items; ++j) {
@@ -601,7 +601,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             if (p.tma_ys) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmYS) : "memory");
             if (p.tma_mask) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmM) : "memory");
         }
-        asm volatile("griddepcontrol.wait;" ::: "memory");       // mask tiles, accumulate operands and the outputs themselves
+        pdl_wait();                                               // mask tiles, accumulate operands and the outputs themselves
         uint8_t* mask_buf = base_ptr + p.epi_off + 4 * 8192 + q * 4096;
         const uint32_t bar_mask = bar_accf + 8 * (4 + q);
         uint32_t mask_phase = 0;
@@ -887,14 +887,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         p.dbg = dbg_buf;
     }
     {
-        static const int pdl = []() { const char* e = getenv("PWC_PDL"); return e ? atoi(e) : 1; }();
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(HL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, conv3x3_tc_halo_kernel, tmX, tmY, tmYS, tmM, p);
+        cudaError_t le = launch_pdl(conv3x3_tc_halo_kernel, dim3((unsigned)grid), dim3(HL_THREADS), smem, st, tmX, tmY, tmYS, tmM, p);
         if (le != cudaSuccess) { set_error("conv3x3_tc_halo_kernel: launch: %s", cudaGetErrorString(le)); return (int)le; }
     }
     PWC_CHECK_LAUNCH("conv3x3_tc_halo_kernel");
