@@ -59,6 +59,7 @@ struct HaloParams {
     int tap_dy[9], tap_dx[9], tap_id[9];     // tap offsets in box rows / pixels (times dil for dx), and the tap's index in the packed weights
     int tma_y, tma_ys;    // the epilogue stores the fp32 / split output through TMA (shared-memory staging + bulk tensor store)
     int epi_off;          // byte offset of the epilogue staging area: 4 warps x 2 buffers x (32 pixels x 128 or 64 bytes)
+    int single_pass;      // Cout = 16 or 32, one plainly TMA-stored output (no mask, no reduce-add), no channel-split tail: the software-pipelined epilogue
     int tma_mask;         // dgrad: the leaky-derivative mask tile of a pass is TMA-loaded into a per-warp buffer behind the staging area
     int tma_red;          // accumulate through the TMA engine's reduce-add store (UTMAREDG) instead of a read-modify-write
     int exp_direct_store; // experiment (PWC_HALO_EXP=3): 16-byte-per-lane stores (round-1 pattern)
@@ -397,6 +398,194 @@ __device__ __forceinline__ void hl_epilogue_pass(const HaloParams& p, const floa
     if (n0 == 0) HL_DBG(9, tcount);
 }
 
+// Same as hl_stage_and_store with the 16-byte chunks produced on the fly (chunk(j) -> uint4): no G-word array is live while the
+// next tile's tcgen05.ld is in flight (the pipelined epilogue below runs at the 128-register limit).
+template <int G, typename F>
+__device__ __forceinline__ void hl_stage_and_store_fn(const CUtensorMap* map, uint8_t* buf, int lane, int c0, int x, int y, int b, F chunk) {
+    constexpr int NCH = G / 4;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    const int sw = NCH == 8 ? (lane & 7) : ((lane >> 1) & 3);
+    uint8_t* row = buf + lane * (16 * NCH);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = chunk(j);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        hl_tma_store_4d(map, smem_u32(buf), c0, x, y, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+
+// ---- software-pipelined epilogue of the 16-channel layers on the TMA-store path (pyramid level 1: 2 x 121 us of a forward).  Their tile period is the epilogue's latency chain (wait accumulator -> tcgen05.ld ~0.5 k clk
+// -> bias / leaky -> stage -> TMA store), not any throughput.  When the NEXT tile's accumulators are already complete, its
+// tcgen05.ld is issued before this tile's stores, so the TMEM read latency runs behind them.  tcgen05.ld writes its
+// destination registers asynchronously until tcgen05.wait::ld: rm / rc are not touched between the issue and hl_ld_pin().
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void hl_pin16(uint32_t* r) {       // orders every later use of r[0..15] after this point
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+}
+template <int G>
+__device__ __forceinline__ void hl_ld_issue(uint32_t tbase, uint32_t (&rm)[16], uint32_t (&rc)[16]) {
+#pragma unroll
+    for (int g = 0; g < G; g += 16) {
+        tmem_ld16(tbase + G + g, rc + g);
+        tmem_ld16(tbase + g, rm + g);
+    }
+}
+template <int G>
+__device__ __forceinline__ void hl_single_item(const HaloParams& p, const float* s_bias, uint32_t tmem_q, int tcount, bool& pre,
+                                               uint32_t (&rm)[16], uint32_t (&rc)[16], bool may_prefetch,
+                                               uint32_t bar_accf, uint32_t bar_acce, const CUtensorMap* tmY, const CUtensorMap* tmYS,
+                                               uint8_t* stage, int& nbuf, int lane, int wx, int wy, int wb) {
+    const int a = tcount & 1, u = tcount >> 1;
+    if (!pre) {
+        mbar_wait(bar_accf + 8 * a, u & 1);
+        tc_fence_after();
+        hl_ld_issue<G>(tmem_q + a * 256, rm, rc);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < G; g += 16) { hl_pin16(rm + g); hl_pin16(rc + g); }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_acce + 8 * a);              // this accumulator set is in registers
+    float acc[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) acc[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]) * HL_INV_SCALE;
+    pre = false;
+    if (may_prefetch) {
+        const int a2 = (tcount + 1) & 1, u2 = (tcount + 1) >> 1;
+        if (__any_sync(0xffffffffu, mbar_try(bar_accf + 8 * a2, u2 & 1))) {
+            tc_fence_after();
+            hl_ld_issue<G>(tmem_q + a2 * 256, rm, rc);
+            pre = true;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < G; j += 4) {
+        const float4 bq = *reinterpret_cast<const float4*>(s_bias + j);
+        acc[j] = leaky(acc[j] + bq.x, p.alpha); acc[j + 1] = leaky(acc[j + 1] + bq.y, p.alpha);
+        acc[j + 2] = leaky(acc[j + 2] + bq.z, p.alpha); acc[j + 3] = leaky(acc[j + 3] + bq.w, p.alpha);
+    }
+    if (p.tma_ys && G == 32) {
+        // split rows [h: 32 x fp16 | l * 2^11: 32 x fp16]: chunk j < 4 = h of channels 8j .. 8j+7, chunk j >= 4 = their l
+        hl_stage_and_store_fn<G>(tmYS, stage + (nbuf & 1) * (32 * 4 * G), lane, 0, wx, wy, wb, [&](int j) {
+            const int c = 8 * (j & 3);
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __half2 h2 = __floats2half2_rn(acc[c + 2 * k], acc[c + 2 * k + 1]);
+                if (j < 4) o[k] = *reinterpret_cast<const uint32_t*>(&h2);
+                else {
+                    const float2 f2 = __half22float2(h2);
+                    const __half2 l2 = __floats2half2_rn((acc[c + 2 * k] - f2.x) * HL_SCALE, (acc[c + 2 * k + 1] - f2.y) * HL_SCALE);
+                    o[k] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+            }
+            return make_uint4(o[0], o[1], o[2], o[3]);
+        });
+        ++nbuf;
+    }
+    if (p.tma_y) {
+        hl_stage_and_store_fn<G>(tmY, stage + (nbuf & 1) * (32 * 4 * G), lane, 0, wx, wy, wb, [&](int j) {
+            return make_uint4(__float_as_uint(acc[4 * j]), __float_as_uint(acc[4 * j + 1]), __float_as_uint(acc[4 * j + 2]), __float_as_uint(acc[4 * j + 3]));
+        });
+        ++nbuf;
+    }
+}
+
+// 32-channel layers: the same pipeline at a granularity of 16 channels (a whole 32-channel tile in flight next to the one being
+// stored does not fit 128 registers): half 1's tcgen05.ld runs behind half 0's arithmetic and staging, the next tile's half 0
+// behind half 1's; the two halves fill one 128-byte staging row per pixel and leave as one TMA store.
+__device__ __forceinline__ void hl_single_item32(const HaloParams& p, const float* s_bias, uint32_t tmem_q, int tcount, bool& pre,
+                                                 uint32_t (&rm)[16], uint32_t (&rc)[16], bool may_prefetch,
+                                                 uint32_t bar_accf, uint32_t bar_acce, const CUtensorMap* tmY, const CUtensorMap* tmYS,
+                                                 uint8_t* stage, int& nbuf, int lane, int wx, int wy, int wb) {
+    const int a = tcount & 1, u = tcount >> 1;
+    const uint32_t tb = tmem_q + a * 256;
+    if (!pre) {
+        mbar_wait(bar_accf + 8 * a, u & 1);
+        tc_fence_after();
+        tmem_ld16(tb + 32, rc); tmem_ld16(tb, rm);                    // half 0: main columns 0..15, correction columns 32..47
+    }
+    uint8_t* buf = stage + (nbuf & 1) * 4096;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the store that last read this buffer is done
+    __syncwarp();
+    const int sw = lane & 7;
+    uint8_t* row = buf + lane * 128;
+    pre = false;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        tmem_ld_wait();
+        hl_pin16(rm); hl_pin16(rc);
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]) * HL_INV_SCALE;
+        if (half == 0) {
+            tmem_ld16(tb + 48, rc); tmem_ld16(tb + 16, rm);            // half 1 in flight
+        } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acce + 8 * a);             // the whole accumulator set has been read
+            if (may_prefetch) {
+                const int a2 = (tcount + 1) & 1, u2 = (tcount + 1) >> 1;
+                if (__any_sync(0xffffffffu, mbar_try(bar_accf + 8 * a2, u2 & 1))) {
+                    tc_fence_after();
+                    const uint32_t tb2 = tmem_q + a2 * 256;
+                    tmem_ld16(tb2 + 32, rc); tmem_ld16(tb2, rm);
+                    pre = true;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 bq = *reinterpret_cast<const float4*>(s_bias + 16 * half + j);
+            acc[j] = leaky(acc[j] + bq.x, p.alpha); acc[j + 1] = leaky(acc[j + 1] + bq.y, p.alpha);
+            acc[j + 2] = leaky(acc[j + 2] + bq.z, p.alpha); acc[j + 3] = leaky(acc[j + 3] + bq.w, p.alpha);
+        }
+        if (p.tma_ys) {
+            // split row [h: 32 x fp16 | l * 2^11: 32 x fp16]: this half's h goes to chunks 2 half, 2 half + 1, its l to 4 + ...
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float v0 = acc[8 * c + 2 * k], v1 = acc[8 * c + 2 * k + 1];
+                    const __half2 h2 = __floats2half2_rn(v0, v1);
+                    const float2 f2 = __half22float2(h2);
+                    const __half2 l2 = __floats2half2_rn((v0 - f2.x) * HL_SCALE, (v1 - f2.y) * HL_SCALE);
+                    hw[k] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lw[k] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                const int jc = 2 * half + c;
+                *reinterpret_cast<uint4*>(row + ((jc ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(row + (((jc + 4) ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int jc = 4 * half + c;
+                *reinterpret_cast<uint4*>(row + ((jc ^ sw) << 4)) =
+                    make_uint4(__float_as_uint(acc[4 * c]), __float_as_uint(acc[4 * c + 1]), __float_as_uint(acc[4 * c + 2]), __float_as_uint(acc[4 * c + 3]));
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        hl_tma_store_4d(p.tma_ys ? tmYS : tmY, smem_u32(buf), 0, wx, wy, wb);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    ++nbuf;
+}
+
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                        const __grid_constant__ CUtensorMap tmYS, const __grid_constant__ CUtensorMap tmM, const HaloParams p) {
@@ -605,6 +794,10 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         uint8_t* mask_buf = base_ptr + p.epi_off + 4 * 8192 + q * 4096;
         const uint32_t bar_mask = bar_accf + 8 * (4 + q);
         uint32_t mask_phase = 0;
+        // one-pass layers on the TMA-store path: software-pipelined epilogue (hl_single_item)
+        const bool single = p.single_pass != 0;
+        bool pre = false;                                     // the current tile's tcgen05.ld was issued during the previous tile
+        uint32_t rm[16], rc[16];
         int tcount = 0;
         // tile coordinates advance by the (constant) tile step without divisions: image b, tile r of the image =
         // (row ty, column tile tx) in row mode
@@ -629,6 +822,13 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             tx += d_x; ty += d_y;
             if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
             if (ty >= p.H) ty -= p.H;                      // row mode: tiles_per_img = tiles_x * H, the image carry is in b
+            if (single) {
+                // (a channel-split tail item has narrower accumulators: p.single_pass excludes split tails)
+                const uint32_t tmem_q = tmem_acc + ((uint32_t)(q * 32) << 16);
+                if (p.Cout == 32) hl_single_item32(p, s_bias, tmem_q, tcount, pre, rm, rc, j + 1 < n_items, bar_accf, bar_acce, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now);
+                else hl_single_item<16>(p, s_bias, tmem_q, tcount, pre, rm, rc, j + 1 < n_items, bar_accf, bar_acce, &tmY, &tmYS, stage, nbuf, lane, x - lane, y, b_now);
+                continue;
+            }
             const int a = tcount & 1, u = tcount >> 1;
             if (p.tma_mask && lane == 0) {            // first pass's mask tile: in flight while the MMAs of this tile run
                 mbar_expect_tx(bar_mask, (p.Cout & 31) == 0 ? 4096 : 2048);
@@ -846,6 +1046,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         p.tma_ys = 1;
     }
     const size_t epi_bytes = (p.tma_y || p.tma_ys) ? 4 * 8192 + (p.tma_mask ? 4 * 4096 : 0) : 0;
+    p.single_pass = ((p.tma_y || p.tma_ys) && !p.tma_mask && !p.tma_red && (Cout == 16 || Cout == 32) && p.n_split == 1 && !(p.tma_y && p.tma_ys) && !getenv("PWC_HALO_NO_PIPE_EPI")) ? 1 : 0;
     if (const char* e = getenv("PWC_HALO_EXP")) { p.exp_skip_conv = atoi(e) == 1; p.exp_skip_store = atoi(e) == 2; p.exp_direct_store = atoi(e) == 3; }
     if (const char* e = getenv("PWC_HALO_DESC")) p.desc_mode = atoi(e);
     // (Rotating accumulator sets over the taps were tried in round 1 and again in round 2 with a separate A_l x W_h chain:
@@ -875,7 +1076,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     }
     size_t smem = (size_t)p.act_stages * p.act_stage + (p.w_resident ? w_all : (size_t)p.w_stages * p.w_stage_bytes) + epi_bytes + 1024;
     if (smem > HL_SMEM_BUDGET) { p.act_stages = 2; smem = (size_t)2 * p.act_stage + (size_t)p.w_stages * p.w_stage_bytes + epi_bytes + 1024; }
-    if (smem > HL_SMEM_BUDGET && epi_bytes) { smem -= epi_bytes; p.tma_y = p.tma_ys = p.tma_mask = p.tma_red = 0; }    // no room for the staging buffers: plain stores
+    if (smem > HL_SMEM_BUDGET && epi_bytes) { smem -= epi_bytes; p.tma_y = p.tma_ys = p.tma_mask = p.tma_red = p.single_pass = 0; }    // no room for the staging buffers: plain stores
     if (smem > HL_SMEM_BUDGET) return -1000;
     p.epi_off = (int)(smem - 1024 - ((p.tma_y || p.tma_ys) ? epi_bytes : 0));               // 1024-byte aligned: every part before it is
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

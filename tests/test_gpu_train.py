@@ -118,11 +118,13 @@ def test_conv_dgrad_mask_accumulate_and_slots(P):
     assert float(dxbuf[..., :8].abs().max()) == 0 and float(dxbuf[..., 44:].abs().max()) == 0
 
 
+@pytest.mark.parametrize("use_mask", [True, False])
 @pytest.mark.parametrize("shape,cout,accumulate", [((1, 6, 160, 64), 32, True), ((2, 5, 300, 128), 128, False), ((1, 4, 130, 32), 64, True),
-                                                   ((1, 3, 129, 16), 16, False)])
-def test_conv_dgrad_wide_rows_tma_epilogue(P, shape, cout, accumulate):
+                                                   ((1, 3, 129, 16), 16, False), ((1, 5, 200, 16), 32, True), ((2, 3, 140, 32), 32, False)])
+def test_conv_dgrad_wide_rows_tma_epilogue(P, shape, cout, accumulate, use_mask):
     """Row-tile mode of the halo kernel (rows of >= 128 pixels: the level-2/3 layers of a training step): the leaky mask tile
-    arrives through TMA and `accumulate` is a reduce-add bulk store (conv_tc_halo.cu, hl_epilogue_pass); ragged right edges."""
+    arrives through TMA and `accumulate` is a reduce-add bulk store (conv_tc_halo.cu, hl_epilogue_pass); ragged right edges;
+    without a mask the 16- and 32-channel cases take the software-pipelined epilogue unless they accumulate."""
     from pwcnet_b200 import ops_bwd
     B, H, W, Cin = shape
     x = torch.from_numpy(_rand((B, H, W, Cin), 1))
@@ -131,12 +133,12 @@ def test_conv_dgrad_wide_rows_tma_epilogue(P, shape, cout, accumulate):
     prev = torch.from_numpy(_rand((B, H, W, Cin), 5))
     xr = x.clone().requires_grad_(True)
     O.conv2d_same(xr, k, None, 1, 1).backward(dy)
-    ref = xr.grad * torch.where(x > 0, torch.ones_like(x), torch.full_like(x, 0.1))
+    ref = xr.grad * torch.where(x > 0, torch.ones_like(x), torch.full_like(x, 0.1)) if use_mask else xr.grad
     if accumulate:
         ref = ref + prev
     dxbuf = torch.zeros((B, H, W, Cin + 16), device="cuda"); dxbuf[..., 8:8 + Cin] = _cuda(prev.numpy())
-    ops_bwd.conv3x3_dgrad(_cuda(dy.numpy()), _cuda(k.numpy()), dxbuf[..., 8:8 + Cin], mask=_cuda(x.numpy()), mask_alpha=0.1,
-                          accumulate=accumulate)
+    ops_bwd.conv3x3_dgrad(_cuda(dy.numpy()), _cuda(k.numpy()), dxbuf[..., 8:8 + Cin], mask=_cuda(x.numpy()) if use_mask else None,
+                          mask_alpha=0.1, accumulate=accumulate)
     _close(dxbuf[..., 8:8 + Cin], ref, name="dx (row tiles)")
     assert float(dxbuf[..., :8].abs().max()) == 0 and float(dxbuf[..., 8 + Cin:].abs().max()) == 0
 
