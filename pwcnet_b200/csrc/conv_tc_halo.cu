@@ -27,12 +27,12 @@ namespace pwc {
 constexpr int HL_M = 128;                          // output pixels per tile (one row segment)
 constexpr int HL_BH = 3;                           // halo box: 3 rows (y-d, y, y+d) x (128 + 2d) pixels
 constexpr int HL_BK = 32;
-constexpr int HL_MAX_ACT_STAGES = 4;                   // activation stages: 2, up to 4 for layers with resident weights
+constexpr int HL_MAX_ACT_STAGES = 8;                   // activation stages: 2 (streamed weights), up to 8 for layers with resident weights
 constexpr int HL_W_STAGES = 16;                        // barriers of the weight ring; the ring itself is p.w_stages (4..16, power of two) deep
 constexpr int HL_W_MIN_STAGES = 4;
 constexpr int HL_CONV_THREADS = 256;
 constexpr int HL_THREADS = 64 + 128 + HL_CONV_THREADS + 32;   // act TMA, MMA, 4 epilogue, 8 converter, weight producer
-constexpr size_t HL_SMEM_BUDGET = 226 * 1024;         // dynamic shared memory: 227 KB per CTA minus the static barriers + bias
+constexpr size_t HL_SMEM_BUDGET = 225 * 1024;         // dynamic shared memory: 227 KB per CTA minus the static barriers + bias (~1.2 KB)
 constexpr float HL_SCALE = 2048.f, HL_INV_SCALE = 1.f / 2048.f;
 
 struct HaloParams {
@@ -59,6 +59,7 @@ struct HaloParams {
     int tap_dy[9], tap_dx[9], tap_id[9];     // tap offsets in box rows / pixels (times dil for dx), and the tap's index in the packed weights
     int tma_y, tma_ys;    // the epilogue stores the fp32 / split output through TMA (shared-memory staging + bulk tensor store)
     int epi_off;          // byte offset of the epilogue staging area: 4 warps x 2 buffers x (32 pixels x 128 or 64 bytes)
+    int row64;            // 16-channel input, row tiles: 64-byte shared-memory rows (box of 16 channels, 64B swizzle) instead of half-empty 128-byte ones
     int single_pass;      // Cout = 16 or 32, one plainly TMA-stored output (no mask, no reduce-add), no channel-split tail: the software-pipelined epilogue
     int tma_mask;         // dgrad: the leaky-derivative mask tile of a pass is TMA-loaded into a per-warp buffer behind the staging area
     int tma_red;          // accumulate through the TMA engine's reduce-add store (UTMAREDG) instead of a read-modify-write
@@ -89,8 +90,10 @@ struct HaloParams {
 // between the MMAs of a tile, so the issuing thread does 32-bit adds instead of 64-bit descriptor arithmetic.
 constexpr uint32_t HL_ADESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // A: 128-byte K-major rows, 128B swizzle, 8-row groups 1024 B apart
 constexpr uint32_t HL_BDESC_HI = (512u >> 4) | (1u << 14) | (4u << 29);    // B: 64-byte K-major rows, 64B swizzle, 8-row groups 512 B apart
-template <bool ACC>
+template <bool ACC, bool ROW64 = false>
 __device__ __forceinline__ void hl_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    // ROW64: the A tile has 64-byte rows ([h: 16 x fp16 | l: 16 x fp16] of a 16-channel layer) in the 64B swizzle -- the B layout
+    constexpr uint32_t A_HI = ROW64 ? HL_BDESC_HI : HL_ADESC_HI;
     if (ACC) {
         asm volatile(
             "{\n\t"
@@ -100,7 +103,7 @@ __device__ __forceinline__ void hl_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32
             "mov.b64 da, {%1, %2};\n\t"
             "mov.b64 db, {%3, %4};\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-            "}" ::"r"(d_tmem), "r"(a_lo), "r"(HL_ADESC_HI), "r"(b_lo), "r"(HL_BDESC_HI), "r"(idesc) : "memory");
+            "}" ::"r"(d_tmem), "r"(a_lo), "r"(A_HI), "r"(b_lo), "r"(HL_BDESC_HI), "r"(idesc) : "memory");
     } else {
         asm volatile(
             "{\n\t"
@@ -110,7 +113,7 @@ __device__ __forceinline__ void hl_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32
             "mov.b64 da, {%1, %2};\n\t"
             "mov.b64 db, {%3, %4};\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-            "}" ::"r"(d_tmem), "r"(a_lo), "r"(HL_ADESC_HI), "r"(b_lo), "r"(HL_BDESC_HI), "r"(idesc), "r"(accumulate) : "memory");
+            "}" ::"r"(d_tmem), "r"(a_lo), "r"(A_HI), "r"(b_lo), "r"(HL_BDESC_HI), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
 
@@ -122,7 +125,7 @@ struct IssueCtx {
 // K = 16 steps.  The issuing thread is the critical path of the narrow layers (a 16 -> 16 tile is 18 tiny MMAs: the
 // round-1 loop spent ~55 instructions per tap, ~90 clk per MMA -- as long as a 128 x 256 x 16 MMA executes, so it also
 // held the wide layers below the tensor pipe's rate; profiles/r02_halo_epilogue.log), so everything per tap is a 32-bit add.
-template <bool RESIDENT, bool KS2, int NT>
+template <bool RESIDENT, bool KS2, int NT, bool ROW64 = false>
 __device__ __forceinline__ void hl_issue_chunk(const IssueCtx& cx, uint32_t d_main, uint32_t a_lo, uint32_t b_lo, uint32_t first, uint32_t& wt) {
     const uint32_t d_corr = d_main + cx.cout;
 #pragma unroll
@@ -134,11 +137,11 @@ __device__ __forceinline__ void hl_issue_chunk(const IssueCtx& cx, uint32_t d_ma
             b_lo = cx.w_lo0 + ws * cx.wsb16;
         }
         const uint32_t al = a_lo + cx.tapoff[tap];
-        if (tap == 0) hl_mma_lo<false>(d_main, al, b_lo, cx.idesc_w, first);      // A_h x [W_h | W_l] -> main | corr
-        else hl_mma_lo<true>(d_main, al, b_lo, cx.idesc_w, 1u);
-        if (KS2) hl_mma_lo<true>(d_main, al + 2, b_lo + 2, cx.idesc_w, 1u);
-        hl_mma_lo<true>(d_corr, al + 4, b_lo, cx.idesc_n, 1u);                      // A_l x W_h -> corr
-        if (KS2) hl_mma_lo<true>(d_corr, al + 6, b_lo + 2, cx.idesc_n, 1u);
+        if (tap == 0) hl_mma_lo<false, ROW64>(d_main, al, b_lo, cx.idesc_w, first);      // A_h x [W_h | W_l] -> main | corr
+        else hl_mma_lo<true, ROW64>(d_main, al, b_lo, cx.idesc_w, 1u);
+        if (KS2) hl_mma_lo<true, ROW64>(d_main, al + 2, b_lo + 2, cx.idesc_w, 1u);
+        hl_mma_lo<true, ROW64>(d_corr, al + (ROW64 ? 2 : 4), b_lo, cx.idesc_n, 1u);        // A_l x W_h -> corr (l sits 32 / 64 bytes into the row)
+        if (KS2) hl_mma_lo<true, ROW64>(d_corr, al + 6, b_lo + 2, cx.idesc_n, 1u);
         if (RESIDENT) b_lo += cx.wsb16;
         else { tc_commit(cx.bar_wempty + 8 * (wt & cx.w_mask)); ++wt; }
     }
@@ -665,7 +668,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 for (int c = 0; c < KC; ++c, ++it) {
                     mbar_wait(bar_aempty + 8 * s, ph ^ 1);
                     HL_DBG(0, it);
-                    mbar_expect_tx(bar_afull + 8 * s, (uint32_t)n_rows * 128);
+                    mbar_expect_tx(bar_afull + 8 * s, (uint32_t)n_rows * (p.row64 ? 64 : 128));
                     const int c0 = c * (p.in_split ? 2 * HL_BK : HL_BK);      // element offset of the slice (fp32 or halfs)
                     if (p.s2d) {
                         const int py = c / p.kc_per_py;                         // row phase; the slice is 32 (px, c) values of it
@@ -728,7 +731,7 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             cx.idesc_n = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
             cx.idesc_w = (1u << 4) | ((uint32_t)((2 * p.Cout) >> 3) << 17) | ((uint32_t)(HL_M >> 4) << 24);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) cx.tapoff[tap] = (uint32_t)(p.tap_dy[tap] * p.bw + p.tap_dx[tap]) * 8;   // 128-byte rows, >> 4
+            for (int tap = 0; tap < 9; ++tap) cx.tapoff[tap] = (uint32_t)(p.tap_dy[tap] * p.bw + p.tap_dx[tap]) * (p.row64 ? 4 : 8);   // 128- or 64-byte rows, >> 4
             cx.wsb16 = (uint32_t)p.w_stage_bytes >> 4;
             cx.cout = (uint32_t)p.Cout;
             cx.bar_wfull = bar_wfull; cx.bar_wempty = bar_wempty;
@@ -761,7 +764,10 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     const uint32_t a_lo = (((ast >> 4) & 0x3FFF) | (1u << 16)) + c0off;
                     const bool ks2 = p.Cin - c * HL_BK > 16;             // channels 16..31 of the slice are zero padding otherwise
                     const uint32_t first = c == 0 ? 0u : 1u;
-                    if (p.n_taps == 4) {                                 // stride 2 as a 2 x 2 convolution (slices are always full)
+                    if (p.row64) {                                       // 16-channel input: one K = 16 step per tap, 64-byte rows
+                        if (resident) hl_issue_chunk<true, false, 9, true>(cx, d_tile, a_lo, cx.w_lo0, first, wt);
+                        else hl_issue_chunk<false, false, 9, true>(cx, d_tile, a_lo, 0, first, wt);
+                    } else if (p.n_taps == 4) {                          // stride 2 as a 2 x 2 convolution (slices are always full)
                         if (resident) hl_issue_chunk<true, true, 4>(cx, d_tile, a_lo, cx.w_lo0 + (uint32_t)c * 4 * cx.wsb16, first, wt);
                         else hl_issue_chunk<false, true, 4>(cx, d_tile, a_lo, 0, first, wt);
                     } else if (resident) {
@@ -874,7 +880,22 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
                     const int R = ct + rr * HL_CONV_THREADS;
-                    if (R < n_rows && !p.exp_skip_conv && !p.in_split) {
+                    if (R < n_rows && !p.exp_skip_conv && !p.in_split && p.row64) {
+                        // 64-byte rows (16 fp32 channels), 64B swizzle: logical 16-byte chunk j sits at chunk j ^ ((R >> 1) & 3);
+                        // in place -> [h: chunks 0-1 | l: chunks 2-3]
+                        uint8_t* row = stp + (size_t)R * 64;
+                        const int sw = (R >> 1) & 3;
+                        float4 v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint4 hq, lq;
+                            hl_split8(v[2 * j], v[2 * j + 1], hq, lq);
+                            *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = hq;
+                            *reinterpret_cast<uint4*>(row + (((j + 2) ^ sw) << 4)) = lq;
+                        }
+                    } else if (R < n_rows && !p.exp_skip_conv && !p.in_split) {
                         uint8_t* row = stp + (size_t)R * 128;
                         const int sw = R & 7;              // 128B swizzle: logical 16-byte chunk j sits at chunk j ^ (R & 7)
                         if (half_rows) {
@@ -941,6 +962,9 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     const int span = s2d ? 1 : 2 * dilation;                    // extra box columns (and, in rows, box rows - 1) around a tile
     const int fbw = W + span;                                   // flat mode: slots per padded row
     const int nr = flat ? (HL_M - 1 + fbw - 1) / fbw + 1 + span : 0;
+    // 16-channel inputs in row-tile mode: 64-byte shared-memory rows (the 128-byte rows would be half zero fill: twice the TMA
+    // write traffic and half as many pipeline stages in the same shared memory).  dilation <= 8: the strided 3-row box.
+    const int row64 = (Cin == 16 && !flat && !s2d && !in_split && dilation <= 8 && getenv("PWC_HALO_ROW64")) ? 1 : 0;      // opt-in until measured
     CUtensorMap tmX;
     if (s2d) {
         cuuint64_t dims[5] = {(cuuint64_t)2 * Cin_in, 2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -960,11 +984,11 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         // dilations use one single-row box per row (their row pitch (128+2d)*128 B must keep the 1024-byte swizzle phase)
         const bool strided = dilation <= 8;
         if (!strided && (((HL_M + 2 * dilation) * 128) & 1023)) return -1000;
-        cuuint32_t box[4] = {(cuuint32_t)(in_split ? 2 * HL_BK : HL_BK), (cuuint32_t)(HL_M + 2 * dilation), (cuuint32_t)(strided ? HL_BH * dilation : 1), 1};
+        cuuint32_t box[4] = {(cuuint32_t)(in_split ? 2 * HL_BK : (row64 ? 16 : HL_BK)), (cuuint32_t)(HL_M + 2 * dilation), (cuuint32_t)(strided ? HL_BH * dilation : 1), 1};
         cuuint32_t es[4] = {1, 1, (cuuint32_t)(strided ? dilation : 1), 1};
         if (flat) { box[1] = (cuuint32_t)fbw; box[2] = (cuuint32_t)nr; es[2] = 1; }
         CUresult r = enc(&tmX, in_split ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, row64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3_tc_halo: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return PWC_E_BADARG; }
     }
@@ -1003,7 +1027,8 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
         if (s2d) { p.tap_dy[t] = t >> 1; p.tap_dx[t] = t & 1; p.tap_id[t] = (t >> 1) * 3 + (t & 1); }   // packed as the top-left 2 x 2 of a 3 x 3 kernel
         else { p.tap_dy[t] = t / 3; p.tap_dx[t] = (t % 3) * dilation; p.tap_id[t] = t; }
     }
-    p.act_stage = ((flat ? nr : p.box_rows) * p.bw * 128 + 1023) / 1024 * 1024;
+    p.row64 = row64;
+    p.act_stage = ((flat ? nr : p.box_rows) * p.bw * (row64 ? 64 : 128) + 1023) / 1024 * 1024;
     p.desc_mode = 0;
     // TMA-store epilogue: row tiles (not the flat mode: its tiles hold padding slots between rows), whole passes, plain
     // stores (no dgrad mask / residual / accumulate)
