@@ -964,7 +964,7 @@ int launch_conv_halo(const float* x, int x_cs, const void* w_packed, const float
     const int nr = flat ? (HL_M - 1 + fbw - 1) / fbw + 1 + span : 0;
     // 16-channel inputs in row-tile mode: 64-byte shared-memory rows (the 128-byte rows would be half zero fill: twice the TMA
     // write traffic and half as many pipeline stages in the same shared memory).  dilation <= 8: the strided 3-row box.
-    const int row64 = (Cin == 16 && !flat && !s2d && !in_split && dilation <= 8 && getenv("PWC_HALO_ROW64")) ? 1 : 0;      // opt-in until measured
+    const int row64 = (Cin == 16 && !flat && !s2d && !in_split && dilation <= 8 && !getenv("PWC_HALO_NO_ROW64")) ? 1 : 0;   // 16->16 at 16x224x512: 118 -> 109 us
     CUtensorMap tmX;
     if (s2d) {
         cuuint64_t dims[5] = {(cuuint64_t)2 * Cin_in, 2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
