@@ -17,6 +17,17 @@
 //   * the CTA is persistent with two accumulator sets in TMEM, so the epilogue of tile i overlaps the MMAs of
 //     tile i + 1; weights stream through their own 4-deep ring from the packed images of pwc_conv3x3_pack_weights_f16.
 // Shared-memory traffic per 32-channel slice of a tile drops from ~1008 KB to ~650 KB.
+//
+// Round 2 (what the per-CTA timelines of PWC_HALO_DEBUG=1 led to; DESIGN.md 3.2, profiles/r02_halo_epilogue.log):
+//   * split activations: input and/or output as [h | l * 2^11] fp16 rows (conv -> conv chains skip the converter pass);
+//   * epilogue: bias in shared memory, 32-channel passes, per-warp swizzled staging + TMA tensor stores (dgrad: the leaky
+//     mask tile arrives by TMA, accumulate is a reduce-add store), accumulators released right after tcgen05.wait::ld,
+//     software-pipelined for the 16- / 32-channel layers (the next tile's tcgen05.ld in flight during the stores);
+//   * MMA issue loop with 32-bit descriptor arithmetic (3.6 instructions per MMA), no integer division in any role;
+//   * work items: strided whole tiles, then a channel-split tail round; 16-deep weight ring, per-slice residency barriers;
+//   * stride 2 as a 2 x 2 convolution over a space-to-depth view read through a 5-D tensor map (s2d);
+//   * 16-channel inputs: 64-byte shared-memory rows (64B swizzle) instead of half-empty 128-byte ones;
+//   * programmatic dependent launch: the prologue overlaps the previous kernel's tail (common.cuh).
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <cstdlib>
