@@ -397,7 +397,7 @@ HALO_CASES = [  # rows of >= 96 pixels, stride 1, Cout <= 128 take the halo-resi
     (1, 4, 128, 32, 32, 32, 1), (1, 9, 130, 32, 32, 16, 1), (2, 14, 256, 128, 128, 128, 1), (1, 7, 200, 147, 148, 128, 1),
     (1, 5, 96, 64, 64, 64, 1), (2, 6, 300, 16, 16, 16, 1), (1, 3, 512, 96, 96, 48, 1), (1, 2, 128, 34, 36, 128, 1),
     (1, 9, 130, 32, 32, 32, 2), (2, 20, 256, 128, 128, 128, 4), (1, 30, 200, 128, 128, 96, 8), (1, 40, 256, 96, 96, 64, 16),
-    (1, 5, 100, 64, 64, 32, 16), (3, 1, 97, 32, 32, 16, 1),
+    (1, 5, 100, 64, 64, 32, 16), (3, 1, 97, 32, 32, 16, 1), (1, 12, 160, 16, 16, 32, 2), (1, 10, 140, 16, 20, 16, 4),   # 64-byte-row tiles, dilated
     # rows narrower than a tile: flat mode packs several rows into the 128 MMA rows
     (2, 7, 16, 32, 32, 32, 1), (1, 14, 32, 243, 244, 128, 1), (2, 28, 64, 96, 96, 64, 1), (1, 9, 21, 64, 64, 32, 1),
     (3, 5, 8, 32, 32, 16, 1), (1, 30, 100, 48, 48, 96, 1), (2, 13, 45, 16, 16, 16, 1), (1, 1, 9, 32, 32, 32, 1),
