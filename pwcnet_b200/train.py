@@ -109,6 +109,10 @@ class Trainer(object):
         import os
         self.tc_dgrad_s2 = os.environ.get("PWC_DGRAD_S2_TC", "1") != "0"
         self.tc_wgrad_small = os.environ.get("PWC_WGRAD_TC_SMALL", "0") == "1"
+        # weight gradients on a side stream: a layer's wgrad (transpose/split passes + GEMM) only needs x and dy, the chain
+        # that the step waits for is dgrad -> dgrad; the bandwidth-bound transposes run under the tensor-bound dgrads
+        self.wgrad_stream = os.environ.get("PWC_WGRAD_STREAM", "1") == "1"     # 14.6 -> 13.7 ms per step at B = 8, 384x1024
+        self._ws = None
 
     # ------------------------------------------------------------------ gradient workspace
     def _grad_buffers(self, p) -> _Grads:
@@ -149,6 +153,26 @@ class Trainer(object):
         """wgrad + bias grad into the flat gradient, then dgrad into gx (skipped when gx is None)."""
         m = self.model
         cin, cout = x.shape[3], dy.shape[3]
+        if self.wgrad_stream:
+            # everything enqueued so far (dy is final, grad_flat is cleared) happens before the side stream's work
+            main = torch.cuda.current_stream(self.device)
+            if self._ws is None:
+                self._ws = torch.cuda.Stream(device=self.device)
+            self._ws.wait_stream(main)
+            with torch.cuda.stream(self._ws):
+                self._wgrad(scope, x, dy, stride, dilation)
+        else:
+            self._wgrad(scope, x, dy, stride, dilation)
+        self._dgrad(scope, x, dy, gx, stride, dilation, mask, accumulate)
+
+    def _join_wgrad(self) -> None:
+        """The current stream waits for the weight gradients issued on the side stream so far."""
+        if self.wgrad_stream and self._ws is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._ws)
+
+    def _wgrad(self, scope, x, dy, stride, dilation) -> None:
+        m = self.model
+        cin, cout = x.shape[3], dy.shape[3]
         # (layers with Cin, Cout <= 32 stay on the persistent CUDA-core kernel: measured equal, one launch instead of three)
         if self.tc_wgrad and cout % 16 == 0 and cin % 4 == 0 and (self.tc_wgrad_small or not (cin <= 32 and cout <= 32)) and stride in (1, 2) \
                 and x.stride(2) % 4 == 0 and dy.stride(2) % 4 == 0 and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0:
@@ -165,6 +189,10 @@ class Trainer(object):
         else:
             ops_bwd.conv3x3_wgrad(x, dy, self.grads[scope + "/kernel"], self.grads[scope + "/bias"], stride=stride,
                                   dilation=dilation, cin_map=m._cin_perm.get(scope))
+
+    def _dgrad(self, scope, x, dy, gx, stride, dilation, mask, accumulate) -> None:
+        m = self.model
+        cin, cout = x.shape[3], dy.shape[3]
         if gx is None:
             return
         k = m._k[scope]
@@ -343,6 +371,7 @@ class Trainer(object):
             else:
                 self._conv_bwd(scope(0), p.im, g.pyr[lev][0], None, stride=2)
             self._allreduce_range(scope(0) + "/kernel", scope(2) + "/bias")
+        self._join_wgrad()
 
     # ------------------------------------------------------------------ gradient all-reduce, bucketed
     def _world(self) -> int:
@@ -357,6 +386,7 @@ class Trainer(object):
             return
         import torch.distributed as dist
         lo, hi = self._var_off[first_var][0], self._var_off[last_var][1]
+        self._join_wgrad()
         cur = torch.cuda.current_stream(self.device)
         if self._ar_stream is None:
             self._ar_stream = torch.cuda.Stream(device=self.device)
