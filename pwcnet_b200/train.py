@@ -386,14 +386,19 @@ class Trainer(object):
             return
         import torch.distributed as dist
         lo, hi = self._var_off[first_var][0], self._var_off[last_var][1]
-        self._join_wgrad()
         cur = torch.cuda.current_stream(self.device)
         if self._ar_stream is None:
             self._ar_stream = torch.cuda.Stream(device=self.device)
         ev = torch.cuda.Event()
         ev.record(cur)
+        ev_w = None
+        if self.wgrad_stream and self._ws is not None:      # the range's weight gradients were issued on the side stream:
+            ev_w = torch.cuda.Event()                       # the collective waits for them, the dgrad chain does not
+            ev_w.record(self._ws)
         with torch.cuda.stream(self._ar_stream):
             self._ar_stream.wait_event(ev)
+            if ev_w is not None:
+                self._ar_stream.wait_event(ev_w)
             self._ar_works.append(dist.all_reduce(self.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
     def _allreduce_finish(self) -> int:
