@@ -131,6 +131,9 @@ class PWCDCNet(object):
         self.split_act = precision == "3xf16" and not use_dc and os.environ.get("PWC_SPLIT_ACT", "1") != "0"
         # stride-2 convs as 2x2 convs over the space-to-depth view on the halo kernel (PWC_S2D=0: streaming kernel, round 1)
         self.s2d = os.environ.get("PWC_S2D", "1") != "0"
+        # f0 split producers of all levels on a side stream (see _forward); PWC_SIDE_SPLIT=0: in line
+        self.side_split = os.environ.get("PWC_SIDE_SPLIT", "1") != "0"
+        self._side = None
         if not torch.cuda.is_available():
             raise PwcError("PWCDCNet needs a CUDA device: the compute path is sm_100a CUDA only (no CPU fallback)")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -492,6 +495,26 @@ class PWCDCNet(object):
                 x = self._conv(x, scope, p.pyr[l][j], stride=stride, alpha=0.1)
         pre_total = sum(ESTIMATOR_FILTERS) if self.use_dc else 0
         nest = len(ESTIMATOR_FILTERS)
+        # The f0 producers of the split cost-volume pipeline (split_f16 of every level's first-image features + the copy into
+        # the concat slot) depend on the pyramid only: they run on a side stream under the coarse levels' estimators, which
+        # occupy 8..128 of the 148 SMs (fork / join by events: captured into the CUDA graph like everything else).
+        side_ev = [None] * len(self._lv)
+        if self.side_split and any(t is not None for t in p.f0s):
+            main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                for l, lv in enumerate(self._lv):
+                    if p.f0s[l] is None:
+                        continue
+                    F = p.pyr[self.num_levels - 1 - l][2]
+                    X = p.S[l][..., pre_total:pre_total + lv["cin_int"]]
+                    ops.split_f16(F[:B], out=p.f0s[l], copy=X[..., lv["off_f0"]:lv["off_f0"] + lv["C"]], scale=1.0 / lv["C"])
+                    if l == 0:
+                        ops.split_f16(F[B:], out=p.f1s[l])
+                    side_ev[l] = torch.cuda.Event()
+                    side_ev[l].record(self._side)
         for l, lv in enumerate(self._lv):
             F = p.pyr[self.num_levels - 1 - l][2]
             f0, f1 = F[:B], F[B:]
@@ -503,10 +526,15 @@ class PWCDCNet(object):
             if p.f0s[l] is not None:
                 # split pipeline: 1/C folded into the f0 producer (which also fills the f0 slot), f1 warped straight into
                 # [h|l] fp16 rows, band GEMM on tcgen05
-                f0s = ops.split_f16(f0, out=p.f0s[l], copy=f0slot, scale=1.0 / lv["C"])
                 fsrc = p.flow_up[l] if p.flow_up[l] is not None else flow_up
-                f1s = ops.split_f16(f1, out=p.f1s[l]) if l == 0 else \
-                    ops.warp_split(f1, fsrc, self.scales[l], self.warp_type, out=p.f1s[l])
+                if side_ev[l] is not None:
+                    torch.cuda.current_stream(self.device).wait_event(side_ev[l])
+                    f0s = p.f0s[l]
+                    f1s = p.f1s[l] if l == 0 else ops.warp_split(f1, fsrc, self.scales[l], self.warp_type, out=p.f1s[l])
+                else:
+                    f0s = ops.split_f16(f0, out=p.f0s[l], copy=f0slot, scale=1.0 / lv["C"])
+                    f1s = ops.split_f16(f1, out=p.f1s[l]) if l == 0 else \
+                        ops.warp_split(f1, fsrc, self.scales[l], self.warp_type, out=p.f1s[l])
                 ops.cost_volume_split(f0s, f1s, 0.1, out=cv, prescaled=True, slot=p.cv_slot[l], tail=p.flow_up[l])
             elif l == 0:
                 ops.cost_volume(f0, f1, self.s_range, 0.1, out=cv, f0_copy=f0slot)
