@@ -499,6 +499,7 @@ class PWCDCNet(object):
         # the concat slot) depend on the pyramid only: they run on a side stream under the coarse levels' estimators, which
         # occupy 8..128 of the 148 SMs (fork / join by events: captured into the CUDA graph like everything else).
         side_ev = [None] * len(self._lv)
+        feat_ev = None
         if self.side_split and any(t is not None for t in p.f0s):
             main = torch.cuda.current_stream(self.device)
             if self._side is None:
@@ -547,6 +548,9 @@ class PWCDCNet(object):
                 f1w = ops.warp(f1, flow_up, self.scales[l], self.warp_type, out=p.f1w[l])
                 ops.cost_volume(f0, f1w, self.s_range, 0.1, out=cv, f0_copy=f0slot)
             is_out = l == self.output_level
+            if feat_ev is not None:                       # the up-sampled features of the previous level (side stream)
+                torch.cuda.current_stream(self.device).wait_event(feat_ev)
+                feat_ev = None
             # ---- estimator convs (modules.py:266-274)
             if self.use_dc:
                 start = pre_total
@@ -564,14 +568,27 @@ class PWCDCNet(object):
                     feats = self._conv(feats, scope, t if t.dtype == torch.float16 else t[..., 0:f], alpha=0.1)
             head = f"{n}/optflow_{l}/conv2d_{nest}"
             if not is_out:
-                flows = self._conv(feats, head, p.flows[l], alpha=1.0, residual=flow_up)
                 nxt = self._lv[l + 1]
                 Sn = p.S[l + 1]
                 Xn = Sn[..., pre_total:pre_total + nxt["cin_int"]]
                 h2, w2 = Sn.shape[1], Sn.shape[2]
+                feat_dst = Xn[..., nxt["off_feat"]:nxt["off_feat"] + feats.shape[3]]
+                if self.side_split and feats.dtype == torch.float32:
+                    # the feature up-sampling only feeds the NEXT level's first estimator conv: side stream, next to the flow
+                    # head, the flow up-sampling, the warp and the cost volume
+                    main = torch.cuda.current_stream(self.device)
+                    if self._side is None:
+                        self._side = torch.cuda.Stream(device=self.device)
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        ops.resize_bilinear(feats, h2, w2, out=feat_dst)
+                        feat_ev = torch.cuda.Event()
+                        feat_ev.record(self._side)
+                flows = self._conv(feats, head, p.flows[l], alpha=1.0, residual=flow_up)
                 ops.resize_bilinear(flows, h2, w2, out=p.flow_up[l + 1] if p.flow_up[l + 1] is not None
                                     else Xn[..., nxt["off_flow"]:nxt["off_flow"] + 2])
-                ops.resize_bilinear(feats, h2, w2, out=Xn[..., nxt["off_feat"]:nxt["off_feat"] + feats.shape[3]])
+                if feat_ev is None:
+                    ops.resize_bilinear(feats, h2, w2, out=feat_dst)
             else:
                 # context input buffer = [features | flows(2) | pad(2)]
                 Cbuf = S if self.use_dc else p.tmp[l][-1]
