@@ -603,9 +603,21 @@ class PWCDCNet(object):
                         x = self._conv(x, scope, p.ctx[i], dilation=d, alpha=0.1)
                     else:
                         self._conv(x, scope, p.flows[l], dilation=d, alpha=1.0, residual=flow_slot)
-                ops.resize_bilinear(p.flows[l], p.flows_final.shape[1], p.flows_final.shape[2], mul=20.0,
-                                    out=p.flows_final)
-                ops.count_nonfinite(p.flows[l], p.nonfinite)
+                if self.side_split:
+                    # the range guard's count and the final x4 up-sampling both only read the last flow: side by side
+                    main = torch.cuda.current_stream(self.device)
+                    if self._side is None:
+                        self._side = torch.cuda.Stream(device=self.device)
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        ops.count_nonfinite(p.flows[l], p.nonfinite)
+                    ops.resize_bilinear(p.flows[l], p.flows_final.shape[1], p.flows_final.shape[2], mul=20.0,
+                                        out=p.flows_final)
+                    main.wait_stream(self._side)
+                else:
+                    ops.resize_bilinear(p.flows[l], p.flows_final.shape[1], p.flows_final.shape[2], mul=20.0,
+                                        out=p.flows_final)
+                    ops.count_nonfinite(p.flows[l], p.nonfinite)
 
     @on_device
     def __call__(self, images_0, images_1, with_features=False, reuse=False):
