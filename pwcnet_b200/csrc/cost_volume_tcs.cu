@@ -52,6 +52,7 @@ struct CvSplitParams {
     int vec;
     unsigned long long* dbg;   // optional timeline (clock64), 64 slots per CTA: 8 events x 8 tiles
     int exp;                   // experiments (PWC_CV_EXP, wrong results): 1 = no global stores, 2 = no copy-out at all
+    int tma_out;               // quad kernel, slot mode: the slab quadrants leave through TMA tensor stores (tm_out)
     int wide;                  // quad kernel: also write words [81, 88) of every pixel = [tail 2 | zeros 5] (whole 32-byte sectors)
     const float* tail;         // wide: dense (B,H,W,2) source of words 81, 82 (the up-sampled flow); NULL = zeros
 };
@@ -300,7 +301,8 @@ constexpr int Q_ROLES = 3;                            // extract warps per quadr
 constexpr int Q_XWARPS = 4 * Q_ROLES, Q_SWARPS = 2;   // 16 warps = 4 per SM sub-partition: 128 registers per thread
 constexpr int Q_THREADS = 64 + (Q_XWARPS + Q_SWARPS) * 32;   // 512
 constexpr int Q_PITCH = 84;                        // slab row pitch in words (LDS.128 of a pixel run is conflict-free)
-constexpr uint32_t Q_SLAB_BYTES = 4 * 32 * Q_PITCH * 4;   // one buffer: 4 quadrants x 32 pixels
+constexpr int Q_PITCH_TMA = 88;                    // TMA copy-out (slot mode): dense rows of the 88 words [cv 81 | zeros 7] that leave as one box
+constexpr uint32_t Q_SLAB_BYTES = 4 * 32 * Q_PITCH_TMA * 4;   // one buffer: 4 quadrants x 32 pixels (sized for the larger pitch)
 constexpr uint32_t Q_SMEM_BYTES = Q_STAGES * Q_STAGE_BYTES + 2 * Q_SLAB_BYTES + 1024;
 static_assert(Q_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -368,7 +370,8 @@ __device__ __forceinline__ void q_extract(uint32_t tq, int q, int lane, uint32_t
 }
 
 __global__ void __launch_bounds__(Q_THREADS, 1)
-cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1, const CvSplitParams p) {
+cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_constant__ CUtensorMap tm_f1,
+                        const __grid_constant__ CUtensorMap tm_out, const CvSplitParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -397,6 +400,13 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    const int pitch = p.tma_out ? Q_PITCH_TMA : Q_PITCH;
+    if (p.tma_out) {
+        // words 81..87 of every slab row are the zeros of the 88-word head; the extract warps only ever write words 0..80
+        uint32_t* sl = reinterpret_cast<uint32_t*>(base_ptr + Q_STAGES * Q_STAGE_BYTES);
+        for (int i = threadIdx.x; i < 2 * 128 * 7; i += Q_THREADS) sl[(i / 7) * Q_PITCH_TMA + 81 + i % 7] = 0u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -470,7 +480,7 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
         int tcount = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
             const int buf = tcount & 1;
-            uint32_t* slab_lane = slabs + buf * (Q_SLAB_BYTES / 4) + (q * 32 + lane) * Q_PITCH;
+            uint32_t* slab_lane = slabs + buf * (Q_SLAB_BYTES / 4) + (q * 32 + lane) * pitch;
             if (tcount >= 2) mbar_wait(bar_sempty + 8 * (2 * q + buf), ((tcount >> 1) - 1) & 1);   // the store warp has drained this buffer
             mbar_wait(bar_accf, tcount & 1);
             if (warp == 2 && lane == 0) S_DBG(3, tcount);
@@ -484,6 +494,7 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
                 else if (role == 1) q_extract<1, false>(tq, q, lane, slab_lane, bar_acce, scale, alpha);
                 else                q_extract<2, false>(tq, q, lane, slab_lane, bar_acce, scale, alpha);
             }
+            if (p.tma_out) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slab is read by the TMA engine
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_sfull + 8 * (2 * q + buf));
             if (warp == 2 && lane == 0) S_DBG(4, tcount);
@@ -494,6 +505,39 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
         // A pure copy (scale and leaky were applied by the extract warps): per quadrant 32 pixels x 20 float4 units, unit
         // u = lane + 32 m -> pixel u / 20, unit u % 20 (20 iterations, no divergence), then the 81st word of pixel = lane.
         pdl_wait();                                            // the tail operand and the output rows themselves
+        if (p.tma_out) {
+            // Slot mode: a quadrant's slab (32 pixels x 88 words, dense) is one {88 words, 8 pixels, 4 rows} box of the concat
+            // buffer.  One thread hands it to the TMA engine, which reaches the strided-slot write pattern's ceiling
+            // (~16 B/clk/SM, tools/store_bw_bench.cu) that two warps of LDS + STG could not (~10.5 B/clk/SM measured in this
+            // kernel): the copy-out drops below the extraction time per tile.  Edge tiles are clipped by the tensor map.
+            const uint32_t slab0 = base + Q_STAGES * Q_STAGE_BYTES;
+            const int q_first = 2 * (warp - 2 - Q_XWARPS);
+            int tcount = 0;
+            if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_out) : "memory");
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tcount) {
+                const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, b = t / (p.tiles_x * p.tiles_y);
+                const int buf = tcount & 1;
+                for (int qi = 0; qi < 2; ++qi) {
+                    const int q = q_first + qi;
+                    mbar_wait(bar_sfull + 8 * (2 * q + buf), (tcount >> 1) & 1);
+                    if (warp == 2 + Q_XWARPS && lane == 0 && qi == 0) S_DBG(6, tcount);
+                    if (lane == 0 && !(p.exp & 3)) {
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"(&tm_out), "r"(slab0 + buf * Q_SLAB_BYTES + q * 32 * Q_PITCH_TMA * 4), "r"(0), "r"(tx * Q_TW),
+                                       "r"(ty * Q_TH + 4 * q), "r"(b) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // both quadrants have been read
+                    mbar_arrive(bar_sempty + 8 * (2 * q_first + buf));
+                    mbar_arrive(bar_sempty + 8 * (2 * (q_first + 1) + buf));
+                }
+                __syncwarp();
+                if (warp == 2 + Q_XWARPS && lane == 0) S_DBG(7, tcount);
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else {
         const float* slabs = reinterpret_cast<const float*>(base_ptr + Q_STAGES * Q_STAGE_BYTES);
         const int cs = p.out_cs;
         const int gpitch = p.W * cs;                          // < 2^31 / H (checked by the launcher)
@@ -579,6 +623,7 @@ cost_volume_quad_kernel(const __grid_constant__ CUtensorMap tm_f0, const __grid_
             }
             if (warp == 2 + Q_XWARPS && lane == 0) S_DBG(7, tcount);
         }
+        }   // !tma_out
     }
     __syncwarp();
     tc_fence_before();
@@ -755,6 +800,21 @@ static int cv_split_launch(const void* f0s, const void* f1s, float* out, int out
             p.alpha = alpha; p.scale = scale;
             p.vec = aligned16(out) && (out_cs & 3) == 0;
             p.wide = wide; p.tail = tail;
+            // slot mode without a tail operand, 16-byte aligned rows: TMA copy-out
+            CUtensorMap tm_out;
+            memset(&tm_out, 0, sizeof(tm_out));
+            if (wide && !tail && p.vec && !getenv("PWC_CV_NO_TMA_OUT")) {
+                cuuint64_t od[4] = {88, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+                cuuint64_t os_[3] = {(cuuint64_t)out_cs * 4, (cuuint64_t)W * out_cs * 4, (cuuint64_t)H * W * out_cs * 4};
+                cuuint32_t ob[4] = {88, Q_TW, 4, 1};
+                cuuint32_t oe[4] = {1, 1, 1, 1};
+                EncodeTiledFn enc = pwc::get_encode();
+                PWC_REQUIRE(enc != nullptr, PWC_E_NOTBUILT, "cost_volume_split: cuTensorMapEncodeTiled not available from the driver");
+                CUresult r = enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)out, od, os_, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                PWC_REQUIRE(r == CUDA_SUCCESS, PWC_E_BADARG, "cost_volume_split: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+                p.tma_out = 1;
+            }
             PWC_REQUIRE((long long)H * W * out_cs < (1ll << 31), PWC_E_BADARG, "cost_volume_split: image too large for 32-bit offsets");
             cudaError_t e = cudaFuncSetAttribute(cost_volume_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
             if (e != cudaSuccess) { set_error("cost_volume_split(quad): smem attr: %s", cudaGetErrorString(e)); return (int)e; }
@@ -767,7 +827,7 @@ static int cv_split_launch(const void* f0s, const void* f1s, float* out, int out
                 cudaMemsetAsync(qdbg, 0, 256 * 64 * 8, (cudaStream_t)stream);
                 p.dbg = qdbg;
             }
-            launch_pdl(cost_volume_quad_kernel, dim3(grid), dim3(Q_THREADS), Q_SMEM_BYTES, (cudaStream_t)stream, tm0, tm1, p);
+            launch_pdl(cost_volume_quad_kernel, dim3(grid), dim3(Q_THREADS), Q_SMEM_BYTES, (cudaStream_t)stream, tm0, tm1, tm_out, p);
             PWC_CHECK_LAUNCH("cost_volume_quad_kernel");
             if (p.dbg) {   // debugging aid only (synchronises): timeline of the first tiles of one CTA
                 cudaStreamSynchronize((cudaStream_t)stream);
