@@ -351,7 +351,7 @@ def _bind_to_gpu_numa_node(local: int):
         return None
 
 
-def roofline_cost_volume(P, torch, dev, B, n_sets=4, reps=12):
+def roofline_cost_volume(P, torch, dev, B, n_sets=4, reps=50):
     """Level-2 cost volume as the model runs it (tcgen05 quadrant-block kernel, split fp16 operands, whole-sector writes
     into the 81+7-word head of the 160-wide estimator concat buffer), timed live: `n_sets` rotating operand / output
     sets (n_sets x 140 MB of touched data > 126 MB L2: every launch misses L2 for all of its inputs, and pays the write-back of its
@@ -367,7 +367,7 @@ def roofline_cost_volume(P, torch, dev, B, n_sets=4, reps=12):
     def launch(i):
         a, b, o = sets[i % n_sets]
         P.ops.cost_volume_split(a, b, 0.1, out=o, prescaled=True, slot=True)
-    for i in range(2 * n_sets):
+    for i in range(10 * n_sets):   # warm-up: tensor maps, clocks, L2 state of the rotation
         launch(i)
     torch.cuda.synchronize()
     n = reps * n_sets

@@ -367,11 +367,12 @@ int launch_cv_tc(const CvParams& q, cudaStream_t st) {
     p.backoff = getenv("PWC_CV_NOBACKOFF") ? 0 : 1;
     cudaError_t e = cudaFuncSetAttribute(cost_volume_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X_SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cost_volume_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
+    const int nsm = sm_count();
+    const int grid = p.total_tiles < nsm ? p.total_tiles : nsm;
     static unsigned long long* dbg_buf = nullptr;
     if (getenv("PWC_CV_DEBUG")) {
-        if (!dbg_buf) cudaMalloc(&dbg_buf, 148 * 64 * 8);
-        cudaMemsetAsync(dbg_buf, 0, 148 * 64 * 8, st);
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 256 * 64 * 8);
+        cudaMemsetAsync(dbg_buf, 0, 256 * 64 * 8, st);
         p.dbg = dbg_buf;
     }
     cost_volume_tc_kernel<<<grid, X_THREADS, X_SMEM_BYTES, st>>>(tm0, tm1, p);

@@ -859,11 +859,12 @@ static int cv_split_launch(const void* f0s, const void* f1s, float* out, int out
     p.vec = aligned16(out) && (out_cs & 3) == 0;
     cudaError_t e = cudaFuncSetAttribute(cost_volume_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cost_volume_split: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    const int grid = p.total_tiles < 148 ? p.total_tiles : 148;
+    const int nsm = sm_count();
+    const int grid = p.total_tiles < nsm ? p.total_tiles : nsm;
     static unsigned long long* dbg_buf = nullptr;
     if (getenv("PWC_CV_DEBUG")) {
-        if (!dbg_buf) cudaMalloc(&dbg_buf, 148 * 64 * 8);
-        cudaMemsetAsync(dbg_buf, 0, 148 * 64 * 8, (cudaStream_t)stream);
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 256 * 64 * 8);
+        cudaMemsetAsync(dbg_buf, 0, 256 * 64 * 8, (cudaStream_t)stream);
         p.dbg = dbg_buf;
     }
     cost_volume_split_kernel<<<grid, S_THREADS, S_SMEM_BYTES, (cudaStream_t)stream>>>(tm0, tm1, p);

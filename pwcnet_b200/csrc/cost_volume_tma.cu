@@ -262,7 +262,8 @@ int launch_cv_tma(const CvParams& q, cudaStream_t st) {
     auto kern = vec ? cost_volume_tma_kernel<true> : cost_volume_tma_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cost_volume_tma: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    const int grid = p.total_tiles < 2 * 148 ? p.total_tiles : 2 * 148;
+    const int cap = 2 * sm_count();
+    const int grid = p.total_tiles < cap ? p.total_tiles : cap;
     kern<<<grid, T_THREADS, T_SMEM_BYTES, st>>>(tm0, tm1, tmc, p);
     PWC_CHECK_LAUNCH("cost_volume_tma_kernel");
     return 0;

@@ -6,6 +6,6 @@ import pwcnet_b200 as P
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 torch.cuda.set_device(0)
-for reps in (12, 25):
+for reps in (12, 50):
     r = bench.roofline_cost_volume(P, torch, torch.device("cuda:0"), B, reps=reps)
     print(json.dumps({k: r[k] for k in ("us_per_launch", "achieved", "frac", "launches_timed")}))
