@@ -819,7 +819,12 @@ static int cv_split_launch(const void* f0s, const void* f1s, float* out, int out
             cudaError_t e = cudaFuncSetAttribute(cost_volume_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM_BYTES);
             if (e != cudaSuccess) { set_error("cost_volume_split(quad): smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             const int nsm = sm_count();
-            const int grid = p.total_tiles < nsm ? p.total_tiles : nsm;
+            int grid = p.total_tiles < nsm ? p.total_tiles : nsm;
+            if (const char* gs = getenv("PWC_CV_GRID")) {   // experiment: 0 = balanced (fewest CTAs for the same round count), n = n CTAs
+                const int g = atoi(gs);
+                if (g > 0) grid = g < grid ? g : grid;
+                else { const int rounds = (p.total_tiles + grid - 1) / grid; grid = (p.total_tiles + rounds - 1) / rounds; }
+            }
             static unsigned long long* qdbg = nullptr;
             if (const char* ex = getenv("PWC_CV_EXP")) p.exp = atoi(ex);
             if (getenv("PWC_CV_DEBUG")) {

@@ -120,22 +120,33 @@ class Trainer(object):
         g = self._gbufs.get(key)
         if g is not None:
             return g
-        acts: List[torch.Tensor] = []
+        # (activation, cleared every step?)  A buffer whose FIRST writer in `backward` accumulates (several consumers: pyramid
+        # outputs, concat buffers, flows, the estimator's last buffer / dense buffer) is cleared; a buffer that one dgrad
+        # overwrites completely (pyramid conv 0/1 outputs, estimator conv 0..3 outputs, context outputs, warped features) is
+        # not: ~1.3 of the 1.5 GB at 8 x 384 x 1024.  The cleared ones come first in `flat`, so one fill covers them.
+        acts: List[tuple] = []
         for lev in p.pyr:
-            acts += lev
+            acts += [(a, j == len(lev) - 1) for j, a in enumerate(lev)]
         for l in range(len(p.S)):
-            acts += [p.S[l]] + list(p.tmp[l] or []) + [p.flows[l]] + ([p.f1w[l]] if p.f1w[l] is not None else [])
-        acts += list(p.ctx)
+            tmp = list(p.tmp[l] or [])
+            acts += [(p.S[l], True)] + [(a, j == len(tmp) - 1) for j, a in enumerate(tmp)] + [(p.flows[l], True)] \
+                + ([(p.f1w[l], True)] if p.f1w[l] is not None else [])
+        acts += [(a, False) for a in p.ctx]
         def al(n):   # every view starts on a 256-byte boundary (vector loads / TMA need 16)
             return (n + 63) // 64 * 64
-        total = sum(al(a.numel()) for a in acts)
+        total = sum(al(a.numel()) for a, _ in acts)
         g = _Grads()
         g.flat = torch.zeros(total, dtype=torch.float32, device=self.model.device)
-        off = 0
+        g.n_clear = sum(al(a.numel()) for a, z in acts if z)
+        off_z, off_o = 0, g.n_clear
         views = []
-        for a in acts:
+        for a, z in acts:
+            off = off_z if z else off_o
             views.append(g.flat[off:off + a.numel()].view(a.shape))
-            off += al(a.numel())
+            if z:
+                off_z += al(a.numel())
+            else:
+                off_o += al(a.numel())
         it = iter(views)
         g.pyr = [[next(it) for _ in lev] for lev in p.pyr]
         g.S, g.tmp, g.flows, g.f1w = [], [], [], []
@@ -252,7 +263,7 @@ class Trainer(object):
         nest = len(ESTIMATOR_FILTERS)
         nf = ESTIMATOR_FILTERS[-1]
         g = self._grad_buffers(p)
-        g.flat.zero_()
+        g.flat[:g.n_clear].zero_()          # only the buffers whose first writer accumulates (see _grad_buffers)
         self.grad_flat.zero_()
         # rotated + packed dgrad kernels of every layer seen by an earlier backward pass: one launch (the first pass
         # packs layer by layer and records the parts)

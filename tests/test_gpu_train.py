@@ -479,6 +479,32 @@ def test_trainer_rejects_unsupported_models(P):
         Trainer(P.PWCDCNet(precision="cudnn"))
 
 
+@pytest.mark.parametrize("use_dc", [False, True])
+@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 192, 320)])
+def test_uncleared_gradient_buffers_are_fully_overwritten(P, use_dc, shape):
+    """`Trainer.backward` clears only the activation-gradient buffers whose first writer accumulates (`_grad_buffers`);
+    the others must be overwritten completely by their one dgrad.  Poison them with NaN between two backward passes over
+    the same batch: every gradient stays finite and unchanged (flat-slot and row-tile dgrad epilogues, plain and dense stacks)."""
+    from pwcnet_b200.train import Trainer
+    B, H, W_ = shape
+    W = O.glorot_weights(7, gain=1.2, bias_scale=0.02, use_dc=use_dc)
+    im0, im1 = O.synthetic_pair(B, H, W_, 3, shift=(3, -2))
+    gt = np.random.default_rng(2).normal(0, 4, (B, H, W_, 2)).astype(np.float32)
+    model = P.PWCDCNet(weights=W, use_dc=use_dc)
+    tr = Trainer(model)
+    tr.forward_backward(im0, im1, gt)
+    torch.cuda.synchronize()
+    first = tr.grad_flat.clone()
+    (g,) = tr._gbufs.values()
+    assert 0 < g.n_clear < g.flat.numel()
+    g.flat[g.n_clear:].fill_(float("nan"))
+    tr.forward_backward(im0, im1, gt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(tr.grad_flat).all()
+    # (reduce-add epilogues and split wgrad sums are not order-deterministic: equal up to fp32 summation order)
+    assert float((tr.grad_flat - first).abs().max()) <= 1e-5 * float(first.abs().max())
+
+
 @pytest.mark.parametrize("precision", ["fp32", "3xf16"])
 def test_use_dc_network_gradients_match_oracle_autograd(P, precision):
     """`--use-dc` (train.py:203-207, modules.py:269-270): all 110 gradient tensors of the densely connected estimator
