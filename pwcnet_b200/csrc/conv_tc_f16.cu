@@ -40,6 +40,8 @@ struct F16Params {
     int n_parts, cn, b_bytes_full;   // coarse levels (fewer tiles than SMs): the output channels are split over n_parts CTAs per tile,
                                      // cn channels each (a multiple of 16); b_bytes_full = Cout * 64 = the packed image's W_h -> W_l distance
     int stage_bytes, stages, tmem_cols, n_main, prefetch, shift;
+    int k_parts;       // split-K over a cluster of k_parts CTAs (1 or 3: one kernel row of taps each); rank 0 reduces the partial
+                       // sums the other ranks leave in its shared memory (DSMEM) and runs the epilogue
     unsigned long long* dbg;   // optional per-CTA timeline (clock64), 8 slots per CTA; nullptr in production
     // dgrad use (pwc_conv3x3_tc_f16_dgrad): bias may be null, stores are limited to the first cout_valid channels
     // (Cout is the MMA N, padded to a multiple of 16), the result is multiplied by leaky'(mask) and optionally
@@ -55,6 +57,21 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// One 32-lane x 16-column block of the result: correction group (scaled by 2^-11) first, then the main accumulators, main 0 last.
+__device__ __forceinline__ void f16_load_acc(uint32_t tbase, int n_main, int CN, float (&acc)[16]) {
+    uint32_t r[16];
+    tmem_ld16(tbase + n_main * CN, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]) * F16_INV_SCALE;
+    for (int a2 = n_main - 1; a2 >= 0; --a2) {
+        tmem_ld16(tbase + a2 * CN, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+    }
 }
 
 __global__ void __launch_bounds__(F16_THREADS, 2)
@@ -73,13 +90,18 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
     const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[8]), bar_empty = smem_u32(&bars[16]);
     const uint32_t bar_acc = smem_u32(&bars[24]);
 
-    int t = blockIdx.x / p.n_parts;
-    const int ch0 = (blockIdx.x - t * p.n_parts) * p.cn;     // first output channel of this CTA
+    const int KP = p.k_parts;
+    const int krank = KP > 1 ? (int)(blockIdx.x % KP) : 0;   // == %cluster_ctarank (cluster dims (KP,1,1))
+    const int bid = KP > 1 ? (int)(blockIdx.x / KP) : (int)blockIdx.x;
+    int t = bid / p.n_parts;
+    const int ch0 = (bid - t * p.n_parts) * p.cn;     // first output channel of this CTA
     const int CN = p.cn;
     const int tx = t % p.tiles_x; t /= p.tiles_x;
     const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
     const int x0 = tx * F16_TW, y0 = ty * F16_TH;
-    const int KT = 9 * p.kchunks;
+    // K iterations [IT0, IT0 + KT) of the 9 * kchunks (tap, slice) pairs: all of them, or one kernel row per cluster rank
+    const int KT = (KP > 1 ? 3 : 9) * p.kchunks;
+    const int IT0 = krank * KT;
 
     // (p.shift: experiment knob -- start the fp16 A tiles `shift` bytes into their 512-byte swizzle atom to test that
     //  UMMA and the converter agree on an ABSOLUTE-address swizzle; 1 KB of slack follows the A_l tile)
@@ -116,14 +138,14 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
             const uint32_t tx_bytes = F16_A_RAW + 2 * p.b_bytes;
             const int PF = p.prefetch;   // stages of L2 prefetch distance for the activation boxes
             for (int it = 0; it < PF && it < KT; ++it) {
-                const int tap = it / p.kchunks, kc = it - tap * p.kchunks, ky = tap / 3, kx = tap - ky * 3;
+                const int tap = (IT0 + it) / p.kchunks, kc = (IT0 + it) - tap * p.kchunks, ky = tap / 3, kx = tap - ky * 3;
                 tma_prefetch_4d(&tmX, kc * F16_BK, x0 * p.stride - p.pad_l + kx * p.dil, y0 * p.stride - p.pad_t + ky * p.dil, b);
             }
             // ring stage / phase and the (tap, slice) pairs of the load and of the prefetch as counters: the integer divisions
             // they replace (~40 instructions each) were a visible part of every K iteration of this single thread
-            int s = 0, kc = 0, kx = 0, ky = 0;
+            int s = 0, kc = 0, kx = 0, ky = krank;            // IT0 = krank * 3 * kchunks: tap row krank, first tap, first slice
             uint32_t ph = 0;
-            int pkc = PF % p.kchunks, ptap = PF / p.kchunks, pky = ptap / 3, pkx = ptap - pky * 3;
+            int pkc = (IT0 + PF) % p.kchunks, ptap = (IT0 + PF) / p.kchunks, pky = ptap / 3, pkx = ptap - pky * 3;
             for (int it = 0; it < KT; ++it) {
                 if (it + PF < KT) {
                     tma_prefetch_4d(&tmX, pkc * F16_BK, x0 * p.stride - p.pad_l + pkx * p.dil, y0 * p.stride - p.pad_t + pky * p.dil, b);
@@ -137,11 +159,11 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
                             y0 * p.stride - p.pad_t + ky * p.dil, b);
                 // [h tile | l tile] of this (tap, slice): one linear bulk copy
                 if (p.n_parts > 1) {   // rows ch0 .. ch0 + cn of the W_h and of the W_l image
-                    const uint8_t* img = p.w + (size_t)it * 2 * p.b_bytes_full + (size_t)ch0 * 64;
+                    const uint8_t* img = p.w + (size_t)(IT0 + it) * 2 * p.b_bytes_full + (size_t)ch0 * 64;
                     bulk_load_1d(st + off_bh, img, p.b_bytes, bar_full + 8 * s);
                     bulk_load_1d(st + off_bh + p.b_bytes, img + p.b_bytes_full, p.b_bytes, bar_full + 8 * s);
                 } else {
-                    bulk_load_1d(st + off_bh, p.w + (size_t)it * 2 * p.b_bytes, 2 * p.b_bytes, bar_full + 8 * s);
+                    bulk_load_1d(st + off_bh, p.w + (size_t)(IT0 + it) * 2 * p.b_bytes, 2 * p.b_bytes, bar_full + 8 * s);
                 }
                 if (++kc == p.kchunks) { kc = 0; if (++kx == 3) { kx = 0; ++ky; } }
                 if (++s == S) { s = 0; ph ^= 1; }
@@ -223,11 +245,37 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
             if (dbg && ct == 0 && it == 12) dbg[75] = clock64();
             if (++s == S) { s = 0; ph ^= 1; }
         }
-        // ---- epilogue: warps 2..5 (TMEM lane quadrant = warp % 4); the other converter warps are done
-        if (warp < 6) {
+        // ---- split-K, ranks 1..KP-1: warps 2..5 leave their partial sums in rank 0's shared memory (DSMEM), laid out
+        //      [rank-1][channel group of 4][pixel row] as float4 (consecutive lanes -> consecutive 16 bytes)
+        if (warp < 6 && krank != 0) {
+            mbar_wait(bar_acc, 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            const int m = q * 32 + lane;
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(base + (uint32_t)S * p.stage_bytes), "r"(0));
+            remote += (uint32_t)(krank - 1) * (uint32_t)CN * 512u + (uint32_t)m * 16u;
+            for (int n0 = 0; n0 < CN; n0 += 16) {
+                float acc[16];
+                f16_load_acc(tmem_acc + ((uint32_t)(q * 32) << 16) + n0, p.n_main, CN, acc);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)((n0 + j) >> 2) * 2048u),
+                                 "f"(acc[j]), "f"(acc[j + 1]), "f"(acc[j + 2]), "f"(acc[j + 3]) : "memory");
+            }
+        }
+    }
+    if (KP > 1) {   // every thread of every CTA of the cluster: partial sums are visible to rank 0 afterwards
+        __syncwarp();
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    }
+    // ---- epilogue (rank 0): warps 2..5 (TMEM lane quadrant = warp % 4); the other converter warps are done
+    if (warp >= 2 && warp < 6 && krank == 0) {
+        {
             pdl_wait();                                // mask / residual / accumulate operands
             mbar_wait(bar_acc, 0);
-            if (dbg && ct == 0) dbg[5] = clock64();   // accumulator complete
+            if (dbg && threadIdx.x == 64) dbg[5] = clock64();   // accumulator complete
             tc_fence_after();
             const int q = warp & 3;
             const int m = q * 32 + lane;
@@ -239,20 +287,16 @@ conv3x3_tc_f16_kernel(const __grid_constant__ CUtensorMap tmX, const F16Params p
             const int cvalid = p.cout_valid - ch0;                 // valid channels of this CTA's range (may exceed CN)
             const bool vec = ((p.y_cs & 3) == 0) && aligned16(p.y) && ((p.cout_valid & 3) == 0) && !p.res &&
                              (!p.mask || (((p.mask_cs & 3) == 0) && aligned16(p.mask)));
+            const float4* part = reinterpret_cast<const float4*>(base_ptr + (size_t)S * p.stage_bytes) + m;
             for (int n0 = 0; n0 < CN; n0 += 16) {
-                const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16) + n0;
-                uint32_t r[16];
                 float acc[16];
-                // correction group first (scaled by 2^-11), then the main accumulators, main 0 last
-                tmem_ld16(tbase + p.n_main * CN, r);
-                tmem_ld_wait();
+                f16_load_acc(tmem_acc + ((uint32_t)(q * 32) << 16) + n0, p.n_main, CN, acc);
+                for (int r = 1; r < KP; ++r) {          // partial sums of the other kernel rows, in rank order
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]) * F16_INV_SCALE;
-                for (int a2 = p.n_main - 1; a2 >= 0; --a2) {
-                    tmem_ld16(tbase + a2 * CN, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 v = part[((size_t)(r - 1) * (CN >> 2) + ((n0 + j) >> 2)) * 128];
+                        acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+                    }
                 }
                 if (valid) {
 #pragma unroll
@@ -446,51 +490,92 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     // channel split for the coarse pyramid levels (16 tiles of 128 pixels at level 6): the serial K loop of a CTA streams
     // 2 * Cout * 64 bytes of weights per (tap, slice) and issues N = Cout MMAs while 130 SMs idle
     p.n_parts = 1;
+    p.k_parts = 1;
     if (tiles * 2 <= sm_count() && Cout >= 64 && !getenv("PWC_TC_NO_NSPLIT")) {
         for (int k = (int)(sm_count() / tiles); k >= 2; --k)
             if (Cout % k == 0 && (Cout / k) % 16 == 0 && Cout / k >= 32) { p.n_parts = k; break; }
     }
-    p.cn = Cout / p.n_parts;
-    p.b_bytes_full = Cout * 64;
-    const int Cl = p.cn;
-    p.b_bytes = Cl * 64;
-    p.stage_bytes = (int)(F16_A_RAW + 2 * F16_A_HALF) + 1024 + 2 * p.b_bytes;
-    p.shift = 0;
-    if (const char* e = getenv("PWC_TC_SHIFT")) p.shift = atoi(e) & 0x3C0;
-    p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
-    // Occupancy beats pipeline depth here (measured, profiles/r01_f16_occupancy.log: 2 CTAs/SM with 2 stages each
-    // are 1.38x faster than 1 CTA with 4 stages): a CTA's prologue (descriptor fetch, first TMA latency) and
-    // epilogue (TMEM drain + stores, ~15% of its life) overlap the other CTA's main loop.  So: <= 110 KB of
-    // shared memory and <= 256 TMEM columns per CTA; short K loops (pyramid layers) get 3 CTAs per SM.
     const int budget = 220 * 1024;
-    const int kt = 9 * p.kchunks;
-    p.stages = ((kt <= 18 ? 72 : 110) * 1024) / p.stage_bytes;
-    if (p.stages < 2) p.stages = 2;
-    if (p.stages > 4) p.stages = 4;
-    // small problems (coarse pyramid levels: fewer tiles than SMs) cannot use a second CTA per SM anyway and are bound by
-    // the serial K loop: give the one CTA a deeper ring so the TMA latency is hidden
-    if (tiles <= 148 && !getenv("PWC_TC_NO_DEEP")) { int deep = (200 * 1024) / p.stage_bytes; if (deep > 6) deep = 6; if (deep > p.stages) p.stages = deep; }
-    if (const char* e = getenv("PWC_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 8 && v * p.stage_bytes <= budget) p.stages = v; }
-    PWC_REQUIRE(p.stages >= 2, PWC_E_BADARG, "conv3x3_tc_f16: tile does not fit in shared memory");
-    p.prefetch = 0;   // L2 prefetch of upcoming activation boxes: measured no gain (profiles/r01_f16_prefetch.log)
-    if (const char* e = getenv("PWC_TC_PREFETCH")) p.prefetch = atoi(e);
-    p.n_main = 256 / Cl - 1;   // main accumulators the K loop rotates over (+1 correction accumulator)
-    if (p.n_main > 3) p.n_main = 3;
-    if (p.n_main < 1) p.n_main = 1;
-    if (const char* e = getenv("PWC_TC_NMAIN")) { int v = atoi(e); if (v >= 1 && v <= p.n_main) p.n_main = v; }
+    // everything that follows from the split: channels per CTA, stage size, ring depth, accumulator layout.  Returns the dynamic
+    // shared memory of a CTA (0: does not fit).
+    auto configure = [&](int n_parts, int k_parts) -> size_t {
+        p.n_parts = n_parts; p.k_parts = k_parts;
+        p.cn = Cout / p.n_parts;
+        p.b_bytes_full = Cout * 64;
+        const int Cl = p.cn;
+        p.b_bytes = Cl * 64;
+        p.stage_bytes = (int)(F16_A_RAW + 2 * F16_A_HALF) + 1024 + 2 * p.b_bytes;
+        p.shift = 0;
+        if (const char* e = getenv("PWC_TC_SHIFT")) p.shift = atoi(e) & 0x3C0;
+        p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
+        // Occupancy beats pipeline depth here (measured, profiles/r01_f16_occupancy.log: 2 CTAs/SM with 2 stages each
+        // are 1.38x faster than 1 CTA with 4 stages): a CTA's prologue (descriptor fetch, first TMA latency) and
+        // epilogue (TMEM drain + stores, ~15% of its life) overlap the other CTA's main loop.  So: <= 110 KB of
+        // shared memory and <= 256 TMEM columns per CTA; short K loops (pyramid layers) get 3 CTAs per SM.
+        const int kt = 9 * p.kchunks;
+        p.stages = ((kt <= 18 ? 72 : 110) * 1024) / p.stage_bytes;
+        if (p.stages < 2) p.stages = 2;
+        if (p.stages > 4) p.stages = 4;
+        // small problems (coarse pyramid levels: fewer tiles than SMs) cannot use a second CTA per SM anyway and are bound by
+        // the serial K loop: give the one CTA a deeper ring so the TMA latency is hidden
+        const int part_bytes = p.k_parts > 1 ? (p.k_parts - 1) * p.cn * 512 : 0;   // partial tiles of ranks 1.., next to the ring
+        if (tiles <= 148 && !getenv("PWC_TC_NO_DEEP")) { int deep = (200 * 1024 - part_bytes) / p.stage_bytes; if (deep > 6) deep = 6; if (deep > p.stages) p.stages = deep; }
+        if (const char* e = getenv("PWC_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 8 && v * p.stage_bytes + part_bytes <= budget) p.stages = v; }
+        if (p.stages < 2 || p.stages * p.stage_bytes + part_bytes > budget) return 0;
+        p.prefetch = 0;   // L2 prefetch of upcoming activation boxes: measured no gain (profiles/r01_f16_prefetch.log)
+        if (const char* e = getenv("PWC_TC_PREFETCH")) p.prefetch = atoi(e);
+        p.n_main = 256 / Cl - 1;   // main accumulators the K loop rotates over (+1 correction accumulator)
+        if (p.n_main > 3) p.n_main = 3;
+        if (p.n_main < 1) p.n_main = 1;
+        if (const char* e = getenv("PWC_TC_NMAIN")) { int v = atoi(e); if (v >= 1 && v <= p.n_main) p.n_main = v; }
+        int cols = 32;
+        while (cols < (p.n_main + 1) * Cl) cols *= 2;
+        p.tmem_cols = cols;
+        return (size_t)p.stages * p.stage_bytes + part_bytes + 1024;
+    };
+    // split-K for the same sub-wave layers: a CTA's time is its MMA chain (9 * Cin/16 K-steps x 3 MMAs of ~100+ clk whatever N
+    // is), so splitting Cout further shortens nothing; a cluster of 3 CTAs takes one kernel row of taps each and rank 0 sums
+    // the partial tiles the others leave in its shared memory (pyramid level 6, 192 -> 192 at 16 x 7 x 16: 6 parts of 32 channels
+    // -> 3 parts of 64 channels x 3 kernel rows, 54 -> 18 K iterations per CTA).  Taken only if every cluster is resident at once
+    // (clusters are placed inside one GPC: not every SM count is reachable).
+    // OPT-IN (PWC_TC_KSPLIT=1): measured +0.7 % on the B = 8 forward (level 6: 31 -> 24 us per layer, the launch's fixed costs
+    // remain), but whether a layer is split depends on its tile count, i.e. on the batch size, and the split changes the fp32
+    // summation order -- the default path keeps results bit-identical across batch sizes (tests/test_gpu_fullsize.py).
+    const int n_split_only = p.n_parts;
+    size_t smem = 0;
+    const char* ks = getenv("PWC_TC_KSPLIT");
+    if (ks && atoi(ks) == 1 && tiles * 3 <= sm_count() && Cout >= 64 && 9 * (cpad / F16_BK) >= 18) {
+        for (int n = (int)(sm_count() / (tiles * 3)); n >= 1 && !smem; --n) {
+            if (Cout % n != 0 || (Cout / n) % 16 != 0 || Cout / n < 32 || Cout / n > 128) continue;
+            const size_t sm = configure(n, 3);
+            if (!sm) continue;
+            if (cudaFuncSetAttribute(conv3x3_tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) { cudaGetLastError(); continue; }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(tiles * n * 3)); cfg.blockDim = dim3(F16_THREADS); cfg.dynamicSmemBytes = sm;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 3; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int resident = 0;
+            if (cudaOccupancyMaxActiveClusters(&resident, conv3x3_tc_f16_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+            if ((long long)resident >= tiles * n) smem = sm;
+        }
+    }
+    if (!smem) smem = configure(n_split_only, 1);
+    PWC_REQUIRE(smem != 0, PWC_E_BADARG, "conv3x3_tc_f16: tile does not fit in shared memory");
     PWC_REQUIRE(p.n_main >= 1, PWC_E_BADARG, "conv3x3_tc_f16: Cout too large for the accumulator layout");
-    int cols = 32;
-    while (cols < (p.n_main + 1) * Cl) cols *= 2;
-    p.tmem_cols = cols;
     static unsigned long long* dbg_buf = nullptr;
     if (getenv("PWC_TC_DEBUG")) {
         if (!dbg_buf) cudaMalloc(&dbg_buf, 80 * 8 * 65536);
         p.dbg = tiles <= 65536 ? dbg_buf : nullptr;
     }
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("conv3x3_tc_f16: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    launch_pdl(conv3x3_tc_f16_kernel, dim3((unsigned)(tiles * p.n_parts)), dim3(F16_THREADS), smem, (cudaStream_t)stream, tmX, p);
+    if (p.k_parts > 1)
+        launch_pdl_cluster(conv3x3_tc_f16_kernel, dim3((unsigned)(tiles * p.n_parts * p.k_parts)), dim3(F16_THREADS), smem, (cudaStream_t)stream,
+                           (unsigned)p.k_parts, tmX, p);
+    else
+        launch_pdl(conv3x3_tc_f16_kernel, dim3((unsigned)(tiles * p.n_parts)), dim3(F16_THREADS), smem, (cudaStream_t)stream, tmX, p);
     PWC_CHECK_LAUNCH("conv3x3_tc_f16_kernel");
     if (p.dbg) {   // debugging aid only (synchronises!): print the timeline of a few CTAs
         cudaStreamSynchronize((cudaStream_t)stream);

@@ -392,6 +392,32 @@ def test_conv3x3_tcgen05_f16x3_matches_oracle(P, case):
     np.testing.assert_allclose(out.cpu().numpy(), ref, atol=2e-5, rtol=0)
 
 
+@pytest.mark.parametrize("case", [(2, 14, 32, 128, 128, 192, 1, 2), (1, 16, 32, 192, 192, 192, 1), (1, 14, 32, 243, 244, 128, 1),
+                                  (1, 28, 64, 64, 64, 96, 1, 2), (2, 7, 16, 192, 192, 192, 1), (1, 24, 40, 96, 96, 64, 16)])
+def test_conv3x3_f16x3_split_k_cluster_matches_oracle(P, case, monkeypatch):
+    """Opt-in split-K of the streaming kernel (PWC_TC_KSPLIT=1: clusters of 3 CTAs, one kernel row of taps each, partial
+    tiles reduced through rank 0's shared memory) on sub-wave grids: same fp32-class bar as the default path, and it
+    writes only its channel slot."""
+    from pwcnet_b200 import ops_tc
+    B, H, W, Cin, cs, Cout, dil = case[:7]
+    stride = case[7] if len(case) > 7 else 1
+    buf = _rand((B, H, W, cs), 1)
+    k = _rand((3, 3, Cin, Cout), 2, scale=1.0 / np.sqrt(9 * Cin))
+    b = _rand((Cout,), 3, scale=0.1)
+    x = buf[..., :Cin]
+    ref = O.leaky_relu(O.conv2d_same(torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(k), torch.from_numpy(b), stride, dil), 0.1).numpy()
+    wp = ops_tc.pack_weights_f16(_cuda(k))
+    monkeypatch.setenv("PWC_CONV_HALO", "0")     # the streaming kernel, also for the stride-1 shapes
+    base = ops_tc.conv3x3_tc_f16(_cuda(buf)[..., :Cin], wp, _cuda(b), Cin, Cout, dilation=dil, alpha=0.1, stride=stride)
+    monkeypatch.setenv("PWC_TC_KSPLIT", "1")
+    oh, ow = ref.shape[1:3]
+    out = torch.full((B, oh, ow, Cout + 8), 7.0, device="cuda")
+    ops_tc.conv3x3_tc_f16(_cuda(buf)[..., :Cin], wp, _cuda(b), Cin, Cout, dilation=dil, alpha=0.1, stride=stride, out=out[..., 4:4 + Cout])
+    np.testing.assert_allclose(out[..., 4:4 + Cout].cpu().numpy(), ref, atol=2e-5, rtol=0)
+    np.testing.assert_allclose(out[..., 4:4 + Cout].cpu().numpy(), base.cpu().numpy(), atol=1e-5, rtol=0)
+    assert (out[..., :4] == 7.0).all() and (out[..., 4 + Cout:] == 7.0).all()
+
+
 HALO_CASES = [  # rows of >= 96 pixels, stride 1, Cout <= 128 take the halo-resident kernel (conv_tc_halo.cu)
     # (B, H, W, Cin, channel stride, Cout, dilation)
     (1, 4, 128, 32, 32, 32, 1), (1, 9, 130, 32, 32, 16, 1), (2, 14, 256, 128, 128, 128, 1), (1, 7, 200, 147, 148, 128, 1),
