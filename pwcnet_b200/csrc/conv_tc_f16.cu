@@ -540,7 +540,7 @@ static int launch_conv_f16(const float* x, int x_cs, const void* w_packed, const
     // (clusters are placed inside one GPC: not every SM count is reachable).
     // OPT-IN (PWC_TC_KSPLIT=1): measured +0.7 % on the B = 8 forward (level 6: 31 -> 24 us per layer, the launch's fixed costs
     // remain), but whether a layer is split depends on its tile count, i.e. on the batch size, and the split changes the fp32
-    // summation order -- the default path keeps results bit-identical across batch sizes (tests/test_gpu_fullsize.py).
+    // summation order -- with it a batch of 2 no longer reproduces the single pair bit for bit (tests/test_gpu_fullsize.py).
     const int n_split_only = p.n_parts;
     size_t smem = 0;
     const char* ks = getenv("PWC_TC_KSPLIT");
