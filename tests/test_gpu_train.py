@@ -479,9 +479,10 @@ def test_trainer_rejects_unsupported_models(P):
         Trainer(P.PWCDCNet(precision="cudnn"))
 
 
+@pytest.mark.parametrize("precision", ["3xf16", "fp32"])     # tcgen05 dgrad epilogues / CUDA-core dgrad kernels
 @pytest.mark.parametrize("use_dc", [False, True])
 @pytest.mark.parametrize("shape", [(2, 64, 128), (1, 192, 320)])
-def test_uncleared_gradient_buffers_are_fully_overwritten(P, use_dc, shape):
+def test_uncleared_gradient_buffers_are_fully_overwritten(P, use_dc, shape, precision):
     """`Trainer.backward` clears only the activation-gradient buffers whose first writer accumulates (`_grad_buffers`);
     the others must be overwritten completely by their one dgrad.  Poison them with NaN between two backward passes over
     the same batch: every gradient stays finite and unchanged (flat-slot and row-tile dgrad epilogues, plain and dense stacks)."""
@@ -490,7 +491,7 @@ def test_uncleared_gradient_buffers_are_fully_overwritten(P, use_dc, shape):
     W = O.glorot_weights(7, gain=1.2, bias_scale=0.02, use_dc=use_dc)
     im0, im1 = O.synthetic_pair(B, H, W_, 3, shift=(3, -2))
     gt = np.random.default_rng(2).normal(0, 4, (B, H, W_, 2)).astype(np.float32)
-    model = P.PWCDCNet(weights=W, use_dc=use_dc)
+    model = P.PWCDCNet(weights=W, use_dc=use_dc, precision=precision)
     tr = Trainer(model)
     tr.forward_backward(im0, im1, gt)
     torch.cuda.synchronize()
